@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched EKF-SLAM hot path (BASELINE.json metric).
+
+Metric: EKF predict+update steps/sec at 64K filters x 12 landmarks (fp64, known correspondence), reported
+as filter-steps/s (one filter-step = 1 predict + 12 sequential updates = one iteration of
+nuslam/src/slam.cpp:262-319 with 12 markers) and as a fraction of the measured HBM roofline.
+
+  python bench.py --gpus N --steps K --warmup W          # our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W  # the reference's CPU implementation, host cores
+
+One JSON line on stdout (rank 0). See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_LANDMARKS = 12
+FILTERS_PER_GPU = 65536
+LEN = 3 + 2 * N_LANDMARKS
+# algorithmic bytes per filter-step: read x 216 + Sigma 5832 + u 16 + z 192 + ids 48, write x 216 + Sigma 5832
+BYTES_PER_FILTER_STEP = 2 * 8 * (LEN + LEN * LEN) + 16 + 20 * N_LANDMARKS
+METRIC = "EKF predict+update filter-steps/s (64K filters x 12 landmarks per GPU, fp64, known correspondence)"
+UNIT = "filter-steps/s"
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def make_inputs_device(torch, dev, B, steps_total, seed):
+    """Synthetic config-2 inputs generated on the device (data: synthetic): robot on the reference circle
+    (d_theta 0.02, dx 0.007 per step), 12 landmarks on the benign ring, exact range/bearing + N(0, 0.01^2)."""
+    from shermbot_navigation_b200 import synth
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    tw1 = synth.wheel_twists(steps_total + 1, first_step_straight=True)
+    poses = synth.true_trajectory(tw1)
+    lm = synth.landmark_ring(N_LANDMARKS, 0.20)
+    dxl = lm[None, :, 0] - poses[:, None, 1]
+    dyl = lm[None, :, 1] - poses[:, None, 2]
+    rng_true = torch.tensor(np.sqrt(dxl * dxl + dyl * dyl), device=dev)                      # (T, n)
+    brg_true = torch.tensor(synth.wrap_pi(np.arctan2(dyl, dxl) - poses[:, None, 0]), device=dev)
+    robot0 = (torch.randn((B, 3), generator=g, device=dev, dtype=torch.float64) * 0.01).cpu().numpy()
+    twists = torch.tensor(tw1, device=dev)[:, None, :].expand(-1, B, -1).contiguous()           # (T, B, 3)
+    ids = torch.arange(1, N_LANDMARKS + 1, device=dev, dtype=torch.int32)[None, :].expand(B, -1).contiguous()
+
+    def z_of(t):
+        noise = torch.randn((B, N_LANDMARKS, 2), generator=g, device=dev, dtype=torch.float64) * 0.01
+        z = torch.empty((B, N_LANDMARKS, 2), device=dev, dtype=torch.float64)
+        z[..., 0] = rng_true[t][None, :] + noise[..., 0]
+        b = brg_true[t][None, :] + noise[..., 1]
+        z[..., 1] = torch.atan2(torch.sin(b), torch.cos(b))
+        return z
+
+    return robot0, twists, ids, z_of
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from shermbot_navigation_b200 import nuslam
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.filters, args.steps, args.warmup
+    total_steps = W + K + 2
+    robot0, twists, ids, z_of = make_inputs_device(torch, dev, B, total_steps, seed=1234 + rank)
+    stream = torch.cuda.current_stream(dev)
+    eng = nuslam.BatchedExtendedKalman(robot0, None, n_landmarks=N_LANDMARKS, mode=args.mode, device=local, stream=stream.cuda_stream)
+    # state lives in torch tensors so that the final gather is a plain NCCL collective on them
+    xs = torch.zeros((B, LEN), device=dev, dtype=torch.float64)
+    sig = torch.zeros((B, LEN, LEN), device=dev, dtype=torch.float64)
+    seen = torch.zeros(B, device=dev, dtype=torch.int32)
+    status = torch.zeros(B, device=dev, dtype=torch.int32)
+    x0, s0, n0, st0 = eng.get_state()
+    xs.copy_(torch.from_numpy(x0))
+    sig.copy_(torch.from_numpy(np.ascontiguousarray(np.transpose(s0, (0, 2, 1)))))
+    torch.cuda.synchronize(dev)
+    eng.bind_state(xs, sig, seen, status)
+    zs = [z_of(t) for t in range(total_steps)]          # resident in HBM before the timed region
+    torch.cuda.synchronize(dev)
+
+    # step 0 touches every landmark for the first time (strict arithmetic inside the kernel); then W warm-up steps
+    t = 0
+    eng.step(twists[t], zs[t], ids)
+    t += 1
+    for _ in range(W):
+        eng.step(twists[t], zs[t], ids)
+        t += 1
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    ev0.record(stream)
+    for _ in range(K):
+        eng.step(twists[t], zs[t], ids)
+        t += 1
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max = float(ms_t.item())
+    bad = int((status != 0).sum().item()) + int((~torch.isfinite(xs)).any(dim=1).sum().item())
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    Ke = max(3, min(K, args.e2e_steps))
+    h_tw = [torch.empty((B, 3), dtype=torch.float64).pin_memory() for _ in range(2)]
+    h_z = [torch.empty((B, N_LANDMARKS, 2), dtype=torch.float64).pin_memory() for _ in range(2)]
+    h_ids = ids.cpu().pin_memory()
+    for k in range(2):
+        h_tw[k].copy_(twists[t + k])
+        h_z[k].copy_(zs[t + k])
+    torch.cuda.synchronize(dev)
+    for k in range(2):   # warm the host path (staging buffers, page locks)
+        eng.step(h_tw[k % 2].numpy(), h_z[k % 2].numpy(), h_ids.numpy())
+        _ = eng.getStateVector()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(Ke):
+        eng.step(h_tw[k % 2].numpy(), h_z[k % 2].numpy(), h_ids.numpy())   # H2D inside
+        x_host = eng.getStateVector()                                      # D2H of the step's result
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * Ke / float(e2e_t.item())
+    h2d = B * (3 * 8 + N_LANDMARKS * 2 * 8 + N_LANDMARKS * 4)
+    d2h = B * LEN * 8
+
+    # ---- the only communication of the whole run: gather final states + error statistics (NCCL over NVLink) ----
+    if world > 1:
+        gathered = torch.empty((world * B, LEN), device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(gathered, xs)
+        stats = torch.tensor([float(bad)], device=dev, dtype=torch.float64)
+        dist.all_reduce(stats)
+        bad = int(stats.item())
+
+    out = None
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        per_launch_s = ms_max / 1e3 / K
+        achieved = B * BYTES_PER_FILTER_STEP / per_launch_s / 1e9
+        traffic = None
+        prof = ROOT / "profiles" / "ncu_summary.json"
+        if prof.exists():
+            try:
+                traffic = json.loads(prof.read_text()).get("ekf_step_traffic_bytes_per_launch")
+            except Exception:
+                pass
+        value = world * B * K / (ms_max / 1e3)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[1]: batched 64K independent EKF filters x 12 landmarks, known correspondence, fp64",
+                       "filters_per_gpu": B, "landmarks": N_LANDMARKS, "state_len": LEN, "mode": args.mode,
+                       "batched_steps_per_s": value / (world * B) if B else None,
+                       "l2": f"inputs larger than L2: filter state {B * (LEN + LEN * LEN) * 8 / 1e6:.0f} MB per GPU is streamed every step (L2 126 MB)",
+                       "parallelism": f"filters sharded {world}x, no data-path collective; final NCCL all_gather of states"},
+            "clocks": clocks, "gpu_launches": K, "bad_filters": bad,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_filter_step": BYTES_PER_FILTER_STEP,
+                         "kernel": "k_ekf_fast_step" if args.mode == "fast" else "k_ekf_strict<kOpStep>", "launch_us": per_launch_s * 1e6},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return out
+
+
+def cpu_reference_run(n_filters, n_steps, nthreads):
+    """Time the reference's own CPU implementation (oracle/_ref when built, else the C restatement) on a bounded
+    sample of the same workload: n_filters filters x n_steps fused steps after the first-touch step."""
+    import oracle
+    from shermbot_navigation_b200 import synth
+    orc = oracle.best()
+    sc = synth.ekf_scenario(n_filters, n_steps + 1, n=N_LANDMARKS, seed=4321)
+    first = orc.ekf_run(N_LANDMARKS, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][:1], sc["z"][:1], sc["ids"][:1], nthreads=nthreads)
+    t0 = time.perf_counter()
+    orc.ekf_run(N_LANDMARKS, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][1:], sc["z"][1:], sc["ids"][1:],
+                init=(first["x"], first["sigma"], first["seen"]), nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return n_filters * n_steps / dt, dt, ("reference" if orc.kind.startswith("ref") else "port")
+
+
+def cpu_baseline(target_seconds=12.0):
+    cores = os.cpu_count() or 1
+    # calibrate on a tiny run, then size the sample for ~target_seconds of wall time on all cores
+    rate, _, kind = cpu_reference_run(4 * cores, 10, cores)
+    n_steps = 50
+    n_filters = int(max(cores, min(64 * cores, rate * target_seconds / n_steps)))
+    n_filters = max(cores, (n_filters // cores) * cores)
+    rate, dt, kind = cpu_reference_run(n_filters, n_steps, cores)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{n_filters} filters x {n_steps} fused steps (12 landmarks, known correspondence) on {cores} threads, {dt:.1f} s; "
+                      "naive-loop Armadillo shim, -O2 -ffp-contract=off"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return None
+    cores = os.cpu_count() or 1
+    K, W = args.steps, args.warmup
+    # each "step" = one batched fused step over a bounded sample of the 64K-filter workload
+    rate, _, kind = cpu_reference_run(4 * cores, 5, cores)
+    per_step_budget = min(2.0, 150.0 / max(1, K + W))
+    n_filters = int(max(cores, min(FILTERS_PER_GPU, rate * per_step_budget)))
+    n_filters = max(cores, (n_filters // cores) * cores)
+    import oracle
+    from shermbot_navigation_b200 import synth
+    orc = oracle.best()
+    sc = synth.ekf_scenario(n_filters, 2, n=N_LANDMARKS, seed=4321)
+    st = orc.ekf_run(N_LANDMARKS, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][:1], sc["z"][:1], sc["ids"][:1], nthreads=cores)
+    state = (st["x"], st["sigma"], st["seen"])
+    times = []
+    for k in range(W + K):
+        t0 = time.perf_counter()
+        st = orc.ekf_run(N_LANDMARKS, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][1:2], sc["z"][1:2], sc["ids"][1:2], init=state, nthreads=cores)
+        dt = time.perf_counter() - t0
+        state = (st["x"], st["sigma"], st["seen"])
+        if k >= W:
+            times.append(dt)
+    total = float(np.sum(times))
+    value = n_filters * K / total
+    sample = (f"{n_filters} of {FILTERS_PER_GPU} filters per step x {K} steps on {cores} host threads "
+              f"({'oracle/_ref: unmodified reference sources' if kind == 'reference' else 'oracle C restatement'}, naive-loop Armadillo shim, -O2)")
+    return {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: batched 64K independent EKF filters x 12 landmarks, known correspondence, fp64 "
+                               "(reference CPU implementation timed on a bounded sample)", "filters_per_step": n_filters, "landmarks": N_LANDMARKS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--filters", type=int, default=FILTERS_PER_GPU)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+/* include/nuslam_b200.h -- C ABI of the B200-native batched EKF-SLAM + scan circle-detection engine.
+ *
+ * Drop-in boundary for the hot path of sziselman/Shermbot-Navigation. The reference has no FFI or
+ * plugin layer: its seam is the C++ API of two catkin libraries, `libnuslam`
+ * (nuslam/include/nuslam/slam_library.hpp:18-113, nuslam/include/nuslam/circle_fit_library.hpp:18-28)
+ * and `librigid2d`. Every entry point below is the batched (B filters / S scans per call) form of one
+ * of those functions and cites the interface it replaces; the B = 1 C++ facade that keeps the
+ * reference's class and function names lives in include/nuslam_b200/ (slam_library.hpp,
+ * circle_fit_library.hpp, rigid2d.hpp, diff_drive.hpp).
+ *
+ * Conventions (all inherited from the reference):
+ *   - state vector x = [theta, x, y, m1x, m1y, ...], length len = 3 + 2n   (slam_library.cpp:46-59)
+ *   - landmark ids are 1-based; slot of id j is 3 + 2(j-1)                  (slam_library.cpp:152-153)
+ *   - matrices are column-major (Armadillo): Sigma[b][col*len + row], Q[col*3 + row], R[col*2 + row]
+ *   - a twist is (dth, dx, dy) in that order                                (rigid2d.hpp:150-155)
+ *   - a measurement z is polar (range, bearing)                             (slam_library.cpp:16-22)
+ *
+ * Plain pointers and sizes only. Each array argument is either a host pointer or a device pointer on
+ * the handle's device, as stated by the `mem` argument of the call (NUSLAM_HOST / NUSLAM_DEVICE).
+ * With NUSLAM_DEVICE a call only enqueues work on the handle's stream (use nuslam_ekf_synchronize or
+ * your own stream/event ordering); with NUSLAM_HOST it copies in, runs, copies results out and returns
+ * after they have landed. A handle is not thread-safe; independent handles are.
+ *
+ * There is NO CPU fallback: every compute entry point runs hand-written sm_100a kernels and returns
+ * NUSLAM_ERR_CUDA when no such device is present.
+ */
+#ifndef NUSLAM_B200_H
+#define NUSLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NUSLAM_B200_VERSION 100
+
+/* ---- return codes of every entry point ---- */
+enum
+{
+    NUSLAM_OK = 0,
+    NUSLAM_ERR_INVALID = 1,     /* bad argument (null handle, m < 0, n_landmarks < 1, ...) */
+    NUSLAM_ERR_CUDA = 2,        /* CUDA runtime error or no sm_100 device; see nuslam_last_error() */
+    NUSLAM_ERR_NOMEM = 3,
+    NUSLAM_ERR_UNSUPPORTED = 4  /* configuration outside what the kernels cover (e.g. state too long for the batched path) */
+};
+
+enum
+{
+    NUSLAM_HOST = 0,
+    NUSLAM_DEVICE = 1
+};
+
+/* ---- arithmetic mode ----
+ * STRICT reproduces the operation order of the reference's dense expressions
+ *   A*Sigma*A.t()+Q_bar (slam_library.cpp:104), Sigma*H.t()*inv(H*Sigma*H.t()+R) (:270),
+ *   (I-K*H)*Sigma (:279)
+ * term by term (ascending k, unfused multiply/add), skipping only structurally-zero terms, so Sigma is
+ * bit-identical to the oracle given identical inputs.
+ * FAST uses the algebraically identical rank-2 form Sigma -= K*(H*Sigma) with fused multiply-adds and
+ * keeps Sigma in registers; it falls back to the STRICT arithmetic for any update whose landmark still
+ * carries its INT_MAX prior (first touch, slam_library.cpp:28-31), where the reference's
+ * (I-KH)*Sigma cancels catastrophically and only the same operation order reproduces its result. */
+enum
+{
+    NUSLAM_MODE_STRICT = 0,
+    NUSLAM_MODE_FAST = 1
+};
+
+/* ---- per-filter status word (bit mask, sticky); where the reference throws, the engine flags ---- */
+enum
+{
+    NUSLAM_FILTER_OK = 0,
+    NUSLAM_FILTER_MAP_FULL = 1,   /* associateLandmark with seen == n: Armadillo bounds check throws (slam_library.cpp:206).
+                                     The filter is frozen from that measurement on, as the reference process would be dead. */
+    NUSLAM_FILTER_SINGULAR = 2,   /* det(H Sigma H^T + R) == 0: arma::inv throws (slam_library.cpp:231,270); update skipped */
+    NUSLAM_FILTER_BAD_ID = 4      /* update/initializeLandmark with id outside 1..n: bounds check throws; call skipped */
+};
+
+/* id written by nuslam_ekf_associate / nuslam_ekf_step where the reference throws */
+#define NUSLAM_ID_EXCEPTION (-1000)
+
+typedef struct nuslam_ekf nuslam_ekf;
+
+typedef struct
+{
+    int32_t n_landmarks;   /* n = mapState.n_elem / 2 (slam_library.cpp:42) */
+    int32_t mode;          /* NUSLAM_MODE_* */
+    double Q[9];           /* 3x3 process noise, column-major, (theta,x,y) order (slam_library.cpp:110-125) */
+    double R[4];           /* 2x2 sensor noise, column-major (slam_library.cpp:215,270) */
+    double assoc_min;      /* 0.01 (slam_library.cpp:193) */
+    double assoc_max;      /* 60   (slam_library.cpp:194) */
+} nuslam_ekf_config;
+
+/* Q = 0.1 I, R = 0.001 I (nuslam/config/slam_params.yaml:2-3), thresholds 0.01 / 60, STRICT mode */
+void nuslam_ekf_default_config(nuslam_ekf_config * cfg, int32_t n_landmarks);
+
+const char * nuslam_last_error(void);
+int nuslam_version(void);
+
+/* Create B independent filters on `device`. `cuda_stream` is a cudaStream_t (NULL: the handle creates
+ * its own non-blocking stream). State memory is owned by the handle unless nuslam_ekf_bind_state is
+ * called. Replaces: ExtendedKalman::ExtendedKalman(robotState, mapState, Q, R), slam_library.cpp:39-63
+ * (the state itself is set by nuslam_ekf_init). */
+int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, void * cuda_stream,
+                      nuslam_ekf ** out);
+int nuslam_ekf_destroy(nuslam_ekf * h);
+
+/* Use caller-owned device buffers for the filter state (x: B*len f64, sigma: B*len*len f64,
+ * seen: B i32, status: B i32), e.g. torch tensors that NCCL gathers at the end of a run. */
+int nuslam_ekf_bind_state(nuslam_ekf * h, double * x_dev, double * sigma_dev, int32_t * seen_dev,
+                          int32_t * status_dev);
+int nuslam_ekf_device_pointers(nuslam_ekf * h, double ** x_dev, double ** sigma_dev, int32_t ** seen_dev,
+                               int32_t ** status_dev);
+
+/* Constructor semantics for every filter: x = [robot_state(3), map_state(2n)], Sigma = 0 with INT_MAX on
+ * the landmark diagonal, seen = 0, status = OK.  robot_state: B x 3, map_state: B x 2n (NULL = zeros, as
+ * slam.cpp:140-157 does).  Replaces slam_library.cpp:39-63 + initCov :24-33. */
+int nuslam_ekf_init(nuslam_ekf * h, const double * robot_state, const double * map_state, int mem);
+
+/* Checkpoint / restore / teacher forcing. NULL pointers are skipped. Replaces the getters
+ * getStateVector / getCovariance / getSeenLandmarks (slam_library.cpp:284-297). */
+int nuslam_ekf_set_state(nuslam_ekf * h, const double * x, const double * sigma, const int32_t * seen,
+                         const int32_t * status, int mem);
+int nuslam_ekf_get_state(nuslam_ekf * h, double * x, double * sigma, int32_t * seen, int32_t * status,
+                         int mem);
+
+/* ExtendedKalman::predict(tw), slam_library.cpp:65-69. twists: B x 3 (dth, dx, dy). */
+int nuslam_ekf_predict(nuslam_ekf * h, const double * twists, int mem);
+
+/* ExtendedKalman::associateLandmark(z_i), slam_library.cpp:188-253. z: B x 2; id_out: B
+ * (k >= 1 existing or new landmark, -1 ambiguous, NUSLAM_ID_EXCEPTION when the map is full).
+ * Mutates `seen` exactly as the reference does. */
+int nuslam_ekf_associate(nuslam_ekf * h, const double * z, int32_t * id_out, int mem);
+
+/* ExtendedKalman::initializeLandmark(z_i, id), slam_library.cpp:255-261. id: B (id <= 0: skip that filter). */
+int nuslam_ekf_initialize_landmark(nuslam_ekf * h, const double * z, const int32_t * id, int mem);
+
+/* ExtendedKalman::update(tw, z_id, id), slam_library.cpp:263-282 (tw is unused by the reference).
+ * id: B (id <= 0: skip that filter). */
+int nuslam_ekf_update(nuslam_ekf * h, const double * z, const int32_t * id, int mem);
+
+/* computeTheoreticalMeasurement(j, state) :150-160 and linearizedMeasurementModel(j, state) :162-186,
+ * evaluated at each filter's current state. j: B; zhat: B x 2 (may be NULL); H: B x (2 x len)
+ * column-major (may be NULL). */
+int nuslam_ekf_measurement_model(nuslam_ekf * h, const int32_t * j, double * zhat, double * H, int mem);
+
+/* One iteration of the caller protocol EKFSlam::main_loop, nuslam/src/slam.cpp:262-319, fused:
+ *   seen_snapshot = seen; predict(twist);
+ *   for i in 0..m-1:  id = ids ? ids[i] : associateLandmark(z_i)
+ *                     if id > seen_snapshot: initializeLandmark(z_i, id)
+ *                     else if id < 0: continue
+ *                     update(twist, z_i, id)
+ * twists: B x 3; z: B x m x 2; ids: B x m (NULL = unknown data association; with known
+ * correspondence id <= 0 means "no measurement in this slot" and `seen = max(seen, id)` stands in for
+ * what associateLandmark would have done); ids_out: B x m or NULL. */
+int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, const int32_t * ids, int32_t m,
+                    int32_t * ids_out, int mem);
+
+int nuslam_ekf_synchronize(nuslam_ekf * h);
+
+/* slam_library::cartesian2polar(x, y), slam_library.cpp:16-22, batched: xy count x 2 -> rb count x 2. */
+int nuslam_cartesian2polar(const double * xy, double * rb, int64_t count, int mem, int device,
+                           void * cuda_stream);
+
+/* rigid2d::normalize_angle, rigid2d/src/rigid2d.cpp:9-13, batched. */
+int nuslam_normalize_angle(const double * rad_in, double * rad_out, int64_t count, int mem, int device,
+                           void * cuda_stream);
+
+/* ------------------------------------------------------------------ scan -> landmarks
+ * circle_fit::clusterPoints (circle_fit_library.cpp:136-206), classifyCluster (:208-250), circleFit
+ * (:15-134) and the Landmarks::main_loop protocol (nuslam/src/landmarks.cpp:84-109), batched over S
+ * scans of exactly 360 float ranges.
+ *   cluster_of_beam : S x 360 int16, index of the returned cluster holding the beam, -1 for none
+ *   n_clusters      : S      number of clusters clusterPoints returns (after its erase loop)
+ *   n_circles       : S      number of markers the landmarks node would publish; NUSLAM_SCAN_UB where the
+ *                            reference indexes clusters[0] of an empty vector (undefined behaviour)
+ *   circles         : S x max_circles x 4  (cx, cy, R = scale.x/2, cluster index), detection order
+ */
+#define NUSLAM_SCAN_UB (-2000)
+#define NUSLAM_SCAN_BEAMS 360
+
+int nuslam_scan_detect(const float * ranges, int64_t n_scans, double min_range, double max_range,
+                       int16_t * cluster_of_beam, int32_t * n_clusters, int32_t * n_circles,
+                       double * circles, int32_t max_circles, int mem, int device, void * cuda_stream);
+
+/* circle_fit::classifyCluster / circleFit on explicit point lists: C clusters, cluster c owns points
+ * offsets[c] .. offsets[c+1]-1 of px/py. is_circle: C (0/1); fit: C x 4 (marker.id, cx, cy, R). */
+int nuslam_classify_and_fit(const double * px, const double * py, const int32_t * offsets, int64_t n_clusters,
+                            int32_t * is_circle, double * fit, int mem, int device, void * cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

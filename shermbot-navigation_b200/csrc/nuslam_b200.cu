@@ -1,0 +1,639 @@
+// nuslam_b200.cu -- C ABI (include/nuslam_b200.h) over the sm_100a kernels.
+//
+// Host side of the drop-in boundary: owns device memory, streams and staging, validates arguments and
+// launches the kernels in ekf_strict.cuh / ekf_fast.cuh / scan_detect.cuh. No CPU arithmetic path exists
+// here: without a CUDA device every compute entry point fails with NUSLAM_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include <string>
+
+#include "nuslam_b200.h"
+#include "ekf_common.cuh"
+#include "ekf_strict.cuh"
+#include "ekf_misc.cuh"
+#include "ekf_fast.cuh"
+#include "scan_detect.cuh"
+
+namespace
+{
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char * what)
+{
+    g_last_error = what;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char * where)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s", where, cudaGetErrorString(e));
+    g_last_error = buf;
+    return NUSLAM_ERR_CUDA;
+}
+
+#define CU(call)                                              \
+    do                                                        \
+    {                                                         \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
+    } while (0)
+
+// grow-only device scratch buffer
+struct DevBuf
+{
+    void * p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return NUSLAM_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(staging)");
+        cap = bytes;
+        return NUSLAM_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}   // namespace
+
+struct nuslam_ekf
+{
+    nuslam_ekf_config cfg;
+    int64_t batch = 0;
+    int len = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    // state
+    double * x = nullptr;
+    double * sigma = nullptr;
+    int32_t * seen = nullptr;
+    int32_t * status = nullptr;
+    bool own_state = true;
+    // staging for NUSLAM_HOST calls
+    DevBuf s_tw, s_z, s_ids, s_ids_out, s_misc;
+    size_t strict_smem = 0;   // per-warp shared memory of the strict kernels, bytes
+    int strict_warps = 4;
+};
+
+namespace
+{
+
+int select_device(const nuslam_ekf * h)
+{
+    CU(cudaSetDevice(h->device));
+    return NUSLAM_OK;
+}
+
+// copy `bytes` from a user pointer (host or device) into a staging buffer when it lives on the host
+template <typename T>
+int stage_in(nuslam_ekf * h, DevBuf & buf, const T * user, size_t count, int mem, const T ** dev_out)
+{
+    if (!user)
+    {
+        *dev_out = nullptr;
+        return NUSLAM_OK;
+    }
+    if (mem == NUSLAM_DEVICE)
+    {
+        *dev_out = user;
+        return NUSLAM_OK;
+    }
+    int rc = buf.reserve(count * sizeof(T));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(buf.p, user, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    *dev_out = static_cast<const T *>(buf.p);
+    return NUSLAM_OK;
+}
+
+nuslam::EkfParams make_params(nuslam_ekf * h)
+{
+    nuslam::EkfParams p;
+    memset(&p, 0, sizeof(p));
+    p.batch = h->batch;
+    p.len = h->len;
+    p.n = h->cfg.n_landmarks;
+    p.m = 0;
+    p.x = h->x;
+    p.sigma = h->sigma;
+    p.seen = h->seen;
+    p.status = h->status;
+    memcpy(p.Q, h->cfg.Q, sizeof(p.Q));
+    memcpy(p.R, h->cfg.R, sizeof(p.R));
+    p.amin = h->cfg.assoc_min;
+    p.amax = h->cfg.assoc_max;
+    return p;
+}
+
+template <int OP>
+int launch_strict(nuslam_ekf * h, const nuslam::EkfParams & p)
+{
+    const int warps = h->strict_warps;
+    const size_t smem = h->strict_smem * warps;
+    static thread_local size_t configured[8] = {0};
+    if (configured[OP] < smem)
+    {
+        CU(cudaFuncSetAttribute(nuslam::k_ekf_strict<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        configured[OP] = smem;
+    }
+    const int64_t blocks = (h->batch + warps - 1) / warps;
+    nuslam::k_ekf_strict<OP><<<(unsigned) blocks, warps * 32, smem, h->stream>>>(p);
+    CU(cudaGetLastError());
+    return NUSLAM_OK;
+}
+
+int finish(nuslam_ekf * h, int mem)
+{
+    if (mem == NUSLAM_HOST) CU(cudaStreamSynchronize(h->stream));
+    return NUSLAM_OK;
+}
+
+}   // namespace
+
+extern "C" {
+
+const char * nuslam_last_error(void) { return g_last_error.c_str(); }
+int nuslam_version(void) { return NUSLAM_B200_VERSION; }
+
+void nuslam_ekf_default_config(nuslam_ekf_config * cfg, int32_t n_landmarks)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->n_landmarks = n_landmarks;
+    cfg->mode = NUSLAM_MODE_STRICT;
+    cfg->Q[0] = cfg->Q[4] = cfg->Q[8] = 0.1;   // nuslam/config/slam_params.yaml:3
+    cfg->R[0] = cfg->R[3] = 0.001;             // nuslam/config/slam_params.yaml:2
+    cfg->assoc_min = 0.01;                     // slam_library.cpp:193
+    cfg->assoc_max = 60;                       // slam_library.cpp:194
+}
+
+int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, void * cuda_stream, nuslam_ekf ** out)
+{
+    if (!cfg || !out) return fail(NUSLAM_ERR_INVALID, "null config or output pointer");
+    if (cfg->n_landmarks < 1 || batch < 1) return fail(NUSLAM_ERR_INVALID, "n_landmarks and batch must be >= 1");
+    if (cfg->mode != NUSLAM_MODE_STRICT && cfg->mode != NUSLAM_MODE_FAST) return fail(NUSLAM_ERR_INVALID, "unknown mode");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount (this engine has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(NUSLAM_ERR_CUDA, "no such CUDA device (this engine has no CPU path)");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(NUSLAM_ERR_CUDA, "device is not sm_100 or newer; kernels are built for sm_100a only");
+
+    nuslam_ekf * h = new (std::nothrow) nuslam_ekf();
+    if (!h) return fail(NUSLAM_ERR_NOMEM, "host allocation failed");
+    h->cfg = *cfg;
+    h->batch = batch;
+    h->len = 3 + 2 * cfg->n_landmarks;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->strict_smem = sizeof(double) * (size_t) nuslam::strict_smem_doubles(h->len);
+    h->strict_warps = 4;
+    while (h->strict_warps > 1 && h->strict_smem * h->strict_warps > 200 * 1024) h->strict_warps /= 2;
+    if (h->strict_smem * h->strict_warps > (size_t) prop.sharedMemPerBlockOptin)
+    {
+        delete h;
+        return fail(NUSLAM_ERR_UNSUPPORTED, "state too long for the shared-memory batched path (large-map mode required)");
+    }
+    if (cfg->mode == NUSLAM_MODE_FAST && !nuslam::fast_supported(cfg->n_landmarks))
+    {
+        delete h;
+        return fail(NUSLAM_ERR_UNSUPPORTED, "FAST mode is instantiated for n_landmarks in {6, 12} only");
+    }
+    if (cuda_stream)
+    {
+        h->stream = static_cast<cudaStream_t>(cuda_stream);
+        h->own_stream = false;
+    }
+    else
+    {
+        e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess)
+        {
+            delete h;
+            return cuda_fail(e, "cudaStreamCreate");
+        }
+        h->own_stream = true;
+    }
+    const size_t l = (size_t) h->len;
+    cudaError_t e1 = cudaMalloc(&h->x, sizeof(double) * l * batch);
+    cudaError_t e2 = cudaMalloc(&h->sigma, sizeof(double) * l * l * batch);
+    cudaError_t e3 = cudaMalloc(&h->seen, sizeof(int32_t) * batch);
+    cudaError_t e4 = cudaMalloc(&h->status, sizeof(int32_t) * batch);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess)
+    {
+        nuslam_ekf_destroy(h);
+        return fail(NUSLAM_ERR_NOMEM, "device allocation of the filter state failed");
+    }
+    h->own_state = true;
+    cudaMemsetAsync(h->x, 0, sizeof(double) * l * batch, h->stream);
+    cudaMemsetAsync(h->sigma, 0, sizeof(double) * l * l * batch, h->stream);
+    cudaMemsetAsync(h->seen, 0, sizeof(int32_t) * batch, h->stream);
+    cudaMemsetAsync(h->status, 0, sizeof(int32_t) * batch, h->stream);
+    *out = h;
+    return NUSLAM_OK;
+}
+
+int nuslam_ekf_destroy(nuslam_ekf * h)
+{
+    if (!h) return NUSLAM_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->own_state)
+    {
+        if (h->x) cudaFree(h->x);
+        if (h->sigma) cudaFree(h->sigma);
+        if (h->seen) cudaFree(h->seen);
+        if (h->status) cudaFree(h->status);
+    }
+    h->s_tw.release();
+    h->s_z.release();
+    h->s_ids.release();
+    h->s_ids_out.release();
+    h->s_misc.release();
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return NUSLAM_OK;
+}
+
+int nuslam_ekf_bind_state(nuslam_ekf * h, double * x_dev, double * sigma_dev, int32_t * seen_dev, int32_t * status_dev)
+{
+    if (!h || !x_dev || !sigma_dev || !seen_dev || !status_dev) return fail(NUSLAM_ERR_INVALID, "null pointer");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->own_state)
+    {
+        cudaFree(h->x);
+        cudaFree(h->sigma);
+        cudaFree(h->seen);
+        cudaFree(h->status);
+    }
+    h->own_state = false;
+    h->x = x_dev;
+    h->sigma = sigma_dev;
+    h->seen = seen_dev;
+    h->status = status_dev;
+    return NUSLAM_OK;
+}
+
+int nuslam_ekf_device_pointers(nuslam_ekf * h, double ** x_dev, double ** sigma_dev, int32_t ** seen_dev, int32_t ** status_dev)
+{
+    if (!h) return fail(NUSLAM_ERR_INVALID, "null handle");
+    if (x_dev) *x_dev = h->x;
+    if (sigma_dev) *sigma_dev = h->sigma;
+    if (seen_dev) *seen_dev = h->seen;
+    if (status_dev) *status_dev = h->status;
+    return NUSLAM_OK;
+}
+
+int nuslam_ekf_init(nuslam_ekf * h, const double * robot_state, const double * map_state, int mem)
+{
+    if (!h || !robot_state) return fail(NUSLAM_ERR_INVALID, "null handle or robot_state");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    const int n = h->cfg.n_landmarks;
+    const double * d_robot = nullptr;
+    const double * d_map = nullptr;
+    int rc = stage_in(h, h->s_tw, robot_state, (size_t) h->batch * 3, mem, &d_robot);
+    if (rc) return rc;
+    rc = stage_in(h, h->s_z, map_state, (size_t) h->batch * 2 * n, mem, &d_map);
+    if (rc) return rc;
+    const int64_t total = h->batch * (int64_t) h->len * h->len;
+    const int threads = 256;
+    const int64_t blocks = (total + threads - 1) / threads;
+    nuslam::k_ekf_init<<<(unsigned) blocks, threads, 0, h->stream>>>(h->batch, h->len, d_robot, d_map, h->x, h->sigma, h->seen, h->status);
+    CU(cudaGetLastError());
+    return finish(h, mem);
+}
+
+int nuslam_ekf_set_state(nuslam_ekf * h, const double * x, const double * sigma, const int32_t * seen, const int32_t * status, int mem)
+{
+    if (!h) return fail(NUSLAM_ERR_INVALID, "null handle");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    const cudaMemcpyKind kind = (mem == NUSLAM_HOST) ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const size_t l = (size_t) h->len;
+    if (x) CU(cudaMemcpyAsync(h->x, x, sizeof(double) * l * h->batch, kind, h->stream));
+    if (sigma) CU(cudaMemcpyAsync(h->sigma, sigma, sizeof(double) * l * l * h->batch, kind, h->stream));
+    if (seen) CU(cudaMemcpyAsync(h->seen, seen, sizeof(int32_t) * h->batch, kind, h->stream));
+    if (status) CU(cudaMemcpyAsync(h->status, status, sizeof(int32_t) * h->batch, kind, h->stream));
+    return finish(h, mem);
+}
+
+int nuslam_ekf_get_state(nuslam_ekf * h, double * x, double * sigma, int32_t * seen, int32_t * status, int mem)
+{
+    if (!h) return fail(NUSLAM_ERR_INVALID, "null handle");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    const cudaMemcpyKind kind = (mem == NUSLAM_HOST) ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    const size_t l = (size_t) h->len;
+    if (x) CU(cudaMemcpyAsync(x, h->x, sizeof(double) * l * h->batch, kind, h->stream));
+    if (sigma) CU(cudaMemcpyAsync(sigma, h->sigma, sizeof(double) * l * l * h->batch, kind, h->stream));
+    if (seen) CU(cudaMemcpyAsync(seen, h->seen, sizeof(int32_t) * h->batch, kind, h->stream));
+    if (status) CU(cudaMemcpyAsync(status, h->status, sizeof(int32_t) * h->batch, kind, h->stream));
+    return finish(h, mem);
+}
+
+int nuslam_ekf_predict(nuslam_ekf * h, const double * twists, int mem)
+{
+    if (!h || !twists) return fail(NUSLAM_ERR_INVALID, "null handle or twists");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    nuslam::EkfParams p = make_params(h);
+    int rc = stage_in(h, h->s_tw, twists, (size_t) h->batch * 3, mem, &p.twists);
+    if (rc) return rc;
+    rc = launch_strict<nuslam::kOpPredict>(h, p);   // predict is O(len) in either mode: the strict order costs nothing extra
+    if (rc) return rc;
+    return finish(h, mem);
+}
+
+int nuslam_ekf_associate(nuslam_ekf * h, const double * z, int32_t * id_out, int mem)
+{
+    if (!h || !z || !id_out) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    nuslam::EkfParams p = make_params(h);
+    p.m = 1;
+    int rc = stage_in(h, h->s_z, z, (size_t) h->batch * 2, mem, &p.z);
+    if (rc) return rc;
+    if (mem == NUSLAM_HOST)
+    {
+        rc = h->s_ids_out.reserve(sizeof(int32_t) * h->batch);
+        if (rc) return rc;
+        p.ids_out = static_cast<int32_t *>(h->s_ids_out.p);
+    }
+    else
+        p.ids_out = id_out;
+    rc = launch_strict<nuslam::kOpAssociate>(h, p);
+    if (rc) return rc;
+    if (mem == NUSLAM_HOST) CU(cudaMemcpyAsync(id_out, p.ids_out, sizeof(int32_t) * h->batch, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h, mem);
+}
+
+int nuslam_ekf_initialize_landmark(nuslam_ekf * h, const double * z, const int32_t * id, int mem)
+{
+    if (!h || !z || !id) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    nuslam::EkfParams p = make_params(h);
+    p.m = 1;
+    int rc = stage_in(h, h->s_z, z, (size_t) h->batch * 2, mem, &p.z);
+    if (rc) return rc;
+    rc = stage_in(h, h->s_ids, id, (size_t) h->batch, mem, &p.ids);
+    if (rc) return rc;
+    rc = launch_strict<nuslam::kOpInit>(h, p);
+    if (rc) return rc;
+    return finish(h, mem);
+}
+
+int nuslam_ekf_update(nuslam_ekf * h, const double * z, const int32_t * id, int mem)
+{
+    if (!h || !z || !id) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    nuslam::EkfParams p = make_params(h);
+    p.m = 1;
+    int rc = stage_in(h, h->s_z, z, (size_t) h->batch * 2, mem, &p.z);
+    if (rc) return rc;
+    rc = stage_in(h, h->s_ids, id, (size_t) h->batch, mem, &p.ids);
+    if (rc) return rc;
+    if (h->cfg.mode == NUSLAM_MODE_FAST)
+    {
+        p.twists = nullptr;   // update only
+        rc = nuslam::launch_fast(h->cfg.n_landmarks, p, /*do_predict=*/false, h->sm_count, h->stream);
+        if (rc == -1) return fail(NUSLAM_ERR_UNSUPPORTED, "FAST mode not instantiated for this n_landmarks");
+        if (rc) return cuda_fail((cudaError_t) rc, "fast update launch");
+    }
+    else
+    {
+        rc = launch_strict<nuslam::kOpUpdate>(h, p);
+        if (rc) return rc;
+    }
+    return finish(h, mem);
+}
+
+int nuslam_ekf_measurement_model(nuslam_ekf * h, const int32_t * j, double * zhat, double * H, int mem)
+{
+    if (!h || !j) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    const int32_t * d_j = nullptr;
+    int rc = stage_in(h, h->s_ids, j, (size_t) h->batch, mem, &d_j);
+    if (rc) return rc;
+    double * d_zhat = zhat;
+    double * d_H = H;
+    const size_t hz = (size_t) h->batch * 2, hh = (size_t) h->batch * 2 * h->len;
+    if (mem == NUSLAM_HOST)
+    {
+        rc = h->s_misc.reserve(sizeof(double) * (hz + hh));
+        if (rc) return rc;
+        d_zhat = zhat ? static_cast<double *>(h->s_misc.p) : nullptr;
+        d_H = H ? static_cast<double *>(h->s_misc.p) + hz : nullptr;
+    }
+    const int threads = 128;
+    const int64_t blocks = (h->batch + threads - 1) / threads;
+    nuslam::k_measurement_model<<<(unsigned) blocks, threads, 0, h->stream>>>(h->batch, h->len, h->cfg.n_landmarks, h->x, d_j, d_zhat, d_H);
+    CU(cudaGetLastError());
+    if (mem == NUSLAM_HOST)
+    {
+        if (zhat) CU(cudaMemcpyAsync(zhat, d_zhat, sizeof(double) * hz, cudaMemcpyDeviceToHost, h->stream));
+        if (H) CU(cudaMemcpyAsync(H, d_H, sizeof(double) * hh, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return finish(h, mem);
+}
+
+int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, const int32_t * ids, int32_t m, int32_t * ids_out, int mem)
+{
+    if (!h || !twists) return fail(NUSLAM_ERR_INVALID, "null handle or twists");
+    if (m < 0 || (m > 0 && !z)) return fail(NUSLAM_ERR_INVALID, "m < 0 or null z");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    nuslam::EkfParams p = make_params(h);
+    p.m = m;
+    int rc = stage_in(h, h->s_tw, twists, (size_t) h->batch * 3, mem, &p.twists);
+    if (rc) return rc;
+    rc = stage_in(h, h->s_z, z, (size_t) h->batch * m * 2, mem, &p.z);
+    if (rc) return rc;
+    rc = stage_in(h, h->s_ids, ids, (size_t) h->batch * m, mem, &p.ids);
+    if (rc) return rc;
+    p.ids_out = ids_out;
+    if (ids_out && mem == NUSLAM_HOST)
+    {
+        rc = h->s_ids_out.reserve(sizeof(int32_t) * h->batch * (m > 0 ? m : 1));
+        if (rc) return rc;
+        p.ids_out = static_cast<int32_t *>(h->s_ids_out.p);
+    }
+    if (h->cfg.mode == NUSLAM_MODE_FAST && p.ids != nullptr)
+    {
+        rc = nuslam::launch_fast(h->cfg.n_landmarks, p, /*do_predict=*/true, h->sm_count, h->stream);
+        if (rc == -1) return fail(NUSLAM_ERR_UNSUPPORTED, "FAST mode not instantiated for this n_landmarks");
+        if (rc) return cuda_fail((cudaError_t) rc, "fast step launch");
+    }
+    else
+    {
+        // unknown data association runs the strict kernel in either mode (association is a per-lane
+        // candidate search over Sigma in shared memory)
+        rc = launch_strict<nuslam::kOpStep>(h, p);
+        if (rc) return rc;
+    }
+    if (ids_out && mem == NUSLAM_HOST && m > 0)
+        CU(cudaMemcpyAsync(ids_out, p.ids_out, sizeof(int32_t) * h->batch * m, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h, mem);
+}
+
+int nuslam_ekf_synchronize(nuslam_ekf * h)
+{
+    if (!h) return fail(NUSLAM_ERR_INVALID, "null handle");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    CU(cudaStreamSynchronize(h->stream));
+    return NUSLAM_OK;
+}
+
+namespace
+{
+int elementwise_io(const double * in, double * out, int64_t count, int in_width, int out_width, int mem, int device, void * cuda_stream, int which)
+{
+    if (!in || !out || count < 0) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (count == 0) return NUSLAM_OK;
+    CU(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const double * d_in = in;
+    double * d_out = out;
+    double * tmp = nullptr;
+    if (mem == NUSLAM_HOST)
+    {
+        CU(cudaMalloc(&tmp, sizeof(double) * count * (in_width + out_width)));
+        CU(cudaMemcpyAsync(tmp, in, sizeof(double) * count * in_width, cudaMemcpyHostToDevice, st));
+        d_in = tmp;
+        d_out = tmp + count * in_width;
+    }
+    const int threads = 256;
+    const int64_t blocks = (count + threads - 1) / threads;
+    if (which == 0) nuslam::k_cartesian2polar<<<(unsigned) blocks, threads, 0, st>>>(d_in, d_out, count);
+    else nuslam::k_normalize_angle<<<(unsigned) blocks, threads, 0, st>>>(d_in, d_out, count);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && mem == NUSLAM_HOST)
+    {
+        e = cudaMemcpyAsync(out, d_out, sizeof(double) * count * out_width, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "elementwise kernel");
+    return NUSLAM_OK;
+}
+}   // namespace
+
+int nuslam_cartesian2polar(const double * xy, double * rb, int64_t count, int mem, int device, void * cuda_stream)
+{
+    return elementwise_io(xy, rb, count, 2, 2, mem, device, cuda_stream, 0);
+}
+
+int nuslam_normalize_angle(const double * rad_in, double * rad_out, int64_t count, int mem, int device, void * cuda_stream)
+{
+    return elementwise_io(rad_in, rad_out, count, 1, 1, mem, device, cuda_stream, 1);
+}
+
+int nuslam_scan_detect(const float * ranges, int64_t n_scans, double min_range, double max_range, int16_t * cluster_of_beam,
+                       int32_t * n_clusters, int32_t * n_circles, double * circles, int32_t max_circles, int mem, int device,
+                       void * cuda_stream)
+{
+    if (!ranges || !n_clusters || !n_circles || !circles || n_scans < 0 || max_circles < 1)
+        return fail(NUSLAM_ERR_INVALID, "null argument or bad sizes");
+    if (n_scans == 0) return NUSLAM_OK;
+    CU(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const float * d_ranges = ranges;
+    int16_t * d_cob = cluster_of_beam;
+    int32_t * d_ncl = n_clusters;
+    int32_t * d_nci = n_circles;
+    double * d_circ = circles;
+    char * tmp = nullptr;
+    const size_t b_r = sizeof(float) * 360 * n_scans, b_cob = sizeof(int16_t) * 360 * n_scans;
+    const size_t b_n = sizeof(int32_t) * n_scans, b_c = sizeof(double) * 4 * max_circles * n_scans;
+    if (mem == NUSLAM_HOST)
+    {
+        auto al = [](size_t v) { return (v + 255) & ~(size_t) 255; };
+        CU(cudaMalloc(&tmp, al(b_r) + al(b_cob) + 2 * al(b_n) + al(b_c)));
+        char * q = tmp;
+        d_ranges = reinterpret_cast<float *>(q);
+        q += al(b_r);
+        d_cob = reinterpret_cast<int16_t *>(q);
+        q += al(b_cob);
+        d_ncl = reinterpret_cast<int32_t *>(q);
+        q += al(b_n);
+        d_nci = reinterpret_cast<int32_t *>(q);
+        q += al(b_n);
+        d_circ = reinterpret_cast<double *>(q);
+        CU(cudaMemcpyAsync(const_cast<float *>(d_ranges), ranges, b_r, cudaMemcpyHostToDevice, st));
+    }
+    cudaError_t e = nuslam::launch_scan_detect(d_ranges, n_scans, min_range, max_range, cluster_of_beam ? d_cob : nullptr, d_ncl, d_nci,
+                                               d_circ, max_circles, st);
+    if (e == cudaSuccess && mem == NUSLAM_HOST)
+    {
+        if (cluster_of_beam) e = cudaMemcpyAsync(cluster_of_beam, d_cob, b_cob, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(n_clusters, d_ncl, b_n, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(n_circles, d_nci, b_n, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(circles, d_circ, b_c, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "scan_detect");
+    return NUSLAM_OK;
+}
+
+int nuslam_classify_and_fit(const double * px, const double * py, const int32_t * offsets, int64_t n_clusters, int32_t * is_circle,
+                            double * fit, int mem, int device, void * cuda_stream)
+{
+    if (!px || !py || !offsets || !is_circle || !fit || n_clusters < 0) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (n_clusters == 0) return NUSLAM_OK;
+    CU(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const double * d_px = px;
+    const double * d_py = py;
+    const int32_t * d_off = offsets;
+    int32_t * d_is = is_circle;
+    double * d_fit = fit;
+    char * tmp = nullptr;
+    if (mem == NUSLAM_HOST)
+    {
+        const int64_t npts = offsets[n_clusters];
+        auto al = [](size_t v) { return (v + 255) & ~(size_t) 255; };
+        const size_t b_p = al(sizeof(double) * npts), b_o = al(sizeof(int32_t) * (n_clusters + 1));
+        const size_t b_i = al(sizeof(int32_t) * n_clusters), b_f = al(sizeof(double) * 4 * n_clusters);
+        CU(cudaMalloc(&tmp, 2 * b_p + b_o + b_i + b_f));
+        char * q = tmp;
+        CU(cudaMemcpyAsync(q, px, sizeof(double) * npts, cudaMemcpyHostToDevice, st));
+        d_px = reinterpret_cast<double *>(q);
+        q += b_p;
+        CU(cudaMemcpyAsync(q, py, sizeof(double) * npts, cudaMemcpyHostToDevice, st));
+        d_py = reinterpret_cast<double *>(q);
+        q += b_p;
+        CU(cudaMemcpyAsync(q, offsets, sizeof(int32_t) * (n_clusters + 1), cudaMemcpyHostToDevice, st));
+        d_off = reinterpret_cast<int32_t *>(q);
+        q += b_o;
+        d_is = reinterpret_cast<int32_t *>(q);
+        q += b_i;
+        d_fit = reinterpret_cast<double *>(q);
+    }
+    const int threads = 128;
+    const int64_t blocks = (n_clusters + threads - 1) / threads;
+    nuslam::k_classify_and_fit<<<(unsigned) blocks, threads, 0, st>>>(d_px, d_py, d_off, n_clusters, d_is, d_fit);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && mem == NUSLAM_HOST)
+    {
+        e = cudaMemcpyAsync(is_circle, d_is, sizeof(int32_t) * n_clusters, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(fit, d_fit, sizeof(double) * 4 * n_clusters, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "classify_and_fit");
+    return NUSLAM_OK;
+}
+
+}   // extern "C"

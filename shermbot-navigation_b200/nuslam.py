@@ -1,0 +1,277 @@
+"""Host-side mirror of the reference's ``nuslam`` library API over the C ABI (include/nuslam_b200.h).
+
+``BatchedExtendedKalman`` keeps the member names of ``slam_library::ExtendedKalman``
+(nuslam/include/nuslam/slam_library.hpp:23-113) -- ``predict``, ``associateLandmark``,
+``initializeLandmark``, ``update``, ``computeTheoreticalMeasurement``, ``linearizedMeasurementModel``,
+``getStateVector``, ``getCovariance``, ``getSeenLandmarks`` -- with a leading batch dimension, plus the
+fused ``step`` (one iteration of nuslam/src/slam.cpp:262-319). Arguments are numpy arrays (host) or
+torch CUDA tensors on the engine's device (device pointers, no copies); ids are 1-based as in the
+reference; matrices are exchanged as [batch, row, col].
+
+The CUDA library is mandatory: importing this module without ``libnuslam_b200.so`` raises, and the
+library itself refuses to run without an sm_100 device. There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libnuslam_b200.so"
+
+NUSLAM_HOST, NUSLAM_DEVICE = 0, 1
+MODE_STRICT, MODE_FAST = 0, 1
+FILTER_MAP_FULL, FILTER_SINGULAR, FILTER_BAD_ID = 1, 2, 4
+ID_EXCEPTION = -1000
+SCAN_UB = -2000
+
+EXPORTS = [
+    "nuslam_last_error", "nuslam_version", "nuslam_ekf_default_config", "nuslam_ekf_create", "nuslam_ekf_destroy",
+    "nuslam_ekf_bind_state", "nuslam_ekf_device_pointers", "nuslam_ekf_init", "nuslam_ekf_set_state",
+    "nuslam_ekf_get_state", "nuslam_ekf_predict", "nuslam_ekf_associate", "nuslam_ekf_initialize_landmark",
+    "nuslam_ekf_update", "nuslam_ekf_measurement_model", "nuslam_ekf_step", "nuslam_ekf_synchronize",
+    "nuslam_cartesian2polar", "nuslam_normalize_angle", "nuslam_scan_detect", "nuslam_classify_and_fit",
+]
+
+
+class NuslamError(RuntimeError):
+    pass
+
+
+class EkfConfig(C.Structure):
+    _fields_ = [("n_landmarks", C.c_int32), ("mode", C.c_int32), ("Q", C.c_double * 9), ("R", C.c_double * 4),
+                ("assoc_min", C.c_double), ("assoc_max", C.c_double)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; fail loudly when it is missing (no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise NuslamError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                              "(python -m shermbot_navigation_b200.build). There is no CPU fallback.")
+        l = C.CDLL(str(LIB_PATH))
+        l.nuslam_last_error.restype = C.c_char_p
+        vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+        l.nuslam_ekf_default_config.argtypes = [C.POINTER(EkfConfig), i32]
+        l.nuslam_ekf_default_config.restype = None
+        l.nuslam_ekf_create.argtypes = [C.POINTER(EkfConfig), i64, C.c_int, vp, C.POINTER(vp)]
+        l.nuslam_ekf_destroy.argtypes = [vp]
+        l.nuslam_ekf_bind_state.argtypes = [vp, vp, vp, vp, vp]
+        l.nuslam_ekf_device_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        l.nuslam_ekf_init.argtypes = [vp, vp, vp, C.c_int]
+        l.nuslam_ekf_set_state.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+        l.nuslam_ekf_get_state.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+        l.nuslam_ekf_predict.argtypes = [vp, vp, C.c_int]
+        l.nuslam_ekf_associate.argtypes = [vp, vp, vp, C.c_int]
+        l.nuslam_ekf_initialize_landmark.argtypes = [vp, vp, vp, C.c_int]
+        l.nuslam_ekf_update.argtypes = [vp, vp, vp, C.c_int]
+        l.nuslam_ekf_measurement_model.argtypes = [vp, vp, vp, vp, C.c_int]
+        l.nuslam_ekf_step.argtypes = [vp, vp, vp, vp, i32, vp, C.c_int]
+        l.nuslam_ekf_synchronize.argtypes = [vp]
+        l.nuslam_cartesian2polar.argtypes = [vp, vp, i64, C.c_int, C.c_int, vp]
+        l.nuslam_normalize_angle.argtypes = [vp, vp, i64, C.c_int, C.c_int, vp]
+        l.nuslam_scan_detect.argtypes = [vp, i64, C.c_double, C.c_double, vp, vp, vp, vp, i32, C.c_int, C.c_int, vp]
+        l.nuslam_classify_and_fit.argtypes = [vp, vp, vp, i64, vp, vp, C.c_int, C.c_int, vp]
+        _lib = l
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise NuslamError(f"{what} failed (code {rc}): {lib().nuslam_last_error().decode()}")
+
+
+def _is_torch(a) -> bool:
+    return a is not None and type(a).__module__.startswith("torch")
+
+
+def _ptr(a, dtype, mem_expected=None):
+    """(pointer, keepalive, mem) for a numpy array / torch tensor / None."""
+    if a is None:
+        return None, None, mem_expected
+    if _is_torch(a):
+        import torch
+        want = {np.float64: torch.float64, np.int32: torch.int32, np.float32: torch.float32, np.int16: torch.int16}[dtype]
+        if a.dtype != want or not a.is_contiguous():
+            raise NuslamError(f"tensor must be contiguous {want}")
+        return a.data_ptr(), a, (NUSLAM_DEVICE if a.is_cuda else NUSLAM_HOST)
+    arr = np.ascontiguousarray(a, dtype=dtype)
+    return arr.ctypes.data, arr, NUSLAM_HOST
+
+
+def _mem_of(*ptrs):
+    mems = {p[2] for p in ptrs if p[0] is not None}
+    if len(mems) > 1:
+        raise NuslamError("all arrays of one call must live on the same side (all numpy or all CUDA tensors)")
+    return mems.pop() if mems else NUSLAM_HOST
+
+
+class BatchedExtendedKalman:
+    """B independent ``slam_library::ExtendedKalman`` filters on one B200."""
+
+    def __init__(self, robotState, mapState=None, Q=None, R=None, n_landmarks=None, mode="strict", device=0,
+                 stream=None, assoc_min=0.01, assoc_max=60.0):
+        l = lib()
+        robot = np.atleast_2d(np.asarray(robotState, dtype=np.float64))
+        self.batch = robot.shape[0]
+        if mapState is not None:
+            mp = np.atleast_2d(np.asarray(mapState, dtype=np.float64))
+            n_landmarks = mp.shape[1] // 2
+            mp = np.ascontiguousarray(np.broadcast_to(mp, (self.batch, 2 * n_landmarks)))
+        else:
+            mp = None
+        if n_landmarks is None:
+            raise NuslamError("give mapState or n_landmarks")
+        self.n = int(n_landmarks)
+        self.len = 3 + 2 * self.n
+        self.device = int(device)
+        cfg = EkfConfig()
+        l.nuslam_ekf_default_config(C.byref(cfg), self.n)
+        cfg.mode = {"strict": MODE_STRICT, "fast": MODE_FAST}[mode]
+        if Q is not None:
+            cfg.Q[:] = list(np.asarray(Q, dtype=np.float64).reshape(3, 3).T.ravel())
+        if R is not None:
+            cfg.R[:] = list(np.asarray(R, dtype=np.float64).reshape(2, 2).T.ravel())
+        cfg.assoc_min, cfg.assoc_max = float(assoc_min), float(assoc_max)
+        self.mode = mode
+        h = C.c_void_p()
+        _check(l.nuslam_ekf_create(C.byref(cfg), self.batch, self.device, stream, C.byref(h)), "nuslam_ekf_create")
+        self._h = h
+        self._keep = None
+        robot = np.ascontiguousarray(robot)
+        _check(l.nuslam_ekf_init(self._h, robot.ctypes.data, mp.ctypes.data if mp is not None else None, NUSLAM_HOST),
+               "nuslam_ekf_init")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nuslam_ekf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state ----
+    def bind_state(self, x, sigma, seen, status):
+        """Run on caller-owned CUDA tensors (x [B,len] f64, sigma [B,len,len] f64 holding column-major
+        matrices, seen [B] i32, status [B] i32)."""
+        _check(lib().nuslam_ekf_bind_state(self._h, x.data_ptr(), sigma.data_ptr(), seen.data_ptr(), status.data_ptr()),
+               "nuslam_ekf_bind_state")
+        self._keep = (x, sigma, seen, status)
+
+    def set_state(self, x=None, sigma=None, seen=None, status=None):
+        """sigma is [B,row,col]; transposed to the column-major wire format here."""
+        if sigma is not None and not _is_torch(sigma):
+            sigma = np.ascontiguousarray(np.transpose(np.asarray(sigma, dtype=np.float64).reshape(self.batch, self.len, self.len), (0, 2, 1)))
+        px, ps = _ptr(x, np.float64), _ptr(sigma, np.float64)
+        pn, pt = _ptr(seen, np.int32), _ptr(status, np.int32)
+        _check(lib().nuslam_ekf_set_state(self._h, px[0], ps[0], pn[0], pt[0], _mem_of(px, ps, pn, pt)), "nuslam_ekf_set_state")
+
+    def get_state(self):
+        x = np.empty((self.batch, self.len))
+        s = np.empty((self.batch, self.len, self.len))
+        seen = np.empty(self.batch, dtype=np.int32)
+        status = np.empty(self.batch, dtype=np.int32)
+        _check(lib().nuslam_ekf_get_state(self._h, x.ctypes.data, s.ctypes.data, seen.ctypes.data, status.ctypes.data, NUSLAM_HOST),
+               "nuslam_ekf_get_state")
+        return x, np.transpose(s, (0, 2, 1)).copy(), seen, status
+
+    def getStateVector(self):
+        return self.get_state()[0]
+
+    def getCovariance(self):
+        return self.get_state()[1]
+
+    def getSeenLandmarks(self):
+        return self.get_state()[2]
+
+    def getStatus(self):
+        return self.get_state()[3]
+
+    # ---- ExtendedKalman members, batched ----
+    def predict(self, twists):
+        p = _ptr(twists, np.float64)
+        _check(lib().nuslam_ekf_predict(self._h, p[0], p[2]), "nuslam_ekf_predict")
+
+    def associateLandmark(self, z):
+        pz = _ptr(z, np.float64)
+        if pz[2] == NUSLAM_DEVICE:
+            import torch
+            out = torch.empty(self.batch, dtype=torch.int32, device=z.device)
+            _check(lib().nuslam_ekf_associate(self._h, pz[0], out.data_ptr(), NUSLAM_DEVICE), "nuslam_ekf_associate")
+            return out
+        out = np.empty(self.batch, dtype=np.int32)
+        _check(lib().nuslam_ekf_associate(self._h, pz[0], out.ctypes.data, NUSLAM_HOST), "nuslam_ekf_associate")
+        return out
+
+    def initializeLandmark(self, z, ids):
+        pz, pi = _ptr(z, np.float64), _ptr(ids, np.int32)
+        _check(lib().nuslam_ekf_initialize_landmark(self._h, pz[0], pi[0], _mem_of(pz, pi)), "nuslam_ekf_initialize_landmark")
+
+    def update(self, z, ids, twists=None):
+        """``twists`` is accepted for signature parity with update(tw, z, id) and ignored, as in the reference."""
+        pz, pi = _ptr(z, np.float64), _ptr(ids, np.int32)
+        _check(lib().nuslam_ekf_update(self._h, pz[0], pi[0], _mem_of(pz, pi)), "nuslam_ekf_update")
+
+    def computeTheoreticalMeasurement(self, j):
+        j = np.ascontiguousarray(np.broadcast_to(np.asarray(j, dtype=np.int32), (self.batch,)))
+        out = np.zeros((self.batch, 2))
+        _check(lib().nuslam_ekf_measurement_model(self._h, j.ctypes.data, out.ctypes.data, None, NUSLAM_HOST), "nuslam_ekf_measurement_model")
+        return out
+
+    def linearizedMeasurementModel(self, j):
+        j = np.ascontiguousarray(np.broadcast_to(np.asarray(j, dtype=np.int32), (self.batch,)))
+        out = np.zeros((self.batch, self.len, 2))
+        _check(lib().nuslam_ekf_measurement_model(self._h, j.ctypes.data, None, out.ctypes.data, NUSLAM_HOST), "nuslam_ekf_measurement_model")
+        return np.transpose(out, (0, 2, 1)).copy()
+
+    def step(self, twists, z, ids=None, return_ids=False):
+        """One iteration of EKFSlam::main_loop (slam.cpp:262-319). z: [B,m,2]; ids: [B,m] or None."""
+        pt, pz, pi = _ptr(twists, np.float64), _ptr(z, np.float64), _ptr(ids, np.int32)
+        mem = _mem_of(pt, pz, pi)
+        m = int(z.shape[1]) if z is not None else 0
+        out = None
+        optr = None
+        if return_ids:
+            if mem == NUSLAM_DEVICE:
+                import torch
+                out = torch.empty((self.batch, m), dtype=torch.int32, device=z.device)
+                optr = out.data_ptr()
+            else:
+                out = np.empty((self.batch, m), dtype=np.int32)
+                optr = out.ctypes.data
+        _check(lib().nuslam_ekf_step(self._h, pt[0], pz[0], pi[0], m, optr, mem), "nuslam_ekf_step")
+        return out
+
+    def synchronize(self):
+        _check(lib().nuslam_ekf_synchronize(self._h), "nuslam_ekf_synchronize")
+
+
+def cartesian2polar(xy, device=0):
+    """slam_library::cartesian2polar (slam_library.cpp:16-22), batched: [N,2] -> [N,2]."""
+    if _is_torch(xy) and xy.is_cuda:
+        import torch
+        out = torch.empty_like(xy)
+        _check(lib().nuslam_cartesian2polar(xy.data_ptr(), out.data_ptr(), xy.shape[0], NUSLAM_DEVICE, xy.device.index, None), "nuslam_cartesian2polar")
+        torch.cuda.synchronize(xy.device)
+        return out
+    a = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+    out = np.empty_like(a)
+    _check(lib().nuslam_cartesian2polar(a.ctypes.data, out.ctypes.data, a.shape[0], NUSLAM_HOST, device, None), "nuslam_cartesian2polar")
+    return out
+
+
+def normalize_angle(rad, device=0):
+    """rigid2d::normalize_angle (rigid2d.cpp:9-13), batched."""
+    a = np.ascontiguousarray(rad, dtype=np.float64).ravel()
+    out = np.empty_like(a)
+    _check(lib().nuslam_normalize_angle(a.ctypes.data, out.ctypes.data, a.shape[0], NUSLAM_HOST, device, None), "nuslam_normalize_angle")
+    return out.reshape(np.shape(rad))
