@@ -184,17 +184,24 @@ class BatchedExtendedKalman:
                "nuslam_ekf_get_state")
         return x, np.transpose(s, (0, 2, 1)).copy(), seen, status
 
-    def getStateVector(self):
-        return self.get_state()[0]
+    def getStateVector(self, out=None):
+        """Only x travels (B x len f64); pass a pinned numpy buffer as ``out`` to avoid an allocation per call."""
+        x = out if out is not None else np.empty((self.batch, self.len))
+        _check(lib().nuslam_ekf_get_state(self._h, x.ctypes.data, None, None, None, NUSLAM_HOST), "nuslam_ekf_get_state")
+        return x
 
     def getCovariance(self):
         return self.get_state()[1]
 
     def getSeenLandmarks(self):
-        return self.get_state()[2]
+        seen = np.empty(self.batch, dtype=np.int32)
+        _check(lib().nuslam_ekf_get_state(self._h, None, None, seen.ctypes.data, None, NUSLAM_HOST), "nuslam_ekf_get_state")
+        return seen
 
     def getStatus(self):
-        return self.get_state()[3]
+        status = np.empty(self.batch, dtype=np.int32)
+        _check(lib().nuslam_ekf_get_state(self._h, None, None, None, status.ctypes.data, NUSLAM_HOST), "nuslam_ekf_get_state")
+        return status
 
     # ---- ExtendedKalman members, batched ----
     def predict(self, twists):

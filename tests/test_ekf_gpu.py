@@ -56,7 +56,7 @@ def test_constructor_state(cuda_lib, orc, n):
 
 
 @pytest.mark.parametrize("geometry", ["benign", "adversarial"])
-@pytest.mark.parametrize("mode", ["strict"])
+@pytest.mark.parametrize("mode", ["strict", "fast"])
 def test_teacher_forced_substeps(cuda_lib, orc, geometry, mode):
     """L0: every predict and every update starts from the oracle's exact (x, Sigma)."""
     B, T, n = 8, 12, 12
@@ -64,7 +64,14 @@ def test_teacher_forced_substeps(cuda_lib, orc, geometry, mode):
     eng = make_engine(cuda_lib, sc, mode)
     fs = oracle_filters(orc, sc, B)
     worst = dict(px=0.0, ps=0.0, ux=0.0, us=0.0)
-    sigma_bit_exact = True
+    # STRICT: element-wise relative error (it is bit-exact anyway); FAST: max-norm relative per filter
+    # (fused arithmetic re-rounds the cancelling entries of Sigma - K W, so tiny entries differ relatively)
+    if mode == "strict":
+        sig_err = lambda a, b: rel_elem(a, b, 1e-300)
+    else:
+        sig_err = lambda a, b: max(rel_max(a[i], b[i]) for i in range(a.shape[0]))
+    sigma_bit_exact = True      # update: Sigma depends on x only through + - * / sqrt -> must be bit-identical
+    predict_bit_exact = True    # predict: the Jacobian uses sin/cos (CUDA libm vs glibc, ulp-level) -> reported only
     for t in range(T):
         x0, s0, n0 = oracle_state(fs)
         eng.set_state(x0, s0, n0)
@@ -73,9 +80,9 @@ def test_teacher_forced_substeps(cuda_lib, orc, geometry, mode):
             f.predict(*sc["twists"][t, b])
         x1, s1, _ = oracle_state(fs)
         xg, sg, _, _ = eng.get_state()
-        sigma_bit_exact &= np.array_equal(sg, s1)
+        predict_bit_exact &= np.array_equal(sg, s1)
         worst["px"] = max(worst["px"], rel_max(xg, x1))
-        worst["ps"] = max(worst["ps"], rel_elem(sg, s1, 1e-300))
+        worst["ps"] = max(worst["ps"], sig_err(sg, s1))
         for i in range(n):
             ids = sc["ids"][t, :, i]
             z = sc["z"][t, :, i]
@@ -97,8 +104,8 @@ def test_teacher_forced_substeps(cuda_lib, orc, geometry, mode):
             assert not st.any()
             sigma_bit_exact &= np.array_equal(sg, sb)
             worst["ux"] = max(worst["ux"], rel_max(xg, xb))
-            worst["us"] = max(worst["us"], rel_elem(sg, sb, 1e-300))
-    print(f"[teacher-forced {geometry}/{mode}] worst rel: {worst} sigma bit-exact: {sigma_bit_exact}")
+            worst["us"] = max(worst["us"], sig_err(sg, sb))
+    print(f"[teacher-forced {geometry}/{mode}] worst rel: {worst} update Sigma bit-exact: {sigma_bit_exact} predict Sigma bit-exact: {predict_bit_exact}")
     assert max(worst.values()) < TOL
     if mode == "strict":
         assert sigma_bit_exact, "STRICT mode must reproduce the oracle's Sigma bit for bit under teacher forcing"
