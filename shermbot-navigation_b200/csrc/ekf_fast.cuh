@@ -2,19 +2,22 @@
 //
 // Why registers: a rank-2 update reads and writes every element of Sigma once; from shared memory that is
 // 16 B x len^2 per update (11.6 KB at len 27), i.e. ~1100 shared-memory cycles per filter-step at 128 B/clk/SM,
-// above the ~700-880 cycles/filter-step/SM that 60 % of the HBM roofline allows. Registers have no such limit.
+// above the ~900 cycles/filter-step/SM that 60 % of the HBM roofline allows. Registers have no such limit.
 //
-// Layout (one filter per half-warp, two filters per warp):
+// Layout (one filter per half-warp, two filters per warp, 2W filters per CTA of W warps):
 //   * internal index = external index + 1 (slot 0 is a zero dummy), so every landmark occupies an aligned
 //     (even, odd) pair and the padded length LP = 4T is exactly 28 for n = 12 (16 for n = 6)
 //   * the 16 lanes of a half-warp form a 4 x 4 grid (a = row group, b = column group); lane (a,b) holds the
-//     cyclic T x T tile  S[r][q] = Sigma(4r + a, 4q + b)  in registers (49 doubles at n = 12)
-//   * per update the 5 rows and 5 columns that H touches are published to shared memory (static register
-//     indices through a switch on the landmark's tile column), the scalar part (H, S, S^-1, innovation) runs
-//     once per filter, the 16 lanes form K = Sigma H^T S^-1 and W = H Sigma row by row, and the tile update
-//     Sigma -= K W is two FMAs per element with K/W operands fetched as 16-byte pairs.
-//   * Sigma travels HBM -> shared memory by TMA bulk copies (cp.async.bulk + mbarrier), prefetched one pair
-//     ahead of the computation, and goes back from registers with full 32-byte-sector stores.
+//     cyclic T x T tile  S[r][q] = Sigma(4r + a, 4q + b)  in registers (49 doubles at n = 12). In the
+//     column-major HBM image a lane quartet (a = 0..3) owns 32 contiguous bytes, so tile loads and stores
+//     move whole 32-byte sectors; the next group's Sigma is pulled into L2 by a bulk prefetch
+//     (cp.async.bulk.prefetch.L2) while the current one is computed.
+//   * per update: (A) every warp publishes the 5 rows and 5 columns of Sigma that H touches (static register
+//     indices through a switch on the landmark's tile column); (B) ONE warp evaluates the scalar part
+//     (H, S = H Sigma H^T + R, S^-1, innovation; rsqrt / atan2 / reciprocal) for all 2W filters of the CTA, one
+//     filter per lane, instead of every half-warp repeating it 16-fold; (C) the 16 lanes of each filter form
+//     K = Sigma H^T S^-1 and W = H Sigma row by row; (D) the tile update Sigma -= K W is two FMAs per element
+//     with K / W operands fetched as 16-byte pairs.
 //
 // Arithmetic: predict always uses the oracle's operation order (it is O(len)). An update whose landmark still
 // carries the INT_MAX prior (slam_library.cpp:28-31) is evaluated in the STRICT operation order inside the
@@ -39,46 +42,10 @@ struct FastGeom
 
 constexpr int kFastWarps = 4;   // warps per CTA (8 filters)
 
-// ---- PTX helpers: mbarrier + 1-D TMA bulk copy + cp.async ----
-__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t * bar, int count)
+__device__ __forceinline__ void prefetch_l2_bulk(const void * src, uint32_t bytes)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t bytes, uint64_t * bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void cp_async8(void * dst, const void * src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void * dst, const void * src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // wrap an angle known to lie within (-3pi, 3pi) into (-pi, pi]: what normalize_angle returns, to ~1 ulp,
 // without the sin/cos/atan2 round trip (used only by the non-first-touch path)
@@ -90,16 +57,21 @@ __device__ __forceinline__ double wrap_fast(double a)
     return a;
 }
 
-// per-filter shared memory (doubles)
+// per-filter shared memory
 template <int N>
 struct FastSmem
 {
     using G = FastGeom<N>;
+    double2 kt[G::LP];        // K = Sigma H^T S^-1, one (k0,k1) pair per row
+    double2 wt[G::LP];        // W = H Sigma, one (w0,w1) pair per column
     double xs[G::LP];         // state, internal indexing (xs[0] dummy)
-    double col[5 * G::LP];    // published columns {th,x,y,c,c+1}: col[k*LP + i] = Sigma(i, col_k); later K pairs / M columns
-    double row[5 * G::LP];    // published rows    {th,x,y,c,c+1}: row[k*LP + j] = Sigma(row_k, j); later W pairs
-    double sc[16];            // scalar-phase outputs
-    int flags[4];             // [0] update flags, [1] seen, [2] status, [3] seen snapshot
+    double col[5 * G::LP];    // published columns {th,x,y,c,c+1}: col[k*LP + i] = Sigma(i, col_k); M columns on the strict path
+    double row[5 * G::LP];    // published rows    {th,x,y,c,c+1}: row[k*LP + j] = Sigma(row_k, j)
+    double sc[16];            // scalar-phase outputs: H (8), S^-1 (4), innovation (2), predict b10, b20 (2)
+    double z[2 * G::M_MAX];   // this step's measurements (range, bearing)
+    double tw[2];             // this step's twist (dth, dx)
+    int ids[G::M_MAX];        // this step's landmark ids
+    int flags[8];             // [0] update flags, [1] seen, [2] status, [3] seen snapshot, [4] theta owes a wrap, [5] frozen
 };
 
 constexpr int kFlagSkip = 1, kFlagStrict = 2;
@@ -110,12 +82,12 @@ __device__ __forceinline__ void publish_col(double * dst, const double (&S)[T][T
     // dst[4*r] = S[r][q] with static register indices
     switch (q)
     {
-#define NUSLAM_PC(k)                                            \
-    case k:                                                     \
-        if constexpr (T > k)                                    \
-        {                                                       \
+#define NUSLAM_PC(k)                                                                        \
+    case k:                                                                                 \
+        if constexpr (T > k)                                                                \
+        {                                                                                   \
             _Pragma("unroll") for (int r = 0; r < T; ++r) dst[4 * r] = S[r][k < T ? k : 0]; \
-        }                                                       \
+        }                                                                                   \
         break;
         NUSLAM_PC(0)
         NUSLAM_PC(1)
@@ -136,12 +108,12 @@ __device__ __forceinline__ void publish_row(double * dst, const double (&S)[T][T
 {
     switch (r)
     {
-#define NUSLAM_PR(k)                                            \
-    case k:                                                     \
-        if constexpr (T > k)                                    \
-        {                                                       \
+#define NUSLAM_PR(k)                                                                        \
+    case k:                                                                                 \
+        if constexpr (T > k)                                                                \
+        {                                                                                   \
             _Pragma("unroll") for (int q = 0; q < T; ++q) dst[4 * q] = S[k < T ? k : 0][q]; \
-        }                                                       \
+        }                                                                                   \
         break;
         NUSLAM_PR(0)
         NUSLAM_PR(1)
@@ -157,25 +129,71 @@ __device__ __forceinline__ void publish_row(double * dst, const double (&S)[T][T
     }
 }
 
-// Scalar part of one update for one filter (runs in one lane): H, S = H Sigma H^T + R, S^-1, innovation.
+// Scalar part of predict for one filter (one lane): predictEstimate :71-94 and the two Jacobian entries of
+// getA :127-148 (theta read AFTER the motion update, :129), in the oracle's operation order.
+template <int N>
+__device__ __forceinline__ void predict_scalar(FastSmem<N> & f)
+{
+    const double dth = f.tw[0], dx = f.tw[1];
+    const double theta = f.xs[1];
+    double dq_th, dq_x, dq_y, s0, c0, b10, b20;
+    sincos(theta, &s0, &c0);
+    if (dth == 0.0)
+    {
+        dq_th = 0.0;
+        dq_x = mul_(dx, c0);
+        dq_y = mul_(dx, s0);
+    }
+    else
+    {
+        const double q = div_(dx, dth);
+        double s1, c1;
+        sincos(add_(theta, dth), &s1, &c1);
+        dq_th = dth;
+        dq_x = add_(mul_(-q, s0), mul_(q, s1));
+        dq_y = sub_(mul_(q, c0), mul_(q, c1));
+    }
+    const double th1 = add_(theta, dq_th);
+    f.xs[1] = th1;
+    f.xs[2] = add_(f.xs[2], dq_x);
+    f.xs[3] = add_(f.xs[3], dq_y);
+    double s2, c2;
+    sincos(th1, &s2, &c2);
+    if (dth == 0.0)
+    {
+        b10 = mul_(-dx, s2);
+        b20 = mul_(dx, c2);
+    }
+    else
+    {
+        const double q = div_(dx, dth);
+        double s3, c3;
+        sincos(add_(th1, dth), &s3, &c3);
+        b10 = add_(mul_(-q, c2), mul_(q, c3));
+        b20 = add_(mul_(-q, s2), mul_(q, s3));
+    }
+    f.sc[14] = b10;
+    f.sc[15] = b20;
+}
+
+// Scalar part of one update for one filter (one lane): H, S = H Sigma H^T + R, S^-1, innovation.
 // Reads the 5x5 block of Sigma from the published columns. slam_library.cpp:265-272 (+ :255-261 when the
 // landmark is new).
 template <int N>
-__device__ __forceinline__ void scalar_phase(FastSmem<N> & f, double z0, double z1, int id, bool do_init, bool & pend, const double * R)
+__device__ __forceinline__ void scalar_phase(FastSmem<N> & f, double z0, double z1, int id, bool do_init, const double * R)
 {
     using G = FastGeom<N>;
     constexpr int LP = G::LP;
     const int cI = 4 + 2 * (id - 1);   // internal column of the landmark's x
     double th = f.xs[1];
-    if (pend)
+    if (f.flags[4])
     {
         th = wrap_fast(th);   // normalize_angle owed by the previous fused update (slam_library.cpp:276)
         f.xs[1] = th;
-        pend = false;
+        f.flags[4] = 0;
     }
     const double px = f.xs[2], py = f.xs[3];
-    const double vcc = f.col[3 * LP + cI], vc1 = f.col[4 * LP + cI + 1];
-    const bool strict = (vcc > kFirstTouchVariance) || (vc1 > kFirstTouchVariance);
+    const bool strict = (f.col[3 * LP + cI] > kFirstTouchVariance) || (f.col[4 * LP + cI + 1] > kFirstTouchVariance);
     if (do_init)
     {
         // initializeLandmark, slam_library.cpp:255-261
@@ -184,15 +202,11 @@ __device__ __forceinline__ void scalar_phase(FastSmem<N> & f, double z0, double 
         f.xs[cI] = add_(px, mul_(z0, c));
         f.xs[cI + 1] = add_(py, mul_(z0, s));
     }
-    const int ri[5] = {1, 2, 3, cI, cI + 1};
-    double S5[5][5];   // S5[k][j] = Sigma(row_k, col_j)
-#pragma unroll
-    for (int j = 0; j < 5; ++j)
-#pragma unroll
-        for (int k = 0; k < 5; ++k) S5[k][j] = f.col[j * LP + ri[k]];
     HEntries H;
     double zr, zb, i00, i01, i10, i11;
     bool ok = true;
+    // rows of the 5x5 block: Sigma(row_k, col_j) = col[j*LP + row_k], rows {1,2,3,cI,cI+1}
+    const double * c0 = f.col;
     if (strict)
     {
         measurement_model(f.xs + 1, cI - 1, H, zr, zb);
@@ -200,15 +214,16 @@ __device__ __forceinline__ void scalar_phase(FastSmem<N> & f, double z0, double 
 #pragma unroll
         for (int j = 0; j < 5; ++j)
         {
-            double a0 = mul_(H.h01, S5[1][j]);
-            a0 = add_(a0, mul_(H.h02, S5[2][j]));
-            a0 = add_(a0, mul_(H.h0c, S5[3][j]));
-            a0 = add_(a0, mul_(H.h0c1, S5[4][j]));
-            double a1 = -S5[0][j];
-            a1 = add_(a1, mul_(H.h11, S5[1][j]));
-            a1 = add_(a1, mul_(H.h12, S5[2][j]));
-            a1 = add_(a1, mul_(H.h1c, S5[3][j]));
-            a1 = add_(a1, mul_(H.h1c1, S5[4][j]));
+            const double s0 = c0[j * LP + 1], s1 = c0[j * LP + 2], s2 = c0[j * LP + 3], s3 = c0[j * LP + cI], s4 = c0[j * LP + cI + 1];
+            double a0 = mul_(H.h01, s1);
+            a0 = add_(a0, mul_(H.h02, s2));
+            a0 = add_(a0, mul_(H.h0c, s3));
+            a0 = add_(a0, mul_(H.h0c1, s4));
+            double a1 = -s0;
+            a1 = add_(a1, mul_(H.h11, s1));
+            a1 = add_(a1, mul_(H.h12, s2));
+            a1 = add_(a1, mul_(H.h1c, s3));
+            a1 = add_(a1, mul_(H.h1c1, s4));
             g0[j] = a0;
             g1[j] = a1;
         }
@@ -252,17 +267,22 @@ __device__ __forceinline__ void scalar_phase(FastSmem<N> & f, double z0, double 
         H.h1c1 = dx * id2;
         zr = d * rs;
         zb = wrap_fast(atan2(dy, dx) - th);
-        double g0[5], g1[5];
+        double p00 = R[0], p10 = R[1], p01 = R[2], p11 = R[3];
+        // psi = (H Sigma) H^T + R accumulated column by column of the 5x5 block (keeps 10 values live, not 25)
 #pragma unroll
         for (int j = 0; j < 5; ++j)
         {
-            g0[j] = H.h01 * S5[1][j] + H.h02 * S5[2][j] + H.h0c * S5[3][j] + H.h0c1 * S5[4][j];
-            g1[j] = -S5[0][j] + H.h11 * S5[1][j] + H.h12 * S5[2][j] + H.h1c * S5[3][j] + H.h1c1 * S5[4][j];
+            const double s0 = c0[j * LP + 1], s1 = c0[j * LP + 2], s2 = c0[j * LP + 3], s3 = c0[j * LP + cI], s4 = c0[j * LP + cI + 1];
+            const double g0 = H.h01 * s1 + H.h02 * s2 + H.h0c * s3 + H.h0c1 * s4;
+            const double g1 = -s0 + H.h11 * s1 + H.h12 * s2 + H.h1c * s3 + H.h1c1 * s4;
+            // column j of H^T: H(0,j), H(1,j) for j in {th, x, y, c, c+1}
+            const double hj0 = (j == 0) ? 0.0 : (j == 1) ? H.h01 : (j == 2) ? H.h02 : (j == 3) ? H.h0c : H.h0c1;
+            const double hj1 = (j == 0) ? -1.0 : (j == 1) ? H.h11 : (j == 2) ? H.h12 : (j == 3) ? H.h1c : H.h1c1;
+            p00 += g0 * hj0;
+            p10 += g1 * hj0;
+            p01 += g0 * hj1;
+            p11 += g1 * hj1;
         }
-        const double p00 = g0[1] * H.h01 + g0[2] * H.h02 + g0[3] * H.h0c + g0[4] * H.h0c1 + R[0];
-        const double p10 = g1[1] * H.h01 + g1[2] * H.h02 + g1[3] * H.h0c + g1[4] * H.h0c1 + R[1];
-        const double p01 = -g0[0] + g0[1] * H.h11 + g0[2] * H.h12 + g0[3] * H.h1c + g0[4] * H.h1c1 + R[2];
-        const double p11 = -g1[0] + g1[1] * H.h11 + g1[2] * H.h12 + g1[3] * H.h1c + g1[4] * H.h1c1 + R[3];
         const double det = p00 * p11 - p01 * p10;
         ok = det != 0.0;
         const double idet = 1.0 / det;
@@ -292,7 +312,7 @@ __device__ __forceinline__ void scalar_phase(FastSmem<N> & f, double z0, double 
         f.flags[2] |= kStatusSingular;
     }
     f.flags[0] = fl;
-    if (!(fl & (kFlagSkip | kFlagStrict))) pend = true;   // the fused path wraps theta lazily
+    if (fl == 0) f.flags[4] = 1;   // the fused path wraps theta lazily
 }
 
 template <int N>
@@ -300,179 +320,63 @@ __global__ void __launch_bounds__(kFastWarps * 32, 3) k_ekf_fast_step(const EkfP
 {
     using G = FastGeom<N>;
     constexpr int T = G::T, LP = G::LP, LEN = G::LEN, SIG = G::SIG;
+    constexpr int F = 2 * kFastWarps;   // filters per CTA
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    FastSmem<N> * fs = reinterpret_cast<FastSmem<N> *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int hw = lane >> 4;          // which filter of the pair
+    const int hw = lane >> 4;          // which filter of the warp's pair
     const int t16 = lane & 15;
     const int a = t16 >> 2, b = t16 & 3;
     const int m = p.m;
+    const int fl_idx = 2 * warp + hw;   // filter slot within the CTA
+    FastSmem<N> & f = fs[fl_idx];
 
-    // ---- carve shared memory: per warp [stage 2*SIG | xstage 2*LEN | z 2 x 2*M_MAX*2 | ids 2 x 2*M_MAX | tw 2 x 8 | FastSmem x2 | mbar]
-    constexpr size_t kStageB = sizeof(double) * 2 * SIG;                         // 11664 (16-aligned)
-    constexpr size_t kXStageB = (sizeof(double) * 2 * LEN + 15) / 16 * 16;       // 432
-    constexpr size_t kZB = sizeof(double) * 2 * 2 * G::M_MAX * 2;                // double-buffered z of 2 filters
-    constexpr size_t kIdB = sizeof(int) * 2 * 2 * G::M_MAX;
-    constexpr size_t kTwB = sizeof(double) * 2 * 8;
-    constexpr size_t kFB = (sizeof(FastSmem<N>) + 15) / 16 * 16;
-    constexpr size_t kWarpB = kStageB + kXStageB + kZB + kIdB + kTwB + 2 * kFB + 16;
-    unsigned char * wbase = smem_raw + (size_t) warp * kWarpB;
-    double * stage = reinterpret_cast<double *>(wbase);
-    double * xstage = reinterpret_cast<double *>(wbase + kStageB);
-    double * zbuf = reinterpret_cast<double *>(wbase + kStageB + kXStageB);
-    int * idbuf = reinterpret_cast<int *>(wbase + kStageB + kXStageB + kZB);
-    double * twbuf = reinterpret_cast<double *>(wbase + kStageB + kXStageB + kZB + kIdB);
-    FastSmem<N> * fs = reinterpret_cast<FastSmem<N> *>(wbase + kStageB + kXStageB + kZB + kIdB + kTwB);
-    uint64_t * mbar = reinterpret_cast<uint64_t *>(wbase + kStageB + kXStageB + kZB + kIdB + kTwB + 2 * kFB);
-    FastSmem<N> & f = fs[hw];
-
-    const int64_t npairs = (p.batch + 1) / 2;
-    const int64_t pair_stride = (int64_t) gridDim.x * kFastWarps;
-    int64_t pair = (int64_t) blockIdx.x * kFastWarps + warp;
-    if (pair >= npairs) return;   // warps are independent: no CTA-wide barrier anywhere below
-
-    if (lane == 0)
+    const int64_t ngroups = (p.batch + F - 1) / F;
+    for (int64_t group = blockIdx.x; group < ngroups; group += gridDim.x)
     {
-        mbar_init(mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
-    // prefetch of one pair: Sigma + x by TMA bulk copy (full pairs), small inputs by cp.async
-    auto prefetch = [&](int64_t pr, int buf)
-    {
-        const int64_t b0 = 2 * pr;
-        const int nvalid = (int) ((p.batch - b0) < 2 ? (p.batch - b0) : 2);
-        if (nvalid == 2)
+        const int64_t bf = group * F + fl_idx;
+        const bool valid = bf < p.batch;
+        // pull the next group's Sigma towards L2 while this group is computed
         {
-            if (lane == 0)
-            {
-                mbar_expect_tx(mbar, (uint32_t) (kStageB + sizeof(double) * 2 * LEN));
-                bulk_g2s(stage, p.sigma + b0 * SIG, (uint32_t) kStageB, mbar);
-                bulk_g2s(xstage, p.x + b0 * LEN, (uint32_t) (sizeof(double) * 2 * LEN), mbar);
-            }
+            const int64_t nb = (group + gridDim.x) * F + 2 * warp;
+            if (lane == 0 && nb + 1 < p.batch) prefetch_l2_bulk(p.sigma + nb * SIG, (uint32_t) (sizeof(double) * 2 * SIG));
         }
-        else
-        {
-            for (int e = lane; e < SIG; e += 32) cp_async8(stage + e, p.sigma + b0 * SIG + e);
-            for (int e = lane; e < LEN; e += 32) cp_async8(xstage + e, p.x + b0 * LEN + e);
-        }
-        double * zb_ = zbuf + buf * (2 * G::M_MAX * 2);
-        int * ib_ = idbuf + buf * (2 * G::M_MAX);
-        double * tb_ = twbuf + buf * 8;
-        for (int e = lane; e < nvalid * m * 2; e += 32)
-        {
-            const int fi = e / (2 * m), r = e - fi * 2 * m;
-            cp_async8(zb_ + fi * (G::M_MAX * 2) + r, p.z + (b0 + fi) * m * 2 + r);
-        }
-        for (int e = lane; e < nvalid * m; e += 32)
-        {
-            const int fi = e / m, r = e - fi * m;
-            cp_async4(ib_ + fi * G::M_MAX + r, p.ids + (b0 + fi) * m + r);
-        }
-        if (do_predict && lane < nvalid * 3) cp_async8(tb_ + (lane / 3) * 4 + (lane % 3), p.twists + b0 * 3 + lane);
-    };
-
-    uint32_t parity = 0;
-    int buf = 0;
-    prefetch(pair, buf);
-
-    for (; pair < npairs; pair += pair_stride, buf ^= 1)
-    {
-        const int64_t b0 = 2 * pair;
-        const int nvalid = (int) ((p.batch - b0) < 2 ? (p.batch - b0) : 2);
-        const bool valid = hw < nvalid;
-        const int64_t bf = b0 + (valid ? hw : 0);
-
-        // ---- wait for the staged pair, build the register tile ----
-        cp_async_wait_all();
-        if (nvalid == 2)
-        {
-            mbar_wait(mbar, parity);
-            parity ^= 1;
-        }
-        __syncwarp();
+        // ---- load: Sigma tile straight into registers (32-byte runs per lane quartet), small inputs into shared memory ----
         double S[T][T];
         {
-            const double * sg = stage + hw * SIG;
+            const double * gs = p.sigma + (valid ? bf : 0) * SIG;
 #pragma unroll
-            for (int r = 0; r < T; ++r)
+            for (int q = 0; q < T; ++q)
 #pragma unroll
-                for (int q = 0; q < T; ++q)
+                for (int r = 0; r < T; ++r)
                 {
                     const int i = 4 * r + a - 1, j = 4 * q + b - 1;   // external indices
-                    S[r][q] = (valid && i >= 0 && j >= 0 && i < LEN && j < LEN) ? sg[j * LEN + i] : 0.0;
+                    S[r][q] = (valid && i >= 0 && j >= 0 && i < LEN && j < LEN) ? __ldcs(gs + j * LEN + i) : 0.0;
                 }
-            for (int e = t16; e < LP; e += 16) f.xs[e] = (valid && e >= 1 && e <= LEN) ? xstage[hw * LEN + e - 1] : 0.0;
+            for (int e = t16; e < LP; e += 16) f.xs[e] = (valid && e >= 1 && e <= LEN) ? p.x[bf * LEN + e - 1] : 0.0;
+            for (int e = t16; e < 2 * m; e += 16) f.z[e] = valid ? p.z[bf * m * 2 + e] : 0.0;
+            for (int e = t16; e < m; e += 16) f.ids[e] = valid ? p.ids[bf * m + e] : 0;
+            if (t16 < 2) f.tw[t16] = (valid && do_predict) ? p.twists[bf * 3 + t16] : 0.0;
             if (t16 == 0)
             {
-                f.flags[1] = valid ? p.seen[bf] : 0;
-                f.flags[2] = valid ? p.status[bf] : 0;
+                const int seen = valid ? p.seen[bf] : 0;
+                const int st = valid ? p.status[bf] : 0;
+                f.flags[1] = seen;
+                f.flags[2] = st;
+                f.flags[3] = seen;   // snapshot, slam.cpp:251
+                f.flags[4] = 0;
+                f.flags[5] = (!valid || (st & (kStatusMapFull | kStatusSingular))) ? 1 : 0;
             }
         }
-        __syncwarp();
-        // staging is free again: prefetch the next pair while this one is computed
-        const int64_t next = pair + pair_stride;
-        if (next < npairs)
-        {
-            fence_proxy_async();
-            prefetch(next, buf ^ 1);
-        }
-        const double * zb_ = zbuf + buf * (2 * G::M_MAX * 2) + hw * (G::M_MAX * 2);
-        const int * ib_ = idbuf + buf * (2 * G::M_MAX) + hw * G::M_MAX;
-        const double * tb_ = twbuf + buf * 8 + hw * 4;
-        const bool frozen = !valid || (f.flags[2] & (kStatusMapFull | kStatusSingular));
-        bool pend = false;   // lane t16 == 0: theta still owes a wrap into (-pi, pi]
-        if (t16 == 0) f.flags[3] = f.flags[1];   // seen snapshot, slam.cpp:251
-        __syncwarp();
+        __syncthreads();
+        const bool frozen = f.flags[5] != 0;
 
         // ---- predict (slam_library.cpp:65-108), always in the oracle's operation order ----
         if (do_predict)
         {
-            double b10 = 0.0, b20 = 0.0;
-            if (t16 == 0 && !frozen)
-            {
-                const double dth = tb_[0], dx = tb_[1];
-                const double theta = f.xs[1];
-                double dq_th, dq_x, dq_y;
-                double s0, c0;
-                sincos(theta, &s0, &c0);
-                if (dth == 0.0)
-                {
-                    dq_th = 0.0;
-                    dq_x = mul_(dx, c0);
-                    dq_y = mul_(dx, s0);
-                }
-                else
-                {
-                    const double q = div_(dx, dth);
-                    double s1, c1;
-                    sincos(add_(theta, dth), &s1, &c1);
-                    dq_th = dth;
-                    dq_x = add_(mul_(-q, s0), mul_(q, s1));
-                    dq_y = sub_(mul_(q, c0), mul_(q, c1));
-                }
-                const double th1 = add_(theta, dq_th);
-                f.xs[1] = th1;
-                f.xs[2] = add_(f.xs[2], dq_x);
-                f.xs[3] = add_(f.xs[3], dq_y);
-                double s2, c2;
-                sincos(th1, &s2, &c2);
-                if (dth == 0.0)
-                {
-                    b10 = mul_(-dx, s2);
-                    b20 = mul_(dx, c2);
-                }
-                else
-                {
-                    const double q = div_(dx, dth);
-                    double s3, c3;
-                    sincos(add_(th1, dth), &s3, &c3);
-                    b10 = add_(mul_(-q, c2), mul_(q, c3));
-                    b20 = add_(mul_(-q, s2), mul_(q, s3));
-                }
-            }
-            b10 = __shfl_sync(0xffffffffu, b10, hw * 16);
-            b20 = __shfl_sync(0xffffffffu, b20, hw * 16);
+            if (warp == 0 && lane < F && !fs[lane].flags[5]) predict_scalar<N>(fs[lane]);
+            __syncthreads();
+            const double b10 = f.sc[14], b20 = f.sc[15];
             // T = A * Sigma: rows x (a = 2, r = 0) and y (a = 3, r = 0) += b * row theta (a = 1, r = 0)
             const int src_row = hw * 16 + 4 + b;
 #pragma unroll
@@ -499,15 +403,13 @@ __global__ void __launch_bounds__(kFastWarps * 32, 3) k_ekf_fast_step(const EkfP
             }
             // + Q_bar on the robot block (internal rows/cols 1..3)
             if (!frozen && a >= 1 && b >= 1) S[0][0] = add_(S[0][0], p.Q[(a - 1) + 3 * (b - 1)]);
-            __syncwarp();
         }
 
         // ---- m sequential updates (slam.cpp:279-319, known correspondence) ----
         for (int i = 0; i < m; ++i)
         {
-            const int id = frozen ? 0 : ib_[i];
+            const int id = frozen ? 0 : f.ids[i];
             const bool live = id >= 1 && id <= N;
-            if (!frozen && id > N && t16 == 0) f.flags[2] |= kStatusBadId;
             const int cI = live ? 4 + 2 * (id - 1) : 4;
             const int cq = cI >> 2, cb = cI & 3;   // tile column and lane group (0 or 2) of the landmark pair
             // A. publish the 5 columns and 5 rows of Sigma that H touches
@@ -523,90 +425,76 @@ __global__ void __launch_bounds__(kFastWarps * 32, 3) k_ekf_fast_step(const EkfP
             }
             if ((b >> 1) == (cb >> 1)) publish_col<T>(f.col + (3 + (b & 1)) * LP + a, S, cq);
             if ((a >> 1) == (cb >> 1)) publish_row<T>(f.row + (3 + (a & 1)) * LP + b, S, cq);
-            __syncwarp();
-            // B. scalar part, once per filter
-            if (t16 == 0)
+            __syncthreads();
+            // B. scalar part of all 2W filters of the CTA, one filter per lane, on one warp (rotating)
+            if (warp == (i & (kFastWarps - 1)) && lane < F)
             {
-                if (live)
+                FastSmem<N> & g = fs[lane];
+                const int gid = g.flags[5] ? 0 : g.ids[i];
+                if (gid >= 1 && gid <= N)
                 {
-                    const bool do_init = do_predict && id > f.flags[3];   // slam.cpp:295 (step protocol only)
-                    if (do_predict && id > f.flags[1]) f.flags[1] = id;    // what associateLandmark would have done to `seen`
-                    scalar_phase<N>(f, zb_[2 * i], zb_[2 * i + 1], id, do_init, pend, p.R);
+                    const bool do_init = do_predict && gid > g.flags[3];   // slam.cpp:295 (step protocol only)
+                    if (do_predict && gid > g.flags[1]) g.flags[1] = gid;    // what associateLandmark would have done to `seen`
+                    scalar_phase<N>(g, g.z[2 * i], g.z[2 * i + 1], gid, do_init, p.R);
                 }
                 else
-                    f.flags[0] = kFlagSkip;
+                {
+                    g.flags[0] = kFlagSkip;
+                    if (gid > N) g.flags[2] |= kStatusBadId;
+                }
             }
-            __syncwarp();
+            __syncthreads();
             const int fl = f.flags[0];
             const bool skip = fl & kFlagSkip, strict = fl & kFlagStrict;
             // C. K = Sigma H^T S^-1 and W = H Sigma, one row / column per lane (two passes of 16)
-            double cv[2][5], rv[2][5];
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2)
-            {
-                const int rr = t16 + 16 * h2;
-                if (rr < LP)
-                {
-#pragma unroll
-                    for (int k = 0; k < 5; ++k)
-                    {
-                        cv[h2][k] = f.col[k * LP + rr];
-                        rv[h2][k] = f.row[k * LP + rr];
-                    }
-                }
-            }
-            const double h01 = f.sc[0], h02 = f.sc[1], h0c = f.sc[2], h0c1 = f.sc[3];
-            const double h11 = f.sc[4], h12 = f.sc[5], h1c = f.sc[6], h1c1 = f.sc[7];
-            const double i00 = f.sc[8], i01 = f.sc[9], i10 = f.sc[10], i11 = f.sc[11];
-            const double dz0 = f.sc[12], dz1 = f.sc[13];
-            __syncwarp();   // col/row are about to be overwritten by the K / W (or M) tables
-            double2 * Ktab = reinterpret_cast<double2 *>(f.col);
-            double2 * Wtab = reinterpret_cast<double2 *>(f.row);
             if (!skip)
             {
+                const double h01 = f.sc[0], h02 = f.sc[1], h0c = f.sc[2], h0c1 = f.sc[3];
+                const double h11 = f.sc[4], h12 = f.sc[5], h1c = f.sc[6], h1c1 = f.sc[7];
+                const double i00 = f.sc[8], i01 = f.sc[9], i10 = f.sc[10], i11 = f.sc[11];
+                const double dz0 = f.sc[12], dz1 = f.sc[13];
 #pragma unroll
                 for (int h2 = 0; h2 < 2; ++h2)
                 {
                     const int rr = t16 + 16 * h2;
                     if (rr < LP)
                     {
+                        const double c0 = f.col[0 * LP + rr], c1 = f.col[1 * LP + rr], c2 = f.col[2 * LP + rr];
+                        const double c3 = f.col[3 * LP + rr], c4 = f.col[4 * LP + rr];
                         if (!strict)
                         {
-                            const double p0 = h01 * cv[h2][1] + h02 * cv[h2][2] + h0c * cv[h2][3] + h0c1 * cv[h2][4];
-                            const double p1 = -cv[h2][0] + h11 * cv[h2][1] + h12 * cv[h2][2] + h1c * cv[h2][3] + h1c1 * cv[h2][4];
+                            const double r0 = f.row[0 * LP + rr], r1 = f.row[1 * LP + rr], r2 = f.row[2 * LP + rr];
+                            const double r3 = f.row[3 * LP + rr], r4 = f.row[4 * LP + rr];
+                            const double p0 = h01 * c1 + h02 * c2 + h0c * c3 + h0c1 * c4;
+                            const double p1 = -c0 + h11 * c1 + h12 * c2 + h1c * c3 + h1c1 * c4;
                             const double k0 = p0 * i00 + p1 * i10, k1 = p0 * i01 + p1 * i11;
                             f.xs[rr] += k0 * dz0 + k1 * dz1;
-                            const double w0 = h01 * rv[h2][1] + h02 * rv[h2][2] + h0c * rv[h2][3] + h0c1 * rv[h2][4];
-                            const double w1 = -rv[h2][0] + h11 * rv[h2][1] + h12 * rv[h2][2] + h1c * rv[h2][3] + h1c1 * rv[h2][4];
-                            Ktab[rr] = make_double2(k0, k1);
-                            Wtab[rr] = make_double2(w0, w1);
+                            const double w0 = h01 * r1 + h02 * r2 + h0c * r3 + h0c1 * r4;
+                            const double w1 = -r0 + h11 * r1 + h12 * r2 + h1c * r3 + h1c1 * r4;
+                            f.kt[rr] = make_double2(k0, k1);
+                            f.wt[rr] = make_double2(w0, w1);
                         }
                         else
                         {
                             // oracle order: P = Sigma*H.t(), K = P*inv(psi), x += K*dz, M = eye - K*H
-                            double pa = mul_(cv[h2][1], h01);
-                            pa = add_(pa, mul_(cv[h2][2], h02));
-                            pa = add_(pa, mul_(cv[h2][3], h0c));
-                            pa = add_(pa, mul_(cv[h2][4], h0c1));
-                            double pb = -cv[h2][0];
-                            pb = add_(pb, mul_(cv[h2][1], h11));
-                            pb = add_(pb, mul_(cv[h2][2], h12));
-                            pb = add_(pb, mul_(cv[h2][3], h1c));
-                            pb = add_(pb, mul_(cv[h2][4], h1c1));
+                            double pa = mul_(c1, h01);
+                            pa = add_(pa, mul_(c2, h02));
+                            pa = add_(pa, mul_(c3, h0c));
+                            pa = add_(pa, mul_(c4, h0c1));
+                            double pb = -c0;
+                            pb = add_(pb, mul_(c1, h11));
+                            pb = add_(pb, mul_(c2, h12));
+                            pb = add_(pb, mul_(c3, h1c));
+                            pb = add_(pb, mul_(c4, h1c1));
                             const double k0 = add_(mul_(pa, i00), mul_(pb, i10));
                             const double k1 = add_(mul_(pa, i01), mul_(pb, i11));
                             f.xs[rr] = add_(f.xs[rr], add_(mul_(k0, dz0), mul_(k1, dz1)));
-                            const double kh0 = -k1;
-                            const double kh1 = add_(mul_(k0, h01), mul_(k1, h11));
-                            const double kh2 = add_(mul_(k0, h02), mul_(k1, h12));
-                            const double khc = add_(mul_(k0, h0c), mul_(k1, h1c));
-                            const double khc1 = add_(mul_(k0, h0c1), mul_(k1, h1c1));
-                            // M columns overwrite col[] (row[] keeps the old rows of Sigma)
-                            f.col[0 * LP + rr] = sub_((rr == 1) ? 1.0 : 0.0, kh0);
-                            f.col[1 * LP + rr] = sub_((rr == 2) ? 1.0 : 0.0, kh1);
-                            f.col[2 * LP + rr] = sub_((rr == 3) ? 1.0 : 0.0, kh2);
-                            f.col[3 * LP + rr] = sub_((rr == cI) ? 1.0 : 0.0, khc);
-                            f.col[4 * LP + rr] = sub_((rr == cI + 1) ? 1.0 : 0.0, khc1);
+                            // M columns overwrite this lane's own entries of col[] (row[] keeps the old rows of Sigma)
+                            f.col[0 * LP + rr] = sub_((rr == 1) ? 1.0 : 0.0, -k1);
+                            f.col[1 * LP + rr] = sub_((rr == 2) ? 1.0 : 0.0, add_(mul_(k0, h01), mul_(k1, h11)));
+                            f.col[2 * LP + rr] = sub_((rr == 3) ? 1.0 : 0.0, add_(mul_(k0, h02), mul_(k1, h12)));
+                            f.col[3 * LP + rr] = sub_((rr == cI) ? 1.0 : 0.0, add_(mul_(k0, h0c), mul_(k1, h1c)));
+                            f.col[4 * LP + rr] = sub_((rr == cI + 1) ? 1.0 : 0.0, add_(mul_(k0, h0c1), mul_(k1, h1c1)));
                         }
                     }
                 }
@@ -619,11 +507,11 @@ __global__ void __launch_bounds__(kFastWarps * 32, 3) k_ekf_fast_step(const EkfP
                 {
                     double2 w[T];
 #pragma unroll
-                    for (int q = 0; q < T; ++q) w[q] = Wtab[4 * q + b];
+                    for (int q = 0; q < T; ++q) w[q] = f.wt[4 * q + b];
 #pragma unroll
                     for (int r = 0; r < T; ++r)
                     {
-                        const double2 k = Ktab[4 * r + a];
+                        const double2 k = f.kt[4 * r + a];
 #pragma unroll
                         for (int q = 0; q < T; ++q)
                         {
@@ -661,19 +549,19 @@ __global__ void __launch_bounds__(kFastWarps * 32, 3) k_ekf_fast_step(const EkfP
             __syncwarp();
         }
 
-        if (t16 == 0 && pend) f.xs[1] = wrap_fast(f.xs[1]);
-        __syncwarp();
         // ---- write back: registers -> HBM (each lane quartet writes 32 contiguous bytes) ----
-        if (valid && !frozen)
+        if (!frozen)
         {
+            if (t16 == 0 && f.flags[4]) f.xs[1] = wrap_fast(f.xs[1]);
+            __syncwarp();
             double * gs = p.sigma + bf * SIG;
 #pragma unroll
-            for (int r = 0; r < T; ++r)
+            for (int q = 0; q < T; ++q)
 #pragma unroll
-                for (int q = 0; q < T; ++q)
+                for (int r = 0; r < T; ++r)
                 {
                     const int i = 4 * r + a - 1, j = 4 * q + b - 1;
-                    if (i >= 0 && j >= 0 && i < LEN && j < LEN) gs[j * LEN + i] = S[r][q];
+                    if (i >= 0 && j >= 0 && i < LEN && j < LEN) __stcs(gs + j * LEN + i, S[r][q]);
                 }
             for (int e = t16 + 1; e <= LEN; e += 16) p.x[bf * LEN + e - 1] = f.xs[e];
             if (t16 == 0)
@@ -682,16 +570,14 @@ __global__ void __launch_bounds__(kFastWarps * 32, 3) k_ekf_fast_step(const EkfP
                 p.status[bf] = f.flags[2];
             }
         }
-        __syncwarp();
+        __syncthreads();   // shared-memory inputs of this group are dead; the next group may overwrite them
     }
 }
 
 template <int N>
 constexpr size_t fast_smem_bytes()
 {
-    using G = FastGeom<N>;
-    return kFastWarps * (sizeof(double) * 2 * G::SIG + (sizeof(double) * 2 * G::LEN + 15) / 16 * 16 + sizeof(double) * 2 * 2 * G::M_MAX * 2 +
-                         sizeof(int) * 2 * 2 * G::M_MAX + sizeof(double) * 2 * 8 + 2 * ((sizeof(FastSmem<N>) + 15) / 16 * 16) + 16);
+    return 2 * kFastWarps * sizeof(FastSmem<N>);
 }
 
 inline bool fast_supported(int n) { return n == 12 || n == 6; }
@@ -711,10 +597,10 @@ int launch_fast_n(const EkfParams & p, bool do_predict, int sm_count, cudaStream
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         configured = true;
     }
-    const int64_t npairs = (p.batch + 1) / 2;
-    int64_t blocks = (npairs + kFastWarps - 1) / kFastWarps;
+    const int64_t ngroups = (p.batch + 2 * kFastWarps - 1) / (2 * kFastWarps);
+    int64_t blocks = ngroups;
     const int64_t resident = (int64_t) sm_count * ctas_per_sm;
-    if (blocks > resident) blocks = resident;   // persistent: each warp strides over pairs, prefetching one ahead
+    if (blocks > resident) blocks = resident;   // persistent CTAs stride over groups of 2W filters
     k_ekf_fast_step<N><<<(unsigned) blocks, kFastWarps * 32, smem, stream>>>(p, do_predict ? 1 : 0);
     return (int) cudaGetLastError();
 }
@@ -723,8 +609,7 @@ int launch_fast_n(const EkfParams & p, bool do_predict, int sm_count, cudaStream
 inline int launch_fast(int n, const EkfParams & p, bool do_predict, int sm_count, cudaStream_t stream)
 {
     if (p.m > FastGeom<12>::M_MAX || p.m < 0 || p.ids == nullptr) return -1;
-    if ((reinterpret_cast<uintptr_t>(p.sigma) & 15) || (reinterpret_cast<uintptr_t>(p.x) & 15)) return -1;
-    if ((reinterpret_cast<uintptr_t>(p.z) & 7) || (reinterpret_cast<uintptr_t>(p.ids) & 3)) return -1;
+    if ((reinterpret_cast<uintptr_t>(p.sigma) & 15) || (reinterpret_cast<uintptr_t>(p.x) & 7)) return -1;
     if (n == 12) return launch_fast_n<12>(p, do_predict, sm_count, stream);
     if (n == 6) return launch_fast_n<6>(p, do_predict, sm_count, stream);
     return -1;
