@@ -4,19 +4,19 @@
 // 16 B x len^2 per update (11.6 KB at len 27), i.e. ~1100 shared-memory cycles per filter-step at 128 B/clk/SM,
 // above the ~900 cycles/filter-step/SM that 60 % of the HBM roofline allows. Registers have no such limit.
 //
-// Layout (one filter per half-warp, two filters per warp, 2W filters per CTA of W warps):
+// Layout (one filter per warp, W filters per CTA of W warps):
 //   * internal index = external index + 1 (slot 0 is a zero dummy), so every landmark occupies an aligned
-//     (even, odd) pair and the padded length LP = 4T is exactly 28 for n = 12 (16 for n = 6)
-//   * the 16 lanes of a half-warp form a 4 x 4 grid (a = row group, b = column group); lane (a,b) holds the
-//     cyclic T x T tile  S[r][q] = Sigma(4r + a, 4q + b)  in registers (49 doubles at n = 12). In the
-//     column-major HBM image a lane quartet (a = 0..3) owns 32 contiguous bytes, so tile loads and stores
-//     move whole 32-byte sectors; the next group's Sigma is pulled into L2 by a bulk prefetch
-//     (cp.async.bulk.prefetch.L2) while the current one is computed.
+//     (even, odd) pair; padded sizes 28 rows x 32 columns at n = 12 (16 x 16 at n = 6)
+//   * the 32 lanes form a 4 x 8 grid (a = lane / 8 row group, b = lane % 8 column group); lane (a,b) holds the
+//     cyclic TR x TC tile  S[r][q] = Sigma(4r + a, 8q + b)  in registers (28 doubles at n = 12), which leaves
+//     room for ~18 resident warps per SM. In the column-major HBM image a lane quartet (a = 0..3) owns 32
+//     contiguous bytes, so tile loads and stores move whole 32-byte sectors; the next group's Sigma is pulled
+//     into L2 by a bulk prefetch (cp.async.bulk.prefetch.L2) while the current one is computed.
 //   * per update: (A) every warp publishes the 5 rows and 5 columns of Sigma that H touches (static register
-//     indices through a switch on the landmark's tile column); (B) ONE warp evaluates the scalar part
-//     (H, S = H Sigma H^T + R, S^-1, innovation; rsqrt / atan2 / reciprocal) for all 2W filters of the CTA, one
-//     filter per lane, instead of every half-warp repeating it 16-fold; (C) the 16 lanes of each filter form
-//     K = Sigma H^T S^-1 and W = H Sigma row by row; (D) the tile update Sigma -= K W is two FMAs per element
+//     indices through one switch on the landmark's tile row); (B) ONE warp evaluates the scalar part
+//     (H, S = H Sigma H^T + R, S^-1, innovation; rsqrt / atan2 / reciprocal) for all W filters of the CTA, one
+//     filter per lane, instead of every warp repeating it 32-fold; (C) lane i forms row i of
+//     K = Sigma H^T S^-1 and column i of W = H Sigma; (D) the tile update Sigma -= K W is two FMAs per element
 //     with K / W operands fetched as 16-byte pairs.
 //
 // Arithmetic: predict always uses the oracle's operation order (it is O(len)). An update whose landmark still
@@ -25,6 +25,7 @@
 // Reference: nuslam/src/slam_library.cpp:65-108 (predict), :263-282 (update), nuslam/src/slam.cpp:262-319.
 #pragma once
 #include "ekf_strict.cuh"
+#include "fastmath.cuh"
 
 namespace nuslam
 {
@@ -34,17 +35,63 @@ struct FastGeom
 {
     static constexpr int LEN = 3 + 2 * N;   // external state length
     static constexpr int LI = LEN + 1;      // internal length (dummy slot 0)
-    static constexpr int T = (LI + 3) / 4;  // tile edge
-    static constexpr int LP = 4 * T;        // padded internal length
+    static constexpr int TR = (LI + 3) / 4; // tile rows per lane
+    static constexpr int TC = (LI + 7) / 8; // tile columns per lane
+    static constexpr int LPR = 4 * TR;      // padded rows
+    static constexpr int LPC = 8 * TC;      // padded columns
     static constexpr int SIG = LEN * LEN;
     static constexpr int M_MAX = 16;        // measurements per step handled by this kernel
 };
 
-constexpr int kFastWarps = 4;   // warps per CTA (8 filters)
+#ifndef NUSLAM_MATRIX_WARPS
+#define NUSLAM_MATRIX_WARPS 16
+#endif
+#ifndef NUSLAM_SCALAR_WARPS
+#define NUSLAM_SCALAR_WARPS 2
+#endif
+constexpr int kMatrixWarps = NUSLAM_MATRIX_WARPS;   // one filter in flight per matrix warp
+constexpr int kScalarWarps = NUSLAM_SCALAR_WARPS;   // scalar-server warps: lane l of server s serves matrix warp l * kScalarWarps + s
+constexpr int kFastThreads = 32 * (kMatrixWarps + kScalarWarps);
+static_assert(kMatrixWarps <= 32 * kScalarWarps, "a scalar server has 32 lanes");
 
 __device__ __forceinline__ void prefetch_l2_bulk(const void * src, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t * bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t * bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// hardware-suspended wait (try_wait sleeps in the barrier unit, it does not spin on the issue port)
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ int ld_acquire_smem(const int * p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_smem(int * p, int v)
+{
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
 // wrap an angle known to lie within (-3pi, 3pi) into (-pi, pi]: what normalize_angle returns, to ~1 ulp,
@@ -62,69 +109,56 @@ template <int N>
 struct FastSmem
 {
     using G = FastGeom<N>;
-    double2 kt[G::LP];        // K = Sigma H^T S^-1, one (k0,k1) pair per row
-    double2 wt[G::LP];        // W = H Sigma, one (w0,w1) pair per column
-    double xs[G::LP];         // state, internal indexing (xs[0] dummy)
-    double col[5 * G::LP];    // published columns {th,x,y,c,c+1}: col[k*LP + i] = Sigma(i, col_k); M columns on the strict path
-    double row[5 * G::LP];    // published rows    {th,x,y,c,c+1}: row[k*LP + j] = Sigma(row_k, j)
+    double2 kt[G::LPR];       // K = Sigma H^T S^-1, one (k0,k1) pair per row
+    double2 wt[G::LPC];       // W = H Sigma, one (w0,w1) pair per column
+    double xs[G::LPC];        // state, internal indexing (xs[0] dummy)
+    double col[5 * G::LPR];   // published columns {th,x,y,c,c+1}: col[k*LPR + i] = Sigma(i, col_k); M columns on the strict path
+    double row[5 * G::LPC];   // published rows    {th,x,y,c,c+1}: row[k*LPC + j] = Sigma(row_k, j)
     double sc[16];            // scalar-phase outputs: H (8), S^-1 (4), innovation (2), predict b10, b20 (2)
     double z[2 * G::M_MAX];   // this step's measurements (range, bearing)
     double tw[2];             // this step's twist (dth, dx)
     int ids[G::M_MAX];        // this step's landmark ids
     int flags[8];             // [0] update flags, [1] seen, [2] status, [3] seen snapshot, [4] theta owes a wrap, [5] frozen
+    int req;                  // mailbox to the scalar server: kReqNone / kReqPredict / kReqExit / kReqUpdate + measurement index
+    int pad_;
+    uint64_t done;            // mbarrier the scalar server arrives on when the request has been served
 };
+constexpr int kReqNone = 0, kReqPredict = 1, kReqExit = 2, kReqUpdate = 16;
 
 constexpr int kFlagSkip = 1, kFlagStrict = 2;
 
-template <int T>
-__device__ __forceinline__ void publish_col(double * dst, const double (&S)[T][T], int q)
+// Publish the landmark's two rows and two columns. cr = cI / 4 is the tile row holding the pair; the tile
+// column is cr / 2. Lanes whose row group (a) matches store their row slice, lanes whose column group (b)
+// matches store their column slice; register indices are static inside every case.
+template <int TR, int TC>
+__device__ __forceinline__ void publish_landmark(double * rdst, double * cdst, bool rmatch, bool cmatch, const double (&S)[TR][TC], int cr)
 {
-    // dst[4*r] = S[r][q] with static register indices
-    switch (q)
+    switch (cr)
     {
-#define NUSLAM_PC(k)                                                                        \
-    case k:                                                                                 \
-        if constexpr (T > k)                                                                \
-        {                                                                                   \
-            _Pragma("unroll") for (int r = 0; r < T; ++r) dst[4 * r] = S[r][k < T ? k : 0]; \
-        }                                                                                   \
+#define NUSLAM_PL(k)                                                                                          \
+    case k:                                                                                                   \
+        if constexpr (TR > k)                                                                                 \
+        {                                                                                                     \
+            if (rmatch)                                                                                       \
+            {                                                                                                 \
+                _Pragma("unroll") for (int q = 0; q < TC; ++q) rdst[8 * q] = S[k < TR ? k : 0][q];            \
+            }                                                                                                 \
+            if (cmatch)                                                                                       \
+            {                                                                                                 \
+                _Pragma("unroll") for (int r = 0; r < TR; ++r) cdst[4 * r] = S[r][(k / 2) < TC ? (k / 2) : 0]; \
+            }                                                                                                 \
+        }                                                                                                     \
         break;
-        NUSLAM_PC(0)
-        NUSLAM_PC(1)
-        NUSLAM_PC(2)
-        NUSLAM_PC(3)
-        NUSLAM_PC(4)
-        NUSLAM_PC(5)
-        NUSLAM_PC(6)
-        NUSLAM_PC(7)
-        NUSLAM_PC(8)
-#undef NUSLAM_PC
-    default: break;
-    }
-}
-
-template <int T>
-__device__ __forceinline__ void publish_row(double * dst, const double (&S)[T][T], int r)
-{
-    switch (r)
-    {
-#define NUSLAM_PR(k)                                                                        \
-    case k:                                                                                 \
-        if constexpr (T > k)                                                                \
-        {                                                                                   \
-            _Pragma("unroll") for (int q = 0; q < T; ++q) dst[4 * q] = S[k < T ? k : 0][q]; \
-        }                                                                                   \
-        break;
-        NUSLAM_PR(0)
-        NUSLAM_PR(1)
-        NUSLAM_PR(2)
-        NUSLAM_PR(3)
-        NUSLAM_PR(4)
-        NUSLAM_PR(5)
-        NUSLAM_PR(6)
-        NUSLAM_PR(7)
-        NUSLAM_PR(8)
-#undef NUSLAM_PR
+        NUSLAM_PL(0)
+        NUSLAM_PL(1)
+        NUSLAM_PL(2)
+        NUSLAM_PL(3)
+        NUSLAM_PL(4)
+        NUSLAM_PL(5)
+        NUSLAM_PL(6)
+        NUSLAM_PL(7)
+        NUSLAM_PL(8)
+#undef NUSLAM_PL
     default: break;
     }
 }
@@ -176,6 +210,67 @@ __device__ __forceinline__ void predict_scalar(FastSmem<N> & f)
     f.sc[15] = b20;
 }
 
+// Common case of the scalar part (landmark already initialised and past its first touch): straight-line,
+// branch-free, short dependency chains. H's structure (h01 = -h0c, h02 = -h0c1, h1c = -h11, h1c1 = -h12) folds
+// every 4- or 5-term contraction with H into two FMAs on pre-formed differences of Sigma entries.
+template <int N>
+__device__ __forceinline__ void scalar_phase_fast(FastSmem<N> & f, double z0, double z1, int cI, const double * R)
+{
+    constexpr int LP = FastGeom<N>::LPR;
+    const double * c = f.col;
+    double s0[5], A[5], B[5];   // per column j of the 5x5 block: Sigma(th,j), Sigma(c,j)-Sigma(x,j), Sigma(c+1,j)-Sigma(y,j)
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+    {
+        s0[j] = c[j * LP + 1];
+        A[j] = c[j * LP + cI] - c[j * LP + 2];
+        B[j] = c[j * LP + cI + 1] - c[j * LP + 3];
+    }
+    const double th_raw = f.xs[1];
+    const double th = f.flags[4] ? wrap_fast(th_raw) : th_raw;   // normalize_angle owed by the previous fused update (:276)
+    const double dx = f.xs[cI] - f.xs[2], dy = f.xs[cI + 1] - f.xs[3];
+    const double d = fma(dx, dx, dy * dy);
+    const double rs = rsqrt_fast(d);
+    const double id2 = rs * rs;
+    double sq = d * rs;
+    sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);   // sqrt(d) to ~1 ulp
+    const double h0c = dx * rs, h0c1 = dy * rs, h11 = dy * id2, h12 = -dx * id2;
+    const double zb = wrap_fast(atan2_fast(dy, dx) - th);
+    double g0[5], g1[5];   // H * Sigma at the 5 columns
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+    {
+        g0[j] = fma(h0c, A[j], h0c1 * B[j]);
+        g1[j] = -fma(h11, A[j], fma(h12, B[j], s0[j]));
+    }
+    // psi = (H Sigma) H^T + R
+    const double p00 = fma(h0c, g0[3] - g0[1], fma(h0c1, g0[4] - g0[2], R[0]));
+    const double p10 = fma(h0c, g1[3] - g1[1], fma(h0c1, g1[4] - g1[2], R[1]));
+    const double p01 = fma(h11, g0[1] - g0[3], fma(h12, g0[2] - g0[4], R[2] - g0[0]));
+    const double p11 = fma(h11, g1[1] - g1[3], fma(h12, g1[2] - g1[4], R[3] - g1[0]));
+    const double det = fma(p00, p11, -p01 * p10);
+    const double idet = rcp_fast(det);
+    const bool ok = det != 0.0;
+    f.xs[1] = th;
+    f.sc[0] = -h0c;
+    f.sc[1] = -h0c1;
+    f.sc[2] = h0c;
+    f.sc[3] = h0c1;
+    f.sc[4] = h11;
+    f.sc[5] = h12;
+    f.sc[6] = -h11;
+    f.sc[7] = -h12;
+    f.sc[8] = ok ? p11 * idet : 0.0;
+    f.sc[9] = ok ? -p01 * idet : 0.0;
+    f.sc[10] = ok ? -p10 * idet : 0.0;
+    f.sc[11] = ok ? p00 * idet : 0.0;
+    f.sc[12] = ok ? z0 - sq : 0.0;   // :272, no wrap
+    f.sc[13] = ok ? z1 - zb : 0.0;
+    f.flags[0] = ok ? 0 : kFlagSkip;
+    f.flags[4] = ok ? 1 : 0;         // the fused path wraps theta lazily
+    if (!ok) f.flags[2] |= kStatusSingular;
+}
+
 // Scalar part of one update for one filter (one lane): H, S = H Sigma H^T + R, S^-1, innovation.
 // Reads the 5x5 block of Sigma from the published columns. slam_library.cpp:265-272 (+ :255-261 when the
 // landmark is new).
@@ -183,8 +278,13 @@ template <int N>
 __device__ __forceinline__ void scalar_phase(FastSmem<N> & f, double z0, double z1, int id, bool do_init, const double * R)
 {
     using G = FastGeom<N>;
-    constexpr int LP = G::LP;
+    constexpr int LP = G::LPR;          // leading dimension of the published columns
     const int cI = 4 + 2 * (id - 1);   // internal column of the landmark's x
+    if (!do_init && !((f.col[3 * LP + cI] > kFirstTouchVariance) || (f.col[4 * LP + cI + 1] > kFirstTouchVariance)))
+    {
+        scalar_phase_fast<N>(f, z0, z1, cI, R);
+        return;
+    }
     double th = f.xs[1];
     if (f.flags[4])
     {
@@ -315,269 +415,307 @@ __device__ __forceinline__ void scalar_phase(FastSmem<N> & f, double z0, double 
     if (fl == 0) f.flags[4] = 1;   // the fused path wraps theta lazily
 }
 
+// filter slot `g` gets a no-op update: K = 0, innovation 0 (branch-free skip in phases C and D)
 template <int N>
-__global__ void __launch_bounds__(kFastWarps * 32, 3) k_ekf_fast_step(const EkfParams p, const int do_predict)
+__device__ __forceinline__ void scalar_skip(FastSmem<N> & g)
+{
+#pragma unroll
+    for (int k = 0; k < 14; ++k) g.sc[k] = 0.0;
+    g.flags[0] = kFlagSkip;
+}
+
+// Scalar server: each lane watches the mailbox of one matrix warp and serves whatever is posted there, so
+// the rsqrt / atan2 / reciprocal chains of up to 32 filters advance together in one instruction stream.
+template <int N>
+__device__ __forceinline__ void scalar_server(FastSmem<N> * fs, int server, int lane, const EkfParams & p, int do_predict)
+{
+    const int w = lane * kScalarWarps + server;
+    bool alive = w < kMatrixWarps;
+    FastSmem<N> & g = fs[alive ? w : 0];
+    while (__any_sync(0xffffffffu, alive))
+    {
+        const int r = alive ? ld_acquire_smem(&g.req) : kReqNone;
+        if (r == kReqPredict)
+        {
+            predict_scalar<N>(g);
+        }
+        else if (r >= kReqUpdate)
+        {
+            const int i = r - kReqUpdate;
+            const int gid = g.ids[i];
+            if (gid >= 1 && gid <= N)
+            {
+                const bool do_init = do_predict && gid > g.flags[3];   // slam.cpp:295 (step protocol only)
+                if (do_predict && gid > g.flags[1]) g.flags[1] = gid;    // what associateLandmark would have done to `seen`
+                scalar_phase<N>(g, g.z[2 * i], g.z[2 * i + 1], gid, do_init, p.R);
+            }
+            else
+            {
+                scalar_skip<N>(g);
+                if (gid > N) g.flags[2] |= kStatusBadId;
+            }
+        }
+        if (r == kReqExit) alive = false;
+        else if (r != kReqNone)
+        {
+            g.req = kReqNone;       // ordered before the arrive (release) below
+            mbar_arrive(&g.done);
+        }
+        if (!__any_sync(0xffffffffu, r != kReqNone)) __nanosleep(40);
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kFastThreads, 1) k_ekf_fast_step(const EkfParams p, const int do_predict)
 {
     using G = FastGeom<N>;
-    constexpr int T = G::T, LP = G::LP, LEN = G::LEN, SIG = G::SIG;
-    constexpr int F = 2 * kFastWarps;   // filters per CTA
+    constexpr int TR = G::TR, TC = G::TC, LPR = G::LPR, LPC = G::LPC, LEN = G::LEN, SIG = G::SIG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastSmem<N> * fs = reinterpret_cast<FastSmem<N> *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int hw = lane >> 4;          // which filter of the warp's pair
-    const int t16 = lane & 15;
-    const int a = t16 >> 2, b = t16 & 3;
-    const int m = p.m;
-    const int fl_idx = 2 * warp + hw;   // filter slot within the CTA
-    FastSmem<N> & f = fs[fl_idx];
-
-    const int64_t ngroups = (p.batch + F - 1) / F;
-    for (int64_t group = blockIdx.x; group < ngroups; group += gridDim.x)
+    if (warp < kMatrixWarps && lane == 0)
     {
-        const int64_t bf = group * F + fl_idx;
-        const bool valid = bf < p.batch;
-        // pull the next group's Sigma towards L2 while this group is computed
+        mbar_init(&fs[warp].done, 1);
+        fs[warp].req = kReqNone;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();   // the only CTA-wide barrier of the kernel
+    if (warp >= kMatrixWarps)
+    {
+        scalar_server<N>(fs, warp - kMatrixWarps, lane, p, do_predict);
+        return;
+    }
+
+    const int a = lane >> 3, b = lane & 7;
+    const int m = p.m;
+    FastSmem<N> & f = fs[warp];
+    // lane-invariant addresses and predicates, hoisted out of every loop
+    const int goff = (b - 1) * LEN + (a - 1);            // HBM offset of S[0][0] inside the filter's Sigma
+    double * const col_robot = f.col + (b - 1) * LPR + a;   // valid for b in 1..3
+    double * const row_robot = f.row + (a - 1) * LPC + b;   // valid for a in 1..3
+    const bool pub_col = (b >= 1) && (b <= 3);
+    const bool pub_row = (a >= 1);
+    double * const rdst = f.row + (3 + (a & 1)) * LPC + b;
+    double * const cdst = f.col + (3 + (b & 1)) * LPR + a;
+    const bool lane_row = lane < LPR;
+    uint32_t parity = 0;
+
+    const int64_t stride = (int64_t) gridDim.x * kMatrixWarps;
+    for (int64_t bf = (int64_t) blockIdx.x * kMatrixWarps + warp; bf < p.batch; bf += stride)
+    {
+        // pull this warp's next Sigma towards L2 while the current one is computed
+        if (lane == 0)
         {
-            const int64_t nb = (group + gridDim.x) * F + 2 * warp;
-            if (lane == 0 && nb + 1 < p.batch) prefetch_l2_bulk(p.sigma + nb * SIG, (uint32_t) (sizeof(double) * 2 * SIG));
+            const int64_t nb = bf + stride;
+            if (nb + 1 < p.batch && ((nb & 1) == 0)) prefetch_l2_bulk(p.sigma + nb * SIG, (uint32_t) (sizeof(double) * 2 * SIG));
         }
         // ---- load: Sigma tile straight into registers (32-byte runs per lane quartet), small inputs into shared memory ----
-        double S[T][T];
+        double S[TR][TC];
         {
-            const double * gs = p.sigma + (valid ? bf : 0) * SIG;
+            const double * gs = p.sigma + bf * SIG + goff;
 #pragma unroll
-            for (int q = 0; q < T; ++q)
+            for (int q = 0; q < TC; ++q)
 #pragma unroll
-                for (int r = 0; r < T; ++r)
+                for (int r = 0; r < TR; ++r)
                 {
-                    const int i = 4 * r + a - 1, j = 4 * q + b - 1;   // external indices
-                    S[r][q] = (valid && i >= 0 && j >= 0 && i < LEN && j < LEN) ? __ldcs(gs + j * LEN + i) : 0.0;
+                    const int i = 4 * r + a - 1, j = 8 * q + b - 1;   // external indices
+                    S[r][q] = (i >= 0 && j >= 0 && i < LEN && j < LEN) ? __ldcs(gs + (8 * q) * LEN + 4 * r) : 0.0;
                 }
-            for (int e = t16; e < LP; e += 16) f.xs[e] = (valid && e >= 1 && e <= LEN) ? p.x[bf * LEN + e - 1] : 0.0;
-            for (int e = t16; e < 2 * m; e += 16) f.z[e] = valid ? p.z[bf * m * 2 + e] : 0.0;
-            for (int e = t16; e < m; e += 16) f.ids[e] = valid ? p.ids[bf * m + e] : 0;
-            if (t16 < 2) f.tw[t16] = (valid && do_predict) ? p.twists[bf * 3 + t16] : 0.0;
-            if (t16 == 0)
-            {
-                const int seen = valid ? p.seen[bf] : 0;
-                const int st = valid ? p.status[bf] : 0;
-                f.flags[1] = seen;
-                f.flags[2] = st;
-                f.flags[3] = seen;   // snapshot, slam.cpp:251
-                f.flags[4] = 0;
-                f.flags[5] = (!valid || (st & (kStatusMapFull | kStatusSingular))) ? 1 : 0;
-            }
+            f.xs[lane] = (lane >= 1 && lane <= LEN) ? p.x[bf * LEN + lane - 1] : 0.0;
+            if (lane < 2 * m) f.z[lane] = p.z[bf * m * 2 + lane];
+            if (lane < m) f.ids[lane] = p.ids[bf * m + lane];
+            if (lane < 2) f.tw[lane] = do_predict ? p.twists[bf * 3 + lane] : 0.0;
         }
-        __syncthreads();
-        const bool frozen = f.flags[5] != 0;
+        const int seen0 = p.seen[bf], st0 = p.status[bf];
+        if (lane == 0)
+        {
+            f.flags[1] = seen0;
+            f.flags[2] = st0;
+            f.flags[3] = seen0;   // snapshot, slam.cpp:251
+            f.flags[4] = 0;
+        }
+        if (st0 & (kStatusMapFull | kStatusSingular)) continue;   // the reference process died on an earlier scan
+        __syncwarp();
 
         // ---- predict (slam_library.cpp:65-108), always in the oracle's operation order ----
         if (do_predict)
         {
-            if (warp == 0 && lane < F && !fs[lane].flags[5]) predict_scalar<N>(fs[lane]);
-            __syncthreads();
-            const double b10 = f.sc[14], b20 = f.sc[15];
+            if (lane == 0) st_release_smem(&f.req, kReqPredict);
+            mbar_wait(&f.done, parity);
+            parity ^= 1;
             // T = A * Sigma: rows x (a = 2, r = 0) and y (a = 3, r = 0) += b * row theta (a = 1, r = 0)
-            const int src_row = hw * 16 + 4 + b;
+            const double brow = (a == 2) ? f.sc[14] : f.sc[15];
+            const double bcol = (b == 2) ? f.sc[14] : f.sc[15];
+            const bool do_row = a >= 2;
+            const bool do_col = (b == 2 || b == 3);
 #pragma unroll
-            for (int q = 0; q < T; ++q)
+            for (int q = 0; q < TC; ++q)
             {
-                const double thv = __shfl_sync(0xffffffffu, S[0][q], src_row);
-                if (!frozen)
-                {
-                    if (a == 2) S[0][q] = add_(mul_(b10, thv), S[0][q]);
-                    if (a == 3) S[0][q] = add_(mul_(b20, thv), S[0][q]);
-                }
+                const double thv = __shfl_sync(0xffffffffu, S[0][q], 8 + b);
+                const double v = add_(mul_(brow, thv), S[0][q]);
+                S[0][q] = do_row ? v : S[0][q];
             }
             // U = T * A.t(): columns x (b = 2, q = 0) and y (b = 3, q = 0) += b * column theta (b = 1, q = 0)
-            const int src_col = hw * 16 + 4 * a + 1;
 #pragma unroll
-            for (int r = 0; r < T; ++r)
+            for (int r = 0; r < TR; ++r)
             {
-                const double t0 = __shfl_sync(0xffffffffu, S[r][0], src_col);
-                if (!frozen)
-                {
-                    if (b == 2) S[r][0] = add_(mul_(t0, b10), S[r][0]);
-                    if (b == 3) S[r][0] = add_(mul_(t0, b20), S[r][0]);
-                }
+                const double t0 = __shfl_sync(0xffffffffu, S[r][0], 8 * a + 1);
+                const double v = add_(mul_(t0, bcol), S[r][0]);
+                S[r][0] = do_col ? v : S[r][0];
             }
             // + Q_bar on the robot block (internal rows/cols 1..3)
-            if (!frozen && a >= 1 && b >= 1) S[0][0] = add_(S[0][0], p.Q[(a - 1) + 3 * (b - 1)]);
+            {
+                const bool inq = a >= 1 && b >= 1 && b <= 3;
+                const double qv = inq ? p.Q[(a - 1) + 3 * (b - 1)] : 0.0;
+                const double v = add_(S[0][0], qv);
+                S[0][0] = inq ? v : S[0][0];
+            }
         }
 
         // ---- m sequential updates (slam.cpp:279-319, known correspondence) ----
         for (int i = 0; i < m; ++i)
         {
-            const int id = frozen ? 0 : f.ids[i];
+            const int id = f.ids[i];
             const bool live = id >= 1 && id <= N;
             const int cI = live ? 4 + 2 * (id - 1) : 4;
-            const int cq = cI >> 2, cb = cI & 3;   // tile column and lane group (0 or 2) of the landmark pair
             // A. publish the 5 columns and 5 rows of Sigma that H touches
-            if (b >= 1)
+            if (pub_col)
             {
 #pragma unroll
-                for (int r = 0; r < T; ++r) f.col[(b - 1) * LP + 4 * r + a] = S[r][0];
+                for (int r = 0; r < TR; ++r) col_robot[4 * r] = S[r][0];
             }
-            if (a >= 1)
+            if (pub_row)
             {
 #pragma unroll
-                for (int q = 0; q < T; ++q) f.row[(a - 1) * LP + 4 * q + b] = S[0][q];
+                for (int q = 0; q < TC; ++q) row_robot[8 * q] = S[0][q];
             }
-            if ((b >> 1) == (cb >> 1)) publish_col<T>(f.col + (3 + (b & 1)) * LP + a, S, cq);
-            if ((a >> 1) == (cb >> 1)) publish_row<T>(f.row + (3 + (a & 1)) * LP + b, S, cq);
-            __syncthreads();
-            // B. scalar part of all 2W filters of the CTA, one filter per lane, on one warp (rotating)
-            if (warp == (i & (kFastWarps - 1)) && lane < F)
-            {
-                FastSmem<N> & g = fs[lane];
-                const int gid = g.flags[5] ? 0 : g.ids[i];
-                if (gid >= 1 && gid <= N)
-                {
-                    const bool do_init = do_predict && gid > g.flags[3];   // slam.cpp:295 (step protocol only)
-                    if (do_predict && gid > g.flags[1]) g.flags[1] = gid;    // what associateLandmark would have done to `seen`
-                    scalar_phase<N>(g, g.z[2 * i], g.z[2 * i + 1], gid, do_init, p.R);
-                }
-                else
-                {
-                    g.flags[0] = kFlagSkip;
-                    if (gid > N) g.flags[2] |= kStatusBadId;
-                }
-            }
-            __syncthreads();
-            const int fl = f.flags[0];
-            const bool skip = fl & kFlagSkip, strict = fl & kFlagStrict;
-            // C. K = Sigma H^T S^-1 and W = H Sigma, one row / column per lane (two passes of 16)
-            if (!skip)
+            publish_landmark<TR, TC>(rdst, cdst, (a >> 1) == ((cI & 3) >> 1), (b >> 1) == ((cI & 7) >> 1), S, cI >> 2);
+            __syncwarp();
+            // B. hand the scalar part (H, S, S^-1, innovation) to the scalar server and sleep until it is served
+            if (lane == 0) st_release_smem(&f.req, kReqUpdate + i);
+            mbar_wait(&f.done, parity);
+            parity ^= 1;
+            const bool strict = (f.flags[0] & kFlagStrict) != 0;
+            // C. lane i forms row i of K = Sigma H^T S^-1 and column i of W = H Sigma
             {
                 const double h01 = f.sc[0], h02 = f.sc[1], h0c = f.sc[2], h0c1 = f.sc[3];
                 const double h11 = f.sc[4], h12 = f.sc[5], h1c = f.sc[6], h1c1 = f.sc[7];
                 const double i00 = f.sc[8], i01 = f.sc[9], i10 = f.sc[10], i11 = f.sc[11];
                 const double dz0 = f.sc[12], dz1 = f.sc[13];
-#pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2)
+                const int rr = lane_row ? lane : 0;
+                const double c0 = f.col[0 * LPR + rr], c1 = f.col[1 * LPR + rr], c2 = f.col[2 * LPR + rr];
+                const double c3 = f.col[3 * LPR + rr], c4 = f.col[4 * LPR + rr];
+                if (!strict)
                 {
-                    const int rr = t16 + 16 * h2;
-                    if (rr < LP)
+                    const double r0 = f.row[0 * LPC + lane], r1 = f.row[1 * LPC + lane], r2 = f.row[2 * LPC + lane];
+                    const double r3 = f.row[3 * LPC + lane], r4 = f.row[4 * LPC + lane];
+                    const double p0 = h01 * c1 + h02 * c2 + h0c * c3 + h0c1 * c4;
+                    const double p1 = -c0 + h11 * c1 + h12 * c2 + h1c * c3 + h1c1 * c4;
+                    const double k0 = p0 * i00 + p1 * i10, k1 = p0 * i01 + p1 * i11;
+                    const double w0 = h01 * r1 + h02 * r2 + h0c * r3 + h0c1 * r4;
+                    const double w1 = -r0 + h11 * r1 + h12 * r2 + h1c * r3 + h1c1 * r4;
+                    f.wt[lane] = make_double2(w0, w1);
+                    if (lane_row)
                     {
-                        const double c0 = f.col[0 * LP + rr], c1 = f.col[1 * LP + rr], c2 = f.col[2 * LP + rr];
-                        const double c3 = f.col[3 * LP + rr], c4 = f.col[4 * LP + rr];
-                        if (!strict)
-                        {
-                            const double r0 = f.row[0 * LP + rr], r1 = f.row[1 * LP + rr], r2 = f.row[2 * LP + rr];
-                            const double r3 = f.row[3 * LP + rr], r4 = f.row[4 * LP + rr];
-                            const double p0 = h01 * c1 + h02 * c2 + h0c * c3 + h0c1 * c4;
-                            const double p1 = -c0 + h11 * c1 + h12 * c2 + h1c * c3 + h1c1 * c4;
-                            const double k0 = p0 * i00 + p1 * i10, k1 = p0 * i01 + p1 * i11;
-                            f.xs[rr] += k0 * dz0 + k1 * dz1;
-                            const double w0 = h01 * r1 + h02 * r2 + h0c * r3 + h0c1 * r4;
-                            const double w1 = -r0 + h11 * r1 + h12 * r2 + h1c * r3 + h1c1 * r4;
-                            f.kt[rr] = make_double2(k0, k1);
-                            f.wt[rr] = make_double2(w0, w1);
-                        }
-                        else
-                        {
-                            // oracle order: P = Sigma*H.t(), K = P*inv(psi), x += K*dz, M = eye - K*H
-                            double pa = mul_(c1, h01);
-                            pa = add_(pa, mul_(c2, h02));
-                            pa = add_(pa, mul_(c3, h0c));
-                            pa = add_(pa, mul_(c4, h0c1));
-                            double pb = -c0;
-                            pb = add_(pb, mul_(c1, h11));
-                            pb = add_(pb, mul_(c2, h12));
-                            pb = add_(pb, mul_(c3, h1c));
-                            pb = add_(pb, mul_(c4, h1c1));
-                            const double k0 = add_(mul_(pa, i00), mul_(pb, i10));
-                            const double k1 = add_(mul_(pa, i01), mul_(pb, i11));
-                            f.xs[rr] = add_(f.xs[rr], add_(mul_(k0, dz0), mul_(k1, dz1)));
-                            // M columns overwrite this lane's own entries of col[] (row[] keeps the old rows of Sigma)
-                            f.col[0 * LP + rr] = sub_((rr == 1) ? 1.0 : 0.0, -k1);
-                            f.col[1 * LP + rr] = sub_((rr == 2) ? 1.0 : 0.0, add_(mul_(k0, h01), mul_(k1, h11)));
-                            f.col[2 * LP + rr] = sub_((rr == 3) ? 1.0 : 0.0, add_(mul_(k0, h02), mul_(k1, h12)));
-                            f.col[3 * LP + rr] = sub_((rr == cI) ? 1.0 : 0.0, add_(mul_(k0, h0c), mul_(k1, h1c)));
-                            f.col[4 * LP + rr] = sub_((rr == cI + 1) ? 1.0 : 0.0, add_(mul_(k0, h0c1), mul_(k1, h1c1)));
-                        }
+                        f.xs[lane] += k0 * dz0 + k1 * dz1;
+                        f.kt[lane] = make_double2(k0, k1);
                     }
+                }
+                else if (lane_row)
+                {
+                    // oracle order: P = Sigma*H.t(), K = P*inv(psi), x += K*dz, M = eye - K*H
+                    double pa = mul_(c1, h01);
+                    pa = add_(pa, mul_(c2, h02));
+                    pa = add_(pa, mul_(c3, h0c));
+                    pa = add_(pa, mul_(c4, h0c1));
+                    double pb = -c0;
+                    pb = add_(pb, mul_(c1, h11));
+                    pb = add_(pb, mul_(c2, h12));
+                    pb = add_(pb, mul_(c3, h1c));
+                    pb = add_(pb, mul_(c4, h1c1));
+                    const double k0 = add_(mul_(pa, i00), mul_(pb, i10));
+                    const double k1 = add_(mul_(pa, i01), mul_(pb, i11));
+                    f.xs[lane] = add_(f.xs[lane], add_(mul_(k0, dz0), mul_(k1, dz1)));
+                    // M columns overwrite this lane's own entries of col[] (row[] keeps the old rows of Sigma)
+                    f.col[0 * LPR + lane] = sub_((lane == 1) ? 1.0 : 0.0, -k1);
+                    f.col[1 * LPR + lane] = sub_((lane == 2) ? 1.0 : 0.0, add_(mul_(k0, h01), mul_(k1, h11)));
+                    f.col[2 * LPR + lane] = sub_((lane == 3) ? 1.0 : 0.0, add_(mul_(k0, h02), mul_(k1, h12)));
+                    f.col[3 * LPR + lane] = sub_((lane == cI) ? 1.0 : 0.0, add_(mul_(k0, h0c), mul_(k1, h1c)));
+                    f.col[4 * LPR + lane] = sub_((lane == cI + 1) ? 1.0 : 0.0, add_(mul_(k0, h0c1), mul_(k1, h1c1)));
                 }
             }
             __syncwarp();
             // D. tile update
-            if (!skip)
+            if (!strict)
             {
-                if (!strict)
+                double2 w[TC];
+#pragma unroll
+                for (int q = 0; q < TC; ++q) w[q] = f.wt[8 * q + b];
+#pragma unroll
+                for (int r = 0; r < TR; ++r)
                 {
-                    double2 w[T];
+                    const double2 k = f.kt[4 * r + a];
 #pragma unroll
-                    for (int q = 0; q < T; ++q) w[q] = f.wt[4 * q + b];
+                    for (int q = 0; q < TC; ++q) S[r][q] = fma(-k.y, w[q].y, fma(-k.x, w[q].x, S[r][q]));
+                }
+            }
+            else if (!(f.flags[0] & kFlagSkip))
+            {
+                // Sigma = M * Sigma in the oracle's ascending-k order (see ekf_strict.cuh)
 #pragma unroll
-                    for (int r = 0; r < T; ++r)
+                for (int r = 0; r < TR; ++r)
+                {
+                    const int ii = 4 * r + a;
+                    const double m0 = f.col[0 * LPR + ii], m1 = f.col[1 * LPR + ii], m2 = f.col[2 * LPR + ii];
+                    const double m3 = f.col[3 * LPR + ii], m4 = f.col[4 * LPR + ii];
+#pragma unroll
+                    for (int q = 0; q < TC; ++q)
                     {
-                        const double2 k = f.kt[4 * r + a];
-#pragma unroll
-                        for (int q = 0; q < T; ++q)
-                        {
-                            S[r][q] = fma(-k.x, w[q].x, S[r][q]);
-                            S[r][q] = fma(-k.y, w[q].y, S[r][q]);
-                        }
+                        const int jj = 8 * q + b;
+                        double acc = mul_(m0, f.row[0 * LPC + jj]);
+                        acc = add_(acc, mul_(m1, f.row[1 * LPC + jj]));
+                        acc = add_(acc, mul_(m2, f.row[2 * LPC + jj]));
+                        if (ii >= 4 && ii < cI) acc = add_(acc, S[r][q]);
+                        acc = add_(acc, mul_(m3, f.row[3 * LPC + jj]));
+                        acc = add_(acc, mul_(m4, f.row[4 * LPC + jj]));
+                        if (ii > cI + 1) acc = add_(acc, S[r][q]);
+                        S[r][q] = acc;
                     }
                 }
-                else
-                {
-                    // Sigma = M * Sigma in the oracle's ascending-k order (see ekf_strict.cuh)
-#pragma unroll
-                    for (int r = 0; r < T; ++r)
-                    {
-                        const int ii = 4 * r + a;
-                        const double m0 = f.col[0 * LP + ii], m1 = f.col[1 * LP + ii], m2 = f.col[2 * LP + ii];
-                        const double m3 = f.col[3 * LP + ii], m4 = f.col[4 * LP + ii];
-#pragma unroll
-                        for (int q = 0; q < T; ++q)
-                        {
-                            const int jj = 4 * q + b;
-                            double acc = mul_(m0, f.row[0 * LP + jj]);
-                            acc = add_(acc, mul_(m1, f.row[1 * LP + jj]));
-                            acc = add_(acc, mul_(m2, f.row[2 * LP + jj]));
-                            if (ii >= 4 && ii < cI) acc = add_(acc, S[r][q]);
-                            acc = add_(acc, mul_(m3, f.row[3 * LP + jj]));
-                            acc = add_(acc, mul_(m4, f.row[4 * LP + jj]));
-                            if (ii > cI + 1) acc = add_(acc, S[r][q]);
-                            S[r][q] = acc;
-                        }
-                    }
-                    if (t16 == 0) f.xs[1] = normalize_angle(f.xs[1]);   // :276, exact chain on the strict path
-                }
+                if (lane == 0) f.xs[1] = normalize_angle(f.xs[1]);   // :276, exact chain on the strict path
             }
             __syncwarp();
         }
 
         // ---- write back: registers -> HBM (each lane quartet writes 32 contiguous bytes) ----
-        if (!frozen)
+        if (lane == 0 && f.flags[4]) f.xs[1] = wrap_fast(f.xs[1]);
+        __syncwarp();
         {
-            if (t16 == 0 && f.flags[4]) f.xs[1] = wrap_fast(f.xs[1]);
-            __syncwarp();
-            double * gs = p.sigma + bf * SIG;
+            double * gs = p.sigma + bf * SIG + goff;
 #pragma unroll
-            for (int q = 0; q < T; ++q)
+            for (int q = 0; q < TC; ++q)
 #pragma unroll
-                for (int r = 0; r < T; ++r)
+                for (int r = 0; r < TR; ++r)
                 {
-                    const int i = 4 * r + a - 1, j = 4 * q + b - 1;
-                    if (i >= 0 && j >= 0 && i < LEN && j < LEN) __stcs(gs + j * LEN + i, S[r][q]);
+                    const int i = 4 * r + a - 1, j = 8 * q + b - 1;
+                    if (i >= 0 && j >= 0 && i < LEN && j < LEN) __stcs(gs + (8 * q) * LEN + 4 * r, S[r][q]);
                 }
-            for (int e = t16 + 1; e <= LEN; e += 16) p.x[bf * LEN + e - 1] = f.xs[e];
-            if (t16 == 0)
+            if (lane >= 1 && lane <= LEN) p.x[bf * LEN + lane - 1] = f.xs[lane];
+            if (lane == 0)
             {
                 p.seen[bf] = f.flags[1];
                 p.status[bf] = f.flags[2];
             }
         }
-        __syncthreads();   // shared-memory inputs of this group are dead; the next group may overwrite them
+        __syncwarp();
     }
+    if (lane == 0) st_release_smem(&f.req, kReqExit);
 }
 
 template <int N>
 constexpr size_t fast_smem_bytes()
 {
-    return 2 * kFastWarps * sizeof(FastSmem<N>);
+    return kMatrixWarps * sizeof(FastSmem<N>);
 }
 
 inline bool fast_supported(int n) { return n == 12 || n == 6; }
@@ -586,22 +724,17 @@ template <int N>
 int launch_fast_n(const EkfParams & p, bool do_predict, int sm_count, cudaStream_t stream)
 {
     static thread_local bool configured = false;
-    static thread_local int ctas_per_sm = 1;
     constexpr size_t smem = fast_smem_bytes<N>();
     if (!configured)
     {
         cudaError_t e = cudaFuncSetAttribute(k_ekf_fast_step<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess) return (int) e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_ekf_fast_step<N>, kFastWarps * 32, smem);
-        if (e != cudaSuccess) return (int) e;
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
         configured = true;
     }
-    const int64_t ngroups = (p.batch + 2 * kFastWarps - 1) / (2 * kFastWarps);
-    int64_t blocks = ngroups;
-    const int64_t resident = (int64_t) sm_count * ctas_per_sm;
-    if (blocks > resident) blocks = resident;   // persistent CTAs stride over groups of 2W filters
-    k_ekf_fast_step<N><<<(unsigned) blocks, kFastWarps * 32, smem, stream>>>(p, do_predict ? 1 : 0);
+    // persistent: one CTA per SM (kMatrixWarps independent filters in flight + the scalar servers)
+    int64_t blocks = (p.batch + kMatrixWarps - 1) / kMatrixWarps;
+    if (blocks > sm_count) blocks = sm_count;
+    k_ekf_fast_step<N><<<(unsigned) blocks, kFastThreads, smem, stream>>>(p, do_predict ? 1 : 0);
     return (int) cudaGetLastError();
 }
 

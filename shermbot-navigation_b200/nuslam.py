@@ -19,7 +19,8 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libnuslam_b200.so"
+import os as _os
+LIB_PATH = Path(_os.environ.get("NUSLAM_B200_LIB", HERE / "libnuslam_b200.so"))   # override only for kernel experiments
 
 NUSLAM_HOST, NUSLAM_DEVICE = 0, 1
 MODE_STRICT, MODE_FAST = 0, 1
