@@ -390,16 +390,12 @@ struct EkfParams
     double amin, amax;
 };
 
-// One warp per filter; Sigma staged through shared memory. OP selects which reference call is replayed.
+// One warp replays reference call OP on filter b; Sigma staged through the warp's slice of shared memory.
 template <int OP>
-__global__ void __launch_bounds__(128) k_ekf_strict(const EkfParams p)
+__device__ __forceinline__ void strict_filter(const EkfParams & p, const int64_t b, double * smem_warp, const int lane)
 {
-    extern __shared__ double smem[];
-    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
-    const int64_t b = (int64_t) blockIdx.x * (blockDim.x / kWarp) + warp;
-    if (b >= p.batch) return;
     WarpFilter f;
-    f.carve(smem + (size_t) warp * strict_smem_doubles(p.len), p.len, p.n, lane);
+    f.carve(smem_warp, p.len, p.n, lane);
     double * gx = p.x + b * p.len;
     double * gS = p.sigma + b * (int64_t) p.len * p.len;
     int status = p.status[b];
@@ -487,6 +483,44 @@ __global__ void __launch_bounds__(128) k_ekf_strict(const EkfParams p)
         {
             p.seen[b] = seen;
             p.status[b] = status;
+        }
+    }
+}
+
+// One warp per filter over the whole batch.
+template <int OP>
+__global__ void __launch_bounds__(128) k_ekf_strict(const EkfParams p)
+{
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int64_t b = (int64_t) blockIdx.x * (blockDim.x / kWarp) + warp;
+    if (b >= p.batch) return;
+    strict_filter<OP>(p, b, smem + (size_t) warp * strict_smem_doubles(p.len), lane);
+}
+
+// One warp per filter over a device-side work list (the filters the FAST kernel handed over because their step
+// contains a landmark's first touch). The last block to finish resets the list for the next launch.
+template <int OP>
+__global__ void __launch_bounds__(128) k_ekf_strict_list(const EkfParams p, const int32_t * __restrict__ list, int32_t * count, int32_t * done)
+{
+    extern __shared__ double smem[];
+    const int warps = blockDim.x / kWarp;
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int n = *reinterpret_cast<volatile int32_t *>(count);
+    for (int64_t k = (int64_t) blockIdx.x * warps + warp; k < n; k += (int64_t) gridDim.x * warps)
+    {
+        strict_filter<OP>(p, list[k], smem + (size_t) warp * strict_smem_doubles(p.len), lane);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        if (atomicAdd(done, 1) == (int) gridDim.x - 1)
+        {
+            *count = 0;
+            *done = 0;
+            __threadfence();
         }
     }
 }

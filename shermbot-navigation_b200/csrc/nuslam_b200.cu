@@ -86,6 +86,9 @@ struct nuslam_ekf
     bool own_state = true;
     // staging for NUSLAM_HOST calls
     DevBuf s_tw, s_z, s_ids, s_ids_out, s_misc;
+    // FAST mode: filters whose step contains a first touch are handed to the strict kernel through this list
+    int32_t * worklist = nullptr;   // batch entries
+    int32_t * wl_count = nullptr;   // [0] = entries, [1] = finished blocks of the list kernel
     size_t strict_smem = 0;   // per-warp shared memory of the strict kernels, bytes
     int strict_warps = 4;
 };
@@ -152,6 +155,29 @@ int launch_strict(nuslam_ekf * h, const nuslam::EkfParams & p)
     }
     const int64_t blocks = (h->batch + warps - 1) / warps;
     nuslam::k_ekf_strict<OP><<<(unsigned) blocks, warps * 32, smem, h->stream>>>(p);
+    CU(cudaGetLastError());
+    return NUSLAM_OK;
+}
+
+// FAST mode: the register kernel, then the strict kernel over the filters it handed over (usually none)
+template <int OP>
+int launch_fast_then_strict(nuslam_ekf * h, const nuslam::EkfParams & p, bool do_predict)
+{
+    int rc = nuslam::launch_fast(h->cfg.n_landmarks, p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream);
+    if (rc == -1) return fail(NUSLAM_ERR_UNSUPPORTED, "FAST mode covers n_landmarks in {6, 12}, m <= 16 and known correspondence");
+    if (rc) return cuda_fail((cudaError_t) rc, "fast kernel launch");
+    const int warps = h->strict_warps;
+    const size_t smem = h->strict_smem * warps;
+    static thread_local size_t configured[8] = {0};
+    if (configured[OP] < smem)
+    {
+        CU(cudaFuncSetAttribute(nuslam::k_ekf_strict_list<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        configured[OP] = smem;
+    }
+    int64_t blocks = (h->batch + warps - 1) / warps;
+    const int64_t resident = (int64_t) h->sm_count * 4;
+    if (blocks > resident) blocks = resident;
+    nuslam::k_ekf_strict_list<OP><<<(unsigned) blocks, warps * 32, smem, h->stream>>>(p, h->worklist, h->wl_count, h->wl_count + 1);
     CU(cudaGetLastError());
     return NUSLAM_OK;
 }
@@ -235,6 +261,10 @@ int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, 
     cudaError_t e2 = cudaMalloc(&h->sigma, sizeof(double) * l * l * batch);
     cudaError_t e3 = cudaMalloc(&h->seen, sizeof(int32_t) * batch);
     cudaError_t e4 = cudaMalloc(&h->status, sizeof(int32_t) * batch);
+    cudaError_t e5 = cudaMalloc(&h->worklist, sizeof(int32_t) * batch);
+    cudaError_t e6 = cudaMalloc(&h->wl_count, sizeof(int32_t) * 2);
+    if (e5 != cudaSuccess || e6 != cudaSuccess) e1 = cudaErrorMemoryAllocation;
+    else cudaMemsetAsync(h->wl_count, 0, sizeof(int32_t) * 2, h->stream);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess)
     {
         nuslam_ekf_destroy(h);
@@ -261,6 +291,8 @@ int nuslam_ekf_destroy(nuslam_ekf * h)
         if (h->seen) cudaFree(h->seen);
         if (h->status) cudaFree(h->status);
     }
+    if (h->worklist) cudaFree(h->worklist);
+    if (h->wl_count) cudaFree(h->wl_count);
     h->s_tw.release();
     h->s_z.release();
     h->s_ids.release();
@@ -408,9 +440,8 @@ int nuslam_ekf_update(nuslam_ekf * h, const double * z, const int32_t * id, int 
     if (h->cfg.mode == NUSLAM_MODE_FAST)
     {
         p.twists = nullptr;   // update only
-        rc = nuslam::launch_fast(h->cfg.n_landmarks, p, /*do_predict=*/false, h->sm_count, h->stream);
-        if (rc == -1) return fail(NUSLAM_ERR_UNSUPPORTED, "FAST mode not instantiated for this n_landmarks");
-        if (rc) return cuda_fail((cudaError_t) rc, "fast update launch");
+        rc = launch_fast_then_strict<nuslam::kOpUpdate>(h, p, /*do_predict=*/false);
+        if (rc) return rc;
     }
     else
     {
@@ -471,9 +502,8 @@ int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, con
     }
     if (h->cfg.mode == NUSLAM_MODE_FAST && p.ids != nullptr)
     {
-        rc = nuslam::launch_fast(h->cfg.n_landmarks, p, /*do_predict=*/true, h->sm_count, h->stream);
-        if (rc == -1) return fail(NUSLAM_ERR_UNSUPPORTED, "FAST mode not instantiated for this n_landmarks");
-        if (rc) return cuda_fail((cudaError_t) rc, "fast step launch");
+        rc = launch_fast_then_strict<nuslam::kOpStep>(h, p, /*do_predict=*/true);
+        if (rc) return rc;
     }
     else
     {
@@ -486,6 +516,20 @@ int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, con
         CU(cudaMemcpyAsync(ids_out, p.ids_out, sizeof(int32_t) * h->batch * m, cudaMemcpyDeviceToHost, h->stream));
     return finish(h, mem);
 }
+
+#ifdef NUSLAM_TIMING
+// kernel-experiment builds only (-DNUSLAM_TIMING): per-phase clock64 sums of block 0 / warp 0 of the FAST kernel
+int nuslam_debug_fast_timing(long long * out16, int reset)
+{
+    if (out16) cudaMemcpyFromSymbol(out16, nuslam::g_fast_timing, sizeof(long long) * 16);
+    if (reset)
+    {
+        long long z[16] = {0};
+        cudaMemcpyToSymbol(nuslam::g_fast_timing, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 int nuslam_ekf_synchronize(nuslam_ekf * h)
 {
