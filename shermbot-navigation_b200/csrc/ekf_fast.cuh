@@ -1,11 +1,10 @@
 // ekf_fast.cuh -- FAST arithmetic: fused predict + m sequential updates, one filter per warp, Sigma in REGISTERS.
 //
 // Roofs (MEASURED on B200, tools/ubench_fp64.cu, profiles/ubench_fp64_r01.txt): the fp64 pipe issues 64 FMA/clk/SM
-// for DFMA and for DMMA alike (one pipe: mixing them adds nothing), a dependent DFMA takes 8.7 cycles, a
-// broadcast LDS.128 occupies the shared-memory return path for ~2 cycles. A filter-step is ~21 k fp64 FMAs of
-// rank-2 updates against 12 352 algorithmic bytes, so the fp64 pipe (~550 cycles/filter-step/SM) and HBM
-// (~530 cycles/filter-step/SM at the measured 6.55 TB/s) are co-roofs; everything below is organised to keep the
-// instruction count per update minimal and the per-update latency chain short.
+// for DFMA and for DMMA alike (one pipe: mixing them adds nothing), a dependent DFMA takes 8.7 cycles, shared memory
+// returns 256 B/clk/SM (a broadcast LDS.128 costs 2 cycles). A filter-step is ~21 k fp64 FMAs of rank-2 updates
+// against 12 352 algorithmic bytes, so the fp64 pipe and HBM (~530 cycles/filter-step/SM at the measured 6.55 TB/s)
+// are co-roofs, with the shared-memory pipe close behind; the design below minimises all three per update.
 //
 // Layout of one filter inside its warp (state order [theta, x, y, m1x, m1y, ...], slam_library.cpp:46-59):
 //   * landmark block Sigma(3.., 3..) (2N x 2N): fp64 tensor-core accumulator fragments of mma.m8n8k4 -- block
@@ -14,19 +13,18 @@
 //   * robot rows / columns Sigma({th,x,y}, :) and Sigma(:, {th,x,y}) in VECTOR layout: lane i holds entry i of each
 //     of the 6 vectors Rt, Rx, Ry (rows) and Ct, Cx, Cy (columns); the 3 x 3 robot block lives in both (updated
 //     with bit-identical operations). predict (slam_library.cpp:65-108) touches only these vectors.
-//   * the state x in vector layout too (lane i holds x_i).
+//   * the state x in vector layout (lane i holds x_i); the robot pose (theta, x, y) also replicated in every lane.
 // One update (slam_library.cpp:263-282), with H = D Ht, D = diag(1/sqrt d, 1/d), Ht = [0 -dx -dy dx dy; -d dy -dx
 // -dy dx] free of divisions:   Sigma' = Sigma - Pt Minv Wt,  x' = x + Pt Minv (sqrt d dz0, d dz1),
 //   Pt = Sigma Ht^T (lane i = row i), Wt = Ht Sigma (lane j = column j), M = Wt Ht^T + D^-1 R D^-1.
 //   (A) the landmark's two rows and two columns are published from the fragments through shared memory into
-//       vector layout; (B) lanes form Pt, Wt; the five lanes {th,x,y,c,c+1} hand Wt to the SCALAR WARP, which
-//       evaluates M, Minv (one reciprocal), sqrt d, atan2 and the innovation for all filters of the CTA at once, one
-//       filter per lane; (C) lanes form Kt = Pt Minv, update x and the 6 robot vectors with plain FMAs;
-//   (D) updates are applied to the fragments LAZILY in chunks of CH = 2: the second update of a chunk takes its
+//       vector layout; (B) lanes form Pt, Wt and exchange Wt; every lane evaluates the 2 x 2 part (M, one
+//       reciprocal, sqrt d, atan2, innovation) redundantly -- no cross-warp synchronisation anywhere in the kernel, the
+//       ~20 resident warps of an SM hide each other's dependency chains; (C) lanes form Kt = Pt Minv, update x, the
+//       replicated pose and the 6 robot vectors with plain FMAs;
+//   (D) updates are applied to the fragments LAZILY in chunks of 2: the second update of a chunk takes its
 //       landmark rows / columns from the stale fragments and corrects them in vector layout with the first update
 //       (4 vectors x 2 FMAs), then ONE rank-4 DMMA pass (9 mma.m8n8k4 at N = 12, k = 4 fully used) applies both.
-// CTA = 8 matrix warps + 1 scalar warp, 2 CTAs per SM, persistent over groups of 8 consecutive filters; the two CTAs
-// of an SM run out of phase, so one's scalar phase hides under the other's matrix phase.
 //
 // Arithmetic: predict uses the oracle's operation order (it is O(len)). A filter-step that contains a landmark's
 // FIRST TOUCH (INT_MAX prior, slam_library.cpp:28-31, where only the reference's own operation order reproduces its
@@ -41,8 +39,11 @@
 namespace nuslam
 {
 
-constexpr int kGroup = 8;                          // filters (= matrix warps) per CTA
-constexpr int kFastThreads = 32 * (kGroup + 1);    // + the scalar warp
+constexpr int kFastThreads = 32;                   // one warp = one filter in flight per CTA: no cross-warp state at all
+#ifndef NUSLAM_FAST_CTAS
+#define NUSLAM_FAST_CTAS 16
+#endif
+constexpr int kFastCtasPerSm = NUSLAM_FAST_CTAS;   // 16 single-warp CTAs / SM at 128 registers (20 at 96 registers spill; measured slower)
 constexpr int kFastMMax = 16;                      // measurements per step handled by this kernel
 
 template <int N>
@@ -67,226 +68,70 @@ __device__ __forceinline__ void dmma884(double & c0, double & c1, double a, doub
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// angle -> (-pi, pi]: what rigid2d::normalize_angle (rigid2d.cpp:9-13) returns, to ~1 ulp, without the
-// sin/cos/atan2 round trip
+// angle -> [-pi, pi]: what rigid2d::normalize_angle (rigid2d.cpp:9-13) returns, to ~1 ulp, without the
+// sin/cos/atan2 round trip; the identity for |a| <= pi, branch-free
 __device__ __forceinline__ double wrap_angle(double a)
 {
-    constexpr double kPi = 3.14159265358979323846;
     constexpr double kTwoPiHi = 6.28318530717958623200, kTwoPiLo = 2.44929359829470641435e-16, kInvTwoPi = 0.15915494309189533577;
-    if (a > kPi || a <= -kPi)
-    {
-        const double k = rint(a * kInvTwoPi);
-        a = fma(-k, kTwoPiHi, a);
-        a = fma(-k, kTwoPiLo, a);
-        if (a > kPi) a -= kTwoPiHi;
-        else if (a <= -kPi) a += kTwoPiHi;
-    }
-    return a;
+    const double k = rint(a * kInvTwoPi);
+    return fma(-k, kTwoPiLo, fma(-k, kTwoPiHi, a));
 }
 
-// per-filter shared memory; the stride between filters is padded so that the scalar warp (lane = filter) reads the
-// same field of 8 filters without bank conflicts
+// per-CTA (= per-warp) shared memory: exchange buffers between the fragment and the vector layout. Every vector has
+// 32 + entries, one per lane; entries of lanes that own no state index stay zero.
 template <int N>
-struct __align__(16) FastSmemFields
+struct __align__(16) FastSmem
 {
-    using G = FastGeom<N>;
-    static constexpr int PV = (G::VP + 2) & ~1;   // published row length (+1 shift so that index 3 is 16-byte aligned)
-    static constexpr int KV = G::VP + 1;          // operand vector length (even)
-    double2 kt[2][KV];        // -Kt of the chunk's two updates, kt[s][i] = (-k0, -k1) of state index i; DMMA A operand
-    double2 wt[2][KV];        // Wt of the chunk's two updates; DMMA B operand
-    double rho[2][2][PV];     // per chunk slot: landmark rows c, c+1 in vector layout, entry j at [j + 1]
-    double2 kap[2][KV];       // per chunk slot: landmark columns (c, c+1) interleaved, entry i
-    double xs[34];            // state broadcast copy, x_i at [i + 1] (pairs (x,y) and (mx,my) 16-byte aligned)
-    double2 g[6];             // Wt at {th, x, y, c, c+1} and Pt at th, for the scalar warp
-    double res[8];            // scalar warp results: Minv (4), y = Minv * scaled innovation (2), predict b10, b20
-    double z[2 * kFastMMax];
-    double tw[2];
+    double2 kt[2][32];        // -Kt of the chunk's two updates, kt[s][i] = (-k0, -k1) of state index i; DMMA A operand
+    double2 wt[2][32];        // Wt of the chunk's two updates; DMMA B operand
+    double rho[2][2][40];     // per chunk slot: landmark rows c, c+1 in vector layout, entry j at [j + 1] (index 3 is 16-byte aligned;
+                              // row stride = 16 banks (mod 32): the two rows of a landmark are stored without bank conflicts)
+    double2 kap[2][32];       // per chunk slot: landmark columns (c, c+1) interleaved, entry i
+    double xs[34];            // state broadcast copy, x_i at [i + 1] (the pair (mx, my) is 16-byte aligned)
+    double z[2 * kFastMMax];  // this step's measurements
     int ids[kFastMMax];
-    int status;
 };
-template <int N>
-struct __align__(16) FastSmem : FastSmemFields<N>
-{
-    static constexpr int kPad = (int) ((128 + 16 - sizeof(FastSmemFields<N>) % 128) % 128);
-    unsigned char pad_[kPad == 0 ? 128 : kPad];   // filter stride = 16 (mod 128) bytes
-};
-
-// Scalar part of predict for one filter (one lane): predictEstimate :71-94 and the two Jacobian entries of
-// getA :127-148 (theta read AFTER the motion update, :129), in the oracle's operation order.
-template <int N>
-__device__ __forceinline__ void predict_scalar(FastSmem<N> & f)
-{
-    const double dth = f.tw[0], dx = f.tw[1];
-    const double theta = f.xs[1];
-    double dq_th, dq_x, dq_y, s0, c0, b10, b20;
-    sincos(theta, &s0, &c0);
-    if (dth == 0.0)
-    {
-        dq_th = 0.0;
-        dq_x = mul_(dx, c0);
-        dq_y = mul_(dx, s0);
-    }
-    else
-    {
-        const double q = div_(dx, dth);
-        double s1, c1;
-        sincos(add_(theta, dth), &s1, &c1);
-        dq_th = dth;
-        dq_x = add_(mul_(-q, s0), mul_(q, s1));
-        dq_y = sub_(mul_(q, c0), mul_(q, c1));
-    }
-    const double th1 = add_(theta, dq_th);
-    f.xs[1] = th1;
-    f.xs[2] = add_(f.xs[2], dq_x);
-    f.xs[3] = add_(f.xs[3], dq_y);
-    double s2, c2;
-    sincos(th1, &s2, &c2);
-    if (dth == 0.0)
-    {
-        b10 = mul_(-dx, s2);
-        b20 = mul_(dx, c2);
-    }
-    else
-    {
-        const double q = div_(dx, dth);
-        double s3, c3;
-        sincos(add_(th1, dth), &s3, &c3);
-        b10 = add_(mul_(-q, c2), mul_(q, c3));
-        b20 = add_(mul_(-q, s2), mul_(q, s3));
-    }
-    f.res[6] = b10;
-    f.res[7] = b20;
-}
-
-// Scalar part of one update for one filter (one lane): M = Wt Ht^T + D^-1 R D^-1, Minv, the innovation
-// (slam_library.cpp:150-160 z_hat, :272 dz without wrap) scaled by D^-1, y = Minv * (sqrt d dz0, d dz1).
-template <int N>
-__device__ __forceinline__ void update_scalar(FastSmem<N> & f, int i, const double * R)
-{
-    const int id = f.ids[i];
-    if (id < 1 || id > N)
-    {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) f.res[k] = 0.0;
-        if (id > N) f.status |= kStatusBadId;
-        return;
-    }
-    const int c = 3 + 2 * (id - 1);
-    const double th = f.xs[1];
-    const double dx = f.xs[c + 1] - f.xs[2], dy = f.xs[c + 2] - f.xs[3];
-    const double d = fma(dx, dx, dy * dy);
-    const double2 g0 = f.g[0], g1 = f.g[1], g2 = f.g[2], g3 = f.g[3], g4 = f.g[4];   // (Wt0, Wt1) at th, x, y, c, c+1
-    const double e0 = g3.x - g1.x, f0 = g4.x - g2.x, e1 = g3.y - g1.y, f1 = g4.y - g2.y;
-    const double s00 = fma(dx, e0, dy * f0), s01 = fma(dx, f0, fma(-dy, e0, -d * g0.x));
-    const double s10 = fma(dx, e1, dy * f1), s11 = fma(dx, f1, fma(-dy, e1, -d * g0.y));
-    const double rs = rsqrt_fast(d);
-    double sq = d * rs;
-    sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);   // sqrt(d) to ~1 ulp
-    const double dsq = d * sq;
-    const double m00 = fma(d, R[0], s00), m10 = fma(dsq, R[1], s10), m01 = fma(dsq, R[2], s01), m11 = fma(d * d, R[3], s11);
-    const double det = fma(m00, m11, -m01 * m10);
-    const double idet = rcp_fast(det);
-    const bool ok = (det != 0.0) && (fabs(idet) < 1.0e300) && (idet == idet);
-    const double i00 = m11 * idet, i01 = -m01 * idet, i10 = -m10 * idet, i11 = m00 * idet;
-    const double zb = wrap_angle(atan2_fast(dy, dx) - th);
-    const double n0 = sq * (f.z[2 * i] - sq), n1 = d * (f.z[2 * i + 1] - zb);
-    f.res[0] = ok ? i00 : 0.0;
-    f.res[1] = ok ? i01 : 0.0;
-    f.res[2] = ok ? i10 : 0.0;
-    f.res[3] = ok ? i11 : 0.0;
-    const double y0 = ok ? fma(i00, n0, i01 * n1) : 0.0, y1 = ok ? fma(i10, n0, i11 * n1) : 0.0;
-    f.res[4] = y0;
-    f.res[5] = y1;
-    // theta' = normalize_angle(theta + K(0,:) dz) (slam_library.cpp:275-276); Pt(th,:) comes from lane 0 of the matrix warp
-    const double2 pth = f.g[5];
-    f.xs[1] = wrap_angle(fma(pth.x, y0, fma(pth.y, y1, th)));
-    if (!ok) f.status |= kStatusSingular;   // arma::inv throws (slam_library.cpp:270); the update never happens
-}
 
 #ifdef NUSLAM_TIMING
-#define NUSLAM_T(k) { const int probe_ = *reinterpret_cast<volatile int *>(&f.status); const long long now_ = clock64() + (probe_ & 0); tacc[k] += now_ - tlast; tlast = now_; }
+#define NUSLAM_T(k) { const long long now_ = clock64(); tacc[k] += now_ - tlast; tlast = now_; }
 __device__ long long g_fast_timing[16];
 #else
 #define NUSLAM_T(k)
 #endif
 
 template <int N>
-__global__ void __launch_bounds__(kFastThreads, 2)
+__global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm)
 k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ worklist, int32_t * __restrict__ wl_count)
 {
     using G = FastGeom<N>;
-    using FS = FastSmem<N>;
-    constexpr int LEN = G::LEN, SIG = G::SIG, NB = G::NB, VP = G::VP;
+    constexpr int LEN = G::LEN, SIG = G::SIG, NB = G::NB;
     constexpr unsigned kFull = 0xffffffffu;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FS * fs = reinterpret_cast<FS *>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ FastSmem<N> f;
+    const int lane = threadIdx.x;
     const int m = p.m;
-    const int64_t ngroups = (p.batch + kGroup - 1) / kGroup;
-
-    // ------------------------------------------------------------------ scalar warp: lane = filter of the group
-    if (warp == kGroup)
-    {
-        FS & f = fs[lane < kGroup ? lane : 0];
-        const bool mine = lane < kGroup;
-        for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x)
-        {
-            __syncthreads();   // B0: inputs of the group are in shared memory
-            if (do_predict)
-            {
-                if (mine) predict_scalar<N>(f);
-                __syncthreads();   // B1
-            }
-            for (int i = 0; i < m; ++i)
-            {
-                __syncthreads();   // Ba: Wt at the five H columns is published
-#ifdef NUSLAM_TIMING
-                const int probe0 = *reinterpret_cast<volatile int *>(&f.status);
-                const long long s0 = clock64() + (probe0 & 0);
-#endif
-                if (mine) update_scalar<N>(f, i, p.R);
-#ifdef NUSLAM_TIMING
-                __syncwarp();
-                if (lane == 0 && blockIdx.x == 0) atomicAdd((unsigned long long *) &g_fast_timing[8], (unsigned long long) (clock64() - s0));
-#endif
-                __syncthreads();   // Bb: Minv, y and the new theta are ready
-            }
-        }
-        return;
-    }
-
-    // ------------------------------------------------------------------ matrix warps: one filter each
-    FS & f = fs[warp];
     const int g = lane >> 2, t = lane & 3;
     const bool vlane = lane < LEN;      // lane owns a state index
-    const bool vpad = lane < VP;        // lane owns a (possibly padded) vector slot
-    const int lv = vpad ? lane : VP - 1;
-    // zero the exchange buffers once (padding entries stay zero)
-    for (int k = lane; k < (int) (sizeof(FS) / 8); k += 32) reinterpret_cast<double *>(&f)[k] = 0.0;
+    const double R00 = p.R[0], R10 = p.R[1], R01 = p.R[2], R11 = p.R[3];
+    // zero the exchange buffers once (entries of lanes without a state index stay zero)
+    for (int k = lane; k < (int) (sizeof(f) / 8); k += 32) reinterpret_cast<double *>(&f)[k] = 0.0;
     __syncwarp();
 #ifdef NUSLAM_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
 #endif
 
-    for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x)
+    for (int64_t bf = blockIdx.x; bf < p.batch; bf += gridDim.x)
     {
-        const int64_t bf = grp * kGroup + warp;
-        const bool valid = bf < p.batch;
-        const int64_t bl = valid ? bf : 0;
-        // pull the Sigma of this CTA's next group towards L2 while the current one is computed
+        // pull this warp's next Sigma towards L2 while the current one is computed
+        if (lane == 0 && bf + gridDim.x < p.batch)
         {
-            const int64_t nb = (grp + gridDim.x) * kGroup + warp;
-            if (lane == 0 && nb < p.batch)
-            {
-                const uintptr_t a0 = reinterpret_cast<uintptr_t>(p.sigma + nb * SIG) & ~(uintptr_t) 15;
-                prefetch_l2_bulk(reinterpret_cast<const void *>(a0), (uint32_t) ((sizeof(double) * SIG + 15) & ~15u));
-            }
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(p.sigma + (bf + gridDim.x) * SIG) & ~(uintptr_t) 15;
+            prefetch_l2_bulk(reinterpret_cast<const void *>(a0), (uint32_t) ((sizeof(double) * SIG + 15) & ~15u));
         }
-        // ---- load: every global read of the group is issued before anything depends on one ----
+        // ---- load: every global read of the filter is issued before anything depends on one ----
         double C[NB][NB][2];
         double Rt = 0.0, Rx = 0.0, Ry = 0.0, Ct = 0.0, Cx = 0.0, Cy = 0.0, x = 0.0;
-        const double * gs = p.sigma + bl * SIG;
+        const double * gs = p.sigma + bf * SIG;
 #pragma unroll
         for (int br = 0; br < NB; ++br)
 #pragma unroll
@@ -305,49 +150,64 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             Rt = __ldcs(gs + lane * LEN);
             Rx = __ldcs(gs + lane * LEN + 1);
             Ry = __ldcs(gs + lane * LEN + 2);
-            x = p.x[bl * LEN + lane];
+            x = p.x[bf * LEN + lane];
         }
         const double diag = vlane ? gs[lane * (LEN + 1)] : 0.0;   // Sigma(lane, lane): first-touch detection
-        const int st0 = p.status[bl], seen0 = p.seen[bl];
-        const int my_id = (lane < m) ? p.ids[bl * m + lane] : 0;
-        const double my_z = (lane < 2 * m) ? p.z[bl * m * 2 + lane] : 0.0;
-        const double my_tw = (do_predict && lane < 2) ? p.twists[bl * 3 + lane] : 0.0;
+        const int st0 = p.status[bf], seen0 = p.seen[bf];
+        const int my_id = (lane < m) ? p.ids[bf * m + lane] : 0;
+        const double my_z = (lane < 2 * m) ? p.z[bf * m * 2 + lane] : 0.0;
+        const double my_tw = (do_predict && lane < 2) ? p.twists[bf * 3 + lane] : 0.0;
         // ---- liveness ----
-        bool dead = !valid || (st0 & (kStatusMapFull | kStatusSingular));   // the reference process died on an earlier scan
+        if (st0 & (kStatusMapFull | kStatusSingular)) continue;   // the reference process died on an earlier scan
         {
             const bool idok = (unsigned) (my_id - 1) < (unsigned) N;
             const int c = idok ? 1 + 2 * my_id : 3;
             const double d0 = __shfl_sync(kFull, diag, c), d1 = __shfl_sync(kFull, diag, c + 1);
             // first touch (INT_MAX prior) or initializeLandmark (slam.cpp:295-297): the strict kernel takes this filter-step
             const bool need = idok && ((do_predict && my_id > seen0) || d0 > kFirstTouchVariance || d1 > kFirstTouchVariance);
-            if (__any_sync(kFull, need) && !dead)
+            if (__any_sync(kFull, need))
             {
                 if (lane == 0) worklist[atomicAdd(wl_count, 1)] = (int32_t) bf;
-                dead = true;
+                continue;
             }
         }
-        if (dead)
-        {
-#pragma unroll
-            for (int br = 0; br < NB; ++br)
-#pragma unroll
-                for (int bc = 0; bc < NB; ++bc) C[br][bc][0] = C[br][bc][1] = 0.0;
-            Rt = Rx = Ry = Ct = Cx = Cy = x = 0.0;
-        }
-        if (lane < m) f.ids[lane] = dead ? 0 : my_id;
+        int status = st0;
+        if (lane < m) f.ids[lane] = my_id;
         if (lane < 2 * m) f.z[lane] = my_z;
-        if (lane < 2) f.tw[lane] = dead ? 0.0 : my_tw;
-        if (lane == 0) f.status = st0;
-        f.xs[lane + 1] = x;
+        // robot pose, replicated in every lane; lanes 0..2 own the same values in x (bit-identical updates)
+        double th = __shfl_sync(kFull, x, 0), px = __shfl_sync(kFull, x, 1), py = __shfl_sync(kFull, x, 2);
         NUSLAM_T(0)
-        __syncthreads();   // B0
 
         // ---- predict (slam_library.cpp:65-108), oracle operation order, vector layout only ----
         if (do_predict)
         {
-            __syncthreads();   // B1: the scalar warp has moved the pose and formed b10, b20
-            const double b10 = f.res[6], b20 = f.res[7];
-            if (lane < 3) x = f.xs[lane + 1];
+            const double dth = __shfl_sync(kFull, my_tw, 0), dxx = __shfl_sync(kFull, my_tw, 1);
+            // predictEstimate :71-94, then the two Jacobian entries of getA :127-148 (theta read AFTER the motion update,
+            // :129). sin/cos(theta + dth) of :84-85 and of :131 have the same argument: evaluated once.
+            double s0, c0, b10, b20;
+            sincos(th, &s0, &c0);
+            if (dth == 0.0)
+            {
+                px = add_(px, mul_(dxx, c0));
+                py = add_(py, mul_(dxx, s0));
+                th = add_(th, 0.0);
+                b10 = mul_(-dxx, s0);
+                b20 = mul_(dxx, c0);
+            }
+            else
+            {
+                const double q = div_(dxx, dth);
+                double s1, c1, s3, c3;
+                const double th1 = add_(th, dth);
+                sincos(th1, &s1, &c1);
+                px = add_(px, add_(mul_(-q, s0), mul_(q, s1)));
+                py = add_(py, sub_(mul_(q, c0), mul_(q, c1)));
+                th = th1;
+                sincos(add_(th1, dth), &s3, &c3);
+                b10 = add_(mul_(-q, c1), mul_(q, c3));
+                b20 = add_(mul_(-q, s1), mul_(q, s3));
+            }
+            x = (lane == 0) ? th : (lane == 1) ? px : (lane == 2) ? py : x;
             // T = A * Sigma: rows x, y += b * row theta
             Rx = add_(mul_(b10, Rt), Rx);
             Ry = add_(mul_(b20, Rt), Ry);
@@ -375,7 +235,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 }
             }
             // + Q_bar on the robot block (expanded_process_noise :110-125); Q is column-major
-            if (lane < 3 && !dead)
+            if (lane < 3)
             {
                 Rt = add_(Rt, p.Q[0 + 3 * lane]);
                 Rx = add_(Rx, p.Q[1 + 3 * lane]);
@@ -385,8 +245,10 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 Cy = add_(Cy, p.Q[lane + 3 * 2]);
             }
         }
-
+        f.xs[lane + 1] = x;
+        __syncwarp();
         NUSLAM_T(1)
+
         // ---- m sequential updates in chunks of 2 (slam.cpp:279-319, known correspondence) ----
 #pragma unroll 1
         for (int i0 = 0; i0 < m; i0 += 2)
@@ -397,15 +259,18 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             for (int s = 0; s < 2; ++s)
             {
                 const int id = (i0 + s < m) ? f.ids[i0 + s] : 0;
-                const bool live = (unsigned) (id - 1) < (unsigned) N;
-                const int c = live ? 1 + 2 * id : 3;
-                cc[s] = live ? c : -1;
-                const int tau = c - 3;
-                const int bsel = tau >> 3;
-                const bool rsel = live && ((g >> 1) == ((tau & 7) >> 1));   // this lane holds row c or c+1
-                const bool csel = live && (t == ((tau & 7) >> 1));          // this lane holds columns c, c+1
-                double * const rdst = &f.rho[s][g & 1][4 + 2 * t];
-                double2 * const cdst = &f.kap[s][3 + g];
+                const bool live = (unsigned) (id - 1) < (unsigned) N;   // warp-uniform
+                cc[s] = live ? 1 + 2 * id : -1;
+                if (id > N) status |= kStatusBadId;
+                if (live)
+                {
+                    const int c = cc[s];
+                    const int tau = c - 3;
+                    const int bsel = tau >> 3;
+                    const bool rsel = (g >> 1) == ((tau & 7) >> 1);   // this lane holds row c or c+1
+                    const bool csel = t == ((tau & 7) >> 1);          // this lane holds columns c, c+1
+                    double * const rdst = &f.rho[s][g & 1][4 + 2 * t];
+                    double2 * const cdst = &f.kap[s][3 + g];
 #define NUSLAM_PUBLISH(b)                                                                                                  \
     if constexpr (NB > b)                                                                                                  \
     {                                                                                                                      \
@@ -415,34 +280,35 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             if (csel) cdst[8 * q] = make_double2(C[q][b < NB ? b : 0][0], C[q][b < NB ? b : 0][1]);                        \
         }                                                                                                                  \
     }
-                if (bsel == 0)
-                {
-                    NUSLAM_PUBLISH(0)
-                }
-                else if (bsel == 1)
-                {
-                    NUSLAM_PUBLISH(1)
-                }
-                else if (bsel == 2)
-                {
-                    NUSLAM_PUBLISH(2)
-                }
-                else
-                {
-                    NUSLAM_PUBLISH(3)
-                }
+                    if (bsel == 0)
+                    {
+                        NUSLAM_PUBLISH(0)
+                    }
+                    else if (bsel == 1)
+                    {
+                        NUSLAM_PUBLISH(1)
+                    }
+                    else if (bsel == 2)
+                    {
+                        NUSLAM_PUBLISH(2)
+                    }
+                    else
+                    {
+                        NUSLAM_PUBLISH(3)
+                    }
 #undef NUSLAM_PUBLISH
-                const int e = lane - c;
-                if (live && (e == 0 || e == 1))
-                {
-                    // robot part of row c+e: Sigma(c+e, {th,x,y}) is entry c+e of the column vectors; of column c+e: entry of the row vectors
-                    f.rho[s][e][1] = Ct;
-                    f.rho[s][e][2] = Cx;
-                    f.rho[s][e][3] = Cy;
-                    double * kd = reinterpret_cast<double *>(&f.kap[s][0]) + e;
-                    kd[0] = Rt;
-                    kd[2] = Rx;
-                    kd[4] = Ry;
+                    const int e = lane - c;
+                    if (e == 0 || e == 1)
+                    {
+                        // robot part of row c+e: Sigma(c+e, {th,x,y}) is entry c+e of the column vectors; of column c+e: entry of the row vectors
+                        f.rho[s][e][1] = Ct;
+                        f.rho[s][e][2] = Cx;
+                        f.rho[s][e][3] = Cy;
+                        double * kd = reinterpret_cast<double *>(&f.kap[s][0]) + e;
+                        kd[0] = Rt;
+                        kd[2] = Rx;
+                        kd[4] = Ry;
+                    }
                 }
             }
             __syncwarp();
@@ -451,15 +317,16 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
 #pragma unroll
             for (int s = 0; s < 2; ++s)
             {
-                const int i = i0 + s;
-                if (i < m)   // uniform over the CTA
+                bool done = false;
+                if (cc[s] >= 0)   // warp-uniform
                 {
-                    const bool live = cc[s] >= 0;
-                    const int c = live ? cc[s] : 3;
+                    const int c = cc[s];
                     // landmark rows c, c+1 (lane = column) and columns c, c+1 (lane = row)
-                    double rho0 = f.rho[s][0][lv + 1], rho1 = f.rho[s][1][lv + 1];
-                    const double2 kp = f.kap[s][lv];
+                    double rho0 = f.rho[s][0][lane + 1], rho1 = f.rho[s][1][lane + 1];
+                    const double2 kp = f.kap[s][lane];
                     double kap0 = kp.x, kap1 = kp.y;
+                    const double2 mxy = *reinterpret_cast<const double2 *>(&f.xs[c + 1]);
+                    const double2 zz = *reinterpret_cast<const double2 *>(&f.z[2 * (i0 + s)]);
                     if (s == 1)
                     {
                         // the fragments predate the chunk's first update: bring the four vectors up to date with it
@@ -470,68 +337,72 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                         kap1 = fma(pK0, wb2.x, fma(pK1, wb2.y, kap1));
                     }
                     // (B) Pt (row role) and Wt (column role) of this lane
-                    const double2 pxy = *reinterpret_cast<const double2 *>(&f.xs[2]);
-                    const double2 mxy = *reinterpret_cast<const double2 *>(&f.xs[c + 1]);
-                    const double dx = mxy.x - pxy.x, dy = mxy.y - pxy.y;
+                    const double dx = mxy.x - px, dy = mxy.y - py;
                     const double d = fma(dx, dx, dy * dy);
                     const double pa = kap0 - Cx, pb = kap1 - Cy;
                     const double wa = rho0 - Rx, wb = rho1 - Ry;
-                    const bool on = live && vpad;
-                    const double P0 = on ? fma(dx, pa, dy * pb) : 0.0, P1 = on ? fma(dx, pb, fma(-dy, pa, -d * Ct)) : 0.0;
-                    const double W0 = on ? fma(dx, wa, dy * wb) : 0.0, W1 = on ? fma(dx, wb, fma(-dy, wa, -d * Rt)) : 0.0;
-                    {
-                        const int e = lane - c;
-                        const int slot = (lane < 3) ? lane : ((e == 0 || e == 1) ? 3 + e : -1);
-                        if (slot >= 0) f.g[slot] = make_double2(W0, W1);
-                        if (lane == 0) f.g[5] = make_double2(P0, P1);
-                    }
-                    NUSLAM_T(3)
-                    __syncthreads();   // Ba
-                    __syncthreads();   // Bb
-                    NUSLAM_T(4)
-                    // (C) -Kt = -Pt Minv, x += Pt y
-                    const double2 mi0 = *reinterpret_cast<const double2 *>(&f.res[0]);
-                    const double2 mi1 = *reinterpret_cast<const double2 *>(&f.res[2]);
-                    const double2 yy = *reinterpret_cast<const double2 *>(&f.res[4]);
-                    const double th = f.xs[1];
-                    const double nk0 = fma(-P0, mi0.x, -P1 * mi1.x), nk1 = fma(-P0, mi0.y, -P1 * mi1.y);
-                    x = fma(P0, yy.x, fma(P1, yy.y, x));
-                    x = (lane == 0) ? th : x;   // the scalar warp applied normalize_angle (slam_library.cpp:276)
-                    if (vpad)
-                    {
-                        f.kt[s][lane] = make_double2(nk0, nk1);
-                        f.wt[s][lane] = make_double2(W0, W1);
-                        f.xs[lane + 1] = x;
-                    }
+                    const double P0 = fma(dx, pa, dy * pb), P1 = fma(dx, pb, fma(-dy, pa, -d * Ct));
+                    const double W0 = fma(dx, wa, dy * wb), W1 = fma(dx, wb, fma(-dy, wa, -d * Rt));
+                    f.wt[s][lane] = make_double2(W0, W1);
                     __syncwarp();
-                    // robot rows / columns: Sigma -= Kt Wt restricted to them
+                    NUSLAM_T(3)
+                    // the 2 x 2 part, evaluated by every lane: M = Wt Ht^T + D^-1 R D^-1, Minv, innovation (:150-160, :272 no wrap)
+                    const double2 g0 = f.wt[s][0], g1 = f.wt[s][1], g2 = f.wt[s][2], g3 = f.wt[s][c], g4 = f.wt[s][c + 1];
+                    const double e0 = g3.x - g1.x, f0 = g4.x - g2.x, e1 = g3.y - g1.y, f1 = g4.y - g2.y;
+                    const double s00 = fma(dx, e0, dy * f0), s01 = fma(dx, f0, fma(-dy, e0, -d * g0.x));
+                    const double s10 = fma(dx, e1, dy * f1), s11 = fma(dx, f1, fma(-dy, e1, -d * g0.y));
+                    const double rs = rsqrt_fast(d);
+                    double sq = d * rs;
+                    sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);   // sqrt(d) to ~1 ulp
+                    const double dsq = d * sq;
+                    const double m00 = fma(d, R00, s00), m10 = fma(dsq, R10, s10), m01 = fma(dsq, R01, s01), m11 = fma(d * d, R11, s11);
+                    const double det = fma(m00, m11, -m01 * m10);
+                    const double idet = rcp_fast(det);
+                    if (fabs(idet) < 1.0e300)   // warp-uniform; false for det = 0, inf or nan, where arma::inv throws (slam_library.cpp:270)
                     {
+                        done = true;
+                        const double i00 = m11 * idet, i01 = -m01 * idet, i10 = -m10 * idet, i11 = m00 * idet;
+                        const double zb = wrap_angle(atan2_fast(dy, dx) - th);
+                        const double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);
+                        // (C) -Kt = -Pt Minv, x += Kt n
+                        const double nk0 = fma(-P0, i00, -P1 * i10), nk1 = fma(-P0, i01, -P1 * i11);
+                        f.kt[s][lane] = make_double2(nk0, nk1);
+                        __syncwarp();
+                        NUSLAM_T(4)
                         const double2 k0 = f.kt[s][0], k1 = f.kt[s][1], k2 = f.kt[s][2];
+                        // replicated pose: what lanes 0..2 compute for their own x, evaluated identically by every lane
+                        th = fma(-k0.x, n0, fma(-k0.y, n1, th));
+                        px = fma(-k1.x, n0, fma(-k1.y, n1, px));
+                        py = fma(-k2.x, n0, fma(-k2.y, n1, py));
+                        x = fma(-nk0, n0, fma(-nk1, n1, x));
+                        th = wrap_angle(th);   // slam_library.cpp:275-276
+                        if (lane == 0) x = th;
+                        f.xs[lane + 1] = x;
+                        // robot rows / columns: Sigma -= Kt Wt restricted to them
                         Rt = fma(k0.x, W0, fma(k0.y, W1, Rt));
                         Rx = fma(k1.x, W0, fma(k1.y, W1, Rx));
                         Ry = fma(k2.x, W0, fma(k2.y, W1, Ry));
-                        const double2 w0 = f.wt[s][0], w1 = f.wt[s][1], w2 = f.wt[s][2];
-                        Ct = fma(nk0, w0.x, fma(nk1, w0.y, Ct));
-                        Cx = fma(nk0, w1.x, fma(nk1, w1.y, Cx));
-                        Cy = fma(nk0, w2.x, fma(nk1, w2.y, Cy));
+                        Ct = fma(nk0, g0.x, fma(nk1, g0.y, Ct));
+                        Cx = fma(nk0, g1.x, fma(nk1, g1.y, Cx));
+                        Cy = fma(nk0, g2.x, fma(nk1, g2.y, Cy));
+                        if (s == 0)
+                        {
+                            pW0 = W0;
+                            pW1 = W1;
+                            pK0 = nk0;
+                            pK1 = nk1;
+                        }
+                        __syncwarp();
+                        NUSLAM_T(5)
                     }
-                    if (s == 0)
-                    {
-                        pW0 = W0;
-                        pW1 = W1;
-                        pK0 = nk0;
-                        pK1 = nk1;
-                    }
-                    NUSLAM_T(5)
+                    else
+                        status |= kStatusSingular;
                 }
-                else
+                if (!done)
                 {
-                    // odd tail: the chunk's second slot contributes nothing to the rank-4 pass
-                    if (vpad)
-                    {
-                        f.kt[s][lane] = make_double2(0.0, 0.0);
-                        f.wt[s][lane] = make_double2(0.0, 0.0);
-                    }
+                    // no measurement in this slot (or a singular one): it contributes nothing to the rank-4 pass
+                    f.kt[s][lane] = make_double2(0.0, 0.0);
+                    f.wt[s][lane] = make_double2(0.0, 0.0);
                     __syncwarp();
                 }
             }
@@ -556,7 +427,6 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         }
 
         // ---- write back: registers -> HBM ----
-        if (!dead)
         {
             double * gw = p.sigma + bf * SIG;
 #pragma unroll
@@ -582,20 +452,14 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 }
                 p.x[bf * LEN + lane] = x;
             }
-            if (lane == 0 && f.status != st0) p.status[bf] = f.status;
+            if (lane == 0 && status != st0) p.status[bf] = status;
         }
         NUSLAM_T(7)
     }
 #ifdef NUSLAM_TIMING
-    if (blockIdx.x == 0 && warp == 0 && lane == 0)
+    if (blockIdx.x == 0 && lane == 0)
         for (int k = 0; k < 8; ++k) atomicAdd((unsigned long long *) &g_fast_timing[k], (unsigned long long) tacc[k]);
 #endif
-}
-
-template <int N>
-constexpr size_t fast_smem_bytes()
-{
-    return kGroup * sizeof(FastSmem<N>);
 }
 
 inline bool fast_supported(int n) { return n == 12 || n == 6; }
@@ -603,23 +467,14 @@ inline bool fast_supported(int n) { return n == 12 || n == 6; }
 template <int N>
 int launch_fast_n(const EkfParams & p, bool do_predict, int sm_count, int32_t * worklist, int32_t * wl_count, cudaStream_t stream)
 {
-    static_assert(sizeof(FastSmem<N>) % 128 == 16, "filter stride must be 16 (mod 128) bytes");
-    static thread_local bool configured = false;
-    constexpr size_t smem = fast_smem_bytes<N>();
-    if (!configured)
-    {
-        cudaError_t e = cudaFuncSetAttribute(k_ekf_fast_step<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (e != cudaSuccess) return (int) e;
-        configured = true;
-    }
-    // persistent: two CTAs per SM, each looping over groups of kGroup consecutive filters
-    int64_t blocks = (p.batch + kGroup - 1) / kGroup;
-    int ctas_per_sm = 2;
+    // persistent: kFastCtasPerSm single-warp CTAs per SM, each striding over the filters
+    int64_t blocks = p.batch;
+    int ctas_per_sm = kFastCtasPerSm;
 #ifdef NUSLAM_TIMING
     if (const char * e = getenv("NUSLAM_FAST_CTAS_PER_SM")) ctas_per_sm = atoi(e);
 #endif
     if (blocks > ctas_per_sm * (int64_t) sm_count) blocks = ctas_per_sm * (int64_t) sm_count;
-    k_ekf_fast_step<N><<<(unsigned) blocks, kFastThreads, smem, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
+    k_ekf_fast_step<N><<<(unsigned) blocks, kFastThreads, 0, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
     return (int) cudaGetLastError();
 }
 

@@ -30,11 +30,10 @@ for t in range(3, 3 + K):
 eng.synchronize()
 lib.nuslam_debug_fast_timing(out, 0)
 v = np.array(list(out), dtype=np.float64)
-nblk = 148 * int(os.environ.get("NUSLAM_FAST_CTAS_PER_SM", "2"))
-groups = K * ((B // 8 + nblk - 1) // nblk)   # groups processed by block 0
-names = ["load", "predict(+B0,B1)", "publish", "pre (Pt,Wt,g)", "barrier wait (Ba..Bb)", "post (Kt,x,robot)", "dmma", "store"]
+nblk = 148 * int(os.environ.get("NUSLAM_FAST_CTAS_PER_SM", "20"))
+filters = K * ((B + nblk - 1) // nblk)   # filters processed by block 0 / warp 0
+names = ["load", "predict", "publish", "pre (Pt,Wt)", "2x2 part + Kt", "post (x, robot)", "dmma", "store"]
 tot = v[:8].sum()
-print(f"block 0 / warp 0: {groups} groups, {tot / groups:.0f} cycles per group ({tot / groups / 12:.0f} per update)")
+print(f"block 0 / warp 0: {filters} filter-steps, {tot / filters:.0f} cycles per filter-step ({tot / filters / 12:.0f} per update)")
 for k, nm in enumerate(names):
-    print(f"  {nm:<24}{v[k] / groups:>10.0f} cycles/group {100 * v[k] / tot:>6.1f} %")
-print(f"  scalar warp compute     {v[8] / groups:>10.0f} cycles/group  ({v[8] / groups / 12:.0f} per update)")
+    print(f"  {nm:<24}{v[k] / filters:>10.0f} cycles/filter-step {100 * v[k] / tot:>6.1f} %")
