@@ -308,7 +308,8 @@ namespace
                 const int cand = (i + tries) % 360;
                 const double px = r[cand] * cos(rigid2d::deg2rad(cand));
                 const double py = r[cand] * sin(rigid2d::deg2rad(cand));
-                if (px == cl[k].x && py == cl[k].y)
+                // a NaN range counts as in range (circle_fit_library.cpp:149) and stores a NaN point: match it by NaN-ness
+                if ((px == cl[k].x && py == cl[k].y) || (px != px && cl[k].x != cl[k].x))
                 {
                     found = cand;
                     break;
@@ -392,7 +393,7 @@ int orc_scan_detect(const float * ranges360, double minR, double maxR, int * clu
         int mx = -1;
         for (size_t k = 0; k < cl.size(); ++k)
         {
-            cluster_of_beam[beams[k]] = c;
+            if (beams[k] >= 0) cluster_of_beam[beams[k]] = c;
             if (!(c == 0 && k + 1 == cl.size() && beams[k] == 359 && cl.size() > 1 && beams[k - 1] != 358)) mx = std::max(mx, beams[k]);
         }
         hint = (mx + 1) % 360;

@@ -616,8 +616,10 @@ int nuslam_scan_detect(const float * ranges, int64_t n_scans, double min_range, 
         d_circ = reinterpret_cast<double *>(q);
         CU(cudaMemcpyAsync(const_cast<float *>(d_ranges), ranges, b_r, cudaMemcpyHostToDevice, st));
     }
+    int sm_count = 0;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaError_t e = nuslam::launch_scan_detect(d_ranges, n_scans, min_range, max_range, cluster_of_beam ? d_cob : nullptr, d_ncl, d_nci,
-                                               d_circ, max_circles, st);
+                                               d_circ, max_circles, NUSLAM_SCAN_UB, device, sm_count > 0 ? sm_count : 148, st);
     if (e == cudaSuccess && mem == NUSLAM_HOST)
     {
         if (cluster_of_beam) e = cudaMemcpyAsync(cluster_of_beam, d_cob, b_cob, cudaMemcpyDeviceToHost, st);
@@ -665,10 +667,18 @@ int nuslam_classify_and_fit(const double * px, const double * py, const int32_t 
         q += b_i;
         d_fit = reinterpret_cast<double *>(q);
     }
+    // work matrices of the Jacobi SVD: 4 doubles per point
+    int32_t npts_total = 0;
+    if (mem == NUSLAM_HOST) npts_total = offsets[n_clusters];
+    else CU(cudaMemcpyAsync(&npts_total, offsets + n_clusters, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (mem != NUSLAM_HOST) CU(cudaStreamSynchronize(st));
+    double * scratch = nullptr;
+    CU(cudaMalloc(&scratch, sizeof(double) * 4 * (size_t) (npts_total > 0 ? npts_total : 1)));
     const int threads = 128;
     const int64_t blocks = (n_clusters + threads - 1) / threads;
-    nuslam::k_classify_and_fit<<<(unsigned) blocks, threads, 0, st>>>(d_px, d_py, d_off, n_clusters, d_is, d_fit);
+    nuslam::k_classify_and_fit<<<(unsigned) blocks, threads, 0, st>>>(d_px, d_py, d_off, n_clusters, d_is, d_fit, scratch);
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && mem != NUSLAM_HOST) e = cudaStreamSynchronize(st);
     if (e == cudaSuccess && mem == NUSLAM_HOST)
     {
         e = cudaMemcpyAsync(is_circle, d_is, sizeof(int32_t) * n_clusters, cudaMemcpyDeviceToHost, st);
@@ -676,6 +686,7 @@ int nuslam_classify_and_fit(const double * px, const double * py, const int32_t 
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
     if (tmp) cudaFree(tmp);
+    if (scratch) cudaFree(scratch);
     if (e != cudaSuccess) return cuda_fail(e, "classify_and_fit");
     return NUSLAM_OK;
 }

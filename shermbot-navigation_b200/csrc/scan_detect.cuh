@@ -1,11 +1,629 @@
-// scan_detect.cuh -- placeholder until the clustering / circle-fit kernels land.
+// scan_detect.cuh -- batched laser-scan clustering + circle classification + Hyper algebraic circle fit (sm_100a).
+//
+// One warp per 360-beam scan. Reference semantics restated here (paths relative to the reference repo):
+//   nuslam/src/circle_fit_library.cpp:136-206  clusterPoints   (sequential state machine over the beams)
+//   nuslam/src/circle_fit_library.cpp:208-250  classifyCluster (population std of inscribed angles < 10 deg)
+//   nuslam/src/circle_fit_library.cpp:15-134   circleFit       (SVD of Z, eig of Y Hinv Y, solve)
+//   nuslam/src/landmarks.cpp:84-109            caller protocol (id < 0 skip, R > 1 skip, detection order)
+// Parallel form of clusterPoints: with inr_i = !(r_i > max || r_i < min),
+// sim_i = |r_i - r_(i+1 mod 360)| < 0.04, closer_i = inr_i && !sim_i, the cluster of an in-range beam is the number of
+// closers before it (warp ballots + popcounts); beams after the last closer form the open cluster the reference
+// drops; beam 359 similar to beam 0 is appended to the END of cluster 0 (and the reference indexes clusters[0] of an
+// empty vector when there is none: reported as NUSLAM_SCAN_UB); the erase loop's index skipping is a two-state
+// walk over the clusters.
+// circleFit is the reference's own algorithm, term by term (one-sided Jacobi SVD of the N x 4 data matrix in the
+// oracle's sweep order, cyclic Jacobi eig_sym of the symmetrised 4 x 4, Gaussian elimination with partial pivoting;
+// see oracle/shim/armadillo for the order the oracle defines), with unfused IEEE multiply/add and IEEE sqrt and
+// division, one cluster per lane, its data matrix in shared memory. Only atan2 (classification) comes from the
+// CUDA math library. Beam directions cos/sin(deg2rad(i)) (circle_fit_library.cpp:162-163) are a 360-entry
+// constant table filled by the host once (host libm, bit-identical to what the reference multiplies with).
 #pragma once
 #include "ekf_common.cuh"
+#include <math.h>
+
 namespace nuslam
 {
-inline cudaError_t launch_scan_detect(const float *, int64_t, double, double, int16_t *, int32_t *, int32_t *, double *, int32_t, cudaStream_t)
+
+constexpr int kBeams = 360;
+constexpr int kScanWarps = 2;   // scans per CTA
+constexpr double kPiRef = 3.14159265358979323846;   // rigid2d.hpp:16
+
+__constant__ double c_beam_cos[kBeams];
+__constant__ double c_beam_sin[kBeams];
+
+struct ScanSmem
 {
-    return cudaErrorNotSupported;
+    double px[kBeams + 2];        // points in the reference's stored order (flat over the pre-erase clusters); [361] = wrap point
+    double py[kBeams + 2];
+    double A[4 * (kBeams + 2)];   // Jacobi work matrices of the clusters being fitted (disjoint slices)
+    float r[kBeams + 8];
+    short cend[kBeams + 2];       // flat position of the last point of pre-erase cluster k
+    short newidx[kBeams + 2];     // index after the erase loop, -1 when erased
+    short kept[kBeams + 2];       // pre-erase index of kept cluster q
+    int nk;
+};
+
+// classifyCluster, circle_fit_library.cpp:208-250. Points P(0..n-1) in stored order.
+template <typename PX, typename PY>
+__device__ __forceinline__ bool classify_cluster(int n, PX X, PY Y)
+{
+    const double p2x = X(0), p2y = Y(0), p3x = X(n - 1), p3y = Y(n - 1);
+    const int na = (n >= 2) ? n - 2 : 0;   // angles.size(): 0 for clusters of 1 or 2 points -> 0/0 = NaN -> not a circle
+    double mean = 0.0;
+    for (int i = 1; i < n - 1; ++i)
+    {
+        const double p1x = X(i), p1y = Y(i);
+        // num = p2.y*(p1.x-p3.x) + p1.y*(p3.x-p2.x) + p3.y*(p2.x-p1.x); den = (p2.x-p1.x)*(p1.x-p3.x) + (p2.y-p1.y)*(p1.y-p3.y)
+        const double num = add_(add_(mul_(p2y, sub_(p1x, p3x)), mul_(p1y, sub_(p3x, p2x))), mul_(p3y, sub_(p2x, p1x)));
+        const double den = add_(mul_(sub_(p2x, p1x), sub_(p1x, p3x)), mul_(sub_(p2y, p1y), sub_(p1y, p3y)));
+        const double ang = mul_(div_(180.0, kPiRef), atan2(num, den));   // rigid2d::rad2deg, rigid2d.hpp:49-53
+        mean = add_(mean, div_(ang, (double) na));
+    }
+    double sd = 0.0;
+    for (int i = 1; i < n - 1; ++i)
+    {
+        const double p1x = X(i), p1y = Y(i);
+        const double num = add_(add_(mul_(p2y, sub_(p1x, p3x)), mul_(p1y, sub_(p3x, p2x))), mul_(p3y, sub_(p2x, p1x)));
+        const double den = add_(mul_(sub_(p2x, p1x), sub_(p1x, p3x)), mul_(sub_(p2y, p1y), sub_(p1y, p3y)));
+        const double ang = mul_(div_(180.0, kPiRef), atan2(num, den));
+        const double dv = sub_(ang, mean);
+        sd = add_(sd, mul_(dv, dv));   // pow(angle - mean, 2)
+    }
+    sd = sqrt(div_(sd, (double) na));   // na == 0 -> 0/0 = NaN -> false
+    return sd < 10.0;
 }
-__global__ void k_classify_and_fit(const double *, const double *, const int32_t *, int64_t, int32_t *, double *) {}
+
+// one-sided (Hestenes) Jacobi SVD of the m x 4 matrix A (column-major, overwritten): singular values descending in s,
+// right singular vectors in V (4 x 4 column-major). oracle/shim/armadillo svd().
+__device__ inline void svd_n4(double * A, int m, double * s, double * V)
+{
+    double W[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) W[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep)
+    {
+        bool rotated = false;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q)
+            {
+                double alpha = 0.0, beta = 0.0, gamma = 0.0;
+                for (int i = 0; i < m; ++i)
+                {
+                    const double ap = A[i + p * m], aq = A[i + q * m];
+                    alpha = add_(alpha, mul_(ap, ap));
+                    beta = add_(beta, mul_(aq, aq));
+                    gamma = add_(gamma, mul_(ap, aq));
+                }
+                const bool skip = (gamma == 0.0) || (fabs(gamma) <= 1e-300) ||
+                                  (fabs(gamma) <= mul_(2.220446049250313e-16, sqrt(mul_(alpha, beta))));
+                if (!skip)
+                {
+                    rotated = true;
+                    const double zeta = div_(sub_(beta, alpha), mul_(2.0, gamma));
+                    const double tt = div_((zeta >= 0.0 ? 1.0 : -1.0), add_(fabs(zeta), sqrt(add_(1.0, mul_(zeta, zeta)))));
+                    const double c = div_(1.0, sqrt(add_(1.0, mul_(tt, tt))));
+                    const double sn = mul_(c, tt);
+                    for (int i = 0; i < m; ++i)
+                    {
+                        const double ap = A[i + p * m], aq = A[i + q * m];
+                        A[i + p * m] = sub_(mul_(c, ap), mul_(sn, aq));
+                        A[i + q * m] = add_(mul_(sn, ap), mul_(c, aq));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                    {
+                        const double wp = W[i + p * 4], wq = W[i + q * 4];
+                        W[i + p * 4] = sub_(mul_(c, wp), mul_(sn, wq));
+                        W[i + q * 4] = add_(mul_(sn, wp), mul_(c, wq));
+                    }
+                }
+            }
+        if (!rotated) break;
+    }
+    double norms[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+        double acc = 0.0;
+        for (int i = 0; i < m; ++i) acc = add_(acc, mul_(A[i + j * m], A[i + j * m]));
+        norms[j] = sqrt(acc);
+    }
+    // stable insertion sort, descending (a 4-element network with the same tie behaviour)
+    int order[4] = {0, 1, 2, 3};
+#pragma unroll
+    for (int a = 1; a < 4; ++a)
+    {
+#pragma unroll
+        for (int b = a; b > 0; --b)
+        {
+            const bool sw = norms[order[b - 1]] < norms[order[b]];
+            const int o0 = order[b - 1], o1 = order[b];
+            order[b - 1] = sw ? o1 : o0;
+            order[b] = sw ? o0 : o1;
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+    {
+        s[jj] = norms[order[jj]];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) V[i + jj * 4] = W[i + order[jj] * 4];
+    }
 }
+
+// cyclic two-sided Jacobi on the symmetrised 4 x 4: eigenvalues ascending. oracle/shim/armadillo eig_sym().
+__device__ inline void eig_sym4(const double * X, double * val, double * vec)
+{
+    double A[16], W[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            A[i + j * 4] = mul_(0.5, add_(X[i + j * 4], X[j + i * 4]));
+            W[i + j * 4] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 100; ++sweep)
+    {
+        double off = 0.0, diag = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                if (i == j) diag = add_(diag, mul_(A[i + j * 4], A[i + j * 4]));
+                else off = add_(off, mul_(A[i + j * 4], A[i + j * 4]));
+            }
+        if (off == 0.0 || off <= mul_(1e-40, diag)) break;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q)
+            {
+                const double apq = A[p + q * 4];
+                if (apq != 0.0)
+                {
+                    const double theta = div_(sub_(A[q + q * 4], A[p + p * 4]), mul_(2.0, apq));
+                    const double tt = div_((theta >= 0.0 ? 1.0 : -1.0), add_(fabs(theta), sqrt(add_(1.0, mul_(theta, theta)))));
+                    const double c = div_(1.0, sqrt(add_(1.0, mul_(tt, tt))));
+                    const double sn = mul_(c, tt);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const double akp = A[k + p * 4], akq = A[k + q * 4];
+                        A[k + p * 4] = sub_(mul_(c, akp), mul_(sn, akq));
+                        A[k + q * 4] = add_(mul_(sn, akp), mul_(c, akq));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const double apk = A[p + k * 4], aqk = A[q + k * 4];
+                        A[p + k * 4] = sub_(mul_(c, apk), mul_(sn, aqk));
+                        A[q + k * 4] = add_(mul_(sn, apk), mul_(c, aqk));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const double wp = W[k + p * 4], wq = W[k + q * 4];
+                        W[k + p * 4] = sub_(mul_(c, wp), mul_(sn, wq));
+                        W[k + q * 4] = add_(mul_(sn, wp), mul_(c, wq));
+                    }
+                }
+            }
+    }
+    int order[4] = {0, 1, 2, 3};
+#pragma unroll
+    for (int a = 1; a < 4; ++a)
+    {
+#pragma unroll
+        for (int b = a; b > 0; --b)
+        {
+            const bool sw = A[order[b - 1] * 5] > A[order[b] * 5];
+            const int o0 = order[b - 1], o1 = order[b];
+            order[b - 1] = sw ? o1 : o0;
+            order[b] = sw ? o0 : o1;
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+    {
+        val[jj] = A[order[jj] * 5];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) vec[i + jj * 4] = W[i + order[jj] * 4];
+    }
+}
+
+// Gaussian elimination with partial pivoting, 4 x 4. oracle/shim/armadillo solve(). false when singular.
+__device__ inline bool solve4(const double * Ain, const double * b, double * x)
+{
+    double A[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) A[k] = Ain[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = b[k];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+    {
+        int piv = c;
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r)
+            if (fabs(A[r + c * 4]) > fabs(A[piv + c * 4])) piv = r;
+        if (A[piv + c * 4] == 0.0) return false;
+        if (piv != c)
+        {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                const double t = A[piv + k * 4];
+                A[piv + k * 4] = A[c + k * 4];
+                A[c + k * 4] = t;
+            }
+            const double t = x[piv];
+            x[piv] = x[c];
+            x[c] = t;
+        }
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r)
+        {
+            const double fct = div_(A[r + c * 4], A[c + c * 4]);
+            if (fct != 0.0)
+            {
+#pragma unroll
+                for (int k = c; k < 4; ++k) A[r + k * 4] = sub_(A[r + k * 4], mul_(fct, A[c + k * 4]));
+                x[r] = sub_(x[r], mul_(fct, x[c]));
+            }
+        }
+    }
+#pragma unroll
+    for (int ii = 3; ii >= 0; --ii)
+    {
+        double acc = x[ii];
+#pragma unroll
+        for (int j = ii + 1; j < 4; ++j) acc = sub_(acc, mul_(A[ii + j * 4], x[j]));
+        x[ii] = div_(acc, A[ii + ii * 4]);
+    }
+    return true;
+}
+
+__device__ __forceinline__ void mm4(double * C, const double * A, const double * B)
+{
+    // oracle/shim/armadillo operator*: C(i,j) = sum_k A(i,k) B(k,j), ascending k, unfused
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc = add_(acc, mul_(A[i + k * 4], B[k + j * 4]));
+            C[i + j * 4] = acc;
+        }
+}
+
+constexpr int kFitException = -1000;   // solve() on a singular Y: Armadillo throws
+
+// circleFit, circle_fit_library.cpp:15-134. Z (work matrix, N x 4 column-major) lives in shared memory.
+// Returns marker.id (0, or -1 when N < 4); out = (pose.x, pose.y, scale.x / 2).
+template <typename PX, typename PY>
+__device__ inline int circle_fit(int N, PX X, PY Y, double * Z, double * out3)
+{
+    out3[0] = out3[1] = out3[2] = 0.0;
+    double x_hat = 0.0, y_hat = 0.0;
+    for (int i = 0; i < N; ++i)
+    {
+        x_hat = add_(x_hat, div_(X(i), (double) N));   // :23-24, size_t divisor converts to double
+        y_hat = add_(y_hat, div_(Y(i), (double) N));
+    }
+    double z_bar = 0.0;
+    for (int j = 0; j < N; ++j)
+    {
+        const double dx = sub_(X(j), x_hat), dy = sub_(Y(j), y_hat);
+        const double z = add_(mul_(dx, dx), mul_(dy, dy));   // pow(x, 2) + pow(y, 2)
+        z_bar = add_(z_bar, div_(z, (double) N));
+        Z[j + 0 * N] = z;
+        Z[j + 1 * N] = dx;
+        Z[j + 2 * N] = dy;
+        Z[j + 3 * N] = 1.0;
+    }
+    if (N < 4) return -1;   // s.size() < 4 (:72-76)
+    double s[4], V[16], Aco[4];
+    svd_n4(Z, N, s, V);
+    if (s[3] < 1e-12)   // :78-80
+    {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Aco[i] = V[i + 12];
+    }
+    else
+    {
+        double Hinv[16], D[16], VD[16], Vt[16], Yq[16], YH[16], Q[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+        {
+            Hinv[k] = 0.0;
+            D[k] = 0.0;
+        }
+        Hinv[5] = 1.0;
+        Hinv[10] = 1.0;
+        Hinv[0 + 3 * 4] = 0.5;
+        Hinv[3 + 0 * 4] = 0.5;
+        Hinv[15] = mul_(-2.0, z_bar);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) D[i * 5] = s[i];
+        mm4(VD, V, D);   // Y = V * diagmat(s) * V.t() (:82)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Vt[i + j * 4] = V[j + i * 4];
+        mm4(Yq, VD, Vt);
+        mm4(YH, Yq, Hinv);   // Q = Y * Hinv * Y (:83)
+        mm4(Q, YH, Yq);
+        double eigval[4], eigvec[16];
+        eig_sym4(Q, eigval, eigvec);
+        int eig_index = 0;
+        double eig_max = 2147483647.0;   // INT_MAX (:92)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (eigval[i] > 0.0 && eigval[i] < eig_max)
+            {
+                eig_index = i;
+                eig_max = eigval[i];
+            }
+        double Astar[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            Astar[i] = (eig_index == 0) ? eigvec[i] : (eig_index == 1) ? eigvec[i + 4] : (eig_index == 2) ? eigvec[i + 8] : eigvec[i + 12];
+        if (!solve4(Yq, Astar, Aco)) return kFitException;
+    }
+    const double a = div_(-Aco[1], mul_(2.0, Aco[0]));
+    const double b = div_(-Aco[2], mul_(2.0, Aco[0]));
+    const double R2 = div_(sub_(add_(mul_(Aco[1], Aco[1]), mul_(Aco[2], Aco[2])), mul_(mul_(4.0, Aco[0]), Aco[3])),
+                           mul_(4.0, mul_(Aco[0], Aco[0])));
+    const double tube_radius = sqrt(R2);
+    out3[0] = add_(a, x_hat);
+    out3[1] = add_(b, y_hat);
+    out3[2] = div_(mul_(2.0, tube_radius), 2.0);   // scale.x = 2R (:124); callers read scale.x / 2 (landmarks.cpp:95)
+    return 0;
+}
+
+// One warp per scan. cluster_of_beam may be null.
+__global__ void __launch_bounds__(32 * kScanWarps)
+k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_range, double max_range, int16_t * __restrict__ cluster_of_beam,
+              int32_t * __restrict__ n_clusters, int32_t * __restrict__ n_circles, double * __restrict__ circles, int max_circles, int scan_ub)
+{
+    extern __shared__ __align__(16) unsigned char scan_smem_raw[];
+    ScanSmem & sm = reinterpret_cast<ScanSmem *>(scan_smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    constexpr unsigned kFull = 0xffffffffu;
+    constexpr int kChunks = (kBeams + 31) / 32;   // 12
+    for (int64_t s = (int64_t) blockIdx.x * kScanWarps + (threadIdx.x >> 5); s < n_scans; s += (int64_t) gridDim.x * kScanWarps)
+    {
+        const float * rs = ranges + s * kBeams;
+        for (int i = lane; i < kBeams; i += 32) sm.r[i] = rs[i];
+        __syncwarp();
+        if (lane == 0) sm.r[kBeams] = sm.r[0];
+        __syncwarp();
+        // ---- per-beam predicates and their ballots ----
+        unsigned inr_m[kChunks], clo_m[kChunks];
+        bool wrap = false;
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k)
+        {
+            const int i = 32 * k + lane;
+            bool inr = false, sim = false;
+            if (i < kBeams)
+            {
+                const float r = sm.r[i];
+                inr = !(((double) r > max_range) || ((double) r < min_range));           // :149, NaN counts as in range
+                sim = fabs((double) r - (double) sm.r[i + 1]) < 0.04;                    // :166
+            }
+            inr_m[k] = __ballot_sync(kFull, inr);
+            clo_m[k] = __ballot_sync(kFull, inr && !sim);
+            if (k == kChunks - 1) wrap = ((inr_m[k] >> ((kBeams - 1) & 31)) & 1u) && !((clo_m[k] >> ((kBeams - 1) & 31)) & 1u);
+        }
+        // beam 359 in range and similar to beam 0: it is not stored in the flat list but appended to cluster 0
+        if (wrap) inr_m[kChunks - 1] &= ~(1u << ((kBeams - 1) & 31));
+        int nc = 0;
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k) nc += __popc(clo_m[k]);
+        int64_t sb = s * kBeams;
+        if (wrap && nc == 0)
+        {
+            // clusters[0].push_back on an empty vector (:173): undefined behaviour in the reference
+            if (cluster_of_beam)
+                for (int i = lane; i < kBeams; i += 32) cluster_of_beam[sb + i] = -1;
+            if (lane == 0)
+            {
+                n_clusters[s] = 0;
+                n_circles[s] = scan_ub;
+            }
+            __syncwarp();
+            continue;
+        }
+        // ---- flat positions, cluster ends, points ----
+        int pos_base = 0, clu_base = 0;
+        int my_pos[kChunks], my_clu[kChunks];
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k)
+        {
+            const int i = 32 * k + lane;
+            const bool inr = (inr_m[k] >> lane) & 1u, clo = (clo_m[k] >> lane) & 1u;
+            my_pos[k] = pos_base + __popc(inr_m[k] & lt);
+            my_clu[k] = clu_base + __popc(clo_m[k] & lt);
+            if (inr)
+            {
+                const double r = (double) sm.r[i];
+                sm.px[my_pos[k]] = mul_(r, c_beam_cos[i]);   // :162-163
+                sm.py[my_pos[k]] = mul_(r, c_beam_sin[i]);
+                if (clo) sm.cend[my_clu[k]] = (short) my_pos[k];
+            }
+            pos_base += __popc(inr_m[k]);
+            clu_base += __popc(clo_m[k]);
+        }
+        if (wrap && lane == 0)
+        {
+            const double r = (double) sm.r[kBeams - 1];
+            sm.px[kBeams + 1] = mul_(r, c_beam_cos[kBeams - 1]);
+            sm.py[kBeams + 1] = mul_(r, c_beam_sin[kBeams - 1]);
+        }
+        __syncwarp();
+        // ---- erase loop (:198-204): a cluster following an erased one is never examined ----
+        if (lane == 0)
+        {
+            int nk = 0;
+            bool unchecked = false;
+            int prev_end = -1;
+            for (int k = 0; k < nc; ++k)
+            {
+                const int e = sm.cend[k];
+                const int size = e - prev_end + ((k == 0 && wrap) ? 1 : 0);
+                prev_end = e;
+                if (!unchecked && size < 3)
+                {
+                    sm.newidx[k] = -1;
+                    unchecked = true;
+                }
+                else
+                {
+                    sm.newidx[k] = (short) nk;
+                    sm.kept[nk] = (short) k;
+                    ++nk;
+                    unchecked = false;
+                }
+            }
+            sm.nk = nk;
+        }
+        __syncwarp();
+        const int nk = sm.nk;
+        if (cluster_of_beam)
+        {
+#pragma unroll
+            for (int k = 0; k < kChunks; ++k)
+            {
+                const int i = 32 * k + lane;
+                if (i < kBeams)
+                {
+                    const bool inr = (inr_m[k] >> lane) & 1u;
+                    int out = -1;
+                    if (inr && my_clu[k] < nc) out = sm.newidx[my_clu[k]];
+                    if (wrap && i == kBeams - 1) out = sm.newidx[0];
+                    cluster_of_beam[sb + i] = (int16_t) out;
+                }
+            }
+        }
+        // ---- classification + circle fit, one kept cluster per lane; publication in detection order ----
+        int published = 0;
+        double * cout = circles + s * (int64_t) max_circles * 4;
+        for (int q0 = 0; q0 < nk; q0 += 32)
+        {
+            const int q = q0 + lane;
+            bool pub = false;
+            double fit[3] = {0.0, 0.0, 0.0};
+            if (q < nk)
+            {
+                const int k = sm.kept[q];
+                const int start = (k == 0) ? 0 : sm.cend[k - 1] + 1;
+                const int nmain = sm.cend[k] - start + 1;
+                const bool wr = (k == 0) && wrap;
+                const int n = nmain + (wr ? 1 : 0);
+                const double * bx = sm.px + start;
+                const double * by = sm.py + start;
+                const double wx = sm.px[kBeams + 1], wy = sm.py[kBeams + 1];
+                auto X = [&](int i) { return (i < nmain) ? bx[i] : wx; };
+                auto Y = [&](int i) { return (i < nmain) ? by[i] : wy; };
+                if (classify_cluster(n, X, Y))
+                {
+                    double * Z = sm.A + 4 * (start + (k > 0 ? 1 : 0));
+                    const int id = circle_fit(n, X, Y, Z, fit);
+                    pub = (id >= 0) && !(fit[2] > 1.0);   // landmarks.cpp:91-97
+                }
+            }
+            const unsigned pm = __ballot_sync(kFull, pub);
+            if (pub)
+            {
+                const int slot = published + __popc(pm & lt);
+                if (slot < max_circles)
+                {
+                    cout[4 * slot + 0] = fit[0];
+                    cout[4 * slot + 1] = fit[1];
+                    cout[4 * slot + 2] = fit[2];
+                    cout[4 * slot + 3] = (double) q;
+                }
+            }
+            published += __popc(pm);
+        }
+        if (lane == 0)
+        {
+            n_clusters[s] = nk;
+            n_circles[s] = published;
+        }
+        __syncwarp();
+    }
+}
+
+// circle_fit::classifyCluster / circleFit on explicit point lists: one cluster per thread, work matrix in global scratch
+__global__ void k_classify_and_fit(const double * __restrict__ px, const double * __restrict__ py, const int32_t * __restrict__ offsets,
+                                   int64_t n_clusters, int32_t * __restrict__ is_circle, double * __restrict__ fit, double * __restrict__ scratch)
+{
+    const int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_clusters) return;
+    const int o = offsets[c], n = offsets[c + 1] - offsets[c];
+    const double * bx = px + o;
+    const double * by = py + o;
+    auto X = [&](int i) { return bx[i]; };
+    auto Y = [&](int i) { return by[i]; };
+    is_circle[c] = (n >= 1 && classify_cluster(n, X, Y)) ? 1 : 0;
+    double out3[3] = {0.0, 0.0, 0.0};
+    int id = -1;
+    if (n >= 1) id = circle_fit(n, X, Y, scratch + 4 * (int64_t) o, out3);
+    fit[4 * c + 0] = (double) id;
+    fit[4 * c + 1] = out3[0];
+    fit[4 * c + 2] = out3[1];
+    fit[4 * c + 3] = out3[2];
+}
+
+// host: fill the beam-direction table once per device with the host libm (the reference's own cos / sin)
+inline cudaError_t scan_tables_init(int device)
+{
+    static bool done[64] = {false};
+    if (device >= 0 && device < 64 && done[device]) return cudaSuccess;
+    double hc[kBeams], hs[kBeams];
+    for (int i = 0; i < kBeams; ++i)
+    {
+        const double rad = (kPiRef / (double) 180) * (double) i;   // rigid2d::deg2rad, rigid2d.hpp:40-44
+        hc[i] = cos(rad);
+        hs[i] = sin(rad);
+    }
+    cudaError_t e = cudaMemcpyToSymbol(c_beam_cos, hc, sizeof(hc));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_beam_sin, hs, sizeof(hs));
+    if (e != cudaSuccess) return e;
+    if (device >= 0 && device < 64) done[device] = true;
+    return cudaSuccess;
+}
+
+inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, double min_range, double max_range, int16_t * cluster_of_beam,
+                                      int32_t * n_clusters, int32_t * n_circles, double * circles, int32_t max_circles, int scan_ub,
+                                      int device, int sm_count, cudaStream_t stream)
+{
+    cudaError_t e = scan_tables_init(device);
+    if (e != cudaSuccess) return e;
+    const size_t smem = sizeof(ScanSmem) * kScanWarps;
+    static bool configured = false;
+    if (!configured)
+    {
+        e = cudaFuncSetAttribute(k_scan_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    int64_t blocks = (n_scans + kScanWarps - 1) / kScanWarps;
+    const int64_t resident = (int64_t) sm_count * 5;
+    if (blocks > resident) blocks = resident;
+    k_scan_detect<<<(unsigned) blocks, 32 * kScanWarps, smem, stream>>>(ranges, n_scans, min_range, max_range, cluster_of_beam, n_clusters,
+                                                                       n_circles, circles, max_circles, scan_ub);
+    return cudaGetLastError();
+}
+
+}   // namespace nuslam

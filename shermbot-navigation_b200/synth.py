@@ -203,3 +203,36 @@ def scan_scenario(S, seed=777, noise_sigma=0.0, wall_frac=0.10, wrap_frac=0.05, 
     walls[has_wall, 0, 3] = (cyw - half * np.cos(wa))[has_wall]
     ranges = simulate_scans(poses, tubes, walls=walls, noise_sigma=noise_sigma, seed=seed)
     return dict(ranges=ranges, poses=poses, min_range=MIN_RANGE, max_range=MAX_RANGE)
+
+
+def edge_scans(n_random=200, seed=3):
+    """Hand-made scans for the corner cases of clusterPoints (circle_fit_library.cpp:136-206): empty scan, one open cluster
+    with the wrap rule and no closed cluster (undefined behaviour in the reference), wrap onto a cluster that does not
+    contain beam 0, clusters of sizes 1..5 (erase-loop skip), NaN ranges (count as in range), every beam closing a
+    cluster, wrap with a dropped open tail, plus random sparse scans."""
+    scans = []
+    scans.append(np.full(360, 2.0, np.float32))
+    scans.append(np.full(360, 0.5, np.float32))
+    a = np.full(360, 2.0, np.float32)
+    a[357:360] = 0.5
+    a[0:3] = 0.5
+    a[100:110] = 0.6
+    a[110] = 0.9
+    scans.append(a)
+    b = np.full(360, 2.0, np.float32)
+    for k in range(0, 350, 7):
+        b[k:k + (k // 7) % 5 + 1] = 0.3 + 0.001 * k
+    scans.append(b)
+    c = np.full(360, 2.0, np.float32)
+    c[10:20] = np.nan
+    c[20] = 0.4
+    scans.append(c)
+    scans.append((0.1 + 0.05 * (np.arange(360) % 17)).astype(np.float32))
+    e = np.full(360, 2.0, np.float32)
+    e[0:5] = 0.5
+    e[355:360] = 0.52
+    scans.append(e)
+    rng = np.random.default_rng(seed)
+    for _ in range(n_random):
+        scans.append(np.where(rng.random(360) < 0.6, rng.uniform(0.04, 1.1, 360), 2.0).astype(np.float32))
+    return np.stack(scans)
