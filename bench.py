@@ -46,56 +46,78 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region (NVML every ~4 ms in a thread; nvidia-smi as fallback)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
+        self.handle = None
+        self.max_sm = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.nvml = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _read_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        except Exception:
+            pw = float("nan")
+        try:
+            rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            try:
+                rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                rs = 0
+        return sm, pw, rs
+
+    def _read_smi(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.max_sm = float(out[1])
+        return float(out[0]), float(out[2]), int(out[3].strip(), 16)
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(self._read_nvml() if self.nvml else self._read_smi())
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [v.strip() for v in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-                pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=5)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples"]}
+        sm = [v[0] for v in self.samples]
+        pw = [v[1] for v in self.samples if v[1] == v[1]]
+        bits = 0
+        for v in self.samples:
+            bits |= v[2]
+        reasons = sorted(nm for b, nm in self.REASONS.items() if bits & b)
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": self.max_sm, "power_w_max": float(max(pw)) if pw else None,
+                "samples": len(sm), "reasons": reasons, "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def make_inputs_device(torch, dev, B, steps_total, seed):
@@ -221,10 +243,10 @@ def run_ours(args):
 
     # ---- the only communication of the whole run: gather final states + error statistics (NCCL over NVLink) ----
     if world > 1:
-        gathered = torch.empty((world * B, LEN), device=dev, dtype=torch.float64)
-        dist.all_gather_into_tensor(gathered, xs)
-        stats = torch.tensor([float(bad)], device=dev, dtype=torch.float64)
-        dist.all_reduce(stats)
+        from shermbot_navigation_b200 import shard
+        gathered = shard.gather_states(xs, world * B)
+        assert gathered.shape == (world * B, LEN)
+        stats = shard.allreduce_stats(torch.tensor([float(bad)], device=dev, dtype=torch.float64))
         bad = int(stats.item())
 
     out = None
@@ -249,11 +271,12 @@ def run_ours(args):
                        "batched_steps_per_s": value / (world * B) if B else None,
                        "l2": f"inputs larger than L2: filter state {B * (LEN + LEN * LEN) * 8 / 1e6:.0f} MB per GPU is streamed every step (L2 126 MB)",
                        "parallelism": f"filters sharded {world}x, no data-path collective; final NCCL all_gather of states"},
-            "clocks": clocks, "gpu_launches": K, "bad_filters": bad,
+            "clocks": clocks, "gpu_launches": (2 * K if args.mode == "fast" else K), "bad_filters": bad,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_filter_step": BYTES_PER_FILTER_STEP,
-                         "kernel": "k_ekf_fast_step" if args.mode == "fast" else "k_ekf_strict<kOpStep>", "launch_us": per_launch_s * 1e6},
+                         "kernel": "k_ekf_fast_step<12> (+ k_ekf_strict_list over the first-touch work list, empty in steady state)" if args.mode == "fast" else "k_ekf_strict<kOpStep>",
+                         "launch_us": per_launch_s * 1e6, "launches_per_step": 2 if args.mode == "fast" else 1},
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
@@ -335,7 +358,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])

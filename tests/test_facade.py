@@ -1,0 +1,69 @@
+"""The C++ facade (include/nuslam_b200/slam_library.hpp) keeps the reference's class / function signatures: a caller written
+like nuslam/src/slam.cpp:262-319 compiles and links against libnuslam_b200.so (CPU check) and reproduces the oracle (GPU check)."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+EXE = ROOT / "build" / "facade_main"
+
+
+def build_facade(cuda_lib):
+    EXE.parent.mkdir(exist_ok=True)
+    libdir = cuda_lib.LIB_PATH.parent
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", f"-I{ROOT / 'include'}", "-o", str(EXE), str(ROOT / "tests" / "facade_main.cpp"),
+           f"-L{libdir}", "-lnuslam_b200", f"-Wl,-rpath,{libdir}"]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+
+
+def test_facade_compiles_and_links(cuda_lib):
+    build_facade(cuda_lib)
+    assert EXE.exists()
+
+
+@pytest.mark.gpu
+def test_facade_matches_oracle(cuda_lib, orc):
+    build_facade(cuda_lib)
+    out = subprocess.run([str(EXE)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = {}
+    ids = []
+    for ln in out.stdout.splitlines():
+        tok = ln.split()
+        if tok[0] == "ID":
+            ids.append(int(tok[3]))
+        else:
+            lines.setdefault(tok[0], []).append(tok[1:])
+    # the same sequence of calls on the oracle (slam.cpp:262-319)
+    f = orc.ekf(3, np.array([0.1, -0.2, 0.3]), np.zeros(6), 0.1 * np.eye(3), 0.001 * np.eye(2))
+    want_ids = []
+    zs = [np.array([1.0, 0.1]), np.array([2.0, -1.0]), np.array([3.0, 2.0])]
+    for step in range(3):
+        f.predict(0.02, 0.007)
+        seen0 = f.get()[2]
+        for z in zs:
+            i = f.associate(z)
+            want_ids.append(i)
+            if i > seen0:
+                f.init_landmark(z, i)
+            elif i < 0:
+                continue
+            f.update(z, i)
+    x, S, seen = f.get()
+    assert ids == want_ids
+    gx = np.array([float(v) for v in lines["X"][0]])
+    gS = np.array([float(v) for v in lines["S"][0]]).reshape(9, 9).T     # printed column-major
+    assert np.abs(gx - x).max() <= 1e-9 * np.abs(x).max()
+    assert np.abs(gS - S).max() <= 1e-9 * np.abs(S).max()
+    assert int(lines["SEEN"][0][0]) == seen
+    c2p = [float(v) for v in lines["C2P"][0]]
+    assert c2p[0] == 5.0 and abs(c2p[1] - np.arctan2(-4.0, 3.0)) < 1e-15
+    zh = np.array([float(v) for v in lines["ZHAT"][0]])
+    assert np.abs(zh - f.zhat(1)).max() < 1e-13
+    assert lines["FULL"][0][0] == "EXC"                                    # map full: std::logic_error, as Armadillo's bounds check
+    fit = lines["FIT"][0]
+    assert int(fit[0]) == 0 and abs(float(fit[1]) - 4.615482) < 1e-4 and abs(float(fit[3]) / 2 - 4.827575) < 1e-4   # scale.x = 2R
+    assert lines["CLUSTERS"][0] == ["1", "7"] and lines["CIRCLE"][0] == ["1"]
