@@ -64,7 +64,12 @@ enum
 enum
 {
     NUSLAM_MODE_STRICT = 0,
-    NUSLAM_MODE_FAST = 1
+    NUSLAM_MODE_FAST = 1,
+    /* LARGE-MAP mode (BASELINE.json config 5): Sigma stays in HBM; the m updates of a step are DELAYED -- each needs only
+     * rows / columns {theta, x, y, c, c+1} of the current Sigma, formed on the fly from Sigma_0 and the stored K_u, W_u -- and
+     * applied in ONE rank-2m pass on the fp64 tensor pipe: one read + one write of Sigma per scan whatever m is. Selected
+     * automatically when the state is too long for the on-chip kernels (n_landmarks > ~70); known correspondence only. */
+    NUSLAM_MODE_LARGE = 2
 };
 
 /* ---- per-filter status word (bit mask, sticky); where the reference throws, the engine flags ---- */

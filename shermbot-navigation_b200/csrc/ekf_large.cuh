@@ -1,0 +1,389 @@
+// ekf_large.cuh -- LARGE-MAP mode: a few filters whose Sigma does not fit on chip (e.g. 4096 landmarks: len 8195, Sigma 537 MB).
+//
+// One scan with m measurements costs ONE read + ONE write of Sigma, whatever m is (BASELINE.json config 5):
+//   predict   (slam_library.cpp:65-108): A = I + B touches rows/columns 1, 2 only                     -> O(len) kernel
+//   updates   (slam_library.cpp:263-282) are DELAYED: with Sigma_i = Sigma_0 - sum_{u<i} K_u W_u  (K_u len x 2, W_u 2 x len),
+//             update i needs only rows/columns {th, x, y, c, c+1} of Sigma_i, which are formed on the fly from Sigma_0 and
+//             the stored K_u, W_u (O(len * i) per update): W_i = H Sigma_i, P_i = Sigma_i H^T, S = W_i H^T + R,
+//             K_i = P_i S^-1, x += K_i dz                                                               -> 2 small kernels / update
+//   one pass  Sigma <- Sigma_0 - [K_0 .. K_{m-1}] [W_0; ..; W_{m-1}]: a rank-2m update on the fp64 tensor pipe (DMMA m8n8k4,
+//             accumulators initialised from Sigma, 32 x 32 tile per warp), HBM-bound: 16 len^2 bytes.
+// The same kernels with m = 1 give the immediate (sequential) form used for the single `update` call and as the in-engine
+// cross-check of the delayed form. Arithmetic: plain fp64 with FMAs in the reference's expressions (H entries by division and
+// sqrt as slam_library.cpp:172-183, double normalize_angle of z_hat as :20,:157); parity <= 1e-9 after the first touch of a
+// landmark (the first touch itself cancels catastrophically in the reference).
+#pragma once
+#include "ekf_strict.cuh"
+
+namespace nuslam
+{
+
+constexpr int kLargeMMax = 16;   // measurements per delayed pass (rank 32)
+
+struct LargeParams
+{
+    int64_t batch;
+    int len, n;
+    double * x;        // B x len (current)
+    double * x2;       // B x len (ping-pong)
+    double * sigma;    // B x len x len
+    double * U;        // B x (2 kLargeMMax) x len : K_u columns, U[(2u+a) * len + j] = K_u(j, a)
+    double * V;        // B x (2 kLargeMMax) x len : W_u rows,    V[(2u+a) * len + j] = W_u(a, j)
+    double * P;        // B x 2 x len              : P_i = Sigma_i H^T of the update in flight
+    int32_t * status;
+    double Q[9], R[4];
+};
+
+// predict, part 1: pose and the two Jacobian entries (predictEstimate :71-94, getA :127-148 with theta AFTER the motion
+// update), one thread per filter; b10, b20 go to the head of the P scratch.
+__global__ void k_large_predict_pose(const LargeParams p, const double * __restrict__ twists)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.batch) return;
+    double * x = p.x + (int64_t) b * p.len;
+    double * scratch = p.P + (int64_t) b * 2 * p.len;
+    const double dth = twists[3 * b], dx = twists[3 * b + 1];
+    const double theta = x[0];
+    double s0, c0, th1, x1, y1, b10, b20;
+    sincos(theta, &s0, &c0);
+    if (dth == 0.0)
+    {
+        th1 = add_(theta, 0.0);
+        x1 = add_(x[1], mul_(dx, c0));
+        y1 = add_(x[2], mul_(dx, s0));
+        b10 = mul_(-dx, s0);
+        b20 = mul_(dx, c0);
+    }
+    else
+    {
+        const double q = div_(dx, dth);
+        double s1, c1, s3, c3;
+        th1 = add_(theta, dth);
+        sincos(th1, &s1, &c1);
+        x1 = add_(x[1], add_(mul_(-q, s0), mul_(q, s1)));
+        y1 = add_(x[2], sub_(mul_(q, c0), mul_(q, c1)));
+        sincos(add_(th1, dth), &s3, &c3);
+        b10 = add_(mul_(-q, c1), mul_(q, c3));
+        b20 = add_(mul_(-q, s1), mul_(q, s3));
+    }
+    x[0] = th1;
+    x[1] = x1;
+    x[2] = y1;
+    scratch[0] = b10;
+    scratch[1] = b20;
+}
+
+// predict, part 2: Sigma <- A Sigma A^T + Q_bar in the oracle's operation order; only rows / columns 1, 2 change. Thread j >= 3
+// owns entries (1, j), (2, j), (j, 1), (j, 2); thread 0 the 3 x 3 robot block (T = A Sigma, then U = T A^T, then + Q).
+__global__ void k_large_predict_cov(const LargeParams p)
+{
+    const int b = blockIdx.y;
+    const int len = p.len;
+    double * S = p.sigma + (int64_t) b * len * len;
+    const double * scratch = p.P + (int64_t) b * 2 * len;
+    const double b10 = scratch[0], b20 = scratch[1];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 3 && j < len)
+    {
+        const double t0 = S[0 + (int64_t) j * len];
+        S[1 + (int64_t) j * len] = add_(mul_(b10, t0), S[1 + (int64_t) j * len]);
+        S[2 + (int64_t) j * len] = add_(mul_(b20, t0), S[2 + (int64_t) j * len]);
+        const double u0 = S[j];
+        S[j + (int64_t) len] = add_(mul_(u0, b10), S[j + (int64_t) len]);
+        S[j + 2 * (int64_t) len] = add_(mul_(u0, b20), S[j + 2 * (int64_t) len]);
+    }
+    if (j == 0)
+    {
+        double B3[3][3];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) B3[r][c] = S[r + (int64_t) c * len];
+        for (int c = 0; c < 3; ++c)
+        {
+            B3[1][c] = add_(mul_(b10, B3[0][c]), B3[1][c]);
+            B3[2][c] = add_(mul_(b20, B3[0][c]), B3[2][c]);
+        }
+        for (int r = 0; r < 3; ++r)
+        {
+            B3[r][1] = add_(mul_(B3[r][0], b10), B3[r][1]);
+            B3[r][2] = add_(mul_(B3[r][0], b20), B3[r][2]);
+        }
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) S[r + (int64_t) c * len] = add_(B3[r][c], p.Q[r + 3 * c]);
+    }
+}
+
+inline cudaError_t launch_large_predict(const LargeParams & p, const double * twists, cudaStream_t st)
+{
+    k_large_predict_pose<<<(unsigned) ((p.batch + 63) / 64), 64, 0, st>>>(p, twists);
+    k_large_predict_cov<<<dim3((p.len + 255) / 256, (unsigned) p.batch), 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// H entries and z_hat at state x for landmark slot c (reference expressions)
+struct LargeModel
+{
+    double h[2][5];   // H(a, q) at q = {0, 1, 2, c, c+1}
+    double zr, zb;
+};
+__device__ __forceinline__ LargeModel large_model(const double * x, int c)
+{
+    LargeModel mdl;
+    HEntries H;
+    measurement_model(x, c, H, mdl.zr, mdl.zb);
+    mdl.h[0][0] = 0.0;
+    mdl.h[0][1] = H.h01;
+    mdl.h[0][2] = H.h02;
+    mdl.h[0][3] = H.h0c;
+    mdl.h[0][4] = H.h0c1;
+    mdl.h[1][0] = -1.0;
+    mdl.h[1][1] = H.h11;
+    mdl.h[1][2] = H.h12;
+    mdl.h[1][3] = H.h1c;
+    mdl.h[1][4] = H.h1c1;
+    return mdl;
+}
+
+// W_i = H Sigma_i (2 x len) and P_i = Sigma_i H^T (len x 2) for update slot i of the pass; thread j owns index j.
+__global__ void __launch_bounds__(256) k_large_wp(const LargeParams p, const int32_t * __restrict__ ids, int m, int i)
+{
+    const int b = blockIdx.y;
+    const int len = p.len;
+    const int id = ids[b * m + i];
+    if (id < 1 || id > p.n) return;
+    const int c = 3 + 2 * (id - 1);
+    const double * x = p.x + (int64_t) b * len;
+    const double * S = p.sigma + (int64_t) b * len * len;
+    const double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
+    double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
+    double * P = p.P + (int64_t) b * 2 * len;
+    const int idx[5] = {0, 1, 2, c, c + 1};
+    // K_u at the five rows and W_u at the five columns of every earlier update of the pass: shared by the block
+    __shared__ double ku[2 * kLargeMMax][5], wu[2 * kLargeMMax][5];
+    for (int k = threadIdx.x; k < 2 * i * 5; k += blockDim.x)
+    {
+        const int r = k / 5, q = k % 5;
+        ku[r][q] = U[(int64_t) r * len + idx[q]];
+        wu[r][q] = V[(int64_t) r * len + idx[q]];
+    }
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= len) return;
+    const LargeModel mdl = large_model(x, c);
+    double row[5], col[5];   // Sigma_i(idx[q], j) and Sigma_i(j, idx[q])
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+    {
+        row[q] = S[idx[q] + (int64_t) j * len];
+        col[q] = S[j + (int64_t) idx[q] * len];
+    }
+    for (int r = 0; r < 2 * i; ++r)
+    {
+        const double wj = V[(int64_t) r * len + j], kj = U[(int64_t) r * len + j];
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+        {
+            row[q] = fma(-ku[r][q], wj, row[q]);
+            col[q] = fma(-kj, wu[r][q], col[q]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+    {
+        double w = 0.0, pp = 0.0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+        {
+            w = fma(mdl.h[a][q], row[q], w);
+            pp = fma(col[q], mdl.h[a][q], pp);
+        }
+        V[(int64_t) (2 * i + a) * len + j] = w;
+        P[(int64_t) a * len + j] = pp;
+    }
+}
+
+// K_i = P_i S^-1, x_new = x + K_i dz (slam_library.cpp:270-276); thread j owns index j, every thread forms the 2 x 2 part.
+__global__ void __launch_bounds__(256) k_large_gain(const LargeParams p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
+                                                    const double * __restrict__ x_old, double * __restrict__ x_new)
+{
+    const int b = blockIdx.y;
+    const int len = p.len;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= len) return;
+    const int id = ids[b * m + i];
+    const double * x = x_old + (int64_t) b * len;
+    double * xo = x_new + (int64_t) b * len;
+    double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
+    const double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
+    const double * P = p.P + (int64_t) b * 2 * len;
+    if (id < 1 || id > p.n)
+    {
+        // no measurement in this slot: K = 0, W = 0 contribute nothing to the pass
+        xo[j] = x[j];   // U, V of the slot were cleared at the start of the pass
+        if (j == 0 && id > p.n) p.status[b] |= kStatusBadId;
+        return;
+    }
+    const int c = 3 + 2 * (id - 1);
+    const int idx[5] = {0, 1, 2, c, c + 1};
+    const LargeModel mdl = large_model(x, c);
+    double s[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+        {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) acc = fma(V[(int64_t) (2 * i + a) * len + idx[q]], mdl.h[e][q], acc);
+            s[a][e] = acc + p.R[a + 2 * e];
+        }
+    const double det = s[0][0] * s[1][1] - s[0][1] * s[1][0];
+    if (det == 0.0)
+    {
+        U[(int64_t) (2 * i) * len + j] = 0.0;
+        U[(int64_t) (2 * i + 1) * len + j] = 0.0;
+        xo[j] = x[j];
+        if (j == 0) p.status[b] |= kStatusSingular;
+        return;
+    }
+    const double i00 = s[1][1] / det, i01 = -s[0][1] / det, i10 = -s[1][0] / det, i11 = s[0][0] / det;
+    const double p0 = P[j], p1 = P[(int64_t) len + j];
+    const double k0 = p0 * i00 + p1 * i10, k1 = p0 * i01 + p1 * i11;
+    U[(int64_t) (2 * i) * len + j] = k0;
+    U[(int64_t) (2 * i + 1) * len + j] = k1;
+    const double dz0 = z[(int64_t) (b * m + i) * 2] - mdl.zr, dz1 = z[(int64_t) (b * m + i) * 2 + 1] - mdl.zb;   // :272, no wrap
+    double xn = x[j] + (k0 * dz0 + k1 * dz1);
+    if (j == 0) xn = normalize_angle(xn);   // :276
+    xo[j] = xn;
+}
+
+// singular / skipped slots must not leave stale W rows behind
+__global__ void k_large_clear_w(const LargeParams p, int i)
+{
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.len) return;
+    double * V = p.V + (int64_t) b * 2 * kLargeMMax * p.len;
+    double * U = p.U + (int64_t) b * 2 * kLargeMMax * p.len;
+    V[(int64_t) (2 * i) * p.len + j] = 0.0;
+    V[(int64_t) (2 * i + 1) * p.len + j] = 0.0;
+    U[(int64_t) (2 * i) * p.len + j] = 0.0;
+    U[(int64_t) (2 * i + 1) * p.len + j] = 0.0;
+}
+
+__device__ __forceinline__ void dmma884_large(double & c0, double & c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Sigma <- Sigma - K W with K = U^T (len x 2m), W = V (2m x len): CTA tile 64 x 64 (4 warps of 32 x 32), operands staged in
+// shared memory, accumulators initialised from Sigma. kk = padded 2m (multiple of 4).
+constexpr int kLargeTile = 64;
+__global__ void __launch_bounds__(128) k_large_rank_update(const LargeParams p, int kk)
+{
+    __shared__ double su[2 * kLargeMMax][kLargeTile + 1];   // -K: su[k][r]
+    __shared__ double sv[2 * kLargeMMax][kLargeTile + 1];   //  W: sv[k][c]
+    const int b = blockIdx.z;
+    const int len = p.len;
+    const int r0 = blockIdx.x * kLargeTile, c0 = blockIdx.y * kLargeTile;
+    double * S = p.sigma + (int64_t) b * len * len;
+    const double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
+    const double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
+    for (int e = threadIdx.x; e < kk * kLargeTile; e += blockDim.x)
+    {
+        const int k = e / kLargeTile, o = e % kLargeTile;
+        su[k][o] = (r0 + o < len) ? -U[(int64_t) k * len + r0 + o] : 0.0;
+        sv[k][o] = (c0 + o < len) ? V[(int64_t) k * len + c0 + o] : 0.0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wr = r0 + 32 * (warp >> 1), wc = c0 + 32 * (warp & 1);
+    double C[4][4][2];
+#pragma unroll
+    for (int br = 0; br < 4; ++br)
+#pragma unroll
+        for (int bc = 0; bc < 4; ++bc)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+            {
+                const int row = wr + 8 * br + g, col = wc + 8 * bc + 2 * t + e;
+                C[br][bc][e] = (row < len && col < len) ? __ldcs(S + (int64_t) col * len + row) : 0.0;
+            }
+    for (int k0 = 0; k0 < kk; k0 += 4)
+    {
+        double a[4], bb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            a[q] = su[k0 + t][32 * (warp >> 1) + 8 * q + g];
+            bb[q] = sv[k0 + t][32 * (warp & 1) + 8 * q + g];
+        }
+#pragma unroll
+        for (int br = 0; br < 4; ++br)
+#pragma unroll
+            for (int bc = 0; bc < 4; ++bc) dmma884_large(C[br][bc][0], C[br][bc][1], a[br], bb[bc]);
+    }
+#pragma unroll
+    for (int br = 0; br < 4; ++br)
+#pragma unroll
+        for (int bc = 0; bc < 4; ++bc)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+            {
+                const int row = wr + 8 * br + g, col = wc + 8 * bc + 2 * t + e;
+                if (row < len && col < len) __stcs(S + (int64_t) col * len + row, C[br][bc][e]);
+            }
+}
+
+// initializeLandmark (slam_library.cpp:255-261) for measurement i of the step when its id exceeds the scan's seen snapshot
+// (slam.cpp:295-297), or unconditionally (snapshot == nullptr: the single initializeLandmark call); one thread per filter.
+__global__ void k_large_init_landmark(const LargeParams p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
+                                      const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.batch) return;
+    const int id = ids[b * m + i];
+    if (id < 1) return;
+    if (id > p.n)
+    {
+        p.status[b] |= kStatusBadId;
+        return;
+    }
+    if (seen_snapshot)
+    {
+        if (id > seen[b]) seen[b] = id;   // what associateLandmark would have done to `seen`
+        if (id <= seen_snapshot[b]) return;
+    }
+    double * x = p.x + (int64_t) b * p.len;
+    const int c = 3 + 2 * (id - 1);
+    const double z0 = z[(int64_t) (b * m + i) * 2], z1 = z[(int64_t) (b * m + i) * 2 + 1];
+    double sn, cs;
+    sincos(add_(z1, x[0]), &sn, &cs);
+    x[c] = add_(x[1], mul_(z0, cs));
+    x[c + 1] = add_(x[2], mul_(z0, sn));
+}
+
+// host: one delayed pass over measurements [i0, i0 + cnt) of the step (cnt <= kLargeMMax); x ping-pongs between p.x and p.x2
+inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const int32_t * ids, int m, int i0, int cnt,
+                                        const int32_t * seen_snapshot, int32_t * seen, cudaStream_t st)
+{
+    const int threads = 256;
+    const dim3 grid((p.len + threads - 1) / threads, (unsigned) p.batch);
+    const int kk = (2 * cnt + 3) & ~3;
+    for (int k = 0; k < kk / 2; ++k) k_large_clear_w<<<grid, threads, 0, st>>>(p, k);   // empty slots contribute nothing
+    for (int k = 0; k < cnt; ++k)
+    {
+        // slot k of the pass holds measurement i0 + k: the kernels index ids / z with (b * m + k) from the shifted base pointers
+        if (seen) k_large_init_landmark<<<(unsigned) ((p.batch + 63) / 64), 64, 0, st>>>(p, z + 2 * (int64_t) i0, ids + i0, m, k, seen_snapshot, seen);
+        k_large_wp<<<grid, threads, 0, st>>>(p, ids + i0, m, k);
+        k_large_gain<<<grid, threads, 0, st>>>(p, z + 2 * (int64_t) i0, ids + i0, m, k, p.x, p.x2);
+        double * tmp = p.x;
+        p.x = p.x2;
+        p.x2 = tmp;
+    }
+    const unsigned tiles = (p.len + kLargeTile - 1) / kLargeTile;
+    k_large_rank_update<<<dim3(tiles, tiles, (unsigned) p.batch), 128, 0, st>>>(p, kk);
+    return cudaGetLastError();
+}
+
+}   // namespace nuslam

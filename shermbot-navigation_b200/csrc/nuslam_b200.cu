@@ -16,6 +16,7 @@
 #include "ekf_misc.cuh"
 #include "ekf_fast.cuh"
 #include "scan_detect.cuh"
+#include "ekf_large.cuh"
 
 namespace
 {
@@ -87,6 +88,13 @@ struct nuslam_ekf
     // staging for NUSLAM_HOST calls
     DevBuf s_tw, s_z, s_ids, s_ids_out, s_misc;
     // FAST mode: filters whose step contains a first touch are handed to the strict kernel through this list
+    // LARGE-MAP mode (state too long for the on-chip batched kernels): delayed-update scratch, see ekf_large.cuh
+    bool large = false;
+    double * lg_x2 = nullptr;
+    double * lg_U = nullptr;
+    double * lg_V = nullptr;
+    double * lg_P = nullptr;
+    int32_t * lg_seen_snap = nullptr;
     int32_t * worklist = nullptr;   // batch entries
     int32_t * wl_count = nullptr;   // [0] = entries, [1] = finished blocks of the list kernel
     size_t strict_smem = 0;   // per-warp shared memory of the strict kernels, bytes
@@ -182,6 +190,43 @@ int launch_fast_then_strict(nuslam_ekf * h, const nuslam::EkfParams & p, bool do
     return NUSLAM_OK;
 }
 
+nuslam::LargeParams make_large_params(nuslam_ekf * h)
+{
+    nuslam::LargeParams p;
+    memset(&p, 0, sizeof(p));
+    p.batch = h->batch;
+    p.len = h->len;
+    p.n = h->cfg.n_landmarks;
+    p.x = h->x;
+    p.x2 = h->lg_x2;
+    p.sigma = h->sigma;
+    p.U = h->lg_U;
+    p.V = h->lg_V;
+    p.P = h->lg_P;
+    p.status = h->status;
+    memcpy(p.Q, h->cfg.Q, sizeof(p.Q));
+    memcpy(p.R, h->cfg.R, sizeof(p.R));
+    return p;
+}
+
+// LARGE-MAP mode: m measurements in delayed passes of at most kLargeMMax; `step_protocol` adds slam.cpp:295-297
+// (initializeLandmark for ids above the scan's seen snapshot, seen = max(seen, id))
+int large_updates(nuslam_ekf * h, const double * z, const int32_t * ids, int m, bool step_protocol)
+{
+    nuslam::LargeParams p = make_large_params(h);
+    if (step_protocol) CU(cudaMemcpyAsync(h->lg_seen_snap, h->seen, sizeof(int32_t) * h->batch, cudaMemcpyDeviceToDevice, h->stream));
+    for (int i0 = 0; i0 < m; i0 += nuslam::kLargeMMax)
+    {
+        const int cnt = (m - i0 < nuslam::kLargeMMax) ? m - i0 : nuslam::kLargeMMax;
+        cudaError_t e = nuslam::launch_large_updates(p, z, ids, m, i0, cnt, step_protocol ? h->lg_seen_snap : nullptr,
+                                                     step_protocol ? h->seen : nullptr, h->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "large-map update pass");
+    }
+    // x ping-pongs between the state buffer and the scratch: leave the result in the state buffer
+    if (p.x != h->x) CU(cudaMemcpyAsync(h->x, p.x, sizeof(double) * (size_t) h->len * h->batch, cudaMemcpyDeviceToDevice, h->stream));
+    return NUSLAM_OK;
+}
+
 int finish(nuslam_ekf * h, int mem)
 {
     if (mem == NUSLAM_HOST) CU(cudaStreamSynchronize(h->stream));
@@ -211,7 +256,7 @@ int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, 
 {
     if (!cfg || !out) return fail(NUSLAM_ERR_INVALID, "null config or output pointer");
     if (cfg->n_landmarks < 1 || batch < 1) return fail(NUSLAM_ERR_INVALID, "n_landmarks and batch must be >= 1");
-    if (cfg->mode != NUSLAM_MODE_STRICT && cfg->mode != NUSLAM_MODE_FAST) return fail(NUSLAM_ERR_INVALID, "unknown mode");
+    if (cfg->mode != NUSLAM_MODE_STRICT && cfg->mode != NUSLAM_MODE_FAST && cfg->mode != NUSLAM_MODE_LARGE) return fail(NUSLAM_ERR_INVALID, "unknown mode");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount (this engine has no CPU path)");
@@ -231,12 +276,8 @@ int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, 
     h->strict_smem = sizeof(double) * (size_t) nuslam::strict_smem_doubles(h->len);
     h->strict_warps = 4;
     while (h->strict_warps > 1 && h->strict_smem * h->strict_warps > 200 * 1024) h->strict_warps /= 2;
-    if (h->strict_smem * h->strict_warps > (size_t) prop.sharedMemPerBlockOptin)
-    {
-        delete h;
-        return fail(NUSLAM_ERR_UNSUPPORTED, "state too long for the shared-memory batched path (large-map mode required)");
-    }
-    if (cfg->mode == NUSLAM_MODE_FAST && !nuslam::fast_supported(cfg->n_landmarks))
+    if (cfg->mode == NUSLAM_MODE_LARGE || h->strict_smem * h->strict_warps > (size_t) prop.sharedMemPerBlockOptin) h->large = true;
+    if (!h->large && cfg->mode == NUSLAM_MODE_FAST && !nuslam::fast_supported(cfg->n_landmarks))
     {
         delete h;
         return fail(NUSLAM_ERR_UNSUPPORTED, "FAST mode is instantiated for n_landmarks in {6, 12} only");
@@ -271,6 +312,19 @@ int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, 
         return fail(NUSLAM_ERR_NOMEM, "device allocation of the filter state failed");
     }
     h->own_state = true;
+    if (h->large)
+    {
+        cudaError_t l1 = cudaMalloc(&h->lg_x2, sizeof(double) * l * batch);
+        cudaError_t l2 = cudaMalloc(&h->lg_U, sizeof(double) * 2 * nuslam::kLargeMMax * l * batch);
+        cudaError_t l3 = cudaMalloc(&h->lg_V, sizeof(double) * 2 * nuslam::kLargeMMax * l * batch);
+        cudaError_t l4 = cudaMalloc(&h->lg_P, sizeof(double) * 2 * l * batch);
+        cudaError_t l5 = cudaMalloc(&h->lg_seen_snap, sizeof(int32_t) * batch);
+        if (l1 != cudaSuccess || l2 != cudaSuccess || l3 != cudaSuccess || l4 != cudaSuccess || l5 != cudaSuccess)
+        {
+            nuslam_ekf_destroy(h);
+            return fail(NUSLAM_ERR_NOMEM, "device allocation of the large-map scratch failed");
+        }
+    }
     cudaMemsetAsync(h->x, 0, sizeof(double) * l * batch, h->stream);
     cudaMemsetAsync(h->sigma, 0, sizeof(double) * l * l * batch, h->stream);
     cudaMemsetAsync(h->seen, 0, sizeof(int32_t) * batch, h->stream);
@@ -291,6 +345,11 @@ int nuslam_ekf_destroy(nuslam_ekf * h)
         if (h->seen) cudaFree(h->seen);
         if (h->status) cudaFree(h->status);
     }
+    if (h->lg_x2) cudaFree(h->lg_x2);
+    if (h->lg_U) cudaFree(h->lg_U);
+    if (h->lg_V) cudaFree(h->lg_V);
+    if (h->lg_P) cudaFree(h->lg_P);
+    if (h->lg_seen_snap) cudaFree(h->lg_seen_snap);
     if (h->worklist) cudaFree(h->worklist);
     if (h->wl_count) cudaFree(h->wl_count);
     h->s_tw.release();
@@ -385,6 +444,12 @@ int nuslam_ekf_predict(nuslam_ekf * h, const double * twists, int mem)
     nuslam::EkfParams p = make_params(h);
     int rc = stage_in(h, h->s_tw, twists, (size_t) h->batch * 3, mem, &p.twists);
     if (rc) return rc;
+    if (h->large)
+    {
+        cudaError_t e = nuslam::launch_large_predict(make_large_params(h), p.twists, h->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "large-map predict");
+        return finish(h, mem);
+    }
     rc = launch_strict<nuslam::kOpPredict>(h, p);   // predict is O(len) in either mode: the strict order costs nothing extra
     if (rc) return rc;
     return finish(h, mem);
@@ -393,6 +458,7 @@ int nuslam_ekf_predict(nuslam_ekf * h, const double * twists, int mem)
 int nuslam_ekf_associate(nuslam_ekf * h, const double * z, int32_t * id_out, int mem)
 {
     if (!h || !z || !id_out) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (h->large) return fail(NUSLAM_ERR_UNSUPPORTED, "large-map mode covers known correspondence only (associateLandmark is not built yet)");
     if (select_device(h)) return NUSLAM_ERR_CUDA;
     nuslam::EkfParams p = make_params(h);
     p.m = 1;
@@ -422,6 +488,12 @@ int nuslam_ekf_initialize_landmark(nuslam_ekf * h, const double * z, const int32
     if (rc) return rc;
     rc = stage_in(h, h->s_ids, id, (size_t) h->batch, mem, &p.ids);
     if (rc) return rc;
+    if (h->large)
+    {
+        nuslam::k_large_init_landmark<<<(unsigned) ((h->batch + 63) / 64), 64, 0, h->stream>>>(make_large_params(h), p.z, p.ids, 1, 0, nullptr, nullptr);
+        CU(cudaGetLastError());
+        return finish(h, mem);
+    }
     rc = launch_strict<nuslam::kOpInit>(h, p);
     if (rc) return rc;
     return finish(h, mem);
@@ -437,6 +509,12 @@ int nuslam_ekf_update(nuslam_ekf * h, const double * z, const int32_t * id, int 
     if (rc) return rc;
     rc = stage_in(h, h->s_ids, id, (size_t) h->batch, mem, &p.ids);
     if (rc) return rc;
+    if (h->large)
+    {
+        rc = large_updates(h, p.z, p.ids, 1, /*step_protocol=*/false);
+        if (rc) return rc;
+        return finish(h, mem);
+    }
     if (h->cfg.mode == NUSLAM_MODE_FAST)
     {
         p.twists = nullptr;   // update only
@@ -500,7 +578,19 @@ int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, con
         if (rc) return rc;
         p.ids_out = static_cast<int32_t *>(h->s_ids_out.p);
     }
-    if (h->cfg.mode == NUSLAM_MODE_FAST && p.ids != nullptr)
+    if (h->large)
+    {
+        if (!p.ids) return fail(NUSLAM_ERR_UNSUPPORTED, "large-map mode covers known correspondence only (associateLandmark is not built yet)");
+        cudaError_t e = nuslam::launch_large_predict(make_large_params(h), p.twists, h->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "large-map predict");
+        if (m > 0)
+        {
+            rc = large_updates(h, p.z, p.ids, m, /*step_protocol=*/true);
+            if (rc) return rc;
+        }
+        if (ids_out && m > 0) CU(cudaMemcpyAsync(p.ids_out, p.ids, sizeof(int32_t) * h->batch * m, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    else if (h->cfg.mode == NUSLAM_MODE_FAST && p.ids != nullptr)
     {
         rc = launch_fast_then_strict<nuslam::kOpStep>(h, p, /*do_predict=*/true);
         if (rc) return rc;

@@ -23,7 +23,7 @@ import os as _os
 LIB_PATH = Path(_os.environ.get("NUSLAM_B200_LIB", HERE / "libnuslam_b200.so"))   # override only for kernel experiments
 
 NUSLAM_HOST, NUSLAM_DEVICE = 0, 1
-MODE_STRICT, MODE_FAST = 0, 1
+MODE_STRICT, MODE_FAST, MODE_LARGE = 0, 1, 2
 FILTER_MAP_FULL, FILTER_SINGULAR, FILTER_BAD_ID = 1, 2, 4
 ID_EXCEPTION = -1000
 SCAN_UB = -2000
@@ -134,7 +134,7 @@ class BatchedExtendedKalman:
         self.device = int(device)
         cfg = EkfConfig()
         l.nuslam_ekf_default_config(C.byref(cfg), self.n)
-        cfg.mode = {"strict": MODE_STRICT, "fast": MODE_FAST}[mode]
+        cfg.mode = {"strict": MODE_STRICT, "fast": MODE_FAST, "large": MODE_LARGE}[mode]
         if Q is not None:
             cfg.Q[:] = list(np.asarray(Q, dtype=np.float64).reshape(3, 3).T.ravel())
         if R is not None:

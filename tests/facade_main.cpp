@@ -6,7 +6,7 @@
 int main()
 {
     using namespace slam_library;
-    colvec robot(3), map(6);
+    colvec robot(3), map(8);
     robot(0) = 0.1;
     robot(1) = -0.2;
     robot(2) = 0.3;
@@ -66,18 +66,27 @@ int main()
     }
     circle_fit::Marker mk = circle_fit::circleFit(data);
     printf("FIT %d %.17g %.17g %.17g\n", mk.id, mk.pose.position.x, mk.pose.position.y, mk.scale.x);
-    // full map: the reference's bounds check throws (slam_library.cpp:206); the facade throws std::logic_error too
-    try
+    // a fourth landmark fills the map (n = 4); the next new one makes the reference's bounds check throw
+    // (slam_library.cpp:206): the facade throws std::logic_error too
     {
         colvec z(2);
         z(0) = 0.3;
         z(1) = -2.5;
         const int id = ekf.associateLandmark(z);
-        printf("FULL id %d\n", id);
-    }
-    catch (const std::logic_error & e)
-    {
-        printf("FULL EXC %s\n", e.what());
+        printf("FOURTH %d\n", id);
+        ekf.initializeLandmark(z, id);
+        ekf.update(tw, z, id);
+        z(0) = 5.0;
+        z(1) = 3.0;
+        try
+        {
+            const int id5 = ekf.associateLandmark(z);
+            printf("FULL id %d\n", id5);
+        }
+        catch (const std::logic_error & e)
+        {
+            printf("FULL EXC %s\n", e.what());
+        }
     }
     std::vector<float> ranges(360, 2.0f);
     for (int i = 40; i < 47; ++i) ranges[i] = 0.5f + 0.002f * (i - 43) * (i - 43);

@@ -38,7 +38,7 @@ def test_facade_matches_oracle(cuda_lib, orc):
         else:
             lines.setdefault(tok[0], []).append(tok[1:])
     # the same sequence of calls on the oracle (slam.cpp:262-319)
-    f = orc.ekf(3, np.array([0.1, -0.2, 0.3]), np.zeros(6), 0.1 * np.eye(3), 0.001 * np.eye(2))
+    f = orc.ekf(4, np.array([0.1, -0.2, 0.3]), np.zeros(8), 0.1 * np.eye(3), 0.001 * np.eye(2))
     want_ids = []
     zs = [np.array([1.0, 0.1]), np.array([2.0, -1.0]), np.array([3.0, 2.0])]
     for step in range(3):
@@ -55,7 +55,7 @@ def test_facade_matches_oracle(cuda_lib, orc):
     x, S, seen = f.get()
     assert ids == want_ids
     gx = np.array([float(v) for v in lines["X"][0]])
-    gS = np.array([float(v) for v in lines["S"][0]]).reshape(9, 9).T     # printed column-major
+    gS = np.array([float(v) for v in lines["S"][0]]).reshape(11, 11).T   # printed column-major
     assert np.abs(gx - x).max() <= 1e-9 * np.abs(x).max()
     assert np.abs(gS - S).max() <= 1e-9 * np.abs(S).max()
     assert int(lines["SEEN"][0][0]) == seen
@@ -63,6 +63,7 @@ def test_facade_matches_oracle(cuda_lib, orc):
     assert c2p[0] == 5.0 and abs(c2p[1] - np.arctan2(-4.0, 3.0)) < 1e-15
     zh = np.array([float(v) for v in lines["ZHAT"][0]])
     assert np.abs(zh - f.zhat(1)).max() < 1e-13
+    assert int(lines["FOURTH"][0][0]) == f.associate(np.array([0.3, -2.5])) == 4
     assert lines["FULL"][0][0] == "EXC"                                    # map full: std::logic_error, as Armadillo's bounds check
     fit = lines["FIT"][0]
     assert int(fit[0]) == 0 and abs(float(fit[1]) - 4.615482) < 1e-4 and abs(float(fit[3]) / 2 - 4.827575) < 1e-4   # scale.x = 2R

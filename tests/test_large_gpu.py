@@ -1,0 +1,132 @@
+"""GPU parity tests of the LARGE-MAP mode (BASELINE.json config 5): delayed rank-2m updates on the fp64 tensor pipe.
+
+Protocol: parity against the oracle at len in {27, 131, 515} after the first touch of the measured
+landmarks (the first touch cancels catastrophically in the reference, Appendix B), <= 1e-9; at 4096 landmarks (len 8195) the
+delayed pass against the engine's own sequential (one pass per measurement) form."""
+import numpy as np
+import pytest
+
+from shermbot_navigation_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def rel_max(a, b):
+    return np.abs(a - b).max() / max(np.abs(a).max(), np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("n,m,T,B", [(12, 12, 6, 3), (64, 20, 4, 2), (256, 6, 3, 1)])
+def test_large_mode_matches_oracle(cuda_lib, orc, n, m, T, B):
+    sc = synth.ekf_scenario(B, T + 1, n=n, seed=61, geometry="benign")
+    # the same m landmarks are measured every step (the others keep their INT_MAX prior and are never touched)
+    pick = np.linspace(0, n - 1, m).astype(int)
+    z = np.ascontiguousarray(sc["z"][:, :, pick])
+    ids = np.ascontiguousarray(sc["ids"][:, :, pick])
+    first = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][:1], z[:1], ids[:1])
+    full = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"], z, ids)
+    eng = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="large")
+    eng.set_state(first["x"], first["sigma"], first["seen"])
+    for t in range(1, T + 1):
+        eng.step(sc["twists"][t], z[t], ids[t])
+    x, s, seen, status = eng.get_state()
+    ex = rel_max(x, full["x"])
+    # compare the block of the robot and the measured landmarks (the others keep INT_MAX on their diagonal, which would
+    # dominate a max-norm), and separately everything else exactly
+    sel = np.concatenate([[0, 1, 2]] + [[3 + 2 * k, 4 + 2 * k] for k in pick])
+    es = max(rel_max(s[b][np.ix_(sel, sel)], full["sigma"][b][np.ix_(sel, sel)]) for b in range(B))
+    rest = np.setdiff1d(np.arange(3 + 2 * n), sel)
+    for b in range(B):
+        if rest.size == 0:
+            break
+        assert np.array_equal(s[b][np.ix_(rest, rest)], full["sigma"][b][np.ix_(rest, rest)])
+        assert np.abs(s[b][np.ix_(sel, rest)] - full["sigma"][b][np.ix_(sel, rest)]).max() <= 1e-9 * np.abs(full["sigma"][b][np.ix_(sel, sel)]).max()
+    print(f"[large n={n} m={m}] after {T} delayed steps: x rel {ex:.2e}, Sigma (touched block) rel {es:.2e}")
+    assert not status.any() and np.array_equal(seen, full["seen"])
+    assert ex < TOL and es < TOL
+    # single calls: predict, then update one measurement at a time (sequential form, rank-2 pass each)
+    eng.set_state(first["x"], first["sigma"], first["seen"])
+    fs = [orc.ekf(n, sc["robot0"][b], sc["map0"][b], sc["Q"], sc["R"]) for b in range(B)]
+    for b, f in enumerate(fs):
+        f.set(first["x"][b], first["sigma"][b], first["seen"][b])
+    eng.predict(sc["twists"][1])
+    for i in range(min(m, 4)):
+        eng.update(z[1][:, i], ids[1][:, i])
+    for b, f in enumerate(fs):
+        f.predict(*sc["twists"][1, b])
+        for i in range(min(m, 4)):
+            f.update(z[1][b, i], ids[1][b, i])
+    x, s, _, _ = eng.get_state()
+    xo = np.stack([f.get()[0] for f in fs])
+    so = np.stack([f.get()[1] for f in fs])
+    assert rel_max(x, xo) < TOL and max(rel_max(s[b][np.ix_(sel, sel)], so[b][np.ix_(sel, sel)]) for b in range(B)) < TOL
+
+
+def test_large_mode_initialises_new_landmarks(cuda_lib, orc):
+    """Step protocol from scratch (slam.cpp:295-297): landmarks are initialised inside the step; state matches loosely (first
+    touches), seen exactly."""
+    n, B, T = 20, 2, 3
+    sc = synth.ekf_scenario(B, T, n=n, seed=62)
+    full = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"], sc["z"], sc["ids"])
+    eng = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="large")
+    for t in range(T):
+        eng.step(sc["twists"][t], sc["z"][t], sc["ids"][t])     # m = 20 > 16: two delayed passes per step
+    x, s, seen, status = eng.get_state()
+    assert np.array_equal(seen, full["seen"]) and not status.any()
+    assert rel_max(x, full["x"]) < 1e-3
+
+
+def test_4096_landmarks_delayed_equals_sequential(cuda_lib):
+    """len 8195, Sigma 537 MB: one delayed rank-24 pass per scan against 12 sequential rank-2 passes."""
+    import torch
+    n, m = 4096, 12
+    length = 3 + 2 * n
+    rng = np.random.default_rng(7)
+    lm = rng.uniform(-3, 3, size=(n, 2))
+    robot = np.array([[0.05, -0.02, 0.01]])
+    Q, R = synth.Q_DEFAULT, synth.R_DEFAULT
+    pick = rng.choice(n, size=m, replace=False)
+    engs = []
+    for _ in range(2):
+        e = cuda_lib.BatchedExtendedKalman(robot, lm.reshape(1, -1), Q, R, mode="large")
+        engs.append(e)
+    dev = torch.device("cuda")
+    # a well-conditioned start: small diagonal Sigma (as after many observations) with mild correlations
+    x0 = torch.tensor(np.concatenate([robot[0], lm.ravel()])[None], device=dev)
+    d = torch.full((length,), 1e-3, dtype=torch.float64, device=dev)
+    d[:3] = 1e-2
+    states = []
+    for e in engs:
+        xs = x0.clone()
+        sig = torch.zeros((1, length, length), dtype=torch.float64, device=dev)
+        sig[0].diagonal().copy_(d)
+        seen = torch.full((1,), n, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        e.bind_state(xs, sig, seen, status)
+        states.append((xs, sig, seen, status))
+    ids = torch.tensor((pick + 1)[None].astype(np.int32), device=dev)
+    for t in range(3):
+        torch.cuda.synchronize()   # the engines run on their own streams: order them after torch's work and before the read below
+        tw = torch.tensor([[0.02, 0.007, 0.0]], device=dev, dtype=torch.float64)
+        px, py, th = float(states[0][0][0, 1]), float(states[0][0][0, 2]), float(states[0][0][0, 0])
+        dl = lm[pick] - np.array([px, py])
+        z = np.stack([np.hypot(dl[:, 0], dl[:, 1]) + rng.normal(0, 0.01, m),
+                      synth.wrap_pi(np.arctan2(dl[:, 1], dl[:, 0]) - th + rng.normal(0, 0.01, m))], axis=1)
+        zt = torch.tensor(z[None], device=dev)
+        engs[0].step(tw, zt, ids)                                  # delayed: one rank-24 pass
+        engs[1].predict(tw)
+        for i in range(m):                                         # sequential: twelve rank-2 passes
+            engs[1].update(zt[:, i].contiguous(), ids[:, i].contiguous())
+    torch.cuda.synchronize()
+    ex = float((states[0][0] - states[1][0]).abs().max() / states[1][0].abs().max())
+    es = float((states[0][1] - states[1][1]).abs().max() / states[1][1].abs().max())
+    moved_x = float((states[0][0] - x0).abs().max())
+    moved_s = float((states[0][1][0].diagonal() - d).abs().max() / d.max())
+    offdiag = float((states[0][1][0] - torch.diag(states[0][1][0].diagonal())).abs().max())
+    print(f"[large n=4096] delayed vs sequential after 3 scans: x rel {ex:.2e}, Sigma rel {es:.2e}; the scans moved x by {moved_x:.2e}, "
+          f"the diagonal by {moved_s:.2e} (relative), largest off-diagonal {offdiag:.2e}")
+    assert moved_x > 1e-4 and moved_s > 1e-2 and offdiag > 1e-6
+    assert ex < 1e-12 and es < 1e-11
+    assert int(states[0][3][0]) == 0 and torch.isfinite(states[0][1]).all()
+    for e in engs:
+        e.close()

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""BASELINE.json config 5: one 4096-landmark map (len 8195, Sigma 537 MB), m measurements per scan folded into one delayed
+rank-2m pass. Prints scan-updates/s and achieved GB/s against the 16 len^2-byte minimum (one read + one write of Sigma)."""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch  # noqa: E402
+from shermbot_navigation_b200 import nuslam, synth  # noqa: E402
+
+
+def main(n=4096, steps=30, warmup=5):
+    length = 3 + 2 * n
+    rng = np.random.default_rng(11)
+    lm = rng.uniform(-3, 3, size=(n, 2))
+    robot = np.zeros((1, 3))
+    dev = torch.device("cuda")
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    eng = nuslam.BatchedExtendedKalman(robot, lm.reshape(1, -1), synth.Q_DEFAULT, synth.R_DEFAULT, mode="large", stream=stream.cuda_stream)
+    xs = torch.tensor(np.concatenate([robot[0], lm.ravel()])[None], device=dev)
+    sig = torch.zeros((1, length, length), dtype=torch.float64, device=dev)
+    sig[0].diagonal().fill_(1e-3)
+    seen = torch.full((1,), n, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    eng.bind_state(xs, sig, seen, status)
+    peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+    out = []
+    for m in (1, 12, 32):
+        pick = rng.choice(n, size=m, replace=False)
+        ids = torch.tensor((pick + 1)[None].astype(np.int32), device=dev)
+        dl = lm[pick]
+        z = torch.tensor(np.stack([np.hypot(dl[:, 0], dl[:, 1]), np.arctan2(dl[:, 1], dl[:, 0])], axis=1)[None], device=dev)
+        tw = torch.tensor([[0.0, 0.0, 0.0]], device=dev, dtype=torch.float64)
+        for _ in range(warmup):
+            eng.step(tw, z, ids)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(steps):
+            eng.step(tw, z, ids)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        nbytes = 16.0 * length * length
+        out.append(dict(m=m, ms_per_scan=ms, scans_per_s=1e3 / ms, achieved_gbs=nbytes / (ms * 1e-3) / 1e9, frac_of_hbm=nbytes / (ms * 1e-3) / 1e9 / peak))
+    print(json.dumps({"workload": "config 5: 4096 landmarks, len 8195, Sigma 537 MB, delayed rank-2m DMMA pass", "algorithmic_bytes_per_scan": 16.0 * length * length,
+                      "hbm_peak_gbs": peak, "results": out, "status": int(status[0]), "finite": bool(torch.isfinite(sig).all())}))
+
+
+if __name__ == "__main__":
+    main()
