@@ -62,6 +62,44 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void * src, uint32_t byte
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t * bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// bulk async copies (TMA engine, no LSU wavefronts on the global side): global -> shared with mbarrier completion, shared -> global
+__device__ __forceinline__ void bulk_g2s(void * dst_smem, const void * src_gmem, uint32_t bytes, uint64_t * bar)
+{
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void * dst_gmem, const void * src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // D(8x8) += A(8x4) * B(4x8) on the fp64 tensor pipe; fragment layout in the header comment
 __device__ __forceinline__ void dmma884(double & c0, double & c1, double a, double b)
 {
@@ -99,64 +137,132 @@ __device__ long long g_fast_timing[16];
 #define NUSLAM_T(k)
 #endif
 
-template <int N>
+// BULK: Sigma travels HBM <-> shared memory by bulk async copies (buffer A: the NEXT filter's image, prefetched while the
+// current one is computed; buffer B: the exchange area during the updates, then the output image), so the global side costs
+// no LSU wavefronts and no exposed latency; !BULK: plain per-lane loads / stores (any 8-byte aligned Sigma).
+template <int N, bool BULK>
 __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm)
 k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ worklist, int32_t * __restrict__ wl_count)
 {
     using G = FastGeom<N>;
     constexpr int LEN = G::LEN, SIG = G::SIG, NB = G::NB;
     constexpr unsigned kFull = 0xffffffffu;
-    __shared__ FastSmem<N> f;
+    constexpr int kImg = SIG * 8;                                   // bytes of one Sigma
+    constexpr int kWin = ((kImg + 8 + 15) / 16) * 16;               // 16-byte aligned window that covers it at either alignment
+    constexpr int kStage = ((kWin > (int) sizeof(FastSmem<N>) ? kWin : (int) sizeof(FastSmem<N>)) + 127) / 128 * 128;
+    __shared__ __align__(128) unsigned char stage[BULK ? 2 : 1][kStage];
+    __shared__ uint64_t full_bar;
+    FastSmem<N> & f = *reinterpret_cast<FastSmem<N> *>(stage[BULK ? 1 : 0]);
     const int lane = threadIdx.x;
     const int m = p.m;
     const int g = lane >> 2, t = lane & 3;
     const bool vlane = lane < LEN;      // lane owns a state index
     const double R00 = p.R[0], R10 = p.R[1], R01 = p.R[2], R11 = p.R[3];
     // zero the exchange buffers once (entries of lanes without a state index stay zero)
-    for (int k = lane; k < (int) (sizeof(f) / 8); k += 32) reinterpret_cast<double *>(&f)[k] = 0.0;
+    for (int k = lane; k < (int) (sizeof(FastSmem<N>) / 8); k += 32) reinterpret_cast<double *>(&f)[k] = 0.0;
     __syncwarp();
 #ifdef NUSLAM_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
 #endif
 
+    // issue the bulk load of filter `b` into buffer A (lane 0 only): the 16-byte aligned window around its Sigma
+    auto issue_load = [&](int64_t b) {
+        const unsigned char * g0 = reinterpret_cast<const unsigned char *>(p.sigma + b * SIG);
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(g0) & ~(uintptr_t) 15;
+        uint32_t bytes = kWin;
+        // never read past the end of the array: the last filter's window loses its tail, fetched separately below
+        const uintptr_t end = reinterpret_cast<uintptr_t>(p.sigma + p.batch * SIG);
+        if (lo + bytes > end) bytes = (uint32_t) ((end - lo) & ~(uintptr_t) 15);
+        mbar_expect_tx(&full_bar, bytes);
+        bulk_g2s(stage[0], reinterpret_cast<const void *>(lo), bytes, &full_bar);
+    };
+    uint32_t full_parity = 0;
+    if (BULK)
+    {
+        if (lane == 0)
+        {
+            mbar_init(&full_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if ((int64_t) blockIdx.x < p.batch) issue_load(blockIdx.x);
+        }
+        __syncwarp();
+    }
+
     for (int64_t bf = blockIdx.x; bf < p.batch; bf += gridDim.x)
     {
-        // pull this warp's next Sigma towards L2 while the current one is computed
-        if (lane == 0 && bf + gridDim.x < p.batch)
-        {
-            const uintptr_t a0 = reinterpret_cast<uintptr_t>(p.sigma + (bf + gridDim.x) * SIG) & ~(uintptr_t) 15;
-            prefetch_l2_bulk(reinterpret_cast<const void *>(a0), (uint32_t) ((sizeof(double) * SIG + 15) & ~15u));
-        }
-        // ---- load: every global read of the filter is issued before anything depends on one ----
+        // ---- load ----
         double C[NB][NB][2];
-        double Rt = 0.0, Rx = 0.0, Ry = 0.0, Ct = 0.0, Cx = 0.0, Cy = 0.0, x = 0.0;
-        const double * gs = p.sigma + bf * SIG;
-#pragma unroll
-        for (int br = 0; br < NB; ++br)
-#pragma unroll
-            for (int bc = 0; bc < NB; ++bc)
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                {
-                    const int row = 3 + 8 * br + g, col = 3 + 8 * bc + 2 * t + e;
-                    C[br][bc][e] = (row < LEN && col < LEN) ? __ldcs(gs + col * LEN + row) : 0.0;
-                }
-        if (vlane)
-        {
-            Ct = __ldcs(gs + lane);
-            Cx = __ldcs(gs + LEN + lane);
-            Cy = __ldcs(gs + 2 * LEN + lane);
-            Rt = __ldcs(gs + lane * LEN);
-            Rx = __ldcs(gs + lane * LEN + 1);
-            Ry = __ldcs(gs + lane * LEN + 2);
-            x = p.x[bf * LEN + lane];
-        }
-        const double diag = vlane ? gs[lane * (LEN + 1)] : 0.0;   // Sigma(lane, lane): first-touch detection
+        double Rt = 0.0, Rx = 0.0, Ry = 0.0, Ct = 0.0, Cx = 0.0, Cy = 0.0, x = 0.0, diag = 0.0;
+        // small inputs: plain loads, issued before anything waits
+        if (vlane) x = p.x[bf * LEN + lane];
         const int st0 = p.status[bf], seen0 = p.seen[bf];
         const int my_id = (lane < m) ? p.ids[bf * m + lane] : 0;
         const double my_z = (lane < 2 * m) ? p.z[bf * m * 2 + lane] : 0.0;
         const double my_tw = (do_predict && lane < 2) ? p.twists[bf * 3 + lane] : 0.0;
+        if (BULK)
+        {
+            // image of this filter inside buffer A: offset 0 or 8 (its alignment in HBM)
+            const double * img = reinterpret_cast<const double *>(stage[0] + (reinterpret_cast<uintptr_t>(p.sigma + bf * SIG) & 15));
+            mbar_wait(&full_bar, full_parity);
+            full_parity ^= 1;
+            if (bf == p.batch - 1 && lane == 0 && ((reinterpret_cast<uintptr_t>(p.sigma + p.batch * SIG) & 15) != 0))
+                const_cast<double *>(img)[SIG - 1] = p.sigma[bf * SIG + SIG - 1];   // tail the clamped window left out
+            __syncwarp();
+#pragma unroll
+            for (int br = 0; br < NB; ++br)
+#pragma unroll
+                for (int bc = 0; bc < NB; ++bc)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                    {
+                        const int row = 3 + 8 * br + g, col = 3 + 8 * bc + 2 * t + e;
+                        C[br][bc][e] = (row < LEN && col < LEN) ? img[col * LEN + row] : 0.0;
+                    }
+            if (vlane)
+            {
+                Ct = img[lane];
+                Cx = img[LEN + lane];
+                Cy = img[2 * LEN + lane];
+                Rt = img[lane * LEN];
+                Rx = img[lane * LEN + 1];
+                Ry = img[lane * LEN + 2];
+                diag = img[lane * (LEN + 1)];   // Sigma(lane, lane): first-touch detection
+            }
+            __syncwarp();
+            // buffer A is free again: prefetch this CTA's next filter while the current one is computed
+            if (lane == 0 && bf + gridDim.x < p.batch) issue_load(bf + gridDim.x);
+        }
+        else
+        {
+            // pull this warp's next Sigma towards L2 while the current one is computed
+            if (lane == 0 && bf + gridDim.x < p.batch)
+            {
+                const uintptr_t a0 = reinterpret_cast<uintptr_t>(p.sigma + (bf + gridDim.x) * SIG) & ~(uintptr_t) 15;
+                prefetch_l2_bulk(reinterpret_cast<const void *>(a0), (uint32_t) ((sizeof(double) * SIG + 15) & ~15u));
+            }
+            const double * gs = p.sigma + bf * SIG;
+#pragma unroll
+            for (int br = 0; br < NB; ++br)
+#pragma unroll
+                for (int bc = 0; bc < NB; ++bc)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                    {
+                        const int row = 3 + 8 * br + g, col = 3 + 8 * bc + 2 * t + e;
+                        C[br][bc][e] = (row < LEN && col < LEN) ? __ldcs(gs + col * LEN + row) : 0.0;
+                    }
+            if (vlane)
+            {
+                Ct = __ldcs(gs + lane);
+                Cx = __ldcs(gs + LEN + lane);
+                Cy = __ldcs(gs + 2 * LEN + lane);
+                Rt = __ldcs(gs + lane * LEN);
+                Rx = __ldcs(gs + lane * LEN + 1);
+                Ry = __ldcs(gs + lane * LEN + 2);
+                diag = gs[lane * (LEN + 1)];
+            }
+        }
         // ---- liveness ----
         if (st0 & (kStatusMapFull | kStatusSingular)) continue;   // the reference process died on an earlier scan
         {
@@ -172,6 +278,25 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             }
         }
         int status = st0;
+        if (BULK)
+        {
+            // buffer B held the previous filter's output image: wait until the bulk store has read it, then restore the zero
+            // entries of the exchange vectors that belong to no state index
+            if (lane == 0) bulk_wait_read();
+            __syncwarp();
+            if (lane >= LEN)
+            {
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2)
+                {
+                    f.rho[s2][0][lane + 1] = 0.0;
+                    f.rho[s2][1][lane + 1] = 0.0;
+                    f.kap[s2][lane] = make_double2(0.0, 0.0);
+                    f.kt[s2][lane] = make_double2(0.0, 0.0);
+                    f.wt[s2][lane] = make_double2(0.0, 0.0);
+                }
+            }
+        }
         if (lane < m) f.ids[lane] = my_id;
         if (lane < 2 * m) f.z[lane] = my_z;
         // robot pose, replicated in every lane; lanes 0..2 own the same values in x (bit-identical updates)
@@ -426,7 +551,51 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             NUSLAM_T(6)
         }
 
-        // ---- write back: registers -> HBM ----
+        // ---- write back ----
+        if (BULK)
+        {
+            // registers -> output image in buffer B (the exchange data is dead) -> one bulk store of the 16-byte aligned interior
+            // + one plain store of the edge element
+            __syncwarp();
+            double * gw = p.sigma + bf * SIG;
+            const int odd = (int) ((reinterpret_cast<uintptr_t>(gw) >> 3) & 1);   // 1: HBM image starts 8 bytes past a 16-byte boundary
+            double * img = reinterpret_cast<double *>(stage[1]) + odd;
+#pragma unroll
+            for (int br = 0; br < NB; ++br)
+#pragma unroll
+                for (int bc = 0; bc < NB; ++bc)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                    {
+                        const int row = 3 + 8 * br + g, col = 3 + 8 * bc + 2 * t + e;
+                        if (row < LEN && col < LEN) img[col * LEN + row] = C[br][bc][e];
+                    }
+            if (vlane)
+            {
+                img[lane * LEN] = Rt;
+                img[lane * LEN + 1] = Rx;
+                img[lane * LEN + 2] = Ry;
+                if (lane >= 3)
+                {
+                    img[lane] = Ct;
+                    img[LEN + lane] = Cx;
+                    img[2 * LEN + lane] = Cy;
+                }
+                p.x[bf * LEN + lane] = x;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0)
+            {
+                constexpr int kInner = ((SIG - 1) * 8) / 16 * 16;   // bytes of the aligned interior (SIG is odd: SIG - 1 elements)
+                static_assert((SIG & 1) == 1 && kInner == (SIG - 1) * 8, "a filter's Sigma is an odd number of doubles");
+                bulk_s2g(gw + odd, img + odd, kInner);
+                const int edge = odd ? 0 : SIG - 1;
+                gw[edge] = img[edge];
+                if (status != st0) p.status[bf] = status;
+            }
+        }
+        else
         {
             double * gw = p.sigma + bf * SIG;
 #pragma unroll
@@ -456,6 +625,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         }
         NUSLAM_T(7)
     }
+    if (BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the last bulk store
 #ifdef NUSLAM_TIMING
     if (blockIdx.x == 0 && lane == 0)
         for (int k = 0; k < 8; ++k) atomicAdd((unsigned long long *) &g_fast_timing[k], (unsigned long long) tacc[k]);
@@ -474,7 +644,18 @@ int launch_fast_n(const EkfParams & p, bool do_predict, int sm_count, int32_t * 
     if (const char * e = getenv("NUSLAM_FAST_CTAS_PER_SM")) ctas_per_sm = atoi(e);
 #endif
     if (blocks > ctas_per_sm * (int64_t) sm_count) blocks = ctas_per_sm * (int64_t) sm_count;
-    k_ekf_fast_step<N><<<(unsigned) blocks, kFastThreads, 0, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
+    static thread_local bool configured = false;
+    if (!configured)
+    {
+        // 16 CTAs x 11.8 KB of static shared memory per SM: ask for the largest shared-memory carve-out
+        cudaFuncSetAttribute(k_ekf_fast_step<N, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_ekf_fast_step<N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        configured = true;
+    }
+    if ((reinterpret_cast<uintptr_t>(p.sigma) & 15) == 0)
+        k_ekf_fast_step<N, true><<<(unsigned) blocks, kFastThreads, 0, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
+    else
+        k_ekf_fast_step<N, false><<<(unsigned) blocks, kFastThreads, 0, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
     return (int) cudaGetLastError();
 }
 

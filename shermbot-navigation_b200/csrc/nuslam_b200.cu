@@ -88,6 +88,15 @@ struct nuslam_ekf
     // staging for NUSLAM_HOST calls
     DevBuf s_tw, s_z, s_ids, s_ids_out, s_misc;
     // FAST mode: filters whose step contains a first touch are handed to the strict kernel through this list
+    // pipelined host-buffer steps (nuslam_ekf_step_async): two slots of staged inputs / state snapshots, copy streams, events
+    struct AsyncSlot
+    {
+        DevBuf tw, z, ids, xsnap;
+        cudaEvent_t h2d_done = nullptr, kernel_done = nullptr, d2h_done = nullptr;
+        bool busy = false;
+    } slots[2];
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    uint64_t async_count = 0;
     // LARGE-MAP mode (state too long for the on-chip batched kernels): delayed-update scratch, see ekf_large.cuh
     bool large = false;
     double * lg_x2 = nullptr;
@@ -345,6 +354,18 @@ int nuslam_ekf_destroy(nuslam_ekf * h)
         if (h->seen) cudaFree(h->seen);
         if (h->status) cudaFree(h->status);
     }
+    for (auto & sl : h->slots)
+    {
+        sl.tw.release();
+        sl.z.release();
+        sl.ids.release();
+        sl.xsnap.release();
+        if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+        if (sl.kernel_done) cudaEventDestroy(sl.kernel_done);
+        if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->lg_x2) cudaFree(h->lg_x2);
     if (h->lg_U) cudaFree(h->lg_U);
     if (h->lg_V) cudaFree(h->lg_V);
@@ -605,6 +626,68 @@ int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, con
     if (ids_out && mem == NUSLAM_HOST && m > 0)
         CU(cudaMemcpyAsync(ids_out, p.ids_out, sizeof(int32_t) * h->batch * m, cudaMemcpyDeviceToHost, h->stream));
     return finish(h, mem);
+}
+
+int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * z, const int32_t * ids, int32_t m, double * x_out)
+{
+    if (!h || !twists || !ids || !x_out) return fail(NUSLAM_ERR_INVALID, "null argument (the pipelined step takes known correspondence)");
+    if (m < 0 || (m > 0 && !z)) return fail(NUSLAM_ERR_INVALID, "m < 0 or null z");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    if (!h->s_in)
+    {
+        CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        for (auto & sl : h->slots)
+        {
+            CU(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&sl.kernel_done, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+        }
+    }
+    auto & sl = h->slots[h->async_count & 1];
+    // the slot's previous step must have left: its kernel has consumed the staged inputs and its snapshot has reached the host
+    if (sl.busy) CU(cudaEventSynchronize(sl.d2h_done));
+    const size_t B = (size_t) h->batch, l = (size_t) h->len;
+    int rc = sl.tw.reserve(sizeof(double) * 3 * B);
+    if (!rc) rc = sl.z.reserve(sizeof(double) * 2 * B * (m > 0 ? m : 1));
+    if (!rc) rc = sl.ids.reserve(sizeof(int32_t) * B * (m > 0 ? m : 1));
+    if (!rc) rc = sl.xsnap.reserve(sizeof(double) * l * B);
+    if (rc) return rc;
+    // stage 1 (copy-in stream): host -> device
+    CU(cudaMemcpyAsync(sl.tw.p, twists, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, h->s_in));
+    if (m > 0)
+    {
+        CU(cudaMemcpyAsync(sl.z.p, z, sizeof(double) * 2 * B * m, cudaMemcpyHostToDevice, h->s_in));
+        CU(cudaMemcpyAsync(sl.ids.p, ids, sizeof(int32_t) * B * m, cudaMemcpyHostToDevice, h->s_in));
+    }
+    CU(cudaEventRecord(sl.h2d_done, h->s_in));
+    // stage 2 (compute stream): the step on device buffers, then a snapshot of x so that the next step may start at once
+    CU(cudaStreamWaitEvent(h->stream, sl.h2d_done, 0));
+    rc = nuslam_ekf_step(h, static_cast<const double *>(sl.tw.p), static_cast<const double *>(sl.z.p), static_cast<const int32_t *>(sl.ids.p), m,
+                         nullptr, NUSLAM_DEVICE);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(sl.xsnap.p, h->x, sizeof(double) * l * B, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaEventRecord(sl.kernel_done, h->stream));
+    // stage 3 (copy-out stream): device -> host
+    CU(cudaStreamWaitEvent(h->s_out, sl.kernel_done, 0));
+    CU(cudaMemcpyAsync(x_out, sl.xsnap.p, sizeof(double) * l * B, cudaMemcpyDeviceToHost, h->s_out));
+    CU(cudaEventRecord(sl.d2h_done, h->s_out));
+    sl.busy = true;
+    h->async_count++;
+    return NUSLAM_OK;
+}
+
+int nuslam_ekf_wait_async(nuslam_ekf * h)
+{
+    if (!h) return fail(NUSLAM_ERR_INVALID, "null handle");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    for (auto & sl : h->slots)
+        if (sl.busy)
+        {
+            CU(cudaEventSynchronize(sl.d2h_done));
+            sl.busy = false;
+        }
+    return NUSLAM_OK;
 }
 
 #ifdef NUSLAM_TIMING

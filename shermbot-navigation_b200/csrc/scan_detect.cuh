@@ -20,6 +20,7 @@
 #pragma once
 #include "ekf_common.cuh"
 #include <math.h>
+#include <string.h>
 
 namespace nuslam
 {
@@ -38,9 +39,18 @@ struct ScanSmem
     double A[4 * (kBeams + 2)];   // Jacobi work matrices of the clusters being fitted (disjoint slices)
     float r[kBeams + 8];
     short cend[kBeams + 2];       // flat position of the last point of pre-erase cluster k
+    short cbeam[kBeams + 2];      // beam index of that point (the closer)
     short newidx[kBeams + 2];     // index after the erase loop, -1 when erased
     short kept[kBeams + 2];       // pre-erase index of kept cluster q
     int nk;
+};
+
+// view of an m x 4 work matrix: element (i, c) at p[(i + c * ld) * stride] (stride > 1: interleaved over the threads of a CTA)
+struct WorkMatrix
+{
+    double * p;
+    int ld, stride;
+    __device__ __forceinline__ double & operator()(int i, int c) const { return p[(i + c * ld) * stride]; }
 };
 
 // classifyCluster, circle_fit_library.cpp:208-250. Points P(0..n-1) in stored order.
@@ -75,7 +85,7 @@ __device__ __forceinline__ bool classify_cluster(int n, PX X, PY Y)
 
 // one-sided (Hestenes) Jacobi SVD of the m x 4 matrix A (column-major, overwritten): singular values descending in s,
 // right singular vectors in V (4 x 4 column-major). oracle/shim/armadillo svd().
-__device__ inline void svd_n4(double * A, int m, double * s, double * V)
+__device__ inline void svd_n4(const WorkMatrix A, int m, double * s, double * V)
 {
     double W[16];
 #pragma unroll
@@ -91,7 +101,7 @@ __device__ inline void svd_n4(double * A, int m, double * s, double * V)
                 double alpha = 0.0, beta = 0.0, gamma = 0.0;
                 for (int i = 0; i < m; ++i)
                 {
-                    const double ap = A[i + p * m], aq = A[i + q * m];
+                    const double ap = A(i, p), aq = A(i, q);
                     alpha = add_(alpha, mul_(ap, ap));
                     beta = add_(beta, mul_(aq, aq));
                     gamma = add_(gamma, mul_(ap, aq));
@@ -107,9 +117,9 @@ __device__ inline void svd_n4(double * A, int m, double * s, double * V)
                     const double sn = mul_(c, tt);
                     for (int i = 0; i < m; ++i)
                     {
-                        const double ap = A[i + p * m], aq = A[i + q * m];
-                        A[i + p * m] = sub_(mul_(c, ap), mul_(sn, aq));
-                        A[i + q * m] = add_(mul_(sn, ap), mul_(c, aq));
+                        const double ap = A(i, p), aq = A(i, q);
+                        A(i, p) = sub_(mul_(c, ap), mul_(sn, aq));
+                        A(i, q) = add_(mul_(sn, ap), mul_(c, aq));
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -127,7 +137,7 @@ __device__ inline void svd_n4(double * A, int m, double * s, double * V)
     for (int j = 0; j < 4; ++j)
     {
         double acc = 0.0;
-        for (int i = 0; i < m; ++i) acc = add_(acc, mul_(A[i + j * m], A[i + j * m]));
+        for (int i = 0; i < m; ++i) acc = add_(acc, mul_(A(i, j), A(i, j)));
         norms[j] = sqrt(acc);
     }
     // stable insertion sort, descending (a 4-element network with the same tie behaviour)
@@ -177,6 +187,10 @@ __device__ inline void eig_sym4(const double * X, double * val, double * vec)
                 else off = add_(off, mul_(A[i + j * 4], A[i + j * 4]));
             }
         if (off == 0.0 || off <= mul_(1e-40, diag)) break;
+        // The oracle's loop practically never meets its criterion (the lower triangle, which no rotation targets, stalls at
+        // ~1e-17 relative) and runs all 100 sweeps, but after ~12 of them a sweep leaves A and W bit for bit unchanged: from a
+        // fixed point every further sweep is the same no-op, so stopping there returns exactly what sweep 100 would.
+        bool changed = false;
 #pragma unroll
         for (int p = 0; p < 3; ++p)
 #pragma unroll
@@ -193,25 +207,32 @@ __device__ inline void eig_sym4(const double * X, double * val, double * vec)
                     for (int k = 0; k < 4; ++k)
                     {
                         const double akp = A[k + p * 4], akq = A[k + q * 4];
-                        A[k + p * 4] = sub_(mul_(c, akp), mul_(sn, akq));
-                        A[k + q * 4] = add_(mul_(sn, akp), mul_(c, akq));
+                        const double n1 = sub_(mul_(c, akp), mul_(sn, akq)), n2 = add_(mul_(sn, akp), mul_(c, akq));
+                        changed |= !(n1 == akp) | !(n2 == akq);
+                        A[k + p * 4] = n1;
+                        A[k + q * 4] = n2;
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                     {
                         const double apk = A[p + k * 4], aqk = A[q + k * 4];
-                        A[p + k * 4] = sub_(mul_(c, apk), mul_(sn, aqk));
-                        A[q + k * 4] = add_(mul_(sn, apk), mul_(c, aqk));
+                        const double n1 = sub_(mul_(c, apk), mul_(sn, aqk)), n2 = add_(mul_(sn, apk), mul_(c, aqk));
+                        changed |= !(n1 == apk) | !(n2 == aqk);
+                        A[p + k * 4] = n1;
+                        A[q + k * 4] = n2;
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                     {
                         const double wp = W[k + p * 4], wq = W[k + q * 4];
-                        W[k + p * 4] = sub_(mul_(c, wp), mul_(sn, wq));
-                        W[k + q * 4] = add_(mul_(sn, wp), mul_(c, wq));
+                        const double n1 = sub_(mul_(c, wp), mul_(sn, wq)), n2 = add_(mul_(sn, wp), mul_(c, wq));
+                        changed |= !(n1 == wp) | !(n2 == wq);
+                        W[k + p * 4] = n1;
+                        W[k + q * 4] = n2;
                     }
                 }
             }
+        if (!changed) break;
     }
     int order[4] = {0, 1, 2, 3};
 #pragma unroll
@@ -307,7 +328,7 @@ constexpr int kFitException = -1000;   // solve() on a singular Y: Armadillo thr
 // circleFit, circle_fit_library.cpp:15-134. Z (work matrix, N x 4 column-major) lives in shared memory.
 // Returns marker.id (0, or -1 when N < 4); out = (pose.x, pose.y, scale.x / 2).
 template <typename PX, typename PY>
-__device__ inline int circle_fit(int N, PX X, PY Y, double * Z, double * out3)
+__device__ inline int circle_fit(int N, PX X, PY Y, const WorkMatrix Z, double * out3)
 {
     out3[0] = out3[1] = out3[2] = 0.0;
     double x_hat = 0.0, y_hat = 0.0;
@@ -322,10 +343,10 @@ __device__ inline int circle_fit(int N, PX X, PY Y, double * Z, double * out3)
         const double dx = sub_(X(j), x_hat), dy = sub_(Y(j), y_hat);
         const double z = add_(mul_(dx, dx), mul_(dy, dy));   // pow(x, 2) + pow(y, 2)
         z_bar = add_(z_bar, div_(z, (double) N));
-        Z[j + 0 * N] = z;
-        Z[j + 1 * N] = dx;
-        Z[j + 2 * N] = dy;
-        Z[j + 3 * N] = 1.0;
+        Z(j, 0) = z;
+        Z(j, 1) = dx;
+        Z(j, 2) = dy;
+        Z(j, 3) = 1.0;
     }
     if (N < 4) return -1;   // s.size() < 4 (:72-76)
     double s[4], V[16], Aco[4];
@@ -387,18 +408,51 @@ __device__ inline int circle_fit(int N, PX X, PY Y, double * Z, double * out3)
     return 0;
 }
 
-// One warp per scan. cluster_of_beam may be null.
+// Work list of the two-stage pipeline: one entry per kept cluster of the chunk of scans in flight
+struct ClusterDesc
+{
+    int32_t scan;          // scan index (global)
+    int32_t beams;         // first beam to examine | last beam << 16 (out-of-range beams in between are skipped)
+    int32_t n_wrap;        // number of points | wrap flag << 16 (beam 359 appended last)
+    int32_t q;             // index among the scan's returned clusters
+};
+struct ClusterFit
+{
+    double pub, cx, cy, R;   // pub = 1: published by the landmarks node (classified circle, id >= 0, R <= 1)
+};
+constexpr int kFitNMax = 32;        // clusters up to this many points are fitted one per THREAD (work matrix interleaved in shared memory)
+constexpr int kFitThreads = 64;
+constexpr int kMaxFastClusters = 32;   // scans returning more clusters than this take the one-warp-per-scan path
+
+struct ScanPipe
+{
+    ClusterDesc * desc;      // chunk * kMaxFastClusters
+    ClusterFit * fit;        // same
+    int32_t * big;           // indices into desc of clusters with more than kFitNMax points
+    int32_t * slow;          // scans (global index) with more than kMaxFastClusters clusters
+    int32_t * scan_base;     // per scan of the chunk: first entry in desc, -1 for slow / UB scans
+    int32_t * counters;      // [0] entries in desc, [1] entries in big, [2] entries in slow
+    int64_t scan0;           // first scan of the chunk
+};
+
+// One warp per scan. cluster_of_beam may be null. INLINE_FIT: classification + fit by the same warp, one cluster per lane
+// (latency path for a few scans, and the slow path of the pipeline: `list` then names the scans); !INLINE_FIT: stage 1 of the
+// pipeline -- clustering only, kept clusters appended to the work list.
+template <bool INLINE_FIT>
 __global__ void __launch_bounds__(32 * kScanWarps)
 k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_range, double max_range, int16_t * __restrict__ cluster_of_beam,
-              int32_t * __restrict__ n_clusters, int32_t * __restrict__ n_circles, double * __restrict__ circles, int max_circles, int scan_ub)
+              int32_t * __restrict__ n_clusters, int32_t * __restrict__ n_circles, double * __restrict__ circles, int max_circles, int scan_ub,
+              const int32_t * __restrict__ list, const int32_t * __restrict__ list_count, ScanPipe pipe)
 {
     extern __shared__ __align__(16) unsigned char scan_smem_raw[];
     ScanSmem & sm = reinterpret_cast<ScanSmem *>(scan_smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     constexpr unsigned kFull = 0xffffffffu;
     constexpr int kChunks = (kBeams + 31) / 32;   // 12
-    for (int64_t s = (int64_t) blockIdx.x * kScanWarps + (threadIdx.x >> 5); s < n_scans; s += (int64_t) gridDim.x * kScanWarps)
+    const int64_t n_work = list ? (int64_t) *list_count : n_scans;
+    for (int64_t w = (int64_t) blockIdx.x * kScanWarps + (threadIdx.x >> 5); w < n_work; w += (int64_t) gridDim.x * kScanWarps)
     {
+        const int64_t s = list ? (int64_t) list[w] : (INLINE_FIT ? w : pipe.scan0 + w);
         const float * rs = ranges + s * kBeams;
         for (int i = lane; i < kBeams; i += 32) sm.r[i] = rs[i];
         __syncwarp();
@@ -437,6 +491,7 @@ k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_ran
             {
                 n_clusters[s] = 0;
                 n_circles[s] = scan_ub;
+                if (!INLINE_FIT) pipe.scan_base[s - pipe.scan0] = -1;
             }
             __syncwarp();
             continue;
@@ -457,7 +512,11 @@ k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_ran
                 const double r = (double) sm.r[i];
                 sm.px[my_pos[k]] = mul_(r, c_beam_cos[i]);   // :162-163
                 sm.py[my_pos[k]] = mul_(r, c_beam_sin[i]);
-                if (clo) sm.cend[my_clu[k]] = (short) my_pos[k];
+                if (clo)
+                {
+                    sm.cend[my_clu[k]] = (short) my_pos[k];
+                    sm.cbeam[my_clu[k]] = (short) i;
+                }
             }
             pos_base += __popc(inr_m[k]);
             clu_base += __popc(clo_m[k]);
@@ -513,6 +572,42 @@ k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_ran
                 }
             }
         }
+        if (!INLINE_FIT)
+        {
+            // ---- stage 1 of the pipeline: hand the kept clusters to the fitting kernels ----
+            int base = -1;
+            if (nk > kMaxFastClusters)
+            {
+                if (lane == 0) pipe.slow[atomicAdd(&pipe.counters[2], 1)] = (int32_t) s;   // cluster_of_beam is final; the rest is redone there
+            }
+            else
+            {
+                if (lane == 0) base = atomicAdd(&pipe.counters[0], nk);
+                base = __shfl_sync(kFull, base, 0);
+                if (lane < nk)
+                {
+                    const int k = sm.kept[lane];
+                    const int start = (k == 0) ? 0 : sm.cend[k - 1] + 1;
+                    const bool wr = (k == 0) && wrap;
+                    const int n = sm.cend[k] - start + 1 + (wr ? 1 : 0);
+                    ClusterDesc d;
+                    d.scan = (int32_t) s;
+                    d.beams = ((k == 0) ? 0 : sm.cbeam[k - 1] + 1) | ((int) sm.cbeam[k] << 16);
+                    d.n_wrap = n | (wr ? 1 << 16 : 0);
+                    d.q = lane;
+                    pipe.desc[base + lane] = d;
+                    if (n > kFitNMax) pipe.big[atomicAdd(&pipe.counters[1], 1)] = base + lane;
+                }
+            }
+            if (lane == 0)
+            {
+                n_clusters[s] = nk;
+                n_circles[s] = 0;
+                pipe.scan_base[s - pipe.scan0] = (nk > kMaxFastClusters) ? -1 : base;
+            }
+            __syncwarp();
+            continue;
+        }
         // ---- classification + circle fit, one kept cluster per lane; publication in detection order ----
         int published = 0;
         double * cout = circles + s * (int64_t) max_circles * 4;
@@ -535,7 +630,7 @@ k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_ran
                 auto Y = [&](int i) { return (i < nmain) ? by[i] : wy; };
                 if (classify_cluster(n, X, Y))
                 {
-                    double * Z = sm.A + 4 * (start + (k > 0 ? 1 : 0));
+                    const WorkMatrix Z = {sm.A + 4 * (start + (k > 0 ? 1 : 0)), n, 1};
                     const int id = circle_fit(n, X, Y, Z, fit);
                     pub = (id >= 0) && !(fit[2] > 1.0);   // landmarks.cpp:91-97
                 }
@@ -577,7 +672,7 @@ __global__ void k_classify_and_fit(const double * __restrict__ px, const double 
     is_circle[c] = (n >= 1 && classify_cluster(n, X, Y)) ? 1 : 0;
     double out3[3] = {0.0, 0.0, 0.0};
     int id = -1;
-    if (n >= 1) id = circle_fit(n, X, Y, scratch + 4 * (int64_t) o, out3);
+    if (n >= 1) id = circle_fit(n, X, Y, WorkMatrix{scratch + 4 * (int64_t) o, n, 1}, out3);
     fit[4 * c + 0] = (double) id;
     fit[4 * c + 1] = out3[0];
     fit[4 * c + 2] = out3[1];
@@ -604,6 +699,176 @@ inline cudaError_t scan_tables_init(int device)
     return cudaSuccess;
 }
 
+// the cluster's points in stored order: in-range beams of [first, last], then beam 359 when the wrap rule appended it
+template <typename F>
+__device__ __forceinline__ int gather_points(const ClusterDesc & d, const float * __restrict__ ranges, double min_range, double max_range, F store)
+{
+    const float * rs = ranges + (int64_t) d.scan * kBeams;
+    const int first = d.beams & 0xffff, last = d.beams >> 16;
+    int i = 0;
+    for (int bm = first; bm <= last; ++bm)
+    {
+        const float r = rs[bm];
+        if (((double) r > max_range) || ((double) r < min_range)) continue;
+        store(i, mul_((double) r, c_beam_cos[bm]), mul_((double) r, c_beam_sin[bm]));
+        ++i;
+    }
+    if (d.n_wrap >> 16)
+    {
+        const float r = rs[kBeams - 1];
+        store(i, mul_((double) r, c_beam_cos[kBeams - 1]), mul_((double) r, c_beam_sin[kBeams - 1]));
+        ++i;
+    }
+    return i;
+}
+
+__device__ __forceinline__ void classify_and_publish(int n, const WorkMatrix Z, ClusterFit & out)
+{
+    // the points live in columns 1, 2 of the work matrix until circleFit overwrites them (after it has read them)
+    auto X = [&](int i) { return Z(i, 1); };
+    auto Y = [&](int i) { return Z(i, 2); };
+    out.pub = 0.0;
+    out.cx = out.cy = out.R = 0.0;
+    if (classify_cluster(n, X, Y))
+    {
+        double fit[3];
+        const int id = circle_fit(n, X, Y, Z, fit);
+        if ((id >= 0) && !(fit[2] > 1.0))   // landmarks.cpp:91-97
+        {
+            out.pub = 1.0;
+            out.cx = fit[0];
+            out.cy = fit[1];
+            out.R = fit[2];
+        }
+    }
+}
+
+// stage 2: one THREAD per cluster of up to kFitNMax points; work matrices interleaved over the CTA's threads in shared memory
+__global__ void __launch_bounds__(kFitThreads) k_scan_fit_small(const float * __restrict__ ranges, double min_range, double max_range, ScanPipe pipe)
+{
+    extern __shared__ __align__(16) unsigned char fit_smem_raw[];
+    double * base = reinterpret_cast<double *>(fit_smem_raw) + threadIdx.x;
+    const WorkMatrix Z = {base, kFitNMax, kFitThreads};
+    const int total = pipe.counters[0];
+    for (int idx = blockIdx.x * kFitThreads + threadIdx.x; idx < total; idx += gridDim.x * kFitThreads)
+    {
+        const ClusterDesc d = pipe.desc[idx];
+        const int n = d.n_wrap & 0xffff;
+        if (n > kFitNMax) continue;   // stage 2b
+        gather_points(d, ranges, min_range, max_range, [&](int i, double x, double y) {
+            Z(i, 1) = x;
+            Z(i, 2) = y;
+        });
+        ClusterFit out;
+        classify_and_publish(n, Z, out);
+        pipe.fit[idx] = out;
+    }
+}
+
+// stage 2b: clusters with more points (walls): one warp per cluster. The inscribed angles of classifyCluster (one atan2
+// each, the expensive part) are evaluated by all lanes into shared memory; lane 0 then accumulates mean and variance in the
+// reference's order (bit-identical to the sequential evaluation) and, for the rare cluster that passes, runs the fit.
+__global__ void __launch_bounds__(64) k_scan_fit_big(const float * __restrict__ ranges, double min_range, double max_range, ScanPipe pipe)
+{
+    __shared__ double zbuf[2][4 * (kBeams + 2)];
+    __shared__ double angbuf[2][kBeams + 2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = pipe.counters[1];
+    for (int w = blockIdx.x * 2 + warp; w < total; w += gridDim.x * 2)
+    {
+        const int idx = pipe.big[w];
+        const ClusterDesc d = pipe.desc[idx];
+        const int n = d.n_wrap & 0xffff;
+        const WorkMatrix Z = {zbuf[warp], n, 1};
+        if (lane == 0)
+            gather_points(d, ranges, min_range, max_range, [&](int i, double x, double y) {
+                Z(i, 1) = x;
+                Z(i, 2) = y;
+            });
+        __syncwarp();
+        {
+            const double p2x = Z(0, 1), p2y = Z(0, 2), p3x = Z(n - 1, 1), p3y = Z(n - 1, 2);
+            for (int i = 1 + lane; i < n - 1; i += 32)
+            {
+                const double p1x = Z(i, 1), p1y = Z(i, 2);
+                const double num = add_(add_(mul_(p2y, sub_(p1x, p3x)), mul_(p1y, sub_(p3x, p2x))), mul_(p3y, sub_(p2x, p1x)));
+                const double den = add_(mul_(sub_(p2x, p1x), sub_(p1x, p3x)), mul_(sub_(p2y, p1y), sub_(p1y, p3y)));
+                angbuf[warp][i] = mul_(div_(180.0, kPiRef), atan2(num, den));
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+        {
+            const int na = n - 2;
+            double mean = 0.0, sd = 0.0;
+            for (int i = 1; i < n - 1; ++i) mean = add_(mean, div_(angbuf[warp][i], (double) na));
+            for (int i = 1; i < n - 1; ++i)
+            {
+                const double dv = sub_(angbuf[warp][i], mean);
+                sd = add_(sd, mul_(dv, dv));
+            }
+            sd = sqrt(div_(sd, (double) na));
+            ClusterFit out;
+            out.pub = 0.0;
+            out.cx = out.cy = out.R = 0.0;
+            if (sd < 10.0)
+            {
+                auto X = [&](int i) { return Z(i, 1); };
+                auto Y = [&](int i) { return Z(i, 2); };
+                double fit[3];
+                const int id = circle_fit(n, X, Y, Z, fit);
+                if ((id >= 0) && !(fit[2] > 1.0))
+                {
+                    out.pub = 1.0;
+                    out.cx = fit[0];
+                    out.cy = fit[1];
+                    out.R = fit[2];
+                }
+            }
+            pipe.fit[idx] = out;
+        }
+        __syncwarp();
+    }
+}
+
+// stage 3: one thread per scan of the chunk: published circles in detection order (landmarks.cpp:84-109)
+__global__ void k_scan_publish(int64_t chunk, int32_t * __restrict__ n_clusters, int32_t * __restrict__ n_circles, double * __restrict__ circles,
+                               int max_circles, ScanPipe pipe)
+{
+    const int64_t w = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= chunk) return;
+    const int base = pipe.scan_base[w];
+    if (base < 0) return;   // UB scans keep their marker, slow scans are written by the one-warp-per-scan kernel
+    const int64_t s = pipe.scan0 + w;
+    const int nk = n_clusters[s];
+    double * cout = circles + s * (int64_t) max_circles * 4;
+    int published = 0;
+    for (int q = 0; q < nk; ++q)
+    {
+        const ClusterFit f = pipe.fit[base + q];
+        if (f.pub != 0.0)
+        {
+            if (published < max_circles)
+            {
+                cout[4 * published + 0] = f.cx;
+                cout[4 * published + 1] = f.cy;
+                cout[4 * published + 2] = f.R;
+                cout[4 * published + 3] = (double) q;
+            }
+            ++published;
+        }
+    }
+    n_circles[s] = published;
+}
+
+constexpr int64_t kScanChunk = 65536;   // scans per pipeline pass (bounds the scratch: 65536 x 32 x 48 B = 100 MB)
+
+struct ScanScratch
+{
+    void * p = nullptr;
+    size_t bytes = 0;
+};
+
 inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, double min_range, double max_range, int16_t * cluster_of_beam,
                                       int32_t * n_clusters, int32_t * n_circles, double * circles, int32_t max_circles, int scan_ub,
                                       int device, int sm_count, cudaStream_t stream)
@@ -611,19 +876,77 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
     cudaError_t e = scan_tables_init(device);
     if (e != cudaSuccess) return e;
     const size_t smem = sizeof(ScanSmem) * kScanWarps;
+    const size_t fit_smem = sizeof(double) * 4 * kFitNMax * kFitThreads;
     static bool configured = false;
     if (!configured)
     {
-        e = cudaFuncSetAttribute(k_scan_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        e = cudaFuncSetAttribute(k_scan_detect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan_detect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan_fit_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fit_smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    int64_t blocks = (n_scans + kScanWarps - 1) / kScanWarps;
     const int64_t resident = (int64_t) sm_count * 5;
-    if (blocks > resident) blocks = resident;
-    k_scan_detect<<<(unsigned) blocks, 32 * kScanWarps, smem, stream>>>(ranges, n_scans, min_range, max_range, cluster_of_beam, n_clusters,
-                                                                       n_circles, circles, max_circles, scan_ub);
-    return cudaGetLastError();
+    ScanPipe none;
+    memset(&none, 0, sizeof(none));
+    if (n_scans <= 256)
+    {
+        // latency path: everything in one launch
+        int64_t blocks = (n_scans + kScanWarps - 1) / kScanWarps;
+        k_scan_detect<true><<<(unsigned) blocks, 32 * kScanWarps, smem, stream>>>(ranges, n_scans, min_range, max_range, cluster_of_beam, n_clusters,
+                                                                               n_circles, circles, max_circles, scan_ub, nullptr, nullptr, none);
+        return cudaGetLastError();
+    }
+    // throughput path: cluster (warp per scan) -> fit (thread per cluster) -> publish (thread per scan), in chunks of scans
+    static thread_local ScanScratch scratch[64];
+    ScanScratch & sc = scratch[(device >= 0 && device < 64) ? device : 0];
+    const int64_t chunk_max = n_scans < kScanChunk ? n_scans : kScanChunk;
+    const size_t n_desc = (size_t) chunk_max * kMaxFastClusters;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t) 255; };
+    const size_t need = al(n_desc * sizeof(ClusterDesc)) + al(n_desc * sizeof(ClusterFit)) + al(n_desc * sizeof(int32_t)) +
+                        al((size_t) chunk_max * sizeof(int32_t)) * 2 + 256;
+    if (sc.bytes < need)
+    {
+        if (sc.p) cudaFree(sc.p);
+        sc.p = nullptr;
+        sc.bytes = 0;
+        e = cudaMalloc(&sc.p, need);
+        if (e != cudaSuccess) return e;
+        sc.bytes = need;
+    }
+    ScanPipe pipe;
+    char * q = static_cast<char *>(sc.p);
+    pipe.desc = reinterpret_cast<ClusterDesc *>(q);
+    q += al(n_desc * sizeof(ClusterDesc));
+    pipe.fit = reinterpret_cast<ClusterFit *>(q);
+    q += al(n_desc * sizeof(ClusterFit));
+    pipe.big = reinterpret_cast<int32_t *>(q);
+    q += al(n_desc * sizeof(int32_t));
+    pipe.slow = reinterpret_cast<int32_t *>(q);
+    q += al((size_t) chunk_max * sizeof(int32_t));
+    pipe.scan_base = reinterpret_cast<int32_t *>(q);
+    q += al((size_t) chunk_max * sizeof(int32_t));
+    pipe.counters = reinterpret_cast<int32_t *>(q);
+    for (int64_t s0 = 0; s0 < n_scans; s0 += kScanChunk)
+    {
+        const int64_t chunk = (n_scans - s0 < kScanChunk) ? n_scans - s0 : kScanChunk;
+        pipe.scan0 = s0;
+        e = cudaMemsetAsync(pipe.counters, 0, 4 * sizeof(int32_t), stream);
+        if (e != cudaSuccess) return e;
+        int64_t blocks = (chunk + kScanWarps - 1) / kScanWarps;
+        if (blocks > resident) blocks = resident;
+        k_scan_detect<false><<<(unsigned) blocks, 32 * kScanWarps, smem, stream>>>(ranges, chunk, min_range, max_range, cluster_of_beam, n_clusters,
+                                                                                n_circles, circles, max_circles, scan_ub, nullptr, nullptr, pipe);
+        k_scan_fit_small<<<(unsigned) (sm_count * 3), kFitThreads, fit_smem, stream>>>(ranges, min_range, max_range, pipe);
+        k_scan_fit_big<<<(unsigned) (sm_count * 2), 64, 0, stream>>>(ranges, min_range, max_range, pipe);
+        k_scan_publish<<<(unsigned) ((chunk + 127) / 128), 128, 0, stream>>>(chunk, n_clusters, n_circles, circles, max_circles, pipe);
+        // scans with more than kMaxFastClusters clusters: the one-warp-per-scan kernel over their list
+        k_scan_detect<true><<<(unsigned) sm_count, 32 * kScanWarps, smem, stream>>>(ranges, n_scans, min_range, max_range, cluster_of_beam, n_clusters,
+                                                                                 n_circles, circles, max_circles, scan_ub, pipe.slow, pipe.counters + 2, pipe);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }   // namespace nuslam

@@ -32,7 +32,8 @@ EXPORTS = [
     "nuslam_last_error", "nuslam_version", "nuslam_ekf_default_config", "nuslam_ekf_create", "nuslam_ekf_destroy",
     "nuslam_ekf_bind_state", "nuslam_ekf_device_pointers", "nuslam_ekf_init", "nuslam_ekf_set_state",
     "nuslam_ekf_get_state", "nuslam_ekf_predict", "nuslam_ekf_associate", "nuslam_ekf_initialize_landmark",
-    "nuslam_ekf_update", "nuslam_ekf_measurement_model", "nuslam_ekf_step", "nuslam_ekf_synchronize",
+    "nuslam_ekf_update", "nuslam_ekf_measurement_model", "nuslam_ekf_step", "nuslam_ekf_step_async", "nuslam_ekf_wait_async",
+    "nuslam_ekf_synchronize",
     "nuslam_cartesian2polar", "nuslam_normalize_angle", "nuslam_scan_detect", "nuslam_classify_and_fit",
 ]
 
@@ -74,6 +75,8 @@ def lib() -> C.CDLL:
         l.nuslam_ekf_update.argtypes = [vp, vp, vp, C.c_int]
         l.nuslam_ekf_measurement_model.argtypes = [vp, vp, vp, vp, C.c_int]
         l.nuslam_ekf_step.argtypes = [vp, vp, vp, vp, i32, vp, C.c_int]
+        l.nuslam_ekf_step_async.argtypes = [vp, vp, vp, vp, i32, vp]
+        l.nuslam_ekf_wait_async.argtypes = [vp]
         l.nuslam_ekf_synchronize.argtypes = [vp]
         l.nuslam_cartesian2polar.argtypes = [vp, vp, i64, C.c_int, C.c_int, vp]
         l.nuslam_normalize_angle.argtypes = [vp, vp, i64, C.c_int, C.c_int, vp]
@@ -258,6 +261,18 @@ class BatchedExtendedKalman:
                 optr = out.ctypes.data
         _check(lib().nuslam_ekf_step(self._h, pt[0], pz[0], pi[0], m, optr, mem), "nuslam_ekf_step")
         return out
+
+    def step_async(self, twists, z, ids, x_out):
+        """Pipelined host-buffer step (nuslam_ekf_step_async): numpy views of page-locked buffers; ``x_out`` [B,len] receives the state
+        vector once the step has left the pipeline (two calls later, or after ``wait_async``)."""
+        for a, dt in ((twists, np.float64), (z, np.float64), (ids, np.int32), (x_out, np.float64)):
+            if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"]):
+                raise NuslamError("step_async takes contiguous numpy arrays of the exact dtype (no hidden copies in a pipelined call)")
+        _check(lib().nuslam_ekf_step_async(self._h, twists.ctypes.data, z.ctypes.data, ids.ctypes.data, int(z.shape[1]), x_out.ctypes.data),
+               "nuslam_ekf_step_async")
+
+    def wait_async(self):
+        _check(lib().nuslam_ekf_wait_async(self._h), "nuslam_ekf_wait_async")
 
     def synchronize(self):
         _check(lib().nuslam_ekf_synchronize(self._h), "nuslam_ekf_synchronize")
