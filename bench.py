@@ -214,9 +214,9 @@ def run_ours(args):
 
     # ---- end to end through the public API with HOST buffers (pinned): every step copies its twists / z / ids host -> device
     # and its resulting state vector device -> host inside the timed region (BatchedExtendedKalman.step_async = the C ABI's
-    # nuslam_ekf_step_async: three streams, two steps in flight, so the copies of neighbouring steps overlap the kernel) ----
+    # nuslam_ekf_step_async: three streams, three steps in flight, so the copies of neighbouring steps overlap the kernel) ----
     Ke = max(3, min(K, args.e2e_steps))
-    nbuf = 2
+    nbuf = 3
     h_tw = [torch.empty((B, 3), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
     h_z = [torch.empty((B, N_LANDMARKS, 2), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
     h_ids = ids.cpu().pin_memory()
@@ -225,7 +225,7 @@ def run_ours(args):
         h_tw[k].copy_(twists[t + k])
         h_z[k].copy_(zs[t + k])
     torch.cuda.synchronize(dev)
-    for k in range(4):   # warm the host path (staging buffers, streams, events)
+    for k in range(6):   # warm the host path (staging buffers, streams, events)
         eng.step_async(h_tw[k % nbuf].numpy(), h_z[k % nbuf].numpy(), h_ids.numpy(), h_x[k % nbuf].numpy())
     eng.wait_async()
     if world > 1:
@@ -234,7 +234,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     for k in range(Ke):
         eng.step_async(h_tw[k % nbuf].numpy(), h_z[k % nbuf].numpy(), h_ids.numpy(), h_x[k % nbuf].numpy())
-        # the host consumes the result of the step that has just left the pipeline (two calls back): robot pose of filter 0
+        # the host consumes the result of the step that has just left the pipeline (three calls back): robot pose of filter 0
         if k >= nbuf:
             checksum += float(h_x[k % nbuf][0, 1])
     eng.wait_async()
@@ -279,7 +279,7 @@ def run_ours(args):
                        "parallelism": f"filters sharded {world}x, no data-path collective; final NCCL all_gather of states"},
             "clocks": clocks, "gpu_launches": (2 * K if args.mode == "fast" else K), "bad_filters": bad,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "api": "BatchedExtendedKalman.step_async (nuslam_ekf_step_async): pinned host buffers, H2D + fused step + D2H of the state vector per step, 2 steps in flight"},
+                    "api": "BatchedExtendedKalman.step_async (nuslam_ekf_step_async): pinned host buffers, H2D + fused step + D2H of the state vector per step, 3 steps in flight"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_filter_step": BYTES_PER_FILTER_STEP,
                          "kernel": "k_ekf_fast_step<12> (+ k_ekf_strict_list over the first-touch work list, empty in steady state)" if args.mode == "fast" else "k_ekf_strict<kOpStep>",
@@ -313,7 +313,7 @@ def cpu_baseline(target_seconds=12.0):
     # calibrate on a tiny run, then size the sample for ~target_seconds of wall time on all cores
     rate, _, kind = cpu_reference_run(4 * cores, 10, cores)
     n_steps = 50
-    n_filters = int(max(cores, min(64 * cores, rate * target_seconds / n_steps)))
+    n_filters = int(max(cores, min(FILTERS_PER_GPU, rate * target_seconds / n_steps)))
     n_filters = max(cores, (n_filters // cores) * cores)
     rate, dt, kind = cpu_reference_run(n_filters, n_steps, cores)
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,

@@ -164,9 +164,9 @@ int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, con
 
 /* Pipelined form of nuslam_ekf_step for HOST buffers (known correspondence): the call enqueues (1) the host->device copy of this
  * step's twists / z / ids, (2) the fused step, (3) the device->host copy of the resulting state vector into x_out (B x len f64),
- * on three streams chained by events, and returns at once; up to two steps are in flight, so the copies of step t+1 and t-1
+ * on three streams chained by events, and returns at once; up to three steps are in flight, so the copies of steps t+1 and t-1
  * overlap the kernel of step t. All host pointers should be page-locked and must stay untouched until a later call has
- * recycled the slot (two calls later) or nuslam_ekf_wait_async has returned. Same semantics and results as the synchronous
+ * recycled the slot (three calls later) or nuslam_ekf_wait_async has returned. Same semantics and results as the synchronous
  * call: one iteration of nuslam/src/slam.cpp:262-319 per filter, followed by getStateVector(). */
 int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * z, const int32_t * ids, int32_t m, double * x_out);
 int nuslam_ekf_wait_async(nuslam_ekf * h);
@@ -180,6 +180,17 @@ int nuslam_cartesian2polar(const double * xy, double * rb, int64_t count, int me
 /* rigid2d::normalize_angle, rigid2d/src/rigid2d.cpp:9-13, batched. */
 int nuslam_normalize_angle(const double * rad_in, double * rad_out, int64_t count, int mem, int device,
                            void * cuda_stream);
+
+/* rigid2d::DiffDrive, batched (rigid2d/include/rigid2d/diff_drive.hpp:13-103): what nuslam/src/slam.cpp:264-265 does with the wheel
+ * angles of one joint-state message -- getTwist(thL, thR) (diff_drive.cpp:80-110) then operator()(thL, thR) (:111-146) -- for
+ * `count` robots. state7: count x 7 = {wheelBase, wheelRad, x, y, th, thL, thR}, updated in place; twists_out: count x 3
+ * (dth, dx, dy = 0), the control input of nuslam_ekf_predict / nuslam_ekf_step. */
+int nuslam_diffdrive_step(double * state7, const double * thL_new, const double * thR_new, double * twists_out, int64_t count, int mem,
+                          int device, void * cuda_stream);
+
+/* DiffDrive::convertTwist (diff_drive.cpp:66-78), batched: twists count x 3 -> wheel velocities count x 2 (uL, uR). */
+int nuslam_diffdrive_convert_twist(double wheel_base, double wheel_rad, const double * twists, double * wheel_vel_out, int64_t count, int mem,
+                                   int device, void * cuda_stream);
 
 /* ------------------------------------------------------------------ scan -> landmarks
  * circle_fit::clusterPoints (circle_fit_library.cpp:136-206), classifyCluster (:208-250), circleFit

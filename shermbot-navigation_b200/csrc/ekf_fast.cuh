@@ -483,12 +483,14 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     const double m00 = fma(d, R00, s00), m10 = fma(dsq, R10, s10), m01 = fma(dsq, R01, s01), m11 = fma(d * d, R11, s11);
                     const double det = fma(m00, m11, -m01 * m10);
                     const double idet = rcp_fast(det);
+                    // the bearing chain (atan2, wrap) is independent of the Minv chain: evaluated before the branch so that the two
+                    // dependency chains interleave
+                    const double zb = wrap_angle(atan2_fast(dy, dx) - th);
+                    const double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);
                     if (fabs(idet) < 1.0e300)   // warp-uniform; false for det = 0, inf or nan, where arma::inv throws (slam_library.cpp:270)
                     {
                         done = true;
                         const double i00 = m11 * idet, i01 = -m01 * idet, i10 = -m10 * idet, i11 = m00 * idet;
-                        const double zb = wrap_angle(atan2_fast(dy, dx) - th);
-                        const double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);
                         // (C) -Kt = -Pt Minv, x += Kt n
                         const double nk0 = fma(-P0, i00, -P1 * i10), nk1 = fma(-P0, i01, -P1 * i11);
                         f.kt[s][lane] = make_double2(nk0, nk1);

@@ -84,4 +84,78 @@ __global__ void k_normalize_angle(const double * __restrict__ in, double * __res
     out[t] = normalize_angle(in[t]);
 }
 
+// rigid2d::DiffDrive, batched: getTwist (diff_drive.cpp:80-110) followed by operator() (:111-146), exactly as the slam node turns
+// wheel angles into the EKF control (nuslam/src/slam.cpp:264-265). state: B x 7 = {wheelBase, wheelRad, x, y, th, thL, thR}
+// (updated in place); twists: B x 3 (dth, dx, dy = 0). integrateTwist: rigid2d.cpp:294-328, Transform2D product / inverse
+// :187-214 in their operation order (unfused); sin / cos / atan from the CUDA math library.
+struct Tf2D
+{
+    double c, s, x, y;
+};
+__device__ __forceinline__ Tf2D tf_mul(const Tf2D & l, const Tf2D & r)
+{
+    Tf2D o;
+    o.c = sub_(mul_(l.c, r.c), mul_(l.s, r.s));
+    o.s = add_(mul_(l.s, r.c), mul_(l.c, r.s));
+    o.x = add_(sub_(mul_(l.c, r.x), mul_(l.s, r.y)), l.x);
+    o.y = add_(add_(mul_(l.s, r.x), mul_(l.c, r.y)), l.y);
+    return o;
+}
+__device__ __forceinline__ Tf2D tf_inv(const Tf2D & t)
+{
+    Tf2D o;
+    o.c = t.c;
+    o.s = -t.s;
+    o.x = add_(mul_(-t.x, t.c), mul_(-t.y, t.s));
+    o.y = add_(mul_(t.x, t.s), mul_(-t.y, t.c));
+    return o;
+}
+__device__ __forceinline__ Tf2D integrate_twist(double dth, double dx, double dy)
+{
+    if (dth == 0.0) return Tf2D{1.0, 0.0, dx, dy};
+    const Tf2D T_sb = {1.0, 0.0, div_(dy, dth), -div_(dx, dth)};
+    double sn, cs;
+    sincos(dth, &sn, &cs);
+    const Tf2D T_ss = {cs, sn, 0.0, 0.0};
+    return tf_mul(tf_mul(tf_inv(T_sb), T_ss), T_sb);   // operator* is left-associative (rigid2d.cpp:211-214,325)
+}
+
+__global__ void k_diffdrive_step(double * __restrict__ state, const double * __restrict__ thL, const double * __restrict__ thR,
+                                 double * __restrict__ twists, int64_t count)
+{
+    const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= count) return;
+    double * s = state + 7 * b;
+    const double wheelBase = s[0], wheelRad = s[1];
+    const double dUL = sub_(thL[b], s[5]), dUR = sub_(thR[b], s[6]);
+    const double dth = mul_(div_(wheelRad, wheelBase), sub_(dUR, dUL));
+    const double dx = mul_(div_(wheelRad, 2.0), add_(dUL, dUR));
+    twists[3 * b] = dth;
+    twists[3 * b + 1] = dx;
+    twists[3 * b + 2] = 0.0;
+    const Tf2D Tbb = integrate_twist(dth, dx, 0.0);
+    const double dqb_th = atan(div_(Tbb.s, Tbb.c));   // :129
+    double sn, cs;
+    sincos(s[4], &sn, &cs);
+    // adj = Transform2D(th); adj(dqb) = rigid2d.cpp:254-261 with x = y = 0
+    const double dq_x = sub_(add_(mul_(0.0, dqb_th), mul_(cs, Tbb.x)), mul_(sn, Tbb.y));
+    const double dq_y = add_(add_(-mul_(0.0, dqb_th), mul_(sn, Tbb.x)), mul_(cs, Tbb.y));
+    s[4] = add_(s[4], dqb_th);
+    s[2] = add_(s[2], dq_x);
+    s[3] = add_(s[3], dq_y);
+    s[5] = thL[b];
+    s[6] = thR[b];
+}
+
+// DiffDrive::convertTwist (diff_drive.cpp:66-78), batched: twists B x 3 -> wheel velocities B x 2 (uL, uR)
+__global__ void k_diffdrive_convert_twist(double wheel_base, double wheel_rad, const double * __restrict__ twists, double * __restrict__ u, int64_t count)
+{
+    const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= count) return;
+    const double d = div_(wheel_base, 2.0), r = wheel_rad;
+    const double omg = twists[3 * b], vbx = twists[3 * b + 1];
+    u[2 * b] = add_(mul_(-div_(d, r), omg), div_(vbx, r));
+    u[2 * b + 1] = add_(mul_(div_(d, r), omg), div_(vbx, r));
+}
+
 }   // namespace nuslam

@@ -88,13 +88,13 @@ struct nuslam_ekf
     // staging for NUSLAM_HOST calls
     DevBuf s_tw, s_z, s_ids, s_ids_out, s_misc;
     // FAST mode: filters whose step contains a first touch are handed to the strict kernel through this list
-    // pipelined host-buffer steps (nuslam_ekf_step_async): two slots of staged inputs / state snapshots, copy streams, events
+    // pipelined host-buffer steps (nuslam_ekf_step_async): kAsyncSlots slots of staged inputs / state snapshots, copy streams, events
     struct AsyncSlot
     {
         DevBuf tw, z, ids, xsnap;
         cudaEvent_t h2d_done = nullptr, kernel_done = nullptr, d2h_done = nullptr;
         bool busy = false;
-    } slots[2];
+    } slots[3];
     cudaStream_t s_in = nullptr, s_out = nullptr;
     uint64_t async_count = 0;
     // LARGE-MAP mode (state too long for the on-chip batched kernels): delayed-update scratch, see ekf_large.cuh
@@ -644,7 +644,7 @@ int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * 
             CU(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
         }
     }
-    auto & sl = h->slots[h->async_count & 1];
+    auto & sl = h->slots[h->async_count % 3];
     // the slot's previous step must have left: its kernel has consumed the staged inputs and its snapshot has reached the host
     if (sl.busy) CU(cudaEventSynchronize(sl.d2h_done));
     const size_t B = (size_t) h->batch, l = (size_t) h->len;
@@ -754,6 +754,73 @@ int nuslam_cartesian2polar(const double * xy, double * rb, int64_t count, int me
 int nuslam_normalize_angle(const double * rad_in, double * rad_out, int64_t count, int mem, int device, void * cuda_stream)
 {
     return elementwise_io(rad_in, rad_out, count, 1, 1, mem, device, cuda_stream, 1);
+}
+
+int nuslam_diffdrive_step(double * state7, const double * thL_new, const double * thR_new, double * twists_out, int64_t count, int mem,
+                          int device, void * cuda_stream)
+{
+    if (!state7 || !thL_new || !thR_new || !twists_out || count < 0) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (count == 0) return NUSLAM_OK;
+    CU(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    double * d_state = state7;
+    const double * d_l = thL_new;
+    const double * d_r = thR_new;
+    double * d_tw = twists_out;
+    double * tmp = nullptr;
+    if (mem == NUSLAM_HOST)
+    {
+        CU(cudaMalloc(&tmp, sizeof(double) * count * 12));
+        CU(cudaMemcpyAsync(tmp, state7, sizeof(double) * count * 7, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(tmp + 7 * count, thL_new, sizeof(double) * count, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(tmp + 8 * count, thR_new, sizeof(double) * count, cudaMemcpyHostToDevice, st));
+        d_state = tmp;
+        d_l = tmp + 7 * count;
+        d_r = tmp + 8 * count;
+        d_tw = tmp + 9 * count;
+    }
+    const int threads = 128;
+    nuslam::k_diffdrive_step<<<(unsigned) ((count + threads - 1) / threads), threads, 0, st>>>(d_state, d_l, d_r, d_tw, count);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && mem == NUSLAM_HOST)
+    {
+        e = cudaMemcpyAsync(state7, d_state, sizeof(double) * count * 7, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(twists_out, d_tw, sizeof(double) * count * 3, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "diffdrive_step");
+    return NUSLAM_OK;
+}
+
+int nuslam_diffdrive_convert_twist(double wheel_base, double wheel_rad, const double * twists, double * wheel_vel_out, int64_t count, int mem,
+                                   int device, void * cuda_stream)
+{
+    if (!twists || !wheel_vel_out || count < 0) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (count == 0) return NUSLAM_OK;
+    CU(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const double * d_tw = twists;
+    double * d_u = wheel_vel_out;
+    double * tmp = nullptr;
+    if (mem == NUSLAM_HOST)
+    {
+        CU(cudaMalloc(&tmp, sizeof(double) * count * 5));
+        CU(cudaMemcpyAsync(tmp, twists, sizeof(double) * count * 3, cudaMemcpyHostToDevice, st));
+        d_tw = tmp;
+        d_u = tmp + 3 * count;
+    }
+    const int threads = 128;
+    nuslam::k_diffdrive_convert_twist<<<(unsigned) ((count + threads - 1) / threads), threads, 0, st>>>(wheel_base, wheel_rad, d_tw, d_u, count);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && mem == NUSLAM_HOST)
+    {
+        e = cudaMemcpyAsync(wheel_vel_out, d_u, sizeof(double) * count * 2, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "diffdrive_convert_twist");
+    return NUSLAM_OK;
 }
 
 int nuslam_scan_detect(const float * ranges, int64_t n_scans, double min_range, double max_range, int16_t * cluster_of_beam,

@@ -35,6 +35,7 @@ EXPORTS = [
     "nuslam_ekf_update", "nuslam_ekf_measurement_model", "nuslam_ekf_step", "nuslam_ekf_step_async", "nuslam_ekf_wait_async",
     "nuslam_ekf_synchronize",
     "nuslam_cartesian2polar", "nuslam_normalize_angle", "nuslam_scan_detect", "nuslam_classify_and_fit",
+    "nuslam_diffdrive_step", "nuslam_diffdrive_convert_twist",
 ]
 
 
@@ -82,6 +83,8 @@ def lib() -> C.CDLL:
         l.nuslam_normalize_angle.argtypes = [vp, vp, i64, C.c_int, C.c_int, vp]
         l.nuslam_scan_detect.argtypes = [vp, i64, C.c_double, C.c_double, vp, vp, vp, vp, i32, C.c_int, C.c_int, vp]
         l.nuslam_classify_and_fit.argtypes = [vp, vp, vp, i64, vp, vp, C.c_int, C.c_int, vp]
+        l.nuslam_diffdrive_step.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.c_int, vp]
+        l.nuslam_diffdrive_convert_twist.argtypes = [C.c_double, C.c_double, vp, vp, i64, C.c_int, C.c_int, vp]
         _lib = l
     return _lib
 
@@ -264,7 +267,7 @@ class BatchedExtendedKalman:
 
     def step_async(self, twists, z, ids, x_out):
         """Pipelined host-buffer step (nuslam_ekf_step_async): numpy views of page-locked buffers; ``x_out`` [B,len] receives the state
-        vector once the step has left the pipeline (two calls later, or after ``wait_async``)."""
+        vector once the step has left the pipeline (three calls later, or after ``wait_async``)."""
         for a, dt in ((twists, np.float64), (z, np.float64), (ids, np.int32), (x_out, np.float64)):
             if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"]):
                 raise NuslamError("step_async takes contiguous numpy arrays of the exact dtype (no hidden copies in a pipelined call)")

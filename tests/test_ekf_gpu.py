@@ -295,7 +295,7 @@ def test_cartesian2polar_and_normalize(cuda_lib, orc):
 
 
 def test_pipelined_host_steps_match_synchronous(cuda_lib):
-    """nuslam_ekf_step_async (three streams, two steps in flight) gives exactly the states of the synchronous host-buffer steps."""
+    """nuslam_ekf_step_async (three streams, three steps in flight) gives exactly the states of the synchronous host-buffer steps."""
     B, T, n = 512, 9, 12
     sc = synth.ekf_scenario(B, T, n=n, seed=71)
     a = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="fast")
@@ -313,3 +313,31 @@ def test_pipelined_host_steps_match_synchronous(cuda_lib):
     xa, sa, na, _ = a.get_state()
     xb, sb, nb, _ = b.get_state()
     assert np.array_equal(xa, xb) and np.array_equal(sa, sb) and np.array_equal(na, nb)
+
+
+def test_diffdrive_matches_oracle(cuda_lib, orc):
+    """rigid2d::DiffDrive getTwist + operator() and convertTwist (diff_drive.cpp:66-146), batched on the device, against the oracle:
+    the arithmetic is + - * / in the reference's order, so everything but sin / cos / atan rounding is bit-identical."""
+    from shermbot_navigation_b200 import rigid2d
+    rng = np.random.default_rng(8)
+    B, T = 257, 40
+    dd = rigid2d.DiffDrive(0.16, 0.033, config=rng.normal(size=(B, 3)))
+    states = dd.state.copy()
+    thL = np.zeros(B)
+    thR = np.zeros(B)
+    for t in range(T):
+        dL = rng.normal(0.2, 0.1, B)
+        dR = rng.normal(0.25, 0.1, B)
+        if t == 3:
+            dR = dL.copy()                # straight segment: the dth == 0 branch of integrateTwist
+        thL, thR = thL + dL, thR + dR
+        tw = dd.step(thL, thR)
+        for b in range(B):
+            s, w = orc.diffdrive_step(states[b], thL[b], thR[b])
+            states[b] = s
+            assert np.array_equal(tw[b], w)                      # the twist is pure + - * /
+        assert np.abs(dd.state - states).max() < 1e-12
+    tws = rng.normal(size=(B, 3))
+    u = dd.convertTwist(tws)
+    for b in range(0, B, 16):
+        assert np.array_equal(u[b], orc.convert_twist(0.16, 0.033, tws[b, 0], tws[b, 1]))

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""BASELINE.json config 4 (single-GPU shard): fused steps with UNKNOWN data association (associateLandmark on the device) for B
+filters x 12 landmarks, steady state (all landmarks seen). Prints filter-steps/s and the id mismatch count against the truth."""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch  # noqa: E402
+from shermbot_navigation_b200 import nuslam, synth  # noqa: E402
+
+
+def main(B=65536, steps=10, warmup=3, mode="fast"):
+    D, n = 256, 12
+    T = warmup + steps + 1
+    sc = synth.ekf_scenario(D, T, n=n, seed=9, shuffle_order=True)
+    rep = lambda a: np.ascontiguousarray(np.tile(a, (B // D,) + (1,) * (a.ndim - 1)))
+    dev = torch.device("cuda")
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    eng = nuslam.BatchedExtendedKalman(rep(sc["robot0"]), rep(sc["map0"]), sc["Q"], sc["R"], mode=mode, stream=stream.cuda_stream)
+    tw = [torch.tensor(rep(sc["twists"][t]), device=dev) for t in range(T)]
+    z = [torch.tensor(rep(sc["z"][t]), device=dev) for t in range(T)]
+    truth = [torch.tensor(rep(sc["ids"][t]), device=dev) for t in range(T)]
+    # step 0 with known ids in detection order 1..n would bias the id numbering: run it with unknown association too
+    t = 0
+    ids0 = eng.step(tw[t], z[t], None, return_ids=True)
+    # ids assigned in detection order: map truth -> assigned
+    perm = torch.zeros((B, n + 1), dtype=torch.int32, device=dev)
+    perm.scatter_(1, truth[0].long(), ids0)
+    mism = 0
+    total = 0
+    for t in range(1, 1 + warmup):
+        got = eng.step(tw[t], z[t], None, return_ids=True)
+        mism += int((got != torch.gather(perm, 1, truth[t].long())).sum())
+        total += got.numel()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for t in range(1 + warmup, 1 + warmup + steps):
+        eng.step(tw[t], z[t], None)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    status = eng.getStatus()
+    print(json.dumps({"workload": f"config 4 shard: {B} filters x {n} landmarks, unknown association (Mahalanobis gating), steady state", "mode": mode,
+                      "ms_per_step": ms, "filter_steps_per_s": B / (ms * 1e-3), "id_mismatches_vs_truth_in_warmup": mism, "decisions": total,
+                      "bad_status": int((status != 0).sum())}))
+
+
+if __name__ == "__main__":
+    main(mode=sys.argv[1] if len(sys.argv) > 1 else "fast")
