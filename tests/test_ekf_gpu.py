@@ -341,3 +341,41 @@ def test_diffdrive_matches_oracle(cuda_lib, orc):
     u = dd.convertTwist(tws)
     for b in range(0, B, 16):
         assert np.array_equal(u[b], orc.convert_twist(0.16, 0.033, tws[b, 0], tws[b, 1]))
+
+
+@pytest.mark.parametrize("B,n,m,dropout", [(1, 12, 12, 0.0), (3, 12, 5, 0.0), (33, 12, 12, 0.3), (7, 6, 6, 0.0), (5, 6, 3, 0.2), (9, 12, 16, 0.0), (2, 12, 1, 0.0)])
+def test_fast_step_shapes(cuda_lib, orc, B, n, m, dropout):
+    """FAST kernel corner cases: odd batch sizes (the bulk-copy window of the last filter is clamped), fewer / more measurements than
+    landmarks (odd m: half-empty rank-4 chunk; m = 16: repeated landmarks inside a step), dropped measurements (id 0), n = 6
+    (padded fragments). Warm start after the first-touch step, then free running; <= 1e-9 against the oracle."""
+    T = 8
+    sc = synth.ekf_scenario(B, T, n=n, seed=100 + B + m, dropout=0.0)
+    rng = np.random.default_rng(B * 131 + m)
+    # per step: m measurement slots drawn from the n landmarks (with repetition when m > n), some dropped
+    sel = np.stack([np.stack([rng.permutation(n)[:m] if m <= n else rng.integers(0, n, m) for _ in range(B)]) for _ in range(T)])
+    z = np.take_along_axis(sc["z"], sel[..., None], axis=2)
+    ids = np.take_along_axis(sc["ids"], sel, axis=2).astype(np.int32)
+    # step 0 touches every landmark once on the oracle side (full measurement set), so that later steps contain no first touch
+    first = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][:1], sc["z"][:1], sc["ids"][:1])
+    ids[1:][rng.random(ids[1:].shape) < dropout] = 0
+    z = np.ascontiguousarray(z)
+    want = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][1:], z[1:], ids[1:],
+                       init=(first["x"], first["sigma"], first["seen"]))
+    eng = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="fast")
+    eng.set_state(first["x"], first["sigma"], first["seen"])
+    for t in range(1, T):
+        eng.step(sc["twists"][t], z[t], ids[t])
+    x, s, seen, status = eng.get_state()
+    assert not status.any() and np.array_equal(seen, want["seen"])
+    assert rel_max(x, want["x"]) < TOL
+    assert max(rel_max(s[b], want["sigma"][b]) for b in range(B)) < TOL
+    # update-only entry point (m = 1, no predict) through the same kernel
+    eng.update(z[1][:, 0], ids[1][:, 0])
+    fs = oracle_filters(orc, sc, B)
+    for b, f in enumerate(fs):
+        f.set(want["x"][b], want["sigma"][b], want["seen"][b])
+        if ids[1][b, 0] > 0:
+            f.update(z[1][b, 0], ids[1][b, 0])
+    xo, so, _ = oracle_state(fs)
+    x, s, _, _ = eng.get_state()
+    assert rel_max(x, xo) < TOL and max(rel_max(s[b], so[b]) for b in range(B)) < TOL
