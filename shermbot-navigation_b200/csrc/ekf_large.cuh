@@ -9,11 +9,12 @@
 //   one pass  Sigma <- Sigma_0 - [K_0 .. K_{m-1}] [W_0; ..; W_{m-1}]: a rank-2m update on the fp64 tensor pipe (DMMA m8n8k4,
 //             accumulators initialised from Sigma, 32 x 32 tile per warp), HBM-bound: 16 len^2 bytes.
 // The same kernels with m = 1 give the immediate (sequential) form used for the single `update` call and as the in-engine
-// cross-check of the delayed form. Arithmetic: plain fp64 with FMAs in the reference's expressions (H entries by division and
-// sqrt as slam_library.cpp:172-183, double normalize_angle of z_hat as :20,:157); parity <= 1e-9 after the first touch of a
-// landmark (the first touch itself cancels catastrophically in the reference).
+// cross-check of the delayed form. Arithmetic: fp64 with FMAs; H and z_hat through the FAST kernel's short-chain helpers; parity
+// <= 1e-9 after the first touch of a landmark (the first touch itself cancels catastrophically in the reference, SURVEY.md
+// Appendix B).
 #pragma once
-#include "ekf_strict.cuh"
+#include "ekf_fast.cuh"
+#include <cooperative_groups.h>
 
 namespace nuslam
 {
@@ -125,33 +126,67 @@ struct LargeModel
     double h[2][5];   // H(a, q) at q = {0, 1, 2, c, c+1}
     double zr, zb;
 };
-__device__ __forceinline__ LargeModel large_model(const double * x, int c)
+// the five state entries H depends on: (theta, x, y, mx, my). When the step protocol initialises the landmark for this very
+// measurement (id above the scan's seen snapshot, slam.cpp:295-297), (mx, my) are what initializeLandmark (slam_library.cpp:255-261)
+// would have written just before the update -- a pure function of the pose and z, so no separate pass over x is needed.
+__device__ __forceinline__ bool large_local_state(const double * x, int c, int id, const double * z2, const int32_t * seen_snapshot, int b, double * xl)
+{
+    xl[0] = x[0];
+    xl[1] = x[1];
+    xl[2] = x[2];
+    const bool init = seen_snapshot != nullptr && id > seen_snapshot[b];
+    if (init)
+    {
+        double sn, cs;
+        sincos(add_(z2[1], xl[0]), &sn, &cs);
+        xl[3] = add_(xl[1], mul_(z2[0], cs));
+        xl[4] = add_(xl[2], mul_(z2[0], sn));
+    }
+    else
+    {
+        xl[3] = x[c];
+        xl[4] = x[c + 1];
+    }
+    return init;
+}
+
+// Every thread of the two update kernels needs H and z_hat; evaluated with the short-chain helpers of the FAST kernel
+// (rsqrt / table atan2 / branch-free wrap, ~80 instructions, 1-2 ulp) instead of the libm chain of the reference's expressions
+// (sincos + 3 atan2 + 8 divisions, ~800 instructions per thread, which dominated the update time of a large map).
+__device__ __forceinline__ LargeModel large_model(const double * xl)
 {
     LargeModel mdl;
-    HEntries H;
-    measurement_model(x, c, H, mdl.zr, mdl.zb);
+    const double dx = xl[3] - xl[1], dy = xl[4] - xl[2];
+    const double d = fma(dx, dx, dy * dy);
+    const double rs = rsqrt_fast(d);
+    double sq = d * rs;
+    sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);   // sqrt(d) to ~1 ulp
+    const double id = rs * rs;                 // 1 / d
     mdl.h[0][0] = 0.0;
-    mdl.h[0][1] = H.h01;
-    mdl.h[0][2] = H.h02;
-    mdl.h[0][3] = H.h0c;
-    mdl.h[0][4] = H.h0c1;
+    mdl.h[0][1] = -dx * rs;
+    mdl.h[0][2] = -dy * rs;
+    mdl.h[0][3] = dx * rs;
+    mdl.h[0][4] = dy * rs;
     mdl.h[1][0] = -1.0;
-    mdl.h[1][1] = H.h11;
-    mdl.h[1][2] = H.h12;
-    mdl.h[1][3] = H.h1c;
-    mdl.h[1][4] = H.h1c1;
+    mdl.h[1][1] = dy * id;
+    mdl.h[1][2] = -dx * id;
+    mdl.h[1][3] = -dy * id;
+    mdl.h[1][4] = dx * id;
+    mdl.zr = sq;
+    mdl.zb = wrap_angle(atan2_fast(dy, dx) - xl[0]);   // normalize(normalize(atan2) - theta), slam_library.cpp:20,157
     return mdl;
 }
 
 // W_i = H Sigma_i (2 x len) and P_i = Sigma_i H^T (len x 2) for update slot i of the pass; thread j owns index j.
-__global__ void __launch_bounds__(256) k_large_wp(const LargeParams p, const int32_t * __restrict__ ids, int m, int i)
+__device__ __forceinline__ void large_wp(const LargeParams & p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
+                                         const int32_t * __restrict__ seen_snapshot, const double * __restrict__ x_cur)
 {
     const int b = blockIdx.y;
     const int len = p.len;
     const int id = ids[b * m + i];
     if (id < 1 || id > p.n) return;
     const int c = 3 + 2 * (id - 1);
-    const double * x = p.x + (int64_t) b * len;
+    const double * x = x_cur + (int64_t) b * len;
     const double * S = p.sigma + (int64_t) b * len * len;
     const double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
     double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
@@ -168,7 +203,9 @@ __global__ void __launch_bounds__(256) k_large_wp(const LargeParams p, const int
     __syncthreads();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= len) return;
-    const LargeModel mdl = large_model(x, c);
+    double xl[5];
+    large_local_state(x, c, id, z + (int64_t) (b * m + i) * 2, seen_snapshot, b, xl);
+    const LargeModel mdl = large_model(xl);
     double row[5], col[5];   // Sigma_i(idx[q], j) and Sigma_i(j, idx[q])
 #pragma unroll
     for (int q = 0; q < 5; ++q)
@@ -202,8 +239,15 @@ __global__ void __launch_bounds__(256) k_large_wp(const LargeParams p, const int
 }
 
 // K_i = P_i S^-1, x_new = x + K_i dz (slam_library.cpp:270-276); thread j owns index j, every thread forms the 2 x 2 part.
-__global__ void __launch_bounds__(256) k_large_gain(const LargeParams p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
-                                                    const double * __restrict__ x_old, double * __restrict__ x_new)
+__global__ void __launch_bounds__(256) k_large_wp(const LargeParams p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
+                                                  const int32_t * __restrict__ seen_snapshot)
+{
+    large_wp(p, z, ids, m, i, seen_snapshot, p.x);
+}
+
+__device__ __forceinline__ void large_gain(const LargeParams & p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
+                                           const double * __restrict__ x_old, double * __restrict__ x_new,
+                                           const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen)
 {
     const int b = blockIdx.y;
     const int len = p.len;
@@ -224,7 +268,11 @@ __global__ void __launch_bounds__(256) k_large_gain(const LargeParams p, const d
     }
     const int c = 3 + 2 * (id - 1);
     const int idx[5] = {0, 1, 2, c, c + 1};
-    const LargeModel mdl = large_model(x, c);
+    double xl[5];
+    const bool init = large_local_state(x, c, id, z + (int64_t) (b * m + i) * 2, seen_snapshot, b, xl);
+    const double xj = (init && j == c) ? xl[3] : (init && j == c + 1) ? xl[4] : x[j];   // x after initializeLandmark
+    if (j == 0 && seen && id > seen[b]) seen[b] = id;                                     // what associateLandmark would have done to `seen`
+    const LargeModel mdl = large_model(xl);
     double s[2][2];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -241,7 +289,7 @@ __global__ void __launch_bounds__(256) k_large_gain(const LargeParams p, const d
     {
         U[(int64_t) (2 * i) * len + j] = 0.0;
         U[(int64_t) (2 * i + 1) * len + j] = 0.0;
-        xo[j] = x[j];
+        xo[j] = xj;
         if (j == 0) p.status[b] |= kStatusSingular;
         return;
     }
@@ -251,23 +299,46 @@ __global__ void __launch_bounds__(256) k_large_gain(const LargeParams p, const d
     U[(int64_t) (2 * i) * len + j] = k0;
     U[(int64_t) (2 * i + 1) * len + j] = k1;
     const double dz0 = z[(int64_t) (b * m + i) * 2] - mdl.zr, dz1 = z[(int64_t) (b * m + i) * 2 + 1] - mdl.zb;   // :272, no wrap
-    double xn = x[j] + (k0 * dz0 + k1 * dz1);
-    if (j == 0) xn = normalize_angle(xn);   // :276
+    double xn = xj + (k0 * dz0 + k1 * dz1);
+    if (j == 0) xn = wrap_angle(xn);   // normalize_angle, slam_library.cpp:276
     xo[j] = xn;
 }
 
-// singular / skipped slots must not leave stale W rows behind
-__global__ void k_large_clear_w(const LargeParams p, int i)
+__global__ void __launch_bounds__(256) k_large_gain(const LargeParams p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
+                                                    const double * __restrict__ x_old, double * __restrict__ x_new,
+                                                    const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen)
+{
+    large_gain(p, z, ids, m, i, x_old, x_new, seen_snapshot, seen);
+}
+
+// all `cnt` delayed updates of a pass in ONE cooperative launch: the two phases of an update are separated by grid barriers
+// (~2 us) instead of kernel boundaries (~12 us of dependent-launch latency each). x ping-pongs between p.x and p.x2.
+__global__ void __launch_bounds__(64) k_large_updates_coop(const LargeParams p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int cnt,
+                                                          const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const double * xc = p.x;
+    double * xn = p.x2;
+    for (int k = 0; k < cnt; ++k)
+    {
+        large_wp(p, z, ids, m, k, seen_snapshot, xc);
+        grid.sync();
+        large_gain(p, z, ids, m, k, xc, xn, seen_snapshot, seen);
+        grid.sync();
+        const double * t = xc;
+        xc = xn;
+        xn = const_cast<double *>(t);
+    }
+}
+
+// empty the first `nslots` update slots of the pass (skipped / singular measurements and the rank padding contribute nothing)
+__global__ void k_large_clear_w(const LargeParams p, int nslots)
 {
     const int b = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= p.len) return;
-    double * V = p.V + (int64_t) b * 2 * kLargeMMax * p.len;
-    double * U = p.U + (int64_t) b * 2 * kLargeMMax * p.len;
-    V[(int64_t) (2 * i) * p.len + j] = 0.0;
-    V[(int64_t) (2 * i + 1) * p.len + j] = 0.0;
-    U[(int64_t) (2 * i) * p.len + j] = 0.0;
-    U[(int64_t) (2 * i + 1) * p.len + j] = 0.0;
+    const int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t) 2 * nslots * p.len) return;
+    (p.V + (int64_t) b * 2 * kLargeMMax * p.len)[e] = 0.0;
+    (p.U + (int64_t) b * 2 * kLargeMMax * p.len)[e] = 0.0;
 }
 
 __device__ __forceinline__ void dmma884_large(double & c0, double & c1, double a, double b)
@@ -367,16 +438,41 @@ __global__ void k_large_init_landmark(const LargeParams p, const double * __rest
 inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const int32_t * ids, int m, int i0, int cnt,
                                         const int32_t * seen_snapshot, int32_t * seen, cudaStream_t st)
 {
-    const int threads = 256;
+    const int threads = 64;   // ~130 small blocks at len 8195: every SM takes part in the latency-bound row / column gathers
     const dim3 grid((p.len + threads - 1) / threads, (unsigned) p.batch);
     const int kk = (2 * cnt + 3) & ~3;
-    for (int k = 0; k < kk / 2; ++k) k_large_clear_w<<<grid, threads, 0, st>>>(p, k);   // empty slots contribute nothing
+    k_large_clear_w<<<dim3((unsigned) (((int64_t) kk * p.len + threads - 1) / threads), (unsigned) p.batch), threads, 0, st>>>(p, kk / 2);
+    // one cooperative launch when the whole grid is co-resident (it is for a few large maps), else two launches per update
+    static thread_local int coop_blocks_per_sm = -1;
+    if (coop_blocks_per_sm < 0)
+    {
+        int dev = 0, sms = 0, nb = 0, can = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_large_updates_coop, threads, 0);
+        coop_blocks_per_sm = can ? nb * sms : 0;
+    }
+    if ((int64_t) grid.x * grid.y <= coop_blocks_per_sm)
+    {
+        const double * zz = z + 2 * (int64_t) i0;
+        const int32_t * ii = ids + i0;
+        void * args[] = {(void *) &p, (void *) &zz, (void *) &ii, (void *) &m, (void *) &cnt, (void *) &seen_snapshot, (void *) &seen};
+        cudaError_t ce = cudaLaunchCooperativeKernel((const void *) k_large_updates_coop, grid, dim3(threads), args, 0, st);
+        if (ce != cudaSuccess) return ce;
+        if (cnt & 1)
+        {
+            double * tmp = p.x;
+            p.x = p.x2;
+            p.x2 = tmp;
+        }
+    }
+    else
     for (int k = 0; k < cnt; ++k)
     {
         // slot k of the pass holds measurement i0 + k: the kernels index ids / z with (b * m + k) from the shifted base pointers
-        if (seen) k_large_init_landmark<<<(unsigned) ((p.batch + 63) / 64), 64, 0, st>>>(p, z + 2 * (int64_t) i0, ids + i0, m, k, seen_snapshot, seen);
-        k_large_wp<<<grid, threads, 0, st>>>(p, ids + i0, m, k);
-        k_large_gain<<<grid, threads, 0, st>>>(p, z + 2 * (int64_t) i0, ids + i0, m, k, p.x, p.x2);
+        k_large_wp<<<grid, threads, 0, st>>>(p, z + 2 * (int64_t) i0, ids + i0, m, k, seen_snapshot);
+        k_large_gain<<<grid, threads, 0, st>>>(p, z + 2 * (int64_t) i0, ids + i0, m, k, p.x, p.x2, seen_snapshot, seen);
         double * tmp = p.x;
         p.x = p.x2;
         p.x2 = tmp;
