@@ -140,7 +140,12 @@ __device__ long long g_fast_timing[16];
 // BULK: Sigma travels HBM <-> shared memory by bulk async copies (buffer A: the NEXT filter's image, prefetched while the
 // current one is computed; buffer B: the exchange area during the updates, then the output image), so the global side costs
 // no LSU wavefronts and no exposed latency; !BULK: plain per-lane loads / stores (any 8-byte aligned Sigma).
-template <int N, bool BULK>
+// ASSOC: unknown data association (p.ids == nullptr): every measurement is first associated on the device
+// (ExtendedKalman::associateLandmark, slam_library.cpp:188-253: one candidate landmark per lane, Mahalanobis distance from the
+// candidate's 5 x 5 block of Sigma, the reference's in-order early exit = lowest deciding lane) and applied at once (rank-2 pass
+// per measurement instead of the lazy chunks). A measurement that opens a NEW landmark (or a singular innovation) hands the whole
+// filter-step to the strict kernel: nothing has been written back yet, so it restarts from the state in HBM.
+template <int N, bool BULK, bool ASSOC>
 __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm)
 k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ worklist, int32_t * __restrict__ wl_count)
 {
@@ -197,7 +202,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         // small inputs: plain loads, issued before anything waits
         if (vlane) x = p.x[bf * LEN + lane];
         const int st0 = p.status[bf], seen0 = p.seen[bf];
-        const int my_id = (lane < m) ? p.ids[bf * m + lane] : 0;
+        const int my_id = (!ASSOC && lane < m) ? p.ids[bf * m + lane] : 0;
         const double my_z = (lane < 2 * m) ? p.z[bf * m * 2 + lane] : 0.0;
         const double my_tw = (do_predict && lane < 2) ? p.twists[bf * 3 + lane] : 0.0;
         if (BULK)
@@ -265,6 +270,16 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         }
         // ---- liveness ----
         if (st0 & (kStatusMapFull | kStatusSingular)) continue;   // the reference process died on an earlier scan
+        if (ASSOC)
+        {
+            // an empty map: the first measurement opens landmark 1 (slam_library.cpp:196-200) -> strict kernel
+            if (seen0 == 0 && m > 0)
+            {
+                if (lane == 0) worklist[atomicAdd(wl_count, 1)] = (int32_t) bf;
+                continue;
+            }
+        }
+        else
         {
             const bool idok = (unsigned) (my_id - 1) < (unsigned) N;
             const int c = idok ? 1 + 2 * my_id : 3;
@@ -297,7 +312,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 }
             }
         }
-        if (lane < m) f.ids[lane] = my_id;
+        if (!ASSOC && lane < m) f.ids[lane] = my_id;
         if (lane < 2 * m) f.z[lane] = my_z;
         // robot pose, replicated in every lane; lanes 0..2 own the same values in x (bit-identical updates)
         double th = __shfl_sync(kFull, x, 0), px = __shfl_sync(kFull, x, 1), py = __shfl_sync(kFull, x, 2);
@@ -375,15 +390,115 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         NUSLAM_T(1)
 
         // ---- m sequential updates in chunks of 2 (slam.cpp:279-319, known correspondence) ----
+        bool handed_over = false;
 #pragma unroll 1
-        for (int i0 = 0; i0 < m; i0 += 2)
+        for (int i0 = 0; i0 < m; i0 += (ASSOC ? 1 : 2))
         {
+            int assoc_id = 0;
+            if (ASSOC)
+            {
+                // ---- associateLandmark(z_i0): one candidate landmark per lane ----
+                // exchange: the six robot vectors and the 2 x 2 diagonal blocks of the landmark block (slot 1 of the exchange
+                // area is free in this mode: one measurement per pass)
+                f.kt[1][lane] = make_double2(Rt, Rx);
+                f.wt[1][lane] = make_double2(Ry, Ct);
+                f.kap[1][lane] = make_double2(Cx, Cy);
+                double2 * dg = reinterpret_cast<double2 *>(&f.rho[1][0][0]);
+#pragma unroll
+                for (int bb = 0; bb < NB; ++bb)
+                    if (t == (g >> 1)) dg[8 * bb + g] = make_double2(C[bb][bb][0], C[bb][bb][1]);
+                __syncwarp();
+                const bool cand = lane < seen0;
+                const int c = cand ? 3 + 2 * lane : 3;
+                double Bm[5][5];   // Sigma at rows / columns (theta, x, y, c, c+1)
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                {
+                    const double2 a = f.kt[1][q], b2 = f.wt[1][q];
+                    Bm[0][q] = a.x;
+                    Bm[1][q] = a.y;
+                    Bm[2][q] = b2.x;
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                {
+                    const double2 a = f.kt[1][c + e], b2 = f.wt[1][c + e], c2 = f.kap[1][c + e];
+                    Bm[0][3 + e] = a.x;    // Sigma(r, c+e) = entry c+e of the row vectors
+                    Bm[1][3 + e] = a.y;
+                    Bm[2][3 + e] = b2.x;
+                    Bm[3 + e][0] = b2.y;   // Sigma(c+e, r) = entry c+e of the column vectors
+                    Bm[3 + e][1] = c2.x;
+                    Bm[3 + e][2] = c2.y;
+                }
+                {
+                    const int tl = cand ? 2 * lane : 0;
+                    const double2 d0 = dg[tl], d1 = dg[tl + 1];
+                    Bm[3][3] = d0.x;
+                    Bm[3][4] = d0.y;
+                    Bm[4][3] = d1.x;
+                    Bm[4][4] = d1.y;
+                }
+                const double2 mxy = *reinterpret_cast<const double2 *>(&f.xs[c + 1]);
+                const double2 zz = *reinterpret_cast<const double2 *>(&f.z[2 * i0]);
+                const double dx = mxy.x - px, dy = mxy.y - py;
+                const double d = fma(dx, dx, dy * dy);
+                const double h0[5] = {0.0, -dx, -dy, dx, dy}, h1[5] = {-d, dy, -dx, -dy, dx};
+                double w0[5], w1[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                {
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 5; ++r)
+                    {
+                        a0 = fma(h0[r], Bm[r][q], a0);
+                        a1 = fma(h1[r], Bm[r][q], a1);
+                    }
+                    w0[q] = a0;
+                    w1[q] = a1;
+                }
+                double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                {
+                    s00 = fma(w0[q], h0[q], s00);
+                    s01 = fma(w0[q], h1[q], s01);
+                    s10 = fma(w1[q], h0[q], s10);
+                    s11 = fma(w1[q], h1[q], s11);
+                }
+                const double rs = rsqrt_fast(d);
+                double sq = d * rs;
+                sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);
+                const double dsq = d * sq;
+                const double m00 = fma(d, R00, s00), m10 = fma(dsq, R10, s10), m01 = fma(dsq, R01, s01), m11 = fma(d * d, R11, s11);
+                const double det = fma(m00, m11, -m01 * m10);
+                const double idet = rcp_fast(det);
+                const double zb = wrap_angle(atan2_fast(dy, dx) - th);
+                const double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);   // no angle wrap (:229-231)
+                const double i00 = m11 * idet, i01 = -m01 * idet, i10 = -m10 * idet, i11 = m00 * idet;
+                const double t0 = fma(n0, i00, n1 * i10), t1 = fma(n0, i01, n1 * i11);
+                const double dist = fma(t0, n0, t1 * n1);   // (dz^T psi^-1) dz
+                const bool sing = cand && !(fabs(idet) < 1.0e300);
+                const unsigned m_sing = __ballot_sync(kFull, sing);
+                const unsigned hitA = __ballot_sync(kFull, cand && !sing && (dist < p.amin));
+                const unsigned hitB = __ballot_sync(kFull, cand && !sing && (dist > p.amin) && (dist < p.amax));
+                const unsigned any = hitA | hitB | m_sing;
+                if (any == 0u || ((m_sing >> (__ffs(any) - 1)) & 1u))
+                {
+                    // no candidate decides: a NEW landmark (initializeLandmark + first touch), or arma::inv would throw: strict kernel
+                    handed_over = true;
+                    break;
+                }
+                assoc_id = ((hitA >> (__ffs(any) - 1)) & 1u) ? __ffs(any) : -1;
+                if (p.ids_out && lane == 0) p.ids_out[bf * m + i0] = assoc_id;
+                __syncwarp();
+            }
             // (A) publish the chunk's landmark rows / columns from the (stale) fragments into vector layout
             int cc[2];
 #pragma unroll
             for (int s = 0; s < 2; ++s)
             {
-                const int id = (i0 + s < m) ? f.ids[i0 + s] : 0;
+                const int id = ASSOC ? (s == 0 ? assoc_id : 0) : ((i0 + s < m) ? f.ids[i0 + s] : 0);
                 const bool live = (unsigned) (id - 1) < (unsigned) N;   // warp-uniform
                 cc[s] = live ? 1 + 2 * id : -1;
                 if (id > N) status |= kStatusBadId;
@@ -443,7 +558,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             for (int s = 0; s < 2; ++s)
             {
                 bool done = false;
-                if (cc[s] >= 0)   // warp-uniform
+                if (cc[s] >= 0)   // warp-uniform (never true for slot 1 in ASSOC mode)
                 {
                     const int c = cc[s];
                     // landmark rows c, c+1 (lane = column) and columns c, c+1 (lane = row)
@@ -553,6 +668,11 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             NUSLAM_T(6)
         }
 
+        if (ASSOC && handed_over)
+        {
+            if (lane == 0) worklist[atomicAdd(wl_count, 1)] = (int32_t) bf;
+            continue;
+        }
         // ---- write back ----
         if (BULK)
         {
@@ -650,21 +770,30 @@ int launch_fast_n(const EkfParams & p, bool do_predict, int sm_count, int32_t * 
     if (!configured)
     {
         // 16 CTAs x 11.8 KB of static shared memory per SM: ask for the largest shared-memory carve-out
-        cudaFuncSetAttribute(k_ekf_fast_step<N, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(k_ekf_fast_step<N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_ekf_fast_step<N, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_ekf_fast_step<N, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_ekf_fast_step<N, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_ekf_fast_step<N, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured = true;
     }
-    if ((reinterpret_cast<uintptr_t>(p.sigma) & 15) == 0)
-        k_ekf_fast_step<N, true><<<(unsigned) blocks, kFastThreads, 0, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
+    const bool bulk = (reinterpret_cast<uintptr_t>(p.sigma) & 15) == 0;
+    if (p.ids == nullptr)
+    {
+        if (bulk) k_ekf_fast_step<N, true, true><<<(unsigned) blocks, kFastThreads, 0, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
+        else k_ekf_fast_step<N, false, true><<<(unsigned) blocks, kFastThreads, 0, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
+    }
+    else if (bulk)
+        k_ekf_fast_step<N, true, false><<<(unsigned) blocks, kFastThreads, 0, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
     else
-        k_ekf_fast_step<N, false><<<(unsigned) blocks, kFastThreads, 0, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
+        k_ekf_fast_step<N, false, false><<<(unsigned) blocks, kFastThreads, 0, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
     return (int) cudaGetLastError();
 }
 
 // returns 0 on success, -1 when this configuration is not covered (caller falls back to the strict kernel), else a cudaError_t
 inline int launch_fast(int n, const EkfParams & p, bool do_predict, int sm_count, int32_t * worklist, int32_t * wl_count, cudaStream_t stream)
 {
-    if (p.m > kFastMMax || p.m < 0 || p.ids == nullptr) return -1;
+    if (p.m > kFastMMax || p.m < 0) return -1;
+    if (p.ids == nullptr && !do_predict) return -1;   // association belongs to the step protocol
     if ((reinterpret_cast<uintptr_t>(p.sigma) & 7) || (reinterpret_cast<uintptr_t>(p.x) & 7)) return -1;
     if (n == 12) return launch_fast_n<12>(p, do_predict, sm_count, worklist, wl_count, stream);
     if (n == 6) return launch_fast_n<6>(p, do_predict, sm_count, worklist, wl_count, stream);

@@ -611,15 +611,16 @@ int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, con
         }
         if (ids_out && m > 0) CU(cudaMemcpyAsync(p.ids_out, p.ids, sizeof(int32_t) * h->batch * m, cudaMemcpyDeviceToDevice, h->stream));
     }
-    else if (h->cfg.mode == NUSLAM_MODE_FAST && p.ids != nullptr)
+    else if (h->cfg.mode == NUSLAM_MODE_FAST && m <= nuslam::kFastMMax)
     {
+        // known correspondence, or on-device association (ids == NULL): the register kernel, then the strict kernel over the
+        // filters it handed over (first touches, new landmarks)
         rc = launch_fast_then_strict<nuslam::kOpStep>(h, p, /*do_predict=*/true);
         if (rc) return rc;
     }
     else
     {
-        // unknown data association runs the strict kernel in either mode (association is a per-lane
-        // candidate search over Sigma in shared memory)
+        // STRICT mode (and steps with more than kFastMMax measurements): the oracle-order kernel, association included
         rc = launch_strict<nuslam::kOpStep>(h, p);
         if (rc) return rc;
     }

@@ -231,13 +231,15 @@ def test_step_from_scratch_reported(cuda_lib, orc, mode):
     assert ex < 1e-3 and es < 1e-3
 
 
-def test_step_unknown_association_teacher_forced(cuda_lib, orc):
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_step_unknown_association_teacher_forced(cuda_lib, orc, mode):
     """Fused step with on-device association: ids bit-exact and state within 1e-9 when every step starts
-    from the oracle's state."""
+    from the oracle's state. FAST mode associates in the register kernel (one candidate per lane) and hands steps that open a
+    new landmark to the strict kernel."""
     B, T, n = 16, 30, 12
     for geometry in ("benign", "adversarial"):
         sc = synth.ekf_scenario(B, T, n=n, geometry=geometry, seed=17, shuffle_order=True)
-        eng = make_engine(cuda_lib, sc)
+        eng = make_engine(cuda_lib, sc, mode)
         state = None
         mism = 0
         worst = 0.0
@@ -252,7 +254,7 @@ def test_step_unknown_association_teacher_forced(cuda_lib, orc):
             worst = max(worst, rel_max(x, o["x"]))
             assert np.array_equal(seen, o["seen"])
             state = (o["x"], o["sigma"], o["seen"])
-        print(f"[step/unknown {geometry}] id mismatches {mism} of {B * T * n}, worst x rel {worst:.3e}")
+        print(f"[step/unknown {geometry}/{mode}] id mismatches {mism} of {B * T * n}, worst x rel {worst:.3e}")
         assert mism == 0
 
 
@@ -379,3 +381,24 @@ def test_fast_step_shapes(cuda_lib, orc, B, n, m, dropout):
     xo, so, _ = oracle_state(fs)
     x, s, _, _ = eng.get_state()
     assert rel_max(x, xo) < TOL and max(rel_max(s[b], so[b]) for b in range(B)) < TOL
+
+
+def test_fast_association_free_running(cuda_lib, orc):
+    """Config-4 style: unknown association, FAST mode, free running for 40 steps after the map has been built (the oracle's state
+    after 3 steps): association ids identical to the oracle's at every step, final state <= 1e-9."""
+    B, T, n = 64, 43, 12
+    sc = synth.ekf_scenario(B, T, n=n, geometry="benign", seed=23, shuffle_order=True)
+    head = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][:3], sc["z"][:3], None)
+    full = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"], sc["z"], None)
+    eng = make_engine(cuda_lib, sc, "fast")
+    eng.set_state(head["x"], head["sigma"], head["seen"])
+    mism = 0
+    for t in range(3, T):
+        ids = eng.step(sc["twists"][t], sc["z"][t], None, return_ids=True)
+        mism += int((ids != full["ids_out"][t]).sum())
+    x, s, seen, status = eng.get_state()
+    ex, es = rel_max(x, full["x"]), max(rel_max(s[b], full["sigma"][b]) for b in range(B))
+    matched = int((full["ids_out"][3:] > 0).sum())
+    print(f"[fast association] {B * (T - 3) * n} decisions, {matched} matches applied, id mismatches {mism}; x rel {ex:.2e}, Sigma rel {es:.2e}")
+    assert mism == 0 and np.array_equal(seen, full["seen"]) and np.array_equal(status, full["status"])
+    assert ex < TOL and es < TOL
