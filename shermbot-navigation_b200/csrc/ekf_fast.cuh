@@ -43,6 +43,10 @@ constexpr int kFastThreads = 32;                   // one warp = one filter in f
 #ifndef NUSLAM_FAST_CTAS
 #define NUSLAM_FAST_CTAS 16
 #endif
+#ifndef NUSLAM_FAST_SINGLE_STAGE
+#define NUSLAM_FAST_SINGLE_STAGE 0   // 1: one staging buffer per CTA (input image -> exchange area -> output image): half the shared memory
+#endif
+constexpr bool kFastSingleStage = NUSLAM_FAST_SINGLE_STAGE != 0;
 constexpr int kFastCtasPerSm = NUSLAM_FAST_CTAS;   // 16 single-warp CTAs / SM at 128 registers (20 at 96 registers spill; measured slower)
 constexpr int kFastMMax = 16;                      // measurements per step handled by this kernel
 
@@ -155,14 +159,14 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
     constexpr int kImg = SIG * 8;                                   // bytes of one Sigma
     constexpr int kWin = ((kImg + 8 + 15) / 16) * 16;               // 16-byte aligned window that covers it at either alignment
     constexpr int kStage = ((kWin > (int) sizeof(FastSmem<N>) ? kWin : (int) sizeof(FastSmem<N>)) + 127) / 128 * 128;
-    __shared__ __align__(128) unsigned char stage[BULK ? 2 : 1][kStage];
+    constexpr int kStages = (BULK && !kFastSingleStage) ? 2 : 1;
+    __shared__ __align__(128) unsigned char stage[kStages][kStage];
     __shared__ uint64_t full_bar;
-    FastSmem<N> & f = *reinterpret_cast<FastSmem<N> *>(stage[BULK ? 1 : 0]);
+    FastSmem<N> & f = *reinterpret_cast<FastSmem<N> *>(stage[kStages - 1]);
     const int lane = threadIdx.x;
     const int m = p.m;
     const int g = lane >> 2, t = lane & 3;
     const bool vlane = lane < LEN;      // lane owns a state index
-    const double R00 = p.R[0], R10 = p.R[1], R01 = p.R[2], R11 = p.R[3];
     // zero the exchange buffers once (entries of lanes without a state index stay zero)
     for (int k = lane; k < (int) (sizeof(FastSmem<N>) / 8); k += 32) reinterpret_cast<double *>(&f)[k] = 0.0;
     __syncwarp();
@@ -235,8 +239,17 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 diag = img[lane * (LEN + 1)];   // Sigma(lane, lane): first-touch detection
             }
             __syncwarp();
-            // buffer A is free again: prefetch this CTA's next filter while the current one is computed
-            if (lane == 0 && bf + gridDim.x < p.batch) issue_load(bf + gridDim.x);
+            if (!kFastSingleStage)
+            {
+                // buffer A is free again: prefetch this CTA's next filter while the current one is computed
+                if (lane == 0 && bf + gridDim.x < p.batch) issue_load(bf + gridDim.x);
+            }
+            else if (lane == 0 && bf + gridDim.x < p.batch)
+            {
+                // single buffer: it becomes the exchange area now; pull the next image towards L2 meanwhile
+                const uintptr_t a0 = reinterpret_cast<uintptr_t>(p.sigma + (bf + gridDim.x) * SIG) & ~(uintptr_t) 15;
+                prefetch_l2_bulk(reinterpret_cast<const void *>(a0), (uint32_t) ((sizeof(double) * SIG + 15) & ~15u));
+            }
         }
         else
         {
@@ -268,14 +281,27 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 diag = gs[lane * (LEN + 1)];
             }
         }
+        // single staging buffer: whoever leaves this iteration must start the next image's copy (nothing is in flight otherwise)
+        auto leave = [&]() {
+            if (BULK && kFastSingleStage)
+            {
+                __syncwarp();
+                if (lane == 0 && bf + gridDim.x < p.batch) issue_load(bf + gridDim.x);
+            }
+        };
         // ---- liveness ----
-        if (st0 & (kStatusMapFull | kStatusSingular)) continue;   // the reference process died on an earlier scan
+        if (st0 & (kStatusMapFull | kStatusSingular))   // the reference process died on an earlier scan
+        {
+            leave();
+            continue;
+        }
         if (ASSOC)
         {
             // an empty map: the first measurement opens landmark 1 (slam_library.cpp:196-200) -> strict kernel
             if (seen0 == 0 && m > 0)
             {
                 if (lane == 0) worklist[atomicAdd(wl_count, 1)] = (int32_t) bf;
+                leave();
                 continue;
             }
         }
@@ -289,6 +315,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             if (__any_sync(kFull, need))
             {
                 if (lane == 0) worklist[atomicAdd(wl_count, 1)] = (int32_t) bf;
+                leave();
                 continue;
             }
         }
@@ -470,7 +497,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 double sq = d * rs;
                 sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);
                 const double dsq = d * sq;
-                const double m00 = fma(d, R00, s00), m10 = fma(dsq, R10, s10), m01 = fma(dsq, R01, s01), m11 = fma(d * d, R11, s11);
+                const double m00 = fma(d, p.R[0], s00), m10 = fma(dsq, p.R[1], s10), m01 = fma(dsq, p.R[2], s01), m11 = fma(d * d, p.R[3], s11);
                 const double det = fma(m00, m11, -m01 * m10);
                 const double idet = rcp_fast(det);
                 const double zb = wrap_angle(atan2_fast(dy, dx) - th);
@@ -553,7 +580,6 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             }
             __syncwarp();
             NUSLAM_T(2)
-            double pW0 = 0.0, pW1 = 0.0, pK0 = 0.0, pK1 = 0.0;   // Wt and -Kt of the chunk's first update
 #pragma unroll
             for (int s = 0; s < 2; ++s)
             {
@@ -571,10 +597,11 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     {
                         // the fragments predate the chunk's first update: bring the four vectors up to date with it
                         const double2 ka = f.kt[0][c], kb = f.kt[0][c + 1], wa2 = f.wt[0][c], wb2 = f.wt[0][c + 1];
-                        rho0 = fma(ka.x, pW0, fma(ka.y, pW1, rho0));
-                        rho1 = fma(kb.x, pW0, fma(kb.y, pW1, rho1));
-                        kap0 = fma(pK0, wa2.x, fma(pK1, wa2.y, kap0));
-                        kap1 = fma(pK0, wb2.x, fma(pK1, wb2.y, kap1));
+                        const double2 pW = f.wt[0][lane], pK = f.kt[0][lane];   // this lane's Wt and -Kt of the chunk's first update
+                        rho0 = fma(ka.x, pW.x, fma(ka.y, pW.y, rho0));
+                        rho1 = fma(kb.x, pW.x, fma(kb.y, pW.y, rho1));
+                        kap0 = fma(pK.x, wa2.x, fma(pK.y, wa2.y, kap0));
+                        kap1 = fma(pK.x, wb2.x, fma(pK.y, wb2.y, kap1));
                     }
                     // (B) Pt (row role) and Wt (column role) of this lane
                     const double dx = mxy.x - px, dy = mxy.y - py;
@@ -595,7 +622,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     double sq = d * rs;
                     sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);   // sqrt(d) to ~1 ulp
                     const double dsq = d * sq;
-                    const double m00 = fma(d, R00, s00), m10 = fma(dsq, R10, s10), m01 = fma(dsq, R01, s01), m11 = fma(d * d, R11, s11);
+                    const double m00 = fma(d, p.R[0], s00), m10 = fma(dsq, p.R[1], s10), m01 = fma(dsq, p.R[2], s01), m11 = fma(d * d, p.R[3], s11);
                     const double det = fma(m00, m11, -m01 * m10);
                     const double idet = rcp_fast(det);
                     // the bearing chain (atan2, wrap) is independent of the Minv chain: evaluated before the branch so that the two
@@ -627,13 +654,6 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                         Ct = fma(nk0, g0.x, fma(nk1, g0.y, Ct));
                         Cx = fma(nk0, g1.x, fma(nk1, g1.y, Cx));
                         Cy = fma(nk0, g2.x, fma(nk1, g2.y, Cy));
-                        if (s == 0)
-                        {
-                            pW0 = W0;
-                            pW1 = W1;
-                            pK0 = nk0;
-                            pK1 = nk1;
-                        }
                         __syncwarp();
                         NUSLAM_T(5)
                     }
@@ -671,6 +691,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         if (ASSOC && handed_over)
         {
             if (lane == 0) worklist[atomicAdd(wl_count, 1)] = (int32_t) bf;
+            leave();
             continue;
         }
         // ---- write back ----
@@ -681,7 +702,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             __syncwarp();
             double * gw = p.sigma + bf * SIG;
             const int odd = (int) ((reinterpret_cast<uintptr_t>(gw) >> 3) & 1);   // 1: HBM image starts 8 bytes past a 16-byte boundary
-            double * img = reinterpret_cast<double *>(stage[1]) + odd;
+            double * img = reinterpret_cast<double *>(stage[kStages - 1]) + odd;
 #pragma unroll
             for (int br = 0; br < NB; ++br)
 #pragma unroll
@@ -715,6 +736,12 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 const int edge = odd ? 0 : SIG - 1;
                 gw[edge] = img[edge];
                 if (status != st0) p.status[bf] = status;
+                if (kFastSingleStage)
+                {
+                    // the buffer is reused for the next input image as soon as the store has read it
+                    bulk_wait_read();
+                    if (bf + gridDim.x < p.batch) issue_load(bf + gridDim.x);
+                }
             }
         }
         else

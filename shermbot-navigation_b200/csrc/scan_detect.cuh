@@ -188,9 +188,11 @@ __device__ inline void eig_sym4(const double * X, double * val, double * vec)
             }
         if (off == 0.0 || off <= mul_(1e-40, diag)) break;
         // The oracle's loop practically never meets its criterion (the lower triangle, which no rotation targets, stalls at
-        // ~1e-17 relative) and runs all 100 sweeps, but after ~12 of them a sweep leaves A and W bit for bit unchanged: from a
-        // fixed point every further sweep is the same no-op, so stopping there returns exactly what sweep 100 would.
-        bool changed = false;
+        // ~1e-17 relative) and runs all 100 sweeps. Its OUTPUT is diag(A) and W. Once a whole sweep consists of rotations with
+        // c == 1 exactly that leave diag(A) and W bit for bit unchanged, every later sweep does too: the off-diagonal entries
+        // only keep shrinking (quadratically), so every later |sn| is smaller and sn * x stays below half an ulp of the entry it
+        // would be added to. Stopping there returns exactly what sweep 100 would (checked bit for bit against the oracle).
+        bool out_changed = false, all_c1 = true;
 #pragma unroll
         for (int p = 0; p < 3; ++p)
 #pragma unroll
@@ -203,36 +205,35 @@ __device__ inline void eig_sym4(const double * X, double * val, double * vec)
                     const double tt = div_((theta >= 0.0 ? 1.0 : -1.0), add_(fabs(theta), sqrt(add_(1.0, mul_(theta, theta)))));
                     const double c = div_(1.0, sqrt(add_(1.0, mul_(tt, tt))));
                     const double sn = mul_(c, tt);
+                    all_c1 &= (c == 1.0);
+                    const double dpp = A[p + p * 4], dqq = A[q + q * 4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                     {
                         const double akp = A[k + p * 4], akq = A[k + q * 4];
-                        const double n1 = sub_(mul_(c, akp), mul_(sn, akq)), n2 = add_(mul_(sn, akp), mul_(c, akq));
-                        changed |= !(n1 == akp) | !(n2 == akq);
-                        A[k + p * 4] = n1;
-                        A[k + q * 4] = n2;
+                        A[k + p * 4] = sub_(mul_(c, akp), mul_(sn, akq));
+                        A[k + q * 4] = add_(mul_(sn, akp), mul_(c, akq));
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                     {
                         const double apk = A[p + k * 4], aqk = A[q + k * 4];
-                        const double n1 = sub_(mul_(c, apk), mul_(sn, aqk)), n2 = add_(mul_(sn, apk), mul_(c, aqk));
-                        changed |= !(n1 == apk) | !(n2 == aqk);
-                        A[p + k * 4] = n1;
-                        A[q + k * 4] = n2;
+                        A[p + k * 4] = sub_(mul_(c, apk), mul_(sn, aqk));
+                        A[q + k * 4] = add_(mul_(sn, apk), mul_(c, aqk));
                     }
+                    out_changed |= !(A[p + p * 4] == dpp) | !(A[q + q * 4] == dqq);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                     {
                         const double wp = W[k + p * 4], wq = W[k + q * 4];
                         const double n1 = sub_(mul_(c, wp), mul_(sn, wq)), n2 = add_(mul_(sn, wp), mul_(c, wq));
-                        changed |= !(n1 == wp) | !(n2 == wq);
+                        out_changed |= !(n1 == wp) | !(n2 == wq);
                         W[k + p * 4] = n1;
                         W[k + q * 4] = n2;
                     }
                 }
             }
-        if (!changed) break;
+        if (!out_changed && all_c1) break;
     }
     int order[4] = {0, 1, 2, 3};
 #pragma unroll
@@ -325,32 +326,10 @@ __device__ __forceinline__ void mm4(double * C, const double * A, const double *
 
 constexpr int kFitException = -1000;   // solve() on a singular Y: Armadillo throws
 
-// circleFit, circle_fit_library.cpp:15-134. Z (work matrix, N x 4 column-major) lives in shared memory.
-// Returns marker.id (0, or -1 when N < 4); out = (pose.x, pose.y, scale.x / 2).
-template <typename PX, typename PY>
-__device__ inline int circle_fit(int N, PX X, PY Y, const WorkMatrix Z, double * out3)
+// circleFit after the SVD (circle_fit_library.cpp:78-125): A from sigma_4 / the eigenproblem of Y Hinv Y, then centre and radius
+__device__ inline int circle_fit_tail(const double * s, const double * V, double z_bar, double x_hat, double y_hat, double * out3)
 {
-    out3[0] = out3[1] = out3[2] = 0.0;
-    double x_hat = 0.0, y_hat = 0.0;
-    for (int i = 0; i < N; ++i)
-    {
-        x_hat = add_(x_hat, div_(X(i), (double) N));   // :23-24, size_t divisor converts to double
-        y_hat = add_(y_hat, div_(Y(i), (double) N));
-    }
-    double z_bar = 0.0;
-    for (int j = 0; j < N; ++j)
-    {
-        const double dx = sub_(X(j), x_hat), dy = sub_(Y(j), y_hat);
-        const double z = add_(mul_(dx, dx), mul_(dy, dy));   // pow(x, 2) + pow(y, 2)
-        z_bar = add_(z_bar, div_(z, (double) N));
-        Z(j, 0) = z;
-        Z(j, 1) = dx;
-        Z(j, 2) = dy;
-        Z(j, 3) = 1.0;
-    }
-    if (N < 4) return -1;   // s.size() < 4 (:72-76)
-    double s[4], V[16], Aco[4];
-    svd_n4(Z, N, s, V);
+    double Aco[4];
     if (s[3] < 1e-12)   // :78-80
     {
 #pragma unroll
@@ -408,6 +387,35 @@ __device__ inline int circle_fit(int N, PX X, PY Y, const WorkMatrix Z, double *
     return 0;
 }
 
+// circleFit, circle_fit_library.cpp:15-134. Z (work matrix, N x 4 column-major) lives in shared memory.
+// Returns marker.id (0, or -1 when N < 4); out = (pose.x, pose.y, scale.x / 2).
+template <typename PX, typename PY>
+__device__ inline int circle_fit(int N, PX X, PY Y, const WorkMatrix Z, double * out3)
+{
+    out3[0] = out3[1] = out3[2] = 0.0;
+    double x_hat = 0.0, y_hat = 0.0;
+    for (int i = 0; i < N; ++i)
+    {
+        x_hat = add_(x_hat, div_(X(i), (double) N));   // :23-24, size_t divisor converts to double
+        y_hat = add_(y_hat, div_(Y(i), (double) N));
+    }
+    double z_bar = 0.0;
+    for (int j = 0; j < N; ++j)
+    {
+        const double dx = sub_(X(j), x_hat), dy = sub_(Y(j), y_hat);
+        const double z = add_(mul_(dx, dx), mul_(dy, dy));   // pow(x, 2) + pow(y, 2)
+        z_bar = add_(z_bar, div_(z, (double) N));
+        Z(j, 0) = z;
+        Z(j, 1) = dx;
+        Z(j, 2) = dy;
+        Z(j, 3) = 1.0;
+    }
+    if (N < 4) return -1;   // s.size() < 4 (:72-76)
+    double s[4], V[16];
+    svd_n4(Z, N, s, V);
+    return circle_fit_tail(s, V, z_bar, x_hat, y_hat, out3);
+}
+
 // Work list of the two-stage pipeline: one entry per kept cluster of the chunk of scans in flight
 struct ClusterDesc
 {
@@ -429,9 +437,10 @@ struct ScanPipe
     ClusterDesc * desc;      // chunk * kMaxFastClusters
     ClusterFit * fit;        // same
     int32_t * big;           // indices into desc of clusters with more than kFitNMax points
+    int32_t * mid;           // indices into desc of clusters with 17 .. kFitNMax points
     int32_t * slow;          // scans (global index) with more than kMaxFastClusters clusters
     int32_t * scan_base;     // per scan of the chunk: first entry in desc, -1 for slow / UB scans
-    int32_t * counters;      // [0] entries in desc, [1] entries in big, [2] entries in slow
+    int32_t * counters;      // [0] entries in desc, [1] entries in big, [2] entries in slow, [3] entries in mid
     int64_t scan0;           // first scan of the chunk
 };
 
@@ -597,6 +606,7 @@ k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_ran
                     d.q = lane;
                     pipe.desc[base + lane] = d;
                     if (n > kFitNMax) pipe.big[atomicAdd(&pipe.counters[1], 1)] = base + lane;
+                    else if (n > 16) pipe.mid[atomicAdd(&pipe.counters[3], 1)] = base + lane;
                 }
             }
             if (lane == 0)
@@ -743,18 +753,21 @@ __device__ __forceinline__ void classify_and_publish(int n, const WorkMatrix Z, 
     }
 }
 
-// stage 2: one THREAD per cluster of up to kFitNMax points; work matrices interleaved over the CTA's threads in shared memory
+// stage 2: one THREAD per cluster; work matrices interleaved over the CTA's threads in shared memory. Two instantiations: up to 16
+// points straight from the work list (most tube clusters; 32 KB per CTA) and 17..32 points from their own dense list.
+template <int NMAX, bool FROM_LIST>
 __global__ void __launch_bounds__(kFitThreads) k_scan_fit_small(const float * __restrict__ ranges, double min_range, double max_range, ScanPipe pipe)
 {
     extern __shared__ __align__(16) unsigned char fit_smem_raw[];
     double * base = reinterpret_cast<double *>(fit_smem_raw) + threadIdx.x;
-    const WorkMatrix Z = {base, kFitNMax, kFitThreads};
-    const int total = pipe.counters[0];
-    for (int idx = blockIdx.x * kFitThreads + threadIdx.x; idx < total; idx += gridDim.x * kFitThreads)
+    const WorkMatrix Z = {base, NMAX, kFitThreads};
+    const int total = FROM_LIST ? pipe.counters[3] : pipe.counters[0];
+    for (int w = blockIdx.x * kFitThreads + threadIdx.x; w < total; w += gridDim.x * kFitThreads)
     {
+        const int idx = FROM_LIST ? pipe.mid[w] : w;
         const ClusterDesc d = pipe.desc[idx];
         const int n = d.n_wrap & 0xffff;
-        if (n > kFitNMax) continue;   // stage 2b
+        if (n > NMAX) continue;   // a larger size class: another stage's cluster
         gather_points(d, ranges, min_range, max_range, [&](int i, double x, double y) {
             Z(i, 1) = x;
             Z(i, 2) = y;
@@ -765,13 +778,110 @@ __global__ void __launch_bounds__(kFitThreads) k_scan_fit_small(const float * __
     }
 }
 
-// stage 2b: clusters with more points (walls): one warp per cluster. The inscribed angles of classifyCluster (one atan2
-// each, the expensive part) are evaluated by all lanes into shared memory; lane 0 then accumulates mean and variance in the
-// reference's order (bit-identical to the sequential evaluation) and, for the rare cluster that passes, runs the fit.
+// Warp-cooperative form of svd_n4 for large m: the products and the rotations are spread over the lanes, every SUM is still
+// accumulated by lane 0 in ascending row order, so the result is bit-identical to the sequential routine.
+__device__ inline void svd_n4_warp(double * A, int m, double * prod, int lane, double * s, double * V)
+{
+    constexpr unsigned kFull = 0xffffffffu;
+    double W[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) W[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep)
+    {
+        bool rotated = false;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q)
+            {
+                for (int i = lane; i < m; i += 32)
+                {
+                    const double ap = A[i + p * m], aq = A[i + q * m];
+                    prod[i] = mul_(ap, ap);
+                    prod[m + i] = mul_(aq, aq);
+                    prod[2 * m + i] = mul_(ap, aq);
+                }
+                __syncwarp();
+                double alpha = 0.0, beta = 0.0, gamma = 0.0;
+                if (lane == 0)
+                    for (int i = 0; i < m; ++i)
+                    {
+                        alpha = add_(alpha, prod[i]);
+                        beta = add_(beta, prod[m + i]);
+                        gamma = add_(gamma, prod[2 * m + i]);
+                    }
+                alpha = __shfl_sync(kFull, alpha, 0);
+                beta = __shfl_sync(kFull, beta, 0);
+                gamma = __shfl_sync(kFull, gamma, 0);
+                const bool skip = (gamma == 0.0) || (fabs(gamma) <= 1e-300) ||
+                                  (fabs(gamma) <= mul_(2.220446049250313e-16, sqrt(mul_(alpha, beta))));
+                if (!skip)
+                {
+                    rotated = true;
+                    const double zeta = div_(sub_(beta, alpha), mul_(2.0, gamma));
+                    const double tt = div_((zeta >= 0.0 ? 1.0 : -1.0), add_(fabs(zeta), sqrt(add_(1.0, mul_(zeta, zeta)))));
+                    const double c = div_(1.0, sqrt(add_(1.0, mul_(tt, tt))));
+                    const double sn = mul_(c, tt);
+                    for (int i = lane; i < m; i += 32)
+                    {
+                        const double ap = A[i + p * m], aq = A[i + q * m];
+                        A[i + p * m] = sub_(mul_(c, ap), mul_(sn, aq));
+                        A[i + q * m] = add_(mul_(sn, ap), mul_(c, aq));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                    {
+                        const double wp = W[i + p * 4], wq = W[i + q * 4];
+                        W[i + p * 4] = sub_(mul_(c, wp), mul_(sn, wq));
+                        W[i + q * 4] = add_(mul_(sn, wp), mul_(c, wq));
+                    }
+                }
+                __syncwarp();
+            }
+        if (!rotated) break;
+    }
+    double norms[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+        for (int i = lane; i < m; i += 32) prod[i] = mul_(A[i + j * m], A[i + j * m]);
+        __syncwarp();
+        double acc = 0.0;
+        if (lane == 0)
+            for (int i = 0; i < m; ++i) acc = add_(acc, prod[i]);
+        norms[j] = sqrt(__shfl_sync(kFull, acc, 0));
+        __syncwarp();
+    }
+    int order[4] = {0, 1, 2, 3};
+#pragma unroll
+    for (int a = 1; a < 4; ++a)
+    {
+#pragma unroll
+        for (int b = a; b > 0; --b)
+        {
+            const bool sw = norms[order[b - 1]] < norms[order[b]];
+            const int o0 = order[b - 1], o1 = order[b];
+            order[b - 1] = sw ? o1 : o0;
+            order[b] = sw ? o0 : o1;
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+    {
+        s[jj] = norms[order[jj]];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) V[i + jj * 4] = W[i + order[jj] * 4];
+    }
+}
+
+// stage 2b: clusters with more than 32 points (walls, very close tubes): one warp per cluster. classifyCluster's inscribed angles
+// (one atan2 each) and the Jacobi SVD's products / rotations are spread over the lanes; every sum is accumulated by lane 0 in the
+// reference's order, so the results are bit-identical to the sequential evaluation. The 4 x 4 tail (eig, solve) is replicated.
 __global__ void __launch_bounds__(64) k_scan_fit_big(const float * __restrict__ ranges, double min_range, double max_range, ScanPipe pipe)
 {
     __shared__ double zbuf[2][4 * (kBeams + 2)];
-    __shared__ double angbuf[2][kBeams + 2];
+    __shared__ double angbuf[2][3 * (kBeams + 2)];
+    constexpr unsigned kFull = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = pipe.counters[1];
     for (int w = blockIdx.x * 2 + warp; w < total; w += gridDim.x * 2)
@@ -779,13 +889,16 @@ __global__ void __launch_bounds__(64) k_scan_fit_big(const float * __restrict__ 
         const int idx = pipe.big[w];
         const ClusterDesc d = pipe.desc[idx];
         const int n = d.n_wrap & 0xffff;
-        const WorkMatrix Z = {zbuf[warp], n, 1};
+        double * Zp = zbuf[warp];
+        double * tmp = angbuf[warp];
+        const WorkMatrix Z = {Zp, n, 1};
         if (lane == 0)
             gather_points(d, ranges, min_range, max_range, [&](int i, double x, double y) {
                 Z(i, 1) = x;
                 Z(i, 2) = y;
             });
         __syncwarp();
+        // classifyCluster (circle_fit_library.cpp:208-250)
         {
             const double p2x = Z(0, 1), p2y = Z(0, 2), p3x = Z(n - 1, 1), p3y = Z(n - 1, 2);
             for (int i = 1 + lane; i < n - 1; i += 32)
@@ -793,40 +906,63 @@ __global__ void __launch_bounds__(64) k_scan_fit_big(const float * __restrict__ 
                 const double p1x = Z(i, 1), p1y = Z(i, 2);
                 const double num = add_(add_(mul_(p2y, sub_(p1x, p3x)), mul_(p1y, sub_(p3x, p2x))), mul_(p3y, sub_(p2x, p1x)));
                 const double den = add_(mul_(sub_(p2x, p1x), sub_(p1x, p3x)), mul_(sub_(p2y, p1y), sub_(p1y, p3y)));
-                angbuf[warp][i] = mul_(div_(180.0, kPiRef), atan2(num, den));
+                tmp[i] = mul_(div_(180.0, kPiRef), atan2(num, den));
             }
         }
         __syncwarp();
+        double sd = 0.0;
         if (lane == 0)
         {
             const int na = n - 2;
-            double mean = 0.0, sd = 0.0;
-            for (int i = 1; i < n - 1; ++i) mean = add_(mean, div_(angbuf[warp][i], (double) na));
+            double mean = 0.0;
+            for (int i = 1; i < n - 1; ++i) mean = add_(mean, div_(tmp[i], (double) na));
             for (int i = 1; i < n - 1; ++i)
             {
-                const double dv = sub_(angbuf[warp][i], mean);
+                const double dv = sub_(tmp[i], mean);
                 sd = add_(sd, mul_(dv, dv));
             }
             sd = sqrt(div_(sd, (double) na));
-            ClusterFit out;
-            out.pub = 0.0;
-            out.cx = out.cy = out.R = 0.0;
-            if (sd < 10.0)
-            {
-                auto X = [&](int i) { return Z(i, 1); };
-                auto Y = [&](int i) { return Z(i, 2); };
-                double fit[3];
-                const int id = circle_fit(n, X, Y, Z, fit);
-                if ((id >= 0) && !(fit[2] > 1.0))
-                {
-                    out.pub = 1.0;
-                    out.cx = fit[0];
-                    out.cy = fit[1];
-                    out.R = fit[2];
-                }
-            }
-            pipe.fit[idx] = out;
         }
+        sd = __shfl_sync(kFull, sd, 0);
+        ClusterFit out;
+        out.pub = 0.0;
+        out.cx = out.cy = out.R = 0.0;
+        if (sd < 10.0)   // warp-uniform
+        {
+            // circleFit (circle_fit_library.cpp:15-134): centroid and z_bar by lane 0 (sequential sums), Z by all lanes
+            double x_hat = 0.0, y_hat = 0.0, z_bar = 0.0;
+            if (lane == 0)
+                for (int i = 0; i < n; ++i)
+                {
+                    x_hat = add_(x_hat, div_(Z(i, 1), (double) n));
+                    y_hat = add_(y_hat, div_(Z(i, 2), (double) n));
+                }
+            x_hat = __shfl_sync(kFull, x_hat, 0);
+            y_hat = __shfl_sync(kFull, y_hat, 0);
+            for (int j = lane; j < n; j += 32)
+            {
+                const double dx = sub_(Z(j, 1), x_hat), dy = sub_(Z(j, 2), y_hat);
+                Z(j, 0) = add_(mul_(dx, dx), mul_(dy, dy));
+                Z(j, 1) = dx;
+                Z(j, 2) = dy;
+                Z(j, 3) = 1.0;
+            }
+            __syncwarp();
+            if (lane == 0)
+                for (int j = 0; j < n; ++j) z_bar = add_(z_bar, div_(Z(j, 0), (double) n));
+            z_bar = __shfl_sync(kFull, z_bar, 0);
+            double sv[4], V[16], fit[3];
+            svd_n4_warp(Zp, n, tmp, lane, sv, V);
+            const int id = circle_fit_tail(sv, V, z_bar, x_hat, y_hat, fit);
+            if ((id >= 0) && !(fit[2] > 1.0))
+            {
+                out.pub = 1.0;
+                out.cx = fit[0];
+                out.cy = fit[1];
+                out.R = fit[2];
+            }
+        }
+        if (lane == 0) pipe.fit[idx] = out;
         __syncwarp();
     }
 }
@@ -876,13 +1012,13 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
     cudaError_t e = scan_tables_init(device);
     if (e != cudaSuccess) return e;
     const size_t smem = sizeof(ScanSmem) * kScanWarps;
-    const size_t fit_smem = sizeof(double) * 4 * kFitNMax * kFitThreads;
+    const size_t fit_smem16 = sizeof(double) * 4 * 16 * kFitThreads, fit_smem32 = sizeof(double) * 4 * kFitNMax * kFitThreads;
     static bool configured = false;
     if (!configured)
     {
         e = cudaFuncSetAttribute(k_scan_detect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan_detect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan_fit_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fit_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan_fit_small<kFitNMax, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fit_smem32);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -903,7 +1039,7 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
     const int64_t chunk_max = n_scans < kScanChunk ? n_scans : kScanChunk;
     const size_t n_desc = (size_t) chunk_max * kMaxFastClusters;
     auto al = [](size_t v) { return (v + 255) & ~(size_t) 255; };
-    const size_t need = al(n_desc * sizeof(ClusterDesc)) + al(n_desc * sizeof(ClusterFit)) + al(n_desc * sizeof(int32_t)) +
+    const size_t need = al(n_desc * sizeof(ClusterDesc)) + al(n_desc * sizeof(ClusterFit)) + 2 * al(n_desc * sizeof(int32_t)) +
                         al((size_t) chunk_max * sizeof(int32_t)) * 2 + 256;
     if (sc.bytes < need)
     {
@@ -922,6 +1058,8 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
     q += al(n_desc * sizeof(ClusterFit));
     pipe.big = reinterpret_cast<int32_t *>(q);
     q += al(n_desc * sizeof(int32_t));
+    pipe.mid = reinterpret_cast<int32_t *>(q);
+    q += al(n_desc * sizeof(int32_t));
     pipe.slow = reinterpret_cast<int32_t *>(q);
     q += al((size_t) chunk_max * sizeof(int32_t));
     pipe.scan_base = reinterpret_cast<int32_t *>(q);
@@ -937,7 +1075,8 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
         if (blocks > resident) blocks = resident;
         k_scan_detect<false><<<(unsigned) blocks, 32 * kScanWarps, smem, stream>>>(ranges, chunk, min_range, max_range, cluster_of_beam, n_clusters,
                                                                                 n_circles, circles, max_circles, scan_ub, nullptr, nullptr, pipe);
-        k_scan_fit_small<<<(unsigned) (sm_count * 3), kFitThreads, fit_smem, stream>>>(ranges, min_range, max_range, pipe);
+        k_scan_fit_small<16, false><<<(unsigned) (sm_count * 6), kFitThreads, fit_smem16, stream>>>(ranges, min_range, max_range, pipe);
+        k_scan_fit_small<kFitNMax, true><<<(unsigned) (sm_count * 3), kFitThreads, fit_smem32, stream>>>(ranges, min_range, max_range, pipe);
         k_scan_fit_big<<<(unsigned) (sm_count * 2), 64, 0, stream>>>(ranges, min_range, max_range, pipe);
         k_scan_publish<<<(unsigned) ((chunk + 127) / 128), 128, 0, stream>>>(chunk, n_clusters, n_circles, circles, max_circles, pipe);
         // scans with more than kMaxFastClusters clusters: the one-warp-per-scan kernel over their list
