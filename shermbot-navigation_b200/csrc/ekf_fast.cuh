@@ -114,9 +114,8 @@ __device__ __forceinline__ void dmma884(double & c0, double & c1, double a, doub
 // sin/cos/atan2 round trip; the identity for |a| <= pi, branch-free
 __device__ __forceinline__ double wrap_angle(double a)
 {
-    constexpr double kTwoPiHi = 6.28318530717958623200, kTwoPiLo = 2.44929359829470641435e-16, kInvTwoPi = 0.15915494309189533577;
-    const double k = rint(a * kInvTwoPi);
-    return fma(-k, kTwoPiLo, fma(-k, kTwoPiHi, a));
+    const double k = rint(a * kFastK[5]);   // 1 / 2 pi; 2 pi = kFastK[3] + kFastK[4]
+    return fma(-k, kFastK[4], fma(-k, kFastK[3], a));
 }
 
 // per-CTA (= per-warp) shared memory: exchange buffers between the fragment and the vector layout. Every vector has
@@ -124,14 +123,14 @@ __device__ __forceinline__ double wrap_angle(double a)
 template <int N>
 struct __align__(16) FastSmem
 {
-    double2 kt[2][32];        // -Kt of the chunk's two updates, kt[s][i] = (-k0, -k1) of state index i; DMMA A operand
-    double2 wt[2][32];        // Wt of the chunk's two updates; DMMA B operand
+    double2 kt[2][36];        // -Kt of the chunk's two updates, kt[s][i] = (-k0, -k1) of state index i < 32; DMMA A operand (slot
+                              // stride 72 doubles = 8 (mod 16): the operand loads of the two slots hit disjoint banks)
+    double2 wt[2][36];        // Wt of the chunk's two updates; DMMA B operand
     double rho[2][2][40];     // per chunk slot: landmark rows c, c+1 in vector layout, entry j at [j + 1] (index 3 is 16-byte aligned;
                               // row stride = 16 banks (mod 32): the two rows of a landmark are stored without bank conflicts)
     double2 kap[2][32];       // per chunk slot: landmark columns (c, c+1) interleaved, entry i
     double xs[34];            // state broadcast copy, x_i at [i + 1] (the pair (mx, my) is 16-byte aligned)
     double z[2 * kFastMMax];  // this step's measurements
-    int ids[kFastMMax];
 };
 
 #ifdef NUSLAM_TIMING
@@ -339,7 +338,16 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 }
             }
         }
-        if (!ASSOC && lane < m) f.ids[lane] = my_id;
+        // known correspondence: the m ids as four ballots (bit i of idb[k] = bit k of measurement i's code; code 0 = skip, 15 = id > N),
+        // so that the update loop reads them without a memory round trip
+        unsigned idb[4] = {0u, 0u, 0u, 0u};
+        if (!ASSOC)
+        {
+            static_assert(N <= 14, "4-bit id codes");
+            const int code = ((unsigned) (my_id - 1) < (unsigned) N) ? my_id : (my_id > N ? 15 : 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) idb[k] = __ballot_sync(kFull, (code >> k) & 1);
+        }
         if (lane < 2 * m) f.z[lane] = my_z;
         // robot pose, replicated in every lane; lanes 0..2 own the same values in x (bit-identical updates)
         double th = __shfl_sync(kFull, x, 0), px = __shfl_sync(kFull, x, 1), py = __shfl_sync(kFull, x, 2);
@@ -525,10 +533,17 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
 #pragma unroll
             for (int s = 0; s < 2; ++s)
             {
-                const int id = ASSOC ? (s == 0 ? assoc_id : 0) : ((i0 + s < m) ? f.ids[i0 + s] : 0);
+                int id;
+                if (ASSOC)
+                    id = (s == 0) ? assoc_id : 0;
+                else
+                {
+                    const int i = i0 + s;
+                    id = (int) (((idb[0] >> i) & 1u) | (((idb[1] >> i) & 1u) << 1) | (((idb[2] >> i) & 1u) << 2) | (((idb[3] >> i) & 1u) << 3));
+                    if (id == 15) status |= kStatusBadId;
+                }
                 const bool live = (unsigned) (id - 1) < (unsigned) N;   // warp-uniform
                 cc[s] = live ? 1 + 2 * id : -1;
-                if (id > N) status |= kStatusBadId;
                 if (live)
                 {
                     const int c = cc[s];
@@ -629,7 +644,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     // dependency chains interleave
                     const double zb = wrap_angle(atan2_fast(dy, dx) - th);
                     const double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);
-                    if (fabs(idet) < 1.0e300)   // warp-uniform; false for det = 0, inf or nan, where arma::inv throws (slam_library.cpp:270)
+                    if (fabs(idet) < kFastK[6])   // < 1e300: warp-uniform; false for det = 0, inf or nan, where arma::inv throws (slam_library.cpp:270)
                     {
                         done = true;
                         const double i00 = m11 * idet, i01 = -m01 * idet, i10 = -m10 * idet, i11 = m00 * idet;
@@ -644,7 +659,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                         px = fma(-k1.x, n0, fma(-k1.y, n1, px));
                         py = fma(-k2.x, n0, fma(-k2.y, n1, py));
                         x = fma(-nk0, n0, fma(-nk1, n1, x));
-                        th = wrap_angle(th);   // slam_library.cpp:275-276
+                        if (fabs(th) > kFastK[7]) th = wrap_angle(th);   // slam_library.cpp:275-276 (the identity inside [-pi, pi]); warp-uniform
                         if (lane == 0) x = th;
                         f.xs[lane + 1] = x;
                         // robot rows / columns: Sigma -= Kt Wt restricted to them

@@ -116,6 +116,11 @@ __constant__ double2 kAtanTab[65] = {
     {0.7775243103733478, -2.6676490951944502e-17},
     {0.7853981633974483, 3.061616997868383e-17}};
 
+// fp64 literals of the per-update scalar chain, kept in the constant bank: an instruction reads them as a c[][] operand, where an
+// immediate would be rebuilt in uniform registers (two UMOVs each) on every pass of the update loop
+__constant__ double kFastK[8] = {-1.0 / 7.0, 0.2, -1.0 / 3.0, 6.28318530717958623200, 2.44929359829470641435e-16, 0.15915494309189533577,
+                                 1.0e300, 3.14159265358979311600};
+
 __device__ __forceinline__ double atan2_fast(double y, double x)
 {
     const double ax = fabs(x), ay = fabs(y);
@@ -133,7 +138,7 @@ __device__ __forceinline__ double atan2_fast(double y, double x)
     double r = num * rc;
     r = fma(fma(-den, r, num), rc, r);   // r = num / den to ~1 ulp
     const double u = r * r;
-    const double pl = fma(fma(fma(-1.0 / 7.0, u, 0.2), u, -1.0 / 3.0), u * r, r);   // atan(r)
+    const double pl = fma(fma(fma(kFastK[0], u, kFastK[1]), u, kFastK[2]), u * r, r);   // atan(r)
     const double a = ak.x + (pl + ak.y);                                              // atan(mn / mx) in [0, pi/4]
     return oc.hi + fma(oc.s, a, oc.lo);
 }
