@@ -192,6 +192,22 @@ int nuslam_diffdrive_step(double * state7, const double * thL_new, const double 
 int nuslam_diffdrive_convert_twist(double wheel_base, double wheel_rad, const double * twists, double * wheel_vel_out, int64_t count, int mem,
                                    int device, void * cuda_stream);
 
+/* ------------------------------------------------------------------ simulator slice (the step before the path)
+ * One iteration of TubeWorld::main_loop (nuturtlesim/src/tube_world.cpp:512-537) for `count` independent simulated robots in one
+ * tube field: desired twist = cmd + twist noise (:177-189), check_collision (:371-389), wheel_vel = convertTwist, joints +=
+ * wheel_vel * dt (:516-523), robot(joints + wheel_vel * slip) (:528-529, DiffDrive::operator()), simulate_lidar_scanner (:405-471).
+ * The four gaussian draws of a step are INPUTS (the reference takes them from a std::mt19937 it seeds from random_device).
+ *   world      : count x 9 = {wheelBase, wheelRad, x, y, th, thL, thR, jointL, jointR}, updated in place
+ *   cmd        : count x 3 commanded body twist (dth, dx, dy)
+ *   noise      : count x 4 = {twist dth, twist dx, slip L, slip R} or NULL (all zero)
+ *   tubes      : n_tubes x 2 tube centres (at most 64)
+ *   ranges_out : count x 360 f32, the sensor_msgs/LaserScan ranges (fill value max_range + 1)
+ *   joints_out : 2 x count (jointL[count] then jointR[count]) or NULL -- the encoder readings, laid out as
+ *                nuslam_diffdrive_step's thL_new / thR_new so that the odometry runs on them in place */
+int nuslam_world_step(double * world, const double * cmd, const double * noise, double dt, const double * tubes, int32_t n_tubes,
+                      double tube_rad, double robot_rad, double max_range, float * ranges_out, double * joints_out, int64_t count,
+                      int mem, int device, void * cuda_stream);
+
 /* ------------------------------------------------------------------ scan -> landmarks
  * circle_fit::clusterPoints (circle_fit_library.cpp:136-206), classifyCluster (:208-250), circleFit
  * (:15-134) and the Landmarks::main_loop protocol (nuslam/src/landmarks.cpp:84-109), batched over S
@@ -213,6 +229,19 @@ int nuslam_scan_detect(const float * ranges, int64_t n_scans, double min_range, 
  * offsets[c] .. offsets[c+1]-1 of px/py. is_circle: C (0/1); fit: C x 4 (marker.id, cx, cy, R). */
 int nuslam_classify_and_fit(const double * px, const double * py, const int32_t * offsets, int64_t n_clusters,
                             int32_t * is_circle, double * fit, int mem, int device, void * cuda_stream);
+
+/* ------------------------------------------------------------------ scan -> landmarks -> EKF, fused
+ * The two nodes back to back without leaving the device: scan b belongs to filter b.
+ *   markers  = Landmarks::main_loop(ranges_b)                     nuslam/src/landmarks.cpp:84-109
+ *   z_i      = cartesian2polar(marker_i.pose.position.{x, y})     nuslam/src/slam.cpp:282-286
+ *   one iteration of EKFSlam::main_loop with associateLandmark    nuslam/src/slam.cpp:262-319
+ * The MarkerArray wire format between the nodes collapses to 16 bytes per landmark in HBM. Only the first m markers of a
+ * scan are used (choose m >= the largest marker count; n_markers_out reports the full count, NUSLAM_SCAN_UB where
+ * clusterPoints is undefined -- such a scan contributes no measurement).
+ *   twists: B x 3; ranges: B x 360 f32; n_markers_out: B or NULL; z_out: B x m x 2 or NULL (range, bearing; zero past the
+ *   filter's last marker); ids_out: B x m or NULL (association results, 0 past the last marker). */
+int nuslam_ekf_scan_step(nuslam_ekf * h, const double * twists, const float * ranges, double min_range, double max_range,
+                         int32_t m, int32_t * n_markers_out, double * z_out, int32_t * ids_out, int mem);
 
 #ifdef __cplusplus
 }

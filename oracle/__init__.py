@@ -151,6 +151,8 @@ class OracleLib:
         c.orc_circle_fit.argtypes = [_dp, _dp, C.c_int, _dp]
         c.orc_scan_detect.argtypes = [_fp, C.c_double, C.c_double, _ip, _ip, _dp, C.c_int]
         c.orc_scan_detect_batch.argtypes = [C.c_long, _fp, C.c_double, C.c_double, _sp, _ip, _ip, _dp, C.c_int, C.c_int]
+        c.orc_world_step_batch.restype = None
+        c.orc_world_step_batch.argtypes = [C.c_long, _dp, _dp, _dp, C.c_double, _dp, C.c_int, C.c_double, C.c_double, C.c_double, _fp]
 
     @property
     def flavour(self) -> str:
@@ -214,6 +216,21 @@ class OracleLib:
                             _d(x), _d(s), _i(seen), _i(status), _i(ids_out),
                             _d(tr) if trace else None, 1 if init is not None else 0, int(nthreads))
         return dict(x=x, sigma=np.transpose(s, (0, 2, 1)).copy(), seen=seen, status=status, ids_out=ids_out, trace=tr)
+
+    # ---- simulator slice ----
+    def world_step(self, world, cmd, noise, dt, tubes, tube_rad, robot_rad, max_range):
+        """One TubeWorld::main_loop iteration per robot (tube_world.cpp:512-537). world (B,9) is updated IN PLACE;
+        returns the scans (B,360) float32."""
+        assert world.dtype == np.float64 and world.flags["C_CONTIGUOUS"]
+        B = world.shape[0]
+        cmd = _f64(np.broadcast_to(cmd, (B, 3)))
+        tubes = _f64(tubes)
+        nz = None if noise is None else _f64(np.broadcast_to(noise, (B, 4)))
+        ranges = np.empty((B, 360), dtype=np.float32)
+        self._c.orc_world_step_batch(B, _d(world), _d(cmd), _d(nz) if nz is not None else None, float(dt), _d(tubes),
+                                     int(tubes.shape[0]), float(tube_rad), float(robot_rad), float(max_range),
+                                     ranges.ctypes.data_as(_fp))
+        return ranges
 
     # ---- circle path ----
     def cluster_points(self, ranges, min_range, max_range):

@@ -1003,3 +1003,13 @@ int orc_scan_detect_batch(long S, const float * ranges, double minR, double maxR
     free(th);
     return 0;
 }
+
+/* simulator slice: restatement in oracle/world_oracle.h, DiffDrive through this flavour's own implementation */
+#include "world_oracle.h"
+void orc_world_step_batch(long B, double * world, const double * cmd, const double * noise, double dt, const double * tubes,
+                          int n_tubes, double tube_rad, double robot_rad, double max_range, float * ranges)
+{
+    for (long b = 0; b < B; ++b)
+        orc_w_step(world + 9 * b, cmd + 3 * b, noise ? noise + 4 * b : NULL, dt, tubes, n_tubes, tube_rad, robot_rad, max_range,
+                   ranges + 360 * b, orc_diffdrive_convert_twist, orc_diffdrive_step);
+}

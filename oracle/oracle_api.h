@@ -72,6 +72,12 @@ int orc_scan_detect(const float * ranges360, double minR, double maxR, int * clu
 int orc_scan_detect_batch(long S, const float * ranges, double minR, double maxR, short * cluster_of_beam,
                           int * n_clusters, int * n_circles, double * circles, int kmax, int nthreads);
 
+/* ---- simulator slice (nuturtlesim/src/tube_world.cpp:371-389, 405-471, 512-537; restated in oracle/world_oracle.h) ----
+ * B robots, one step each: world[B][9] = {wheelBase, wheelRad, x, y, th, thL, thR, jointL, jointR} in/out, cmd[B][3] (dth, dx, dy),
+ * noise[B][4] = {twist dth, twist dx, slip L, slip R} draws or NULL, tubes[n_tubes][2], ranges[B][360] out. */
+void orc_world_step_batch(long B, double * world, const double * cmd, const double * noise, double dt, const double * tubes,
+                          int n_tubes, double tube_rad, double robot_rad, double max_range, float * ranges);
+
 #ifdef __cplusplus
 }
 #endif

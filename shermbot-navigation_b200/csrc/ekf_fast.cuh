@@ -163,7 +163,6 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
     __shared__ uint64_t full_bar;
     FastSmem<N> & f = *reinterpret_cast<FastSmem<N> *>(stage[kStages - 1]);
     const int lane = threadIdx.x;
-    const int m = p.m;
     const int g = lane >> 2, t = lane & 3;
     const bool vlane = lane < LEN;      // lane owns a state index
     // zero the exchange buffers once (entries of lanes without a state index stay zero)
@@ -205,8 +204,9 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         // small inputs: plain loads, issued before anything waits
         if (vlane) x = p.x[bf * LEN + lane];
         const int st0 = p.status[bf], seen0 = p.seen[bf];
-        const int my_id = (!ASSOC && lane < m) ? p.ids[bf * m + lane] : 0;
-        const double my_z = (lane < 2 * m) ? p.z[bf * m * 2 + lane] : 0.0;
+        const int m = p.m_valid ? min(p.m, max(0, p.m_valid[bf])) : p.m;   // measurements of THIS filter (warp-uniform)
+        const int my_id = (!ASSOC && lane < m) ? p.ids[bf * p.m + lane] : 0;
+        const double my_z = (lane < 2 * m) ? p.z[bf * p.m * 2 + lane] : 0.0;
         const double my_tw = (do_predict && lane < 2) ? p.twists[bf * 3 + lane] : 0.0;
         if (BULK)
         {
@@ -291,6 +291,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         // ---- liveness ----
         if (st0 & (kStatusMapFull | kStatusSingular))   // the reference process died on an earlier scan
         {
+            if (p.ids_out && lane < p.m) p.ids_out[bf * p.m + lane] = 0;
             leave();
             continue;
         }
@@ -319,6 +320,8 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             }
         }
         int status = st0;
+        // ids_out of the slots this kernel does not associate: the given id (known correspondence), 0 past this filter's last measurement
+        if (p.ids_out && lane < p.m && (!ASSOC || lane >= m)) p.ids_out[bf * p.m + lane] = (!ASSOC && my_id > 0) ? my_id : 0;
         if (BULK)
         {
             // buffer B held the previous filter's output image: wait until the bulk store has read it, then restore the zero
@@ -525,7 +528,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     break;
                 }
                 assoc_id = ((hitA >> (__ffs(any) - 1)) & 1u) ? __ffs(any) : -1;
-                if (p.ids_out && lane == 0) p.ids_out[bf * m + i0] = assoc_id;
+                if (p.ids_out && lane == 0) p.ids_out[bf * p.m + i0] = assoc_id;
                 __syncwarp();
             }
             // (A) publish the chunk's landmark rows / columns from the (stale) fragments into vector layout

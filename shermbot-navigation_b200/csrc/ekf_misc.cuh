@@ -76,6 +76,31 @@ __global__ void k_cartesian2polar(const double * __restrict__ xy, double * __res
     rb[2 * t + 1] = normalize_angle(atan2(y, x));
 }
 
+// The hand-over between the two nodes, kept on the device: the markers the landmarks node publishes for scan b
+// (landmarks.cpp:84-109, already filtered and in detection order in `circles`) become filter b's measurements
+// z_i = cartesian2polar(marker.pose.position.{x, y}) (slam.cpp:282-286). circles: B x max_circles x 4 (cx, cy, R, cluster);
+// z: B x m x 2; m_valid[b] = min(markers of scan b, m) (0 where the reference's clusterPoints is undefined, n_circles < 0).
+__global__ void k_markers_to_measurements(const double * __restrict__ circles, const int32_t * __restrict__ n_circles, int64_t batch,
+                                          int max_circles, int m, double * __restrict__ z, int32_t * __restrict__ m_valid)
+{
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= batch * m) return;
+    const int64_t b = t / m;
+    const int i = (int) (t - b * m);
+    int mv = n_circles[b];
+    mv = mv < 0 ? 0 : (mv > m ? m : mv);
+    if (i == 0) m_valid[b] = mv;
+    double r = 0.0, bearing = 0.0;
+    if (i < mv && i < max_circles)
+    {
+        const double x = circles[(b * max_circles + i) * 4], y = circles[(b * max_circles + i) * 4 + 1];
+        r = sqrt(add_(mul_(x, x), mul_(y, y)));
+        bearing = normalize_angle(atan2(y, x));
+    }
+    z[2 * t] = r;
+    z[2 * t + 1] = bearing;
+}
+
 // rigid2d::normalize_angle, rigid2d.cpp:9-13
 __global__ void k_normalize_angle(const double * __restrict__ in, double * __restrict__ out, int64_t count)
 {

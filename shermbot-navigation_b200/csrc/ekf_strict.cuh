@@ -385,6 +385,7 @@ struct EkfParams
     const double * twists;   // B x 3
     const double * z;        // B x m x 2
     const int32_t * ids;     // B x m or null
+    const int32_t * m_valid; // B or null: filter b uses only its first m_valid[b] (<= m) measurements (fused scan step)
     int32_t * ids_out;       // B x m or null
     double Q[9], R[4];
     double amin, amax;
@@ -449,7 +450,10 @@ __device__ __forceinline__ void strict_filter(const EkfParams & p, const int64_t
         }
         const int seen_snapshot = seen;                               // slam.cpp:251
         f.predict(p.twists[3 * b], p.twists[3 * b + 1], p.Q);         // slam.cpp:269
-        for (int i = 0; i < p.m; ++i)                                 // slam.cpp:279
+        const int mv = p.m_valid ? min(p.m, max(0, p.m_valid[b])) : p.m;   // markers this filter received (landmarks.cpp:84-109)
+        if (p.ids_out)
+            for (int i = mv + lane; i < p.m; i += kWarp) p.ids_out[mb + i] = 0;
+        for (int i = 0; i < mv; ++i)                                  // slam.cpp:279
         {
             const double z0 = p.z[2 * (mb + i)], z1 = p.z[2 * (mb + i) + 1];
             int id;
@@ -469,7 +473,7 @@ __device__ __forceinline__ void strict_filter(const EkfParams & p, const int64_t
                 if (id == kIdException)
                 {
                     if (p.ids_out)
-                        for (int r = i + lane; r < p.m; r += kWarp) p.ids_out[mb + r] = (r == i) ? kIdException : 0;
+                        for (int r = i + lane; r < mv; r += kWarp) p.ids_out[mb + r] = (r == i) ? kIdException : 0;
                     break;
                 }
             }

@@ -17,6 +17,7 @@
 #include "ekf_fast.cuh"
 #include "scan_detect.cuh"
 #include "ekf_large.cuh"
+#include "world_sim.cuh"
 
 namespace
 {
@@ -87,6 +88,8 @@ struct nuslam_ekf
     bool own_state = true;
     // staging for NUSLAM_HOST calls
     DevBuf s_tw, s_z, s_ids, s_ids_out, s_misc;
+    // fused scan step (nuslam_ekf_scan_step): ranges staging, detection outputs, measurements
+    DevBuf f_ranges, f_ncl, f_nci, f_circ, f_z, f_mv;
     // FAST mode: filters whose step contains a first touch are handed to the strict kernel through this list
     // pipelined host-buffer steps (nuslam_ekf_step_async): kAsyncSlots slots of staged inputs / state snapshots, copy streams, events
     struct AsyncSlot
@@ -378,6 +381,7 @@ int nuslam_ekf_destroy(nuslam_ekf * h)
     h->s_ids.release();
     h->s_ids_out.release();
     h->s_misc.release();
+    for (DevBuf * b : {&h->f_ranges, &h->f_ncl, &h->f_nci, &h->f_circ, &h->f_z, &h->f_mv}) b->release();
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return NUSLAM_OK;
@@ -579,6 +583,37 @@ int nuslam_ekf_measurement_model(nuslam_ekf * h, const int32_t * j, double * zha
     return finish(h, mem);
 }
 
+namespace
+{
+
+// one iteration of slam.cpp:262-319 for every filter; all pointers in `p` are device pointers
+int step_device(nuslam_ekf * h, const nuslam::EkfParams & p)
+{
+    const int m = p.m;
+    if (h->large)
+    {
+        if (!p.ids || p.m_valid)
+            return fail(NUSLAM_ERR_UNSUPPORTED, "large-map mode covers known correspondence only (associateLandmark is not built yet)");
+        cudaError_t e = nuslam::launch_large_predict(make_large_params(h), p.twists, h->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "large-map predict");
+        if (m > 0)
+        {
+            int rc = large_updates(h, p.z, p.ids, m, /*step_protocol=*/true);
+            if (rc) return rc;
+        }
+        if (p.ids_out && m > 0) CU(cudaMemcpyAsync(p.ids_out, p.ids, sizeof(int32_t) * h->batch * m, cudaMemcpyDeviceToDevice, h->stream));
+        return NUSLAM_OK;
+    }
+    if (h->cfg.mode == NUSLAM_MODE_FAST && m <= nuslam::kFastMMax)
+        // known correspondence, or on-device association (ids == NULL): the register kernel, then the strict kernel over the
+        // filters it handed over (first touches, new landmarks)
+        return launch_fast_then_strict<nuslam::kOpStep>(h, p, /*do_predict=*/true);
+    // STRICT mode (and steps with more than kFastMMax measurements): the oracle-order kernel, association included
+    return launch_strict<nuslam::kOpStep>(h, p);
+}
+
+}   // namespace
+
 int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, const int32_t * ids, int32_t m, int32_t * ids_out, int mem)
 {
     if (!h || !twists) return fail(NUSLAM_ERR_INVALID, "null handle or twists");
@@ -599,33 +634,57 @@ int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, con
         if (rc) return rc;
         p.ids_out = static_cast<int32_t *>(h->s_ids_out.p);
     }
-    if (h->large)
-    {
-        if (!p.ids) return fail(NUSLAM_ERR_UNSUPPORTED, "large-map mode covers known correspondence only (associateLandmark is not built yet)");
-        cudaError_t e = nuslam::launch_large_predict(make_large_params(h), p.twists, h->stream);
-        if (e != cudaSuccess) return cuda_fail(e, "large-map predict");
-        if (m > 0)
-        {
-            rc = large_updates(h, p.z, p.ids, m, /*step_protocol=*/true);
-            if (rc) return rc;
-        }
-        if (ids_out && m > 0) CU(cudaMemcpyAsync(p.ids_out, p.ids, sizeof(int32_t) * h->batch * m, cudaMemcpyDeviceToDevice, h->stream));
-    }
-    else if (h->cfg.mode == NUSLAM_MODE_FAST && m <= nuslam::kFastMMax)
-    {
-        // known correspondence, or on-device association (ids == NULL): the register kernel, then the strict kernel over the
-        // filters it handed over (first touches, new landmarks)
-        rc = launch_fast_then_strict<nuslam::kOpStep>(h, p, /*do_predict=*/true);
-        if (rc) return rc;
-    }
-    else
-    {
-        // STRICT mode (and steps with more than kFastMMax measurements): the oracle-order kernel, association included
-        rc = launch_strict<nuslam::kOpStep>(h, p);
-        if (rc) return rc;
-    }
+    rc = step_device(h, p);
+    if (rc) return rc;
     if (ids_out && mem == NUSLAM_HOST && m > 0)
         CU(cudaMemcpyAsync(ids_out, p.ids_out, sizeof(int32_t) * h->batch * m, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h, mem);
+}
+
+int nuslam_ekf_scan_step(nuslam_ekf * h, const double * twists, const float * ranges, double min_range, double max_range, int32_t m,
+                         int32_t * n_markers_out, double * z_out, int32_t * ids_out, int mem)
+{
+    if (!h || !twists || !ranges) return fail(NUSLAM_ERR_INVALID, "null handle, twists or ranges");
+    if (m < 1) return fail(NUSLAM_ERR_INVALID, "m < 1");
+    if (h->large) return fail(NUSLAM_ERR_UNSUPPORTED, "large-map mode covers known correspondence only");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    const size_t B = (size_t) h->batch;
+    nuslam::EkfParams p = make_params(h);
+    p.m = m;
+    int rc = stage_in(h, h->s_tw, twists, B * 3, mem, &p.twists);
+    if (rc) return rc;
+    const float * d_ranges = nullptr;
+    rc = stage_in(h, h->f_ranges, ranges, B * NUSLAM_SCAN_BEAMS, mem, &d_ranges);
+    if (!rc) rc = h->f_ncl.reserve(sizeof(int32_t) * B);
+    if (!rc) rc = h->f_nci.reserve(sizeof(int32_t) * B);
+    if (!rc) rc = h->f_circ.reserve(sizeof(double) * 4 * B * m);
+    if (!rc) rc = h->f_z.reserve(sizeof(double) * 2 * B * m);
+    if (!rc) rc = h->f_mv.reserve(sizeof(int32_t) * B);
+    if (!rc && ids_out && mem == NUSLAM_HOST) rc = h->s_ids_out.reserve(sizeof(int32_t) * B * m);
+    if (rc) return rc;
+    int32_t * d_nci = static_cast<int32_t *>(h->f_nci.p);
+    double * d_circ = static_cast<double *>(h->f_circ.p);
+    double * d_z = static_cast<double *>(h->f_z.p);
+    int32_t * d_mv = static_cast<int32_t *>(h->f_mv.p);
+    // Landmarks::main_loop, landmarks.cpp:84-109: the first m markers of every scan, in detection order
+    cudaError_t e = nuslam::launch_scan_detect(d_ranges, (int64_t) B, min_range, max_range, nullptr, static_cast<int32_t *>(h->f_ncl.p), d_nci, d_circ, m,
+                                               NUSLAM_SCAN_UB, h->device, h->sm_count, h->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "scan_detect");
+    // slam.cpp:282-286: markers -> (range, bearing)
+    const int64_t total = (int64_t) B * m;
+    nuslam::k_markers_to_measurements<<<(unsigned) ((total + 255) / 256), 256, 0, h->stream>>>(d_circ, d_nci, h->batch, m, m, d_z, d_mv);
+    CU(cudaGetLastError());
+    // slam.cpp:262-319 with unknown data association
+    p.z = d_z;
+    p.ids = nullptr;
+    p.m_valid = d_mv;
+    p.ids_out = (ids_out && mem == NUSLAM_HOST) ? static_cast<int32_t *>(h->s_ids_out.p) : ids_out;
+    rc = step_device(h, p);
+    if (rc) return rc;
+    const cudaMemcpyKind kind = (mem == NUSLAM_HOST) ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (n_markers_out) CU(cudaMemcpyAsync(n_markers_out, d_nci, sizeof(int32_t) * B, kind, h->stream));
+    if (z_out) CU(cudaMemcpyAsync(z_out, d_z, sizeof(double) * 2 * B * m, kind, h->stream));
+    if (ids_out && mem == NUSLAM_HOST) CU(cudaMemcpyAsync(ids_out, p.ids_out, sizeof(int32_t) * B * m, cudaMemcpyDeviceToHost, h->stream));
     return finish(h, mem);
 }
 
@@ -791,6 +850,69 @@ int nuslam_diffdrive_step(double * state7, const double * thL_new, const double 
     }
     if (tmp) cudaFree(tmp);
     if (e != cudaSuccess) return cuda_fail(e, "diffdrive_step");
+    return NUSLAM_OK;
+}
+
+int nuslam_world_step(double * world, const double * cmd, const double * noise, double dt, const double * tubes, int32_t n_tubes,
+                      double tube_rad, double robot_rad, double max_range, float * ranges_out, double * joints_out, int64_t count, int mem,
+                      int device, void * cuda_stream)
+{
+    if (!world || !cmd || !ranges_out || count < 0 || n_tubes < 0 || (n_tubes > 0 && !tubes)) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (n_tubes > nuslam::kWorldMaxTubes) return fail(NUSLAM_ERR_UNSUPPORTED, "at most 64 tubes");
+    if (count == 0) return NUSLAM_OK;
+    CU(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    nuslam::WorldParams p;
+    memset(&p, 0, sizeof(p));
+    p.count = count;
+    p.n_tubes = n_tubes;
+    p.dt = dt;
+    p.tube_rad = tube_rad;
+    p.robot_rad = robot_rad;
+    p.max_range = max_range;
+    p.world = world;
+    p.cmd = cmd;
+    p.noise = noise;
+    p.tubes = tubes;
+    p.ranges = ranges_out;
+    p.joints = joints_out;
+    char * tmp = nullptr;
+    const size_t b_w = sizeof(double) * 9 * count, b_c = sizeof(double) * 3 * count, b_n = sizeof(double) * 4 * count;
+    const size_t b_t = sizeof(double) * 2 * (n_tubes > 0 ? n_tubes : 1), b_r = sizeof(float) * 360 * count, b_j = sizeof(double) * 2 * count;
+    if (mem == NUSLAM_HOST)
+    {
+        auto al = [](size_t v) { return (v + 255) & ~(size_t) 255; };
+        CU(cudaMalloc(&tmp, al(b_w) + al(b_c) + al(b_n) + al(b_t) + al(b_r) + al(b_j)));
+        char * q = tmp;
+        p.world = reinterpret_cast<double *>(q);
+        q += al(b_w);
+        double * d_cmd = reinterpret_cast<double *>(q);
+        q += al(b_c);
+        double * d_noise = reinterpret_cast<double *>(q);
+        q += al(b_n);
+        double * d_tubes = reinterpret_cast<double *>(q);
+        q += al(b_t);
+        p.ranges = reinterpret_cast<float *>(q);
+        q += al(b_r);
+        p.joints = reinterpret_cast<double *>(q);
+        CU(cudaMemcpyAsync(p.world, world, b_w, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_cmd, cmd, b_c, cudaMemcpyHostToDevice, st));
+        if (noise) CU(cudaMemcpyAsync(d_noise, noise, b_n, cudaMemcpyHostToDevice, st));
+        if (n_tubes > 0) CU(cudaMemcpyAsync(d_tubes, tubes, sizeof(double) * 2 * n_tubes, cudaMemcpyHostToDevice, st));
+        p.cmd = d_cmd;
+        p.noise = noise ? d_noise : nullptr;
+        p.tubes = d_tubes;
+    }
+    cudaError_t e = nuslam::launch_world_step(p, device, st);
+    if (e == cudaSuccess && mem == NUSLAM_HOST)
+    {
+        e = cudaMemcpyAsync(world, p.world, b_w, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ranges_out, p.ranges, b_r, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && joints_out) e = cudaMemcpyAsync(joints_out, p.joints, b_j, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "world_step");
     return NUSLAM_OK;
 }
 

@@ -33,9 +33,9 @@ EXPORTS = [
     "nuslam_ekf_bind_state", "nuslam_ekf_device_pointers", "nuslam_ekf_init", "nuslam_ekf_set_state",
     "nuslam_ekf_get_state", "nuslam_ekf_predict", "nuslam_ekf_associate", "nuslam_ekf_initialize_landmark",
     "nuslam_ekf_update", "nuslam_ekf_measurement_model", "nuslam_ekf_step", "nuslam_ekf_step_async", "nuslam_ekf_wait_async",
-    "nuslam_ekf_synchronize",
+    "nuslam_ekf_scan_step", "nuslam_ekf_synchronize",
     "nuslam_cartesian2polar", "nuslam_normalize_angle", "nuslam_scan_detect", "nuslam_classify_and_fit",
-    "nuslam_diffdrive_step", "nuslam_diffdrive_convert_twist",
+    "nuslam_diffdrive_step", "nuslam_diffdrive_convert_twist", "nuslam_world_step",
 ]
 
 
@@ -76,6 +76,8 @@ def lib() -> C.CDLL:
         l.nuslam_ekf_update.argtypes = [vp, vp, vp, C.c_int]
         l.nuslam_ekf_measurement_model.argtypes = [vp, vp, vp, vp, C.c_int]
         l.nuslam_ekf_step.argtypes = [vp, vp, vp, vp, i32, vp, C.c_int]
+        l.nuslam_world_step.argtypes = [vp, vp, vp, C.c_double, vp, i32, C.c_double, C.c_double, C.c_double, vp, vp, i64, C.c_int, C.c_int, vp]
+        l.nuslam_ekf_scan_step.argtypes = [vp, vp, vp, C.c_double, C.c_double, i32, vp, vp, vp, C.c_int]
         l.nuslam_ekf_step_async.argtypes = [vp, vp, vp, vp, i32, vp]
         l.nuslam_ekf_wait_async.argtypes = [vp]
         l.nuslam_ekf_synchronize.argtypes = [vp]
@@ -151,6 +153,7 @@ class BatchedExtendedKalman:
         _check(l.nuslam_ekf_create(C.byref(cfg), self.batch, self.device, stream, C.byref(h)), "nuslam_ekf_create")
         self._h = h
         self._keep = None
+        self.stream_ptr = stream   # the cudaStream_t the handle launches on when the caller supplied one (None: the handle's own stream)
         robot = np.ascontiguousarray(robot)
         _check(l.nuslam_ekf_init(self._h, robot.ctypes.data, mp.ctypes.data if mp is not None else None, NUSLAM_HOST),
                "nuslam_ekf_init")
@@ -264,6 +267,27 @@ class BatchedExtendedKalman:
                 optr = out.ctypes.data
         _check(lib().nuslam_ekf_step(self._h, pt[0], pz[0], pi[0], m, optr, mem), "nuslam_ekf_step")
         return out
+
+    def scan_step(self, twists, ranges, min_range, max_range, m, return_all=False):
+        """Landmarks::main_loop (landmarks.cpp:84-109) -> cartesian2polar (slam.cpp:282-286) -> one EKFSlam::main_loop iteration with
+        associateLandmark (slam.cpp:262-319), fused on the device: scan b feeds filter b. twists [B,3] f64, ranges [B,360] f32.
+        With return_all: (n_markers [B], z [B,m,2], ids [B,m])."""
+        pt, pr = _ptr(twists, np.float64), _ptr(ranges, np.float32)
+        mem = _mem_of(pt, pr)
+        outs, ptrs = (None, None, None), (None, None, None)
+        if return_all:
+            if mem == NUSLAM_DEVICE:
+                import torch
+                dev = ranges.device
+                outs = (torch.empty((self.batch,), dtype=torch.int32, device=dev), torch.empty((self.batch, m, 2), dtype=torch.float64, device=dev),
+                        torch.empty((self.batch, m), dtype=torch.int32, device=dev))
+                ptrs = tuple(o.data_ptr() for o in outs)
+            else:
+                outs = (np.empty((self.batch,), np.int32), np.empty((self.batch, m, 2), np.float64), np.empty((self.batch, m), np.int32))
+                ptrs = tuple(o.ctypes.data for o in outs)
+        _check(lib().nuslam_ekf_scan_step(self._h, pt[0], pr[0], float(min_range), float(max_range), int(m), ptrs[0], ptrs[1], ptrs[2], mem),
+               "nuslam_ekf_scan_step")
+        return outs if return_all else None
 
     def step_async(self, twists, z, ids, x_out):
         """Pipelined host-buffer step (nuslam_ekf_step_async): numpy views of page-locked buffers; ``x_out`` [B,len] receives the state

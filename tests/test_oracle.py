@@ -181,3 +181,30 @@ def test_port_matches_reference_edge_scans(oracle_libs):
     assert np.array_equal(a["cluster_of_beam"][ok], b["cluster_of_beam"][ok])
     assert a["n_circles"][1] == -2000 and a["n_clusters"][4] == 5
     assert list(np.nonzero(b["cluster_of_beam"][4] >= 0)[0]) == [11, 13, 15, 17, 19]   # erase-loop skip keeps every second cluster
+
+
+def test_world_step_oracle_flavours_and_geometry(oracle_libs):
+    """Simulator slice (tube_world.cpp:405-471, 512-537; restated in oracle/world_oracle.h): the two flavours agree bit for bit
+    (the DiffDrive part is the unmodified rigid2d in `ref`), and a tube straight ahead is seen at distance - radius."""
+    tubes = np.array([[0.5, 0.5], [-0.5, -0.5], [1.0, 1.0], [-1.0, -1.0], [-0.75, 0.75], [0.75, -0.75]])
+    g = np.random.default_rng(3)
+    B = 64
+    outs = {}
+    for kind, o in oracle_libs.items():
+        w = np.zeros((B, 9))
+        w[:, 0], w[:, 1] = 0.16, 0.033
+        w[:, 2:5] = np.random.default_rng(4).uniform(-1, 1, (B, 3))
+        gg = np.random.default_rng(5)
+        for t in range(4):
+            r = o.world_step(w, gg.uniform(-0.3, 0.3, (B, 3)), gg.normal(0.5, 0.3, (B, 4)), 0.1, tubes, 0.0381, 0.08, 1.0)
+        outs[kind] = (w.copy(), r.copy())
+    if len(outs) == 2:
+        assert np.array_equal(outs["port"][0], outs["ref"][0]) and np.array_equal(outs["port"][1], outs["ref"][1])
+    o = oracle_libs["port"]
+    w = np.zeros((1, 9))
+    w[0, :2] = 0.16, 0.033
+    r = o.world_step(w, np.zeros(3), None, 0.1, np.array([[0.6, 0.0]]), 0.0381, 0.08, 1.0)[0]
+    # beam 0 is a horizontal ray (dy = 0 -> NaN in the reference's dy / fabs(dy)): never stored; its neighbours see the tube
+    assert r[0] == np.float32(2.0)
+    assert abs(r[1] - (0.6 - 0.0381)) < 2e-3 and abs(r[359] - (0.6 - 0.0381)) < 2e-3
+    assert (r < 1.5).sum() == 6 and set(np.nonzero(r < 1.5)[0]) == {1, 2, 3, 357, 358, 359}
