@@ -43,6 +43,9 @@ constexpr int kFastThreads = 32;                   // one warp = one filter in f
 #ifndef NUSLAM_FAST_CTAS
 #define NUSLAM_FAST_CTAS 16
 #endif
+#ifndef NUSLAM_EXP
+#define NUSLAM_EXP 0   // timing experiments only (wrong results): 1 no atan2, 2 no publish stores, 3 no DMMA, 4 no robot-vector updates, 5 no predict
+#endif
 #ifndef NUSLAM_FAST_SINGLE_STAGE
 #define NUSLAM_FAST_SINGLE_STAGE 0   // 1: one staging buffer per CTA (input image -> exchange area -> output image): half the shared memory
 #endif
@@ -204,7 +207,8 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         // small inputs: plain loads, issued before anything waits
         if (vlane) x = p.x[bf * LEN + lane];
         const int st0 = p.status[bf], seen0 = p.seen[bf];
-        const int m = p.m_valid ? min(p.m, max(0, p.m_valid[bf])) : p.m;   // measurements of THIS filter (warp-uniform)
+        // measurements of THIS filter (warp-uniform); ragged counts come with the fused scan step, i.e. with on-device association only
+        const int m = (ASSOC && p.m_valid) ? min(p.m, max(0, p.m_valid[bf])) : p.m;
         const int my_id = (!ASSOC && lane < m) ? p.ids[bf * p.m + lane] : 0;
         const double my_z = (lane < 2 * m) ? p.z[bf * p.m * 2 + lane] : 0.0;
         const double my_tw = (do_predict && lane < 2) ? p.twists[bf * 3 + lane] : 0.0;
@@ -341,15 +345,15 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 }
             }
         }
-        // known correspondence: the m ids as four ballots (bit i of idb[k] = bit k of measurement i's code; code 0 = skip, 15 = id > N),
-        // so that the update loop reads them without a memory round trip
-        unsigned idb[4] = {0u, 0u, 0u, 0u};
+        // known correspondence: the m <= 16 ids as four 16-bit ballots packed in two registers (bit i of ballot k = bit k of measurement
+        // i's code; code 0 = skip, 15 = id > N), so that the update loop reads them without a memory round trip
+        unsigned idb01 = 0u, idb23 = 0u;
         if (!ASSOC)
         {
-            static_assert(N <= 14, "4-bit id codes");
+            static_assert(N <= 14 && kFastMMax <= 16, "4-bit id codes, 16-bit ballots");
             const int code = ((unsigned) (my_id - 1) < (unsigned) N) ? my_id : (my_id > N ? 15 : 0);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) idb[k] = __ballot_sync(kFull, (code >> k) & 1);
+            idb01 = __ballot_sync(kFull, code & 1) | (__ballot_sync(kFull, code & 2) << 16);
+            idb23 = __ballot_sync(kFull, code & 4) | (__ballot_sync(kFull, code & 8) << 16);
         }
         if (lane < 2 * m) f.z[lane] = my_z;
         // robot pose, replicated in every lane; lanes 0..2 own the same values in x (bit-identical updates)
@@ -357,7 +361,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         NUSLAM_T(0)
 
         // ---- predict (slam_library.cpp:65-108), oracle operation order, vector layout only ----
-        if (do_predict)
+        if (do_predict && NUSLAM_EXP != 5)
         {
             const double dth = __shfl_sync(kFull, my_tw, 0), dxx = __shfl_sync(kFull, my_tw, 1);
             // predictEstimate :71-94, then the two Jacobian entries of getA :127-148 (theta read AFTER the motion update,
@@ -375,13 +379,15 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             else
             {
                 const double q = div_(dxx, dth);
-                double s1, c1, s3, c3;
-                const double th1 = add_(th, dth);
-                sincos(th1, &s1, &c1);
+                // sin / cos of theta + dth and theta + 2 dth by the addition theorems from ONE library sincos(theta) and the
+                // small-angle series of dth (the oracle calls libm three times; the difference is a few ulp, far inside the tolerance)
+                double sd, cd;
+                sincos_small(dth, &sd, &cd);
+                const double s1 = fma(s0, cd, c0 * sd), c1 = fma(c0, cd, -s0 * sd);
+                const double s3 = fma(s1, cd, c1 * sd), c3 = fma(c1, cd, -s1 * sd);
                 px = add_(px, add_(mul_(-q, s0), mul_(q, s1)));
                 py = add_(py, sub_(mul_(q, c0), mul_(q, c1)));
-                th = th1;
-                sincos(add_(th1, dth), &s3, &c3);
+                th = add_(th, dth);
                 b10 = add_(mul_(-q, c1), mul_(q, c3));
                 b20 = add_(mul_(-q, s1), mul_(q, s3));
             }
@@ -511,7 +517,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 const double m00 = fma(d, p.R[0], s00), m10 = fma(dsq, p.R[1], s10), m01 = fma(dsq, p.R[2], s01), m11 = fma(d * d, p.R[3], s11);
                 const double det = fma(m00, m11, -m01 * m10);
                 const double idet = rcp_fast(det);
-                const double zb = wrap_angle(atan2_fast(dy, dx) - th);
+                const double zb = wrap_angle(atan2_unit(dy, dx, rs) - th);
                 const double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);   // no angle wrap (:229-231)
                 const double i00 = m11 * idet, i01 = -m01 * idet, i10 = -m10 * idet, i11 = m00 * idet;
                 const double t0 = fma(n0, i00, n1 * i10), t1 = fma(n0, i01, n1 * i11);
@@ -542,7 +548,8 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 else
                 {
                     const int i = i0 + s;
-                    id = (int) (((idb[0] >> i) & 1u) | (((idb[1] >> i) & 1u) << 1) | (((idb[2] >> i) & 1u) << 2) | (((idb[3] >> i) & 1u) << 3));
+                    const unsigned a01 = idb01 >> i, a23 = idb23 >> i;
+                    id = (int) ((a01 & 1u) | ((a01 >> 15) & 2u) | ((a23 & 1u) << 2) | ((a23 >> 13) & 8u));
                     if (id == 15) status |= kStatusBadId;
                 }
                 const bool live = (unsigned) (id - 1) < (unsigned) N;   // warp-uniform
@@ -565,7 +572,11 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             if (csel) cdst[8 * q] = make_double2(C[q][b < NB ? b : 0][0], C[q][b < NB ? b : 0][1]);                        \
         }                                                                                                                  \
     }
+#if NUSLAM_EXP == 2
+                    if (bsel == 7)
+#else
                     if (bsel == 0)
+#endif
                     {
                         NUSLAM_PUBLISH(0)
                     }
@@ -645,7 +656,11 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     const double idet = rcp_fast(det);
                     // the bearing chain (atan2, wrap) is independent of the Minv chain: evaluated before the branch so that the two
                     // dependency chains interleave
-                    const double zb = wrap_angle(atan2_fast(dy, dx) - th);
+#if NUSLAM_EXP == 1
+                    const double zb = zz.y - 1e-3 * dy;
+#else
+                    const double zb = wrap_angle(atan2_unit(dy, dx, rs) - th);
+#endif
                     const double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);
                     if (fabs(idet) < kFastK[6])   // < 1e300: warp-uniform; false for det = 0, inf or nan, where arma::inv throws (slam_library.cpp:270)
                     {
@@ -666,12 +681,14 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                         if (lane == 0) x = th;
                         f.xs[lane + 1] = x;
                         // robot rows / columns: Sigma -= Kt Wt restricted to them
+#if NUSLAM_EXP != 4
                         Rt = fma(k0.x, W0, fma(k0.y, W1, Rt));
                         Rx = fma(k1.x, W0, fma(k1.y, W1, Rx));
                         Ry = fma(k2.x, W0, fma(k2.y, W1, Ry));
                         Ct = fma(nk0, g0.x, fma(nk1, g0.y, Ct));
                         Cx = fma(nk0, g1.x, fma(nk1, g1.y, Cx));
                         Cy = fma(nk0, g2.x, fma(nk1, g2.y, Cy));
+#endif
                         __syncwarp();
                         NUSLAM_T(5)
                     }
@@ -700,7 +717,15 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
 #pragma unroll
                 for (int br = 0; br < NB; ++br)
 #pragma unroll
-                    for (int bc = 0; bc < NB; ++bc) dmma884(C[br][bc][0], C[br][bc][1], a[br], b[bc]);
+                    for (int bc = 0; bc < NB; ++bc)
+                    {
+#if NUSLAM_EXP == 3
+                        C[br][bc][0] += a[br];
+                        C[br][bc][1] += b[bc];
+#else
+                        dmma884(C[br][bc][0], C[br][bc][1], a[br], b[bc]);
+#endif
+                    }
             }
             __syncwarp();
             NUSLAM_T(6)
@@ -839,6 +864,7 @@ inline int launch_fast(int n, const EkfParams & p, bool do_predict, int sm_count
 {
     if (p.m > kFastMMax || p.m < 0) return -1;
     if (p.ids == nullptr && !do_predict) return -1;   // association belongs to the step protocol
+    if (p.ids != nullptr && p.m_valid != nullptr) return -1;   // ragged measurement counts with known ids: strict kernel
     if ((reinterpret_cast<uintptr_t>(p.sigma) & 7) || (reinterpret_cast<uintptr_t>(p.x) & 7)) return -1;
     if (n == 12) return launch_fast_n<12>(p, do_predict, sm_count, worklist, wl_count, stream);
     if (n == 6) return launch_fast_n<6>(p, do_predict, sm_count, worklist, wl_count, stream);

@@ -119,6 +119,16 @@ __global__ void __launch_bounds__(1024) k_tp(double * out, int iters, double see
 #pragma unroll
             for (int k = 0; k < 4; ++k) dmma1684(*reinterpret_cast<double(*)[4]>(&acc[4 * k]), a, c);
         }
+        else if (MODE == 5 || MODE == 6 || MODE == 7)
+        {
+            // DFMA x16 chains with only part of the warp active: does the fp64 pipe skip inactive half / quarter warps?
+            const int active = (MODE == 5) ? 16 : (MODE == 6) ? 8 : 1;
+            if ((threadIdx.x & 31) < active)
+            {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc[k] = fma(acc[k], y, c);
+            }
+        }
     }
     double s = 0;
 #pragma unroll
@@ -203,6 +213,18 @@ int main()
         printf("warps/SM %2d: DFMA %.3f ms (%.1f FMA/ns/SM, %.2f TFLOP/s) | DMMA884 %.3f ms (%.1f FMA/ns/SM, %.2f TF) | mixed %.3f ms (%.1f FMA/ns/SM, %.2f TF) | DMMA1688 %.3f ms (%.2f TF) | DMMA1684 %.3f ms (%.2f TF)\n",
                warps, ms0, f0 / (ms0 * 1e6), 2 * f0 * sms / (ms0 * 1e9), ms1, f1 / (ms1 * 1e6), 2 * f1 * sms / (ms1 * 1e9), ms2,
                f2 / (ms2 * 1e6), 2 * f2 * sms / (ms2 * 1e9), ms3, 2 * f3 * sms / (ms3 * 1e9), ms4, 2 * f4 * sms / (ms4 * 1e9));
+    }
+    for (int warps : {8, 16, 32})
+    {
+        const int threads = warps * 32;
+        float m0 = time_ms([&] { k_tp<0><<<sms, threads>>>(out, iters, 0.0); });
+        float m5 = time_ms([&] { k_tp<5><<<sms, threads>>>(out, iters, 0.0); });
+        float m6 = time_ms([&] { k_tp<6><<<sms, threads>>>(out, iters, 0.0); });
+        float m7 = time_ms([&] { k_tp<7><<<sms, threads>>>(out, iters, 0.0); });
+        CK(cudaDeviceSynchronize());
+        const double wi = 16.0 * warps * iters;   // warp-level DFMA instructions per SM
+        printf("warps/SM %2d: DFMA warp-instr/ns/SM with 32 / 16 / 8 / 1 active lanes: %.2f / %.2f / %.2f / %.2f\n", warps, wi / (m0 * 1e6),
+               wi / (m5 * 1e6), wi / (m6 * 1e6), wi / (m7 * 1e6));
     }
     for (int warps : {8, 16, 32})
     {
