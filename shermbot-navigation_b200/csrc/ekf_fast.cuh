@@ -345,15 +345,15 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 }
             }
         }
-        // known correspondence: the m <= 16 ids as four 16-bit ballots packed in two registers (bit i of ballot k = bit k of measurement
-        // i's code; code 0 = skip, 15 = id > N), so that the update loop reads them without a memory round trip
-        unsigned idb01 = 0u, idb23 = 0u;
+        // known correspondence: the m <= 16 ids as 4-bit codes (0 = skip, 15 = id > N) packed into two warp-uniform words by two
+        // warp reductions, so that the update loop reads them without a memory round trip
+        unsigned idlo = 0u, idhi = 0u;
         if (!ASSOC)
         {
-            static_assert(N <= 14 && kFastMMax <= 16, "4-bit id codes, 16-bit ballots");
-            const int code = ((unsigned) (my_id - 1) < (unsigned) N) ? my_id : (my_id > N ? 15 : 0);
-            idb01 = __ballot_sync(kFull, code & 1) | (__ballot_sync(kFull, code & 2) << 16);
-            idb23 = __ballot_sync(kFull, code & 4) | (__ballot_sync(kFull, code & 8) << 16);
+            static_assert(N <= 14 && kFastMMax <= 16, "4-bit id codes in two 32-bit words");
+            const unsigned code = ((unsigned) (my_id - 1) < (unsigned) N) ? (unsigned) my_id : (my_id > N ? 15u : 0u);
+            idlo = __reduce_or_sync(kFull, lane < 8 ? code << (4 * lane) : 0u);
+            idhi = __reduce_or_sync(kFull, (lane >= 8 && lane < 16) ? code << (4 * (lane - 8)) : 0u);
         }
         if (lane < 2 * m) f.z[lane] = my_z;
         // robot pose, replicated in every lane; lanes 0..2 own the same values in x (bit-identical updates)
@@ -548,8 +548,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 else
                 {
                     const int i = i0 + s;
-                    const unsigned a01 = idb01 >> i, a23 = idb23 >> i;
-                    id = (int) ((a01 & 1u) | ((a01 >> 15) & 2u) | ((a23 & 1u) << 2) | ((a23 >> 13) & 8u));
+                    id = (int) ((((i & 8) ? idhi : idlo) >> (4 * (i & 7))) & 15u);
                     if (id == 15) status |= kStatusBadId;
                 }
                 const bool live = (unsigned) (id - 1) < (unsigned) N;   // warp-uniform
