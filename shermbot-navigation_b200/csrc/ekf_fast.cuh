@@ -345,16 +345,18 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 }
             }
         }
-        // known correspondence: the m <= 16 ids as 4-bit codes (0 = skip, 15 = id > N) packed into two warp-uniform words by two
-        // warp reductions, so that the update loop reads them without a memory round trip
+        // known correspondence: the m <= 16 ids as 4-bit codes (0 = no update in that slot) packed into two warp-uniform words by two
+        // warp reductions; the update loop shifts them out, no memory round trip. An id above N is flagged here once (the flag is sticky).
         unsigned idlo = 0u, idhi = 0u;
         if (!ASSOC)
         {
-            static_assert(N <= 14 && kFastMMax <= 16, "4-bit id codes in two 32-bit words");
-            const unsigned code = ((unsigned) (my_id - 1) < (unsigned) N) ? (unsigned) my_id : (my_id > N ? 15u : 0u);
+            static_assert(N <= 15 && kFastMMax <= 16, "4-bit id codes in two 32-bit words");
+            const unsigned code = ((unsigned) (my_id - 1) < (unsigned) N) ? (unsigned) my_id : 0u;
             idlo = __reduce_or_sync(kFull, lane < 8 ? code << (4 * lane) : 0u);
             idhi = __reduce_or_sync(kFull, (lane >= 8 && lane < 16) ? code << (4 * (lane - 8)) : 0u);
+            if (__any_sync(kFull, my_id > N)) status |= kStatusBadId;
         }
+        unsigned idw = idlo;
         if (lane < 2 * m) f.z[lane] = my_z;
         // robot pose, replicated in every lane; lanes 0..2 own the same values in x (bit-identical updates)
         double th = __shfl_sync(kFull, x, 0), px = __shfl_sync(kFull, x, 1), py = __shfl_sync(kFull, x, 2);
@@ -510,19 +512,20 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     s10 = fma(w1[q], h0[q], s10);
                     s11 = fma(w1[q], h1[q], s11);
                 }
-                const double rs = rsqrt_fast(d);
+                const double rs = rsqrt_1(d);
                 double sq = d * rs;
                 sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);
                 const double dsq = d * sq;
                 const double m00 = fma(d, p.R[0], s00), m10 = fma(dsq, p.R[1], s10), m01 = fma(dsq, p.R[2], s01), m11 = fma(d * d, p.R[3], s11);
                 const double det = fma(m00, m11, -m01 * m10);
                 const double idet = rcp_fast(det);
-                const double zb = wrap_angle(atan2_unit(dy, dx, rs) - th);
+                double zb = atan2_unit(dy, dx, rs) - th;
+                    if (abs_ge_hi(zb, kHiPi)) zb = wrap_angle(zb);   // the identity inside [-pi, pi]
                 const double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);   // no angle wrap (:229-231)
                 const double i00 = m11 * idet, i01 = -m01 * idet, i10 = -m10 * idet, i11 = m00 * idet;
                 const double t0 = fma(n0, i00, n1 * i10), t1 = fma(n0, i01, n1 * i11);
                 const double dist = fma(t0, n0, t1 * n1);   // (dz^T psi^-1) dz
-                const bool sing = cand && !(fabs(idet) < 1.0e300);
+                const bool sing = cand && abs_ge_hi(idet, kHi1e300);
                 const unsigned m_sing = __ballot_sync(kFull, sing);
                 const unsigned hitA = __ballot_sync(kFull, cand && !sing && (dist < p.amin));
                 const unsigned hitB = __ballot_sync(kFull, cand && !sing && (dist > p.amin) && (dist < p.amax));
@@ -547,11 +550,11 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     id = (s == 0) ? assoc_id : 0;
                 else
                 {
-                    const int i = i0 + s;
-                    id = (int) ((((i & 8) ? idhi : idlo) >> (4 * (i & 7))) & 15u);
-                    if (id == 15) status |= kStatusBadId;
+                    if (s == 0 && i0 == 8) idw = idhi;
+                    id = (int) (idw & 15u);
+                    idw >>= 4;
                 }
-                const bool live = (unsigned) (id - 1) < (unsigned) N;   // warp-uniform
+                const bool live = ASSOC ? ((unsigned) (id - 1) < (unsigned) N) : (id != 0);   // warp-uniform
                 cc[s] = live ? 1 + 2 * id : -1;
                 if (live)
                 {
@@ -646,7 +649,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     const double e0 = g3.x - g1.x, f0 = g4.x - g2.x, e1 = g3.y - g1.y, f1 = g4.y - g2.y;
                     const double s00 = fma(dx, e0, dy * f0), s01 = fma(dx, f0, fma(-dy, e0, -d * g0.x));
                     const double s10 = fma(dx, e1, dy * f1), s11 = fma(dx, f1, fma(-dy, e1, -d * g0.y));
-                    const double rs = rsqrt_fast(d);
+                    const double rs = rsqrt_1(d);
                     double sq = d * rs;
                     sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);   // sqrt(d) to ~1 ulp
                     const double dsq = d * sq;
@@ -658,10 +661,11 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
 #if NUSLAM_EXP == 1
                     const double zb = zz.y - 1e-3 * dy;
 #else
-                    const double zb = wrap_angle(atan2_unit(dy, dx, rs) - th);
+                    double zb = atan2_unit(dy, dx, rs) - th;
+                    if (abs_ge_hi(zb, kHiPi)) zb = wrap_angle(zb);   // the identity inside [-pi, pi]
 #endif
                     const double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);
-                    if (fabs(idet) < kFastK[6])   // < 1e300: warp-uniform; false for det = 0, inf or nan, where arma::inv throws (slam_library.cpp:270)
+                    if (!abs_ge_hi(idet, kHi1e300))   // |idet| < ~1e300: warp-uniform; false for det = 0, inf or nan, where arma::inv throws (slam_library.cpp:270)
                     {
                         done = true;
                         const double i00 = m11 * idet, i01 = -m01 * idet, i10 = -m10 * idet, i11 = m00 * idet;
@@ -676,7 +680,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                         px = fma(-k1.x, n0, fma(-k1.y, n1, px));
                         py = fma(-k2.x, n0, fma(-k2.y, n1, py));
                         x = fma(-nk0, n0, fma(-nk1, n1, x));
-                        if (fabs(th) > kFastK[7]) th = wrap_angle(th);   // slam_library.cpp:275-276 (the identity inside [-pi, pi]); warp-uniform
+                        if (abs_ge_hi(th, kHiPi)) th = wrap_angle(th);   // slam_library.cpp:275-276 (the identity inside [-pi, pi]); warp-uniform
                         if (lane == 0) x = th;
                         f.xs[lane + 1] = x;
                         // robot rows / columns: Sigma -= Kt Wt restricted to them

@@ -11,6 +11,16 @@
 namespace nuslam
 {
 
+// Sign / magnitude tests on the bit pattern: integer instructions instead of fp64-pipe DADD |x| and DSETP (the fp64 pipe is the
+// contended resource of the EKF kernel). abs_bits clears the sign; for non-negative doubles the integer order is the fp order.
+__device__ __forceinline__ double abs_bits(double x) { return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x)); }
+__device__ __forceinline__ bool sign_bit(double x) { return __double2hiint(x) < 0; }
+__device__ __forceinline__ bool gt_nonneg(double a, double b) { return __double_as_longlong(a) > __double_as_longlong(b); }
+// |x| >= ~bound, decided on the high word alone (bound_hi = high word of the bound); true for inf / nan
+__device__ __forceinline__ bool abs_ge_hi(double x, int bound_hi) { return (__double2hiint(x) & 0x7fffffff) >= bound_hi; }
+constexpr int kHiPi = 0x400921fb;      // high word of pi: |x| < pi whenever the test fails, and wrapping is the identity up to pi
+constexpr int kHi1e300 = 0x7e37e43c;   // high word of 1e300
+
 // 1/x: MUFU.RCP64H seed (~2^-20) + 2 Newton steps -> <= 1 ulp for normal x
 __device__ __forceinline__ double rcp_fast(double x)
 {
@@ -33,6 +43,16 @@ __device__ __forceinline__ double rsqrt_fast(double x)
     e = fma(-x * y, y, 1.0);
     y = fma(0.5 * y, e, y);
     return y;
+}
+
+// 1/sqrt(x) with ONE Newton step (relative error ~1e-12): enough where a consumer squares the error away -- sqrt(x) = x rs refined once
+// is exact to an ulp -- or tolerates it (the unit vector of atan2_unit: <= 1e-14 rad)
+__device__ __forceinline__ double rsqrt_1(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    return fma(0.5 * y, e, y);
 }
 
 // atan2(y, x) for finite arguments, not both zero, with ONE division. With mn = min(|x|, |y|), mx = max(|x|, |y|) and
@@ -223,10 +243,10 @@ __constant__ AtanEntry kAtanUnit[65] = {
 
 __device__ __forceinline__ double atan2_unit(double y, double x, double rs)
 {
-    const double ax = fabs(x), ay = fabs(y);
-    const bool sw = ay > ax;
+    const double ax = abs_bits(x), ay = abs_bits(y);
+    const bool sw = gt_nonneg(ay, ax);
     const double mx = sw ? ay : ax, mn = sw ? ax : ay;
-    const int idx = (sw ? 1 : 0) | (x < 0.0 ? 2 : 0) | (y < 0.0 ? 4 : 0);
+    const int idx = (sw ? 1 : 0) | (sign_bit(x) ? 2 : 0) | (sign_bit(y) ? 4 : 0);
     const AtanOctant oc = kAtanOct[idx];
     const float tf = __fdividef((float) mn, (float) mx);
     const int k = max(0, min(64, __float2int_rn(tf * 64.0f)));
