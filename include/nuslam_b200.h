@@ -171,6 +171,12 @@ int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, con
 int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * z, const int32_t * ids, int32_t m, double * x_out);
 int nuslam_ekf_wait_async(nuslam_ekf * h);
 
+/* EKFSlam::broadcast_map2odom_tf, nuslam/src/slam.cpp:175-210 (the step after the path): T_mo = T_mb * T_ob.inv() with T_mb from
+ * every filter's current estimate (theta, x, y) and T_ob from the odometry model's configuration.
+ * odom_state7: B x 7 rows {wheelBase, wheelRad, x, y, th, thL, thR} (the array nuslam_diffdrive_step maintains);
+ * out: B x 3 = (translation x, translation y, yaw = normalize_angle(asin(T_mo.getSinTh()))). */
+int nuslam_ekf_map_to_odom(nuslam_ekf * h, const double * odom_state7, double * out, int mem);
+
 int nuslam_ekf_synchronize(nuslam_ekf * h);
 
 /* slam_library::cartesian2polar(x, y), slam_library.cpp:16-22, batched: xy count x 2 -> rb count x 2. */

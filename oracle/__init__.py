@@ -151,6 +151,8 @@ class OracleLib:
         c.orc_circle_fit.argtypes = [_dp, _dp, C.c_int, _dp]
         c.orc_scan_detect.argtypes = [_fp, C.c_double, C.c_double, _ip, _ip, _dp, C.c_int]
         c.orc_scan_detect_batch.argtypes = [C.c_long, _fp, C.c_double, C.c_double, _sp, _ip, _ip, _dp, C.c_int, C.c_int]
+        c.orc_map_to_odom.restype = None
+        c.orc_map_to_odom.argtypes = [_dp, _dp, _dp]
         c.orc_world_step_batch.restype = None
         c.orc_world_step_batch.argtypes = [C.c_long, _dp, _dp, _dp, C.c_double, _dp, C.c_int, C.c_double, C.c_double, C.c_double, _fp]
 
@@ -216,6 +218,12 @@ class OracleLib:
                             _d(x), _d(s), _i(seen), _i(status), _i(ids_out),
                             _d(tr) if trace else None, 1 if init is not None else 0, int(nthreads))
         return dict(x=x, sigma=np.transpose(s, (0, 2, 1)).copy(), seen=seen, status=status, ids_out=ids_out, trace=tr)
+
+    def map_to_odom(self, odom3, est3):
+        """EKFSlam::broadcast_map2odom_tf (slam.cpp:175-210): (tx, ty, yaw) of the map -> odom transform."""
+        o, e, out = _f64(odom3), _f64(est3), np.empty(3)
+        self._c.orc_map_to_odom(_d(o), _d(e), _d(out))
+        return out
 
     # ---- simulator slice ----
     def world_step(self, world, cmd, noise, dt, tubes, tube_rad, robot_rad, max_range):

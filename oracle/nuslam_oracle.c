@@ -1013,3 +1013,14 @@ void orc_world_step_batch(long B, double * world, const double * cmd, const doub
         orc_w_step(world + 9 * b, cmd + 3 * b, noise ? noise + 4 * b : NULL, dt, tubes, n_tubes, tube_rad, robot_rad, max_range,
                    ranges + 360 * b, orc_diffdrive_convert_twist, orc_diffdrive_step);
 }
+
+/* nuslam/src/slam.cpp:175-210 with rigid2d.cpp:166-214 (Transform2D(v, rad), inv, operator*=) */
+void orc_map_to_odom(const double * odom3, const double * est3, double * out3)
+{
+    tf2d T_ob = {ORC_COS(odom3[2]), ORC_SIN(odom3[2]), odom3[0], odom3[1]};
+    tf2d T_mb = {ORC_COS(est3[0]), ORC_SIN(est3[0]), est3[1], est3[2]};
+    tf2d T_mo = tf_mul(T_mb, tf_inv(T_ob));
+    out3[0] = T_mo.x;
+    out3[1] = T_mo.y;
+    out3[2] = orc_normalize_angle(asin(T_mo.s));
+}

@@ -72,6 +72,11 @@ int orc_scan_detect(const float * ranges360, double minR, double maxR, int * clu
 int orc_scan_detect_batch(long S, const float * ranges, double minR, double maxR, short * cluster_of_beam,
                           int * n_clusters, int * n_circles, double * circles, int kmax, int nthreads);
 
+/* ---- the step AFTER the path: EKFSlam::broadcast_map2odom_tf, nuslam/src/slam.cpp:175-210 ----
+ * odom3 = (x, y, th) of the odometry model, est3 = (theta, x, y) = state_estimate(0..2); out3 = (translation x, y, yaw) of
+ * T_mo = T_mb * T_ob.inv(), yaw = normalize_angle(asin(T_mo.getSinTh())). */
+void orc_map_to_odom(const double * odom3, const double * est3, double * out3);
+
 /* ---- simulator slice (nuturtlesim/src/tube_world.cpp:371-389, 405-471, 512-537; restated in oracle/world_oracle.h) ----
  * B robots, one step each: world[B][9] = {wheelBase, wheelRad, x, y, th, thL, thR, jointL, jointR} in/out, cmd[B][3] (dth, dx, dy),
  * noise[B][4] = {twist dth, twist dx, slip L, slip R} draws or NULL, tubes[n_tubes][2], ranges[B][360] out. */

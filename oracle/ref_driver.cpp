@@ -455,3 +455,20 @@ extern "C" void orc_world_step_batch(long B, double * world, const double * cmd,
                    ranges + 360 * b, orc_diffdrive_convert_twist, orc_diffdrive_step);
 }
 
+
+// nuslam/src/slam.cpp:175-210 (the node itself needs ROS): the same three rigid2d calls on the unmodified Transform2D
+extern "C" void orc_map_to_odom(const double * odom3, const double * est3, double * out3)
+{
+    using namespace rigid2d;
+    Vector2D v;
+    v.x = odom3[0];
+    v.y = odom3[1];
+    Transform2D T_ob(v, odom3[2]);
+    v.x = est3[1];
+    v.y = est3[2];
+    Transform2D T_mb(v, est3[0]);
+    Transform2D T_mo = T_mb * T_ob.inv();
+    out3[0] = T_mo.getX();
+    out3[1] = T_mo.getY();
+    out3[2] = normalize_angle(asin(T_mo.getSinTh()));
+}

@@ -172,6 +172,29 @@ __global__ void k_diffdrive_step(double * __restrict__ state, const double * __r
     s[6] = thR[b];
 }
 
+// EKFSlam::broadcast_map2odom_tf (nuslam/src/slam.cpp:175-210), batched: T_mo = T_mb * T_ob.inv() with T_ob from the odometry model
+// (state7 rows {.., x, y, th, ..}) and T_mb from the filter's state estimate (theta, x, y = x[0..2], row stride len); out B x 3 =
+// (translation x, y, yaw = normalize_angle(asin(sin))). Transform2D(v, rad), inv, operator*: rigid2d.cpp:166-214, unfused.
+__global__ void k_map_to_odom(const double * __restrict__ odom_state7, const double * __restrict__ x, int len, double * __restrict__ out,
+                              int64_t count)
+{
+    const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= count) return;
+    const double * o = odom_state7 + 7 * b;
+    const double * e = x + (int64_t) len * b;
+    Tf2D T_ob, T_mb;
+    sincos(o[4], &T_ob.s, &T_ob.c);
+    T_ob.x = o[2];
+    T_ob.y = o[3];
+    sincos(e[0], &T_mb.s, &T_mb.c);
+    T_mb.x = e[1];
+    T_mb.y = e[2];
+    const Tf2D T_mo = tf_mul(T_mb, tf_inv(T_ob));
+    out[3 * b] = T_mo.x;
+    out[3 * b + 1] = T_mo.y;
+    out[3 * b + 2] = normalize_angle(asin(T_mo.s));
+}
+
 // DiffDrive::convertTwist (diff_drive.cpp:66-78), batched: twists B x 3 -> wheel velocities B x 2 (uL, uR)
 __global__ void k_diffdrive_convert_twist(double wheel_base, double wheel_rad, const double * __restrict__ twists, double * __restrict__ u, int64_t count)
 {

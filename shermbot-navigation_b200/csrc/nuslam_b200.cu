@@ -853,6 +853,27 @@ int nuslam_diffdrive_step(double * state7, const double * thL_new, const double 
     return NUSLAM_OK;
 }
 
+int nuslam_ekf_map_to_odom(nuslam_ekf * h, const double * odom_state7, double * out, int mem)
+{
+    if (!h || !odom_state7 || !out) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    const size_t B = (size_t) h->batch;
+    const double * d_odom = nullptr;
+    int rc = stage_in(h, h->s_misc, odom_state7, B * 7, mem, &d_odom);
+    if (rc) return rc;
+    double * d_out = out;
+    if (mem == NUSLAM_HOST)
+    {
+        rc = h->s_z.reserve(sizeof(double) * 3 * B);
+        if (rc) return rc;
+        d_out = static_cast<double *>(h->s_z.p);
+    }
+    nuslam::k_map_to_odom<<<(unsigned) ((B + 127) / 128), 128, 0, h->stream>>>(d_odom, h->x, h->len, d_out, h->batch);
+    CU(cudaGetLastError());
+    if (mem == NUSLAM_HOST) CU(cudaMemcpyAsync(out, d_out, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, h->stream));
+    return finish(h, mem);
+}
+
 int nuslam_world_step(double * world, const double * cmd, const double * noise, double dt, const double * tubes, int32_t n_tubes,
                       double tube_rad, double robot_rad, double max_range, float * ranges_out, double * joints_out, int64_t count, int mem,
                       int device, void * cuda_stream)

@@ -33,7 +33,7 @@ EXPORTS = [
     "nuslam_ekf_bind_state", "nuslam_ekf_device_pointers", "nuslam_ekf_init", "nuslam_ekf_set_state",
     "nuslam_ekf_get_state", "nuslam_ekf_predict", "nuslam_ekf_associate", "nuslam_ekf_initialize_landmark",
     "nuslam_ekf_update", "nuslam_ekf_measurement_model", "nuslam_ekf_step", "nuslam_ekf_step_async", "nuslam_ekf_wait_async",
-    "nuslam_ekf_scan_step", "nuslam_ekf_synchronize",
+    "nuslam_ekf_scan_step", "nuslam_ekf_map_to_odom", "nuslam_ekf_synchronize",
     "nuslam_cartesian2polar", "nuslam_normalize_angle", "nuslam_scan_detect", "nuslam_classify_and_fit",
     "nuslam_diffdrive_step", "nuslam_diffdrive_convert_twist", "nuslam_world_step",
 ]
@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
         l.nuslam_ekf_update.argtypes = [vp, vp, vp, C.c_int]
         l.nuslam_ekf_measurement_model.argtypes = [vp, vp, vp, vp, C.c_int]
         l.nuslam_ekf_step.argtypes = [vp, vp, vp, vp, i32, vp, C.c_int]
+        l.nuslam_ekf_map_to_odom.argtypes = [vp, vp, vp, C.c_int]
         l.nuslam_world_step.argtypes = [vp, vp, vp, C.c_double, vp, i32, C.c_double, C.c_double, C.c_double, vp, vp, i64, C.c_int, C.c_int, vp]
         l.nuslam_ekf_scan_step.argtypes = [vp, vp, vp, C.c_double, C.c_double, i32, vp, vp, vp, C.c_int]
         l.nuslam_ekf_step_async.argtypes = [vp, vp, vp, vp, i32, vp]
@@ -288,6 +289,20 @@ class BatchedExtendedKalman:
         _check(lib().nuslam_ekf_scan_step(self._h, pt[0], pr[0], float(min_range), float(max_range), int(m), ptrs[0], ptrs[1], ptrs[2], mem),
                "nuslam_ekf_scan_step")
         return outs if return_all else None
+
+    def map_to_odom(self, odom_state7):
+        """EKFSlam::broadcast_map2odom_tf (slam.cpp:175-210) for every filter: [B,3] = (tx, ty, yaw) of map -> odom, from the filter's
+        estimate and the odometry model's state rows {wheelBase, wheelRad, x, y, th, thL, thR}."""
+        po = _ptr(odom_state7, np.float64)
+        if po[2] == NUSLAM_DEVICE:
+            import torch
+            out = torch.empty((self.batch, 3), dtype=torch.float64, device=odom_state7.device)
+            optr = out.data_ptr()
+        else:
+            out = np.empty((self.batch, 3))
+            optr = out.ctypes.data
+        _check(lib().nuslam_ekf_map_to_odom(self._h, po[0], optr, po[2]), "nuslam_ekf_map_to_odom")
+        return out
 
     def step_async(self, twists, z, ids, x_out):
         """Pipelined host-buffer step (nuslam_ekf_step_async): numpy views of page-locked buffers; ``x_out`` [B,len] receives the state

@@ -135,3 +135,19 @@ def test_closed_loop_device_resident(cuda_lib):
     err = np.abs(x[:, 1:3] - true[:, 0:2]).max()
     print(f"[closed loop] {T} steps, landmarks seen {seen.mean():.2f}, max position error {err:.3e} m, status bits {np.bitwise_or.reduce(status)}")
     assert seen.min() >= 1 and err < 0.05
+
+
+def test_map_to_odom_matches_oracle(cuda_lib, orc):
+    """EKFSlam::broadcast_map2odom_tf (slam.cpp:175-210), the step after the path: T_mo = T_mb * T_ob.inv()."""
+    B, n = 257, 12
+    g = np.random.default_rng(8)
+    est = np.stack([g.uniform(-3.14, 3.14, B), g.uniform(-2, 2, B), g.uniform(-2, 2, B)], axis=1)
+    eng = cuda_lib.BatchedExtendedKalman(est, n_landmarks=n, mode="fast")
+    odom = np.zeros((B, 7))
+    odom[:, 0], odom[:, 1] = tube_world.WHEEL_BASE, tube_world.WHEEL_RAD
+    odom[:, 2:5] = np.stack([g.uniform(-2, 2, B), g.uniform(-2, 2, B), g.uniform(-6.5, 6.5, B)], axis=1)   # odometry theta is never normalised
+    odom[0, 2:5] = est[0, [1, 2, 0]]   # identical frames: the identity transform
+    got = eng.map_to_odom(odom)
+    want = np.stack([orc.map_to_odom(odom[b, 2:5], est[b]) for b in range(B)])
+    assert np.abs(got - want).max() < 1e-14
+    assert np.abs(got[0]).max() < 1e-15
