@@ -644,6 +644,14 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     f.wt[s][lane] = make_double2(W0, W1);
                     __syncwarp();
                     NUSLAM_T(3)
+#if NUSLAM_EXP == 6
+                    // what-if: the 2 x 2 part arrives from elsewhere (a response read back from shared memory); timing only
+                    const double2 g0 = f.wt[s][0], g1 = f.wt[s][1], g2 = f.wt[s][2];
+                    const double2 q0 = g0, q1 = g1, q2 = g2;
+                    const double m00 = 1.0 + 1e-9 * q0.x, m01 = 1e-9 * q0.y, m10 = 1e-9 * q1.x, m11 = 1.0 + 1e-9 * q1.y;
+                    const double idet = 1.0 + 1e-9 * q2.x;
+                    const double n0 = 1e-6 * (zz.x - dx), n1 = 1e-6 * (zz.y - dy) + 1e-12 * q2.y;
+#else
                     // the 2 x 2 part, evaluated by every lane: M = Wt Ht^T + D^-1 R D^-1, Minv, innovation (:150-160, :272 no wrap)
                     const double2 g0 = f.wt[s][0], g1 = f.wt[s][1], g2 = f.wt[s][2], g3 = f.wt[s][c], g4 = f.wt[s][c + 1];
                     const double e0 = g3.x - g1.x, f0 = g4.x - g2.x, e1 = g3.y - g1.y, f1 = g4.y - g2.y;
@@ -665,6 +673,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     if (abs_ge_hi(zb, kHiPi)) zb = wrap_angle(zb);   // the identity inside [-pi, pi]
 #endif
                     const double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);
+#endif
                     if (!abs_ge_hi(idet, kHi1e300))   // |idet| < ~1e300: warp-uniform; false for det = 0, inf or nan, where arma::inv throws (slam_library.cpp:270)
                     {
                         done = true;
