@@ -23,6 +23,17 @@ constexpr int kStatusSingular = 2;
 constexpr int kStatusBadId = 4;
 constexpr int kIdException = -1000;
 
+// Function attributes and __device__ tables are per DEVICE (per context): one-time setup is remembered per device ordinal, so that
+// a process driving several GPUs (one handle each) configures every one of them. Races between host threads are benign (the setup
+// is idempotent).
+constexpr int kMaxDevices = 64;
+inline int device_slot()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 // unfused IEEE operations: nvcc never contracts these into FMAs, whatever -fmad says
 __device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }

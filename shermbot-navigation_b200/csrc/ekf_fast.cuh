@@ -848,7 +848,8 @@ int launch_fast_n(const EkfParams & p, bool do_predict, int sm_count, int32_t * 
     if (const char * e = getenv("NUSLAM_FAST_CTAS_PER_SM")) ctas_per_sm = atoi(e);
 #endif
     if (blocks > ctas_per_sm * (int64_t) sm_count) blocks = ctas_per_sm * (int64_t) sm_count;
-    static thread_local bool configured = false;
+    static bool configured_dev[kMaxDevices] = {false};
+    bool & configured = configured_dev[device_slot()];
     if (!configured)
     {
         // 16 CTAs x 11.8 KB of static shared memory per SM: ask for the largest shared-memory carve-out

@@ -443,7 +443,12 @@ inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const
     const int kk = (2 * cnt + 3) & ~3;
     k_large_clear_w<<<dim3((unsigned) (((int64_t) kk * p.len + threads - 1) / threads), (unsigned) p.batch), threads, 0, st>>>(p, kk / 2);
     // one cooperative launch when the whole grid is co-resident (it is for a few large maps), else two launches per update
-    static thread_local int coop_blocks_per_sm = -1;
+    static int coop_dev[kMaxDevices];
+    static bool coop_known[kMaxDevices] = {false};
+    const int slot = device_slot();
+    if (!coop_known[slot]) coop_dev[slot] = -1;
+    coop_known[slot] = true;
+    int & coop_blocks_per_sm = coop_dev[slot];
     if (coop_blocks_per_sm < 0)
     {
         int dev = 0, sms = 0, nb = 0, can = 0;

@@ -167,7 +167,8 @@ int launch_strict(nuslam_ekf * h, const nuslam::EkfParams & p)
 {
     const int warps = h->strict_warps;
     const size_t smem = h->strict_smem * warps;
-    static thread_local size_t configured[8] = {0};
+    static size_t configured_dev[nuslam::kMaxDevices][8] = {{0}};
+    size_t * configured = configured_dev[nuslam::device_slot()];
     if (configured[OP] < smem)
     {
         CU(cudaFuncSetAttribute(nuslam::k_ekf_strict<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -188,7 +189,8 @@ int launch_fast_then_strict(nuslam_ekf * h, const nuslam::EkfParams & p, bool do
     if (rc) return cuda_fail((cudaError_t) rc, "fast kernel launch");
     const int warps = h->strict_warps;
     const size_t smem = h->strict_smem * warps;
-    static thread_local size_t configured[8] = {0};
+    static size_t configured_dev[nuslam::kMaxDevices][8] = {{0}};
+    size_t * configured = configured_dev[nuslam::device_slot()];
     if (configured[OP] < smem)
     {
         CU(cudaFuncSetAttribute(nuslam::k_ekf_strict_list<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));

@@ -1013,7 +1013,8 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
     if (e != cudaSuccess) return e;
     const size_t smem = sizeof(ScanSmem) * kScanWarps;
     const size_t fit_smem16 = sizeof(double) * 4 * 16 * kFitThreads, fit_smem32 = sizeof(double) * 4 * kFitNMax * kFitThreads;
-    static bool configured = false;
+    static bool configured_dev[kMaxDevices] = {false};
+    bool & configured = configured_dev[(device >= 0 && device < kMaxDevices) ? device : 0];
     if (!configured)
     {
         e = cudaFuncSetAttribute(k_scan_detect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);

@@ -402,3 +402,30 @@ def test_fast_association_free_running(cuda_lib, orc):
     print(f"[fast association] {B * (T - 3) * n} decisions, {matched} matches applied, id mismatches {mism}; x rel {ex:.2e}, Sigma rel {es:.2e}")
     assert mism == 0 and np.array_equal(seen, full["seen"]) and np.array_equal(status, full["status"])
     assert ex < TOL and es < TOL
+
+
+def test_two_devices_in_one_process(cuda_lib, orc):
+    """One handle per GPU in ONE process (kernel attributes and constant tables are per device): both devices give the same result."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from shermbot_navigation_b200 import circle_fit
+    B, T, n = 64, 4, 12
+    sc = synth.ekf_scenario(B, T, n=n, seed=4)
+    outs = []
+    for dev in (1, 0):   # the second device first: it must not inherit the first one's one-time setup
+        for mode in ("strict", "fast"):
+            eng = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode=mode, device=dev)
+            for t in range(T):
+                eng.step(sc["twists"][t], sc["z"][t], sc["ids"][t])
+            outs.append((dev, mode) + tuple(eng.get_state()))
+            eng.close()
+    for mode in ("strict", "fast"):
+        a = [o for o in outs if o[0] == 0 and o[1] == mode][0]
+        b = [o for o in outs if o[0] == 1 and o[1] == mode][0]
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and not a[5].any() and not b[5].any()
+    sd = synth.scan_scenario(600, seed=3, noise_sigma=0.001)
+    r0 = circle_fit.scan_detect(sd["ranges"], sd["min_range"], sd["max_range"], device=1)
+    r1 = circle_fit.scan_detect(sd["ranges"], sd["min_range"], sd["max_range"], device=0)
+    assert np.array_equal(r0["cluster_of_beam"], r1["cluster_of_beam"]) and np.array_equal(r0["n_circles"], r1["n_circles"])
+    assert np.array_equal(np.nan_to_num(r0["circles"]), np.nan_to_num(r1["circles"]))
