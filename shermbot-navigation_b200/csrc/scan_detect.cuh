@@ -140,26 +140,33 @@ __device__ inline void svd_n4(const WorkMatrix A, int m, double * s, double * V)
         for (int i = 0; i < m; ++i) acc = add_(acc, mul_(A(i, j), A(i, j)));
         norms[j] = sqrt(acc);
     }
-    // stable insertion sort, descending (a 4-element network with the same tie behaviour)
-    int order[4] = {0, 1, 2, 3};
+    // stable insertion sort, descending (a 4-element network with the same tie behaviour); the columns of W travel with their
+    // keys by selects -- no index array, so that W and norms stay in registers (a dynamically indexed array lives in local memory)
 #pragma unroll
     for (int a = 1; a < 4; ++a)
     {
 #pragma unroll
         for (int b = a; b > 0; --b)
         {
-            const bool sw = norms[order[b - 1]] < norms[order[b]];
-            const int o0 = order[b - 1], o1 = order[b];
-            order[b - 1] = sw ? o1 : o0;
-            order[b] = sw ? o0 : o1;
+            const bool sw = norms[b - 1] < norms[b];
+            const double k0 = norms[b - 1], k1 = norms[b];
+            norms[b - 1] = sw ? k1 : k0;
+            norms[b] = sw ? k0 : k1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                const double w0 = W[i + (b - 1) * 4], w1 = W[i + b * 4];
+                W[i + (b - 1) * 4] = sw ? w1 : w0;
+                W[i + b * 4] = sw ? w0 : w1;
+            }
         }
     }
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
     {
-        s[jj] = norms[order[jj]];
+        s[jj] = norms[jj];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) V[i + jj * 4] = W[i + order[jj] * 4];
+        for (int i = 0; i < 4; ++i) V[i + jj * 4] = W[i + jj * 4];
     }
 }
 
@@ -235,25 +242,33 @@ __device__ inline void eig_sym4(const double * X, double * val, double * vec)
             }
         if (!out_changed && all_c1) break;
     }
-    int order[4] = {0, 1, 2, 3};
+    // ascending stable insertion sort of (eigenvalue, eigenvector column) pairs by selects (no index array: registers only)
+    double key[4] = {A[0], A[5], A[10], A[15]};
 #pragma unroll
     for (int a = 1; a < 4; ++a)
     {
 #pragma unroll
         for (int b = a; b > 0; --b)
         {
-            const bool sw = A[order[b - 1] * 5] > A[order[b] * 5];
-            const int o0 = order[b - 1], o1 = order[b];
-            order[b - 1] = sw ? o1 : o0;
-            order[b] = sw ? o0 : o1;
+            const bool sw = key[b - 1] > key[b];
+            const double k0 = key[b - 1], k1 = key[b];
+            key[b - 1] = sw ? k1 : k0;
+            key[b] = sw ? k0 : k1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                const double w0 = W[i + (b - 1) * 4], w1 = W[i + b * 4];
+                W[i + (b - 1) * 4] = sw ? w1 : w0;
+                W[i + b * 4] = sw ? w0 : w1;
+            }
         }
     }
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
     {
-        val[jj] = A[order[jj] * 5];
+        val[jj] = key[jj];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) vec[i + jj * 4] = W[i + order[jj] * 4];
+        for (int i = 0; i < 4; ++i) vec[i + jj * 4] = W[i + jj * 4];
     }
 }
 
@@ -268,23 +283,32 @@ __device__ inline bool solve4(const double * Ain, const double * b, double * x)
 #pragma unroll
     for (int c = 0; c < 4; ++c)
     {
+        // partial pivoting without a dynamic row index (registers only): the first row of maximal |A(r, c)|, then a select-swap
         int piv = c;
+        double best = fabs(A[c + c * 4]);
 #pragma unroll
         for (int r = c + 1; r < 4; ++r)
-            if (fabs(A[r + c * 4]) > fabs(A[piv + c * 4])) piv = r;
-        if (A[piv + c * 4] == 0.0) return false;
-        if (piv != c)
         {
+            const double v = fabs(A[r + c * 4]);
+            const bool gt = v > best;
+            piv = gt ? r : piv;
+            best = gt ? v : best;
+        }
+        if (best == 0.0) return false;
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r)
+        {
+            const bool sw = (piv == r);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
             {
-                const double t = A[piv + k * 4];
-                A[piv + k * 4] = A[c + k * 4];
-                A[c + k * 4] = t;
+                const double t0 = A[r + k * 4], t1 = A[c + k * 4];
+                A[r + k * 4] = sw ? t1 : t0;
+                A[c + k * 4] = sw ? t0 : t1;
             }
-            const double t = x[piv];
-            x[piv] = x[c];
-            x[c] = t;
+            const double u0 = x[r], u1 = x[c];
+            x[r] = sw ? u1 : u0;
+            x[c] = sw ? u0 : u1;
         }
 #pragma unroll
         for (int r = c + 1; r < 4; ++r)
@@ -1005,6 +1029,24 @@ struct ScanScratch
     size_t bytes = 0;
 };
 
+// side streams of the throughput path: the fits of the three size classes (and the slow-scan list) touch disjoint clusters, so the
+// two long-tailed small launches run beside the big one instead of after it
+struct ScanSide
+{
+    cudaStream_t s1 = nullptr, s2 = nullptr;
+    cudaEvent_t fork = nullptr, join1 = nullptr, join2 = nullptr;
+    cudaError_t ensure()
+    {
+        if (s1) return cudaSuccess;
+        cudaError_t e = cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join1, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join2, cudaEventDisableTiming);
+        return e;
+    }
+};
+
 inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, double min_range, double max_range, int16_t * cluster_of_beam,
                                       int32_t * n_clusters, int32_t * n_circles, double * circles, int32_t max_circles, int scan_ub,
                                       int device, int sm_count, cudaStream_t stream)
@@ -1036,7 +1078,11 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
     }
     // throughput path: cluster (warp per scan) -> fit (thread per cluster) -> publish (thread per scan), in chunks of scans
     static thread_local ScanScratch scratch[64];
+    static thread_local ScanSide sides[64];
     ScanScratch & sc = scratch[(device >= 0 && device < 64) ? device : 0];
+    ScanSide & side = sides[(device >= 0 && device < 64) ? device : 0];
+    e = side.ensure();
+    if (e != cudaSuccess) return e;
     const int64_t chunk_max = n_scans < kScanChunk ? n_scans : kScanChunk;
     const size_t n_desc = (size_t) chunk_max * kMaxFastClusters;
     auto al = [](size_t v) { return (v + 255) & ~(size_t) 255; };
@@ -1076,13 +1122,22 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
         if (blocks > resident) blocks = resident;
         k_scan_detect<false><<<(unsigned) blocks, 32 * kScanWarps, smem, stream>>>(ranges, chunk, min_range, max_range, cluster_of_beam, n_clusters,
                                                                                 n_circles, circles, max_circles, scan_ub, nullptr, nullptr, pipe);
+        e = cudaEventRecord(side.fork, stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side.s1, side.fork, 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side.s2, side.fork, 0);
+        if (e != cudaSuccess) return e;
         k_scan_fit_small<16, false><<<(unsigned) (sm_count * 6), kFitThreads, fit_smem16, stream>>>(ranges, min_range, max_range, pipe);
-        k_scan_fit_small<kFitNMax, true><<<(unsigned) (sm_count * 3), kFitThreads, fit_smem32, stream>>>(ranges, min_range, max_range, pipe);
-        k_scan_fit_big<<<(unsigned) (sm_count * 2), 64, 0, stream>>>(ranges, min_range, max_range, pipe);
+        k_scan_fit_small<kFitNMax, true><<<(unsigned) (sm_count * 3), kFitThreads, fit_smem32, side.s1>>>(ranges, min_range, max_range, pipe);
+        k_scan_fit_big<<<(unsigned) (sm_count * 2), 64, 0, side.s2>>>(ranges, min_range, max_range, pipe);
+        // scans with more than kMaxFastClusters clusters: the one-warp-per-scan kernel over their list (it writes those scans' outputs itself)
+        k_scan_detect<true><<<(unsigned) sm_count, 32 * kScanWarps, smem, side.s2>>>(ranges, n_scans, min_range, max_range, cluster_of_beam, n_clusters,
+                                                                                  n_circles, circles, max_circles, scan_ub, pipe.slow, pipe.counters + 2, pipe);
+        e = cudaEventRecord(side.join1, side.s1);
+        if (e == cudaSuccess) e = cudaEventRecord(side.join2, side.s2);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, side.join1, 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, side.join2, 0);
+        if (e != cudaSuccess) return e;
         k_scan_publish<<<(unsigned) ((chunk + 127) / 128), 128, 0, stream>>>(chunk, n_clusters, n_circles, circles, max_circles, pipe);
-        // scans with more than kMaxFastClusters clusters: the one-warp-per-scan kernel over their list
-        k_scan_detect<true><<<(unsigned) sm_count, 32 * kScanWarps, smem, stream>>>(ranges, n_scans, min_range, max_range, cluster_of_beam, n_clusters,
-                                                                                 n_circles, circles, max_circles, scan_ub, pipe.slow, pipe.counters + 2, pipe);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
