@@ -29,8 +29,10 @@ constexpr int kBeams = 360;
 constexpr int kScanWarps = 2;   // scans per CTA
 constexpr double kPiRef = 3.14159265358979323846;   // rigid2d.hpp:16
 
-__constant__ double c_beam_cos[kBeams];
-__constant__ double c_beam_sin[kBeams];
+// beam directions cos / sin(deg2rad(i)) from the HOST libm (the reference's own values). In global memory, read through the
+// read-only path: the lanes of a warp index them with different beams, which the constant cache would serialise.
+__device__ double c_beam_cos[kBeams];
+__device__ double c_beam_sin[kBeams];
 
 struct ScanSmem
 {
@@ -543,8 +545,8 @@ k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_ran
             if (inr)
             {
                 const double r = (double) sm.r[i];
-                sm.px[my_pos[k]] = mul_(r, c_beam_cos[i]);   // :162-163
-                sm.py[my_pos[k]] = mul_(r, c_beam_sin[i]);
+                sm.px[my_pos[k]] = mul_(r, __ldg(&c_beam_cos[i]));   // :162-163
+                sm.py[my_pos[k]] = mul_(r, __ldg(&c_beam_sin[i]));
                 if (clo)
                 {
                     sm.cend[my_clu[k]] = (short) my_pos[k];
@@ -557,8 +559,8 @@ k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_ran
         if (wrap && lane == 0)
         {
             const double r = (double) sm.r[kBeams - 1];
-            sm.px[kBeams + 1] = mul_(r, c_beam_cos[kBeams - 1]);
-            sm.py[kBeams + 1] = mul_(r, c_beam_sin[kBeams - 1]);
+            sm.px[kBeams + 1] = mul_(r, __ldg(&c_beam_cos[kBeams - 1]));
+            sm.py[kBeams + 1] = mul_(r, __ldg(&c_beam_sin[kBeams - 1]));
         }
         __syncwarp();
         // ---- erase loop (:198-204): a cluster following an erased one is never examined ----
@@ -744,13 +746,13 @@ __device__ __forceinline__ int gather_points(const ClusterDesc & d, const float 
     {
         const float r = rs[bm];
         if (((double) r > max_range) || ((double) r < min_range)) continue;
-        store(i, mul_((double) r, c_beam_cos[bm]), mul_((double) r, c_beam_sin[bm]));
+        store(i, mul_((double) r, __ldg(&c_beam_cos[bm])), mul_((double) r, __ldg(&c_beam_sin[bm])));
         ++i;
     }
     if (d.n_wrap >> 16)
     {
         const float r = rs[kBeams - 1];
-        store(i, mul_((double) r, c_beam_cos[kBeams - 1]), mul_((double) r, c_beam_sin[kBeams - 1]));
+        store(i, mul_((double) r, __ldg(&c_beam_cos[kBeams - 1])), mul_((double) r, __ldg(&c_beam_sin[kBeams - 1])));
         ++i;
     }
     return i;
@@ -916,11 +918,37 @@ __global__ void __launch_bounds__(64) k_scan_fit_big(const float * __restrict__ 
         double * Zp = zbuf[warp];
         double * tmp = angbuf[warp];
         const WorkMatrix Z = {Zp, n, 1};
-        if (lane == 0)
-            gather_points(d, ranges, min_range, max_range, [&](int i, double x, double y) {
-                Z(i, 1) = x;
-                Z(i, 2) = y;
-            });
+        // the cluster's points in stored order (gather_points, spread over the lanes: rank among the in-range beams by ballots)
+        {
+            const float * rs = ranges + (int64_t) d.scan * kBeams;
+            const int first = d.beams & 0xffff, last = d.beams >> 16;
+            int count = 0;
+            for (int b0 = first; b0 <= last; b0 += 32)
+            {
+                const int bm = b0 + lane;
+                float r = 0.0f;
+                bool in = false;
+                if (bm <= last)
+                {
+                    r = rs[bm];
+                    in = !(((double) r > max_range) || ((double) r < min_range));
+                }
+                const unsigned bal = __ballot_sync(kFull, in);
+                if (in)
+                {
+                    const int i = count + __popc(bal & ((1u << lane) - 1u));
+                    Z(i, 1) = mul_((double) r, __ldg(&c_beam_cos[bm]));
+                    Z(i, 2) = mul_((double) r, __ldg(&c_beam_sin[bm]));
+                }
+                count += __popc(bal);
+            }
+            if ((d.n_wrap >> 16) && lane == 0)
+            {
+                const float r = rs[kBeams - 1];
+                Z(count, 1) = mul_((double) r, __ldg(&c_beam_cos[kBeams - 1]));
+                Z(count, 2) = mul_((double) r, __ldg(&c_beam_sin[kBeams - 1]));
+            }
+        }
         __syncwarp();
         // classifyCluster (circle_fit_library.cpp:208-250)
         {
@@ -934,20 +962,32 @@ __global__ void __launch_bounds__(64) k_scan_fit_big(const float * __restrict__ 
             }
         }
         __syncwarp();
+        // mean and population variance (:229-241): the quotients and squares by all lanes, the SUMS by lane 0 in the reference's order
+        double * q1 = tmp + (kBeams + 2);
         double sd = 0.0;
-        if (lane == 0)
         {
             const int na = n - 2;
+            for (int i = 1 + lane; i < n - 1; i += 32) q1[i] = div_(tmp[i], (double) na);
+            __syncwarp();
             double mean = 0.0;
-            for (int i = 1; i < n - 1; ++i) mean = add_(mean, div_(tmp[i], (double) na));
-            for (int i = 1; i < n - 1; ++i)
+            if (lane == 0)
+                for (int i = 1; i < n - 1; ++i) mean = add_(mean, q1[i]);
+            mean = __shfl_sync(kFull, mean, 0);
+            __syncwarp();
+            for (int i = 1 + lane; i < n - 1; i += 32)
             {
                 const double dv = sub_(tmp[i], mean);
-                sd = add_(sd, mul_(dv, dv));
+                q1[i] = mul_(dv, dv);
             }
-            sd = sqrt(div_(sd, (double) na));
+            __syncwarp();
+            if (lane == 0)
+            {
+                for (int i = 1; i < n - 1; ++i) sd = add_(sd, q1[i]);
+                sd = sqrt(div_(sd, (double) na));
+            }
+            sd = __shfl_sync(kFull, sd, 0);
+            __syncwarp();
         }
-        sd = __shfl_sync(kFull, sd, 0);
         ClusterFit out;
         out.pub = 0.0;
         out.cx = out.cy = out.R = 0.0;
@@ -955,14 +995,22 @@ __global__ void __launch_bounds__(64) k_scan_fit_big(const float * __restrict__ 
         {
             // circleFit (circle_fit_library.cpp:15-134): centroid and z_bar by lane 0 (sequential sums), Z by all lanes
             double x_hat = 0.0, y_hat = 0.0, z_bar = 0.0;
+            double * q2 = tmp + 2 * (kBeams + 2);
+            for (int i = lane; i < n; i += 32)
+            {
+                q1[i] = div_(Z(i, 1), (double) n);
+                q2[i] = div_(Z(i, 2), (double) n);
+            }
+            __syncwarp();
             if (lane == 0)
                 for (int i = 0; i < n; ++i)
                 {
-                    x_hat = add_(x_hat, div_(Z(i, 1), (double) n));
-                    y_hat = add_(y_hat, div_(Z(i, 2), (double) n));
+                    x_hat = add_(x_hat, q1[i]);
+                    y_hat = add_(y_hat, q2[i]);
                 }
             x_hat = __shfl_sync(kFull, x_hat, 0);
             y_hat = __shfl_sync(kFull, y_hat, 0);
+            __syncwarp();
             for (int j = lane; j < n; j += 32)
             {
                 const double dx = sub_(Z(j, 1), x_hat), dy = sub_(Z(j, 2), y_hat);
@@ -972,9 +1020,12 @@ __global__ void __launch_bounds__(64) k_scan_fit_big(const float * __restrict__ 
                 Z(j, 3) = 1.0;
             }
             __syncwarp();
+            for (int j = lane; j < n; j += 32) q1[j] = div_(Z(j, 0), (double) n);
+            __syncwarp();
             if (lane == 0)
-                for (int j = 0; j < n; ++j) z_bar = add_(z_bar, div_(Z(j, 0), (double) n));
+                for (int j = 0; j < n; ++j) z_bar = add_(z_bar, q1[j]);
             z_bar = __shfl_sync(kFull, z_bar, 0);
+            __syncwarp();
             double sv[4], V[16], fit[3];
             svd_n4_warp(Zp, n, tmp, lane, sv, V);
             const int id = circle_fit_tail(sv, V, z_bar, x_hat, y_hat, fit);
@@ -1128,7 +1179,7 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
         if (e != cudaSuccess) return e;
         k_scan_fit_small<16, false><<<(unsigned) (sm_count * 6), kFitThreads, fit_smem16, stream>>>(ranges, min_range, max_range, pipe);
         k_scan_fit_small<kFitNMax, true><<<(unsigned) (sm_count * 3), kFitThreads, fit_smem32, side.s1>>>(ranges, min_range, max_range, pipe);
-        k_scan_fit_big<<<(unsigned) (sm_count * 2), 64, 0, side.s2>>>(ranges, min_range, max_range, pipe);
+        k_scan_fit_big<<<(unsigned) (sm_count * 5), 64, 0, side.s2>>>(ranges, min_range, max_range, pipe);
         // scans with more than kMaxFastClusters clusters: the one-warp-per-scan kernel over their list (it writes those scans' outputs itself)
         k_scan_detect<true><<<(unsigned) sm_count, 32 * kScanWarps, smem, side.s2>>>(ranges, n_scans, min_range, max_range, cluster_of_beam, n_clusters,
                                                                                   n_circles, circles, max_circles, scan_ub, pipe.slow, pipe.counters + 2, pipe);
