@@ -148,6 +148,23 @@ def make_inputs_device(torch, dev, B, steps_total, seed):
     return robot0, twists, ids, z_of
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Run this rank's host threads on the CPUs next to its GPU (NVML's ideal affinity), so that the page-locked staging buffers of
+    the end-to-end leg are allocated on that NUMA node and their DMA does not cross the socket link. Best effort; returns a note."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = len(os.sched_getaffinity(0))
+        return f"nvml ideal affinity: {after} of {before} cpus"
+    except Exception as e:   # containers often forbid it: not an error
+        return f"unchanged ({type(e).__name__})"
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -160,6 +177,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.filters, args.steps, args.warmup
@@ -279,7 +297,7 @@ def run_ours(args):
                        "parallelism": f"filters sharded {world}x, no data-path collective; final NCCL all_gather of states"},
             "clocks": clocks, "gpu_launches": (2 * K if args.mode == "fast" else K), "bad_filters": bad,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "api": "BatchedExtendedKalman.step_async (nuslam_ekf_step_async): pinned host buffers, H2D + fused step + D2H of the state vector per step, 3 steps in flight"},
+                    "api": "BatchedExtendedKalman.step_async (nuslam_ekf_step_async): pinned host buffers, H2D + fused step + D2H of the state vector per step, 3 steps in flight", "host_affinity": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_filter_step": BYTES_PER_FILTER_STEP,
                          "kernel": "k_ekf_fast_step<12> (+ k_ekf_strict_list over the first-touch work list, empty in steady state)" if args.mode == "fast" else "k_ekf_strict<kOpStep>",
