@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NUSLAM_B200_VERSION 100
+#define NUSLAM_B200_VERSION 101
 
 /* ---- return codes of every entry point ---- */
 enum
@@ -95,7 +95,20 @@ typedef struct
     double R[4];           /* 2x2 sensor noise, column-major (slam_library.cpp:215,270) */
     double assoc_min;      /* 0.01 (slam_library.cpp:193) */
     double assoc_max;      /* 60   (slam_library.cpp:194) */
+    uint32_t options;      /* NUSLAM_OPT_* bit mask; 0 = the reference's behaviour (the default, and the parity contract) */
+    uint32_t reserved;
+    double landmark_prior; /* variance written on the landmark diagonal by nuslam_ekf_init; INT_MAX (slam_library.cpp:30) by default */
 } nuslam_ekf_config;
+
+/* Opt-in departures from the reference, for users who want Monte-Carlo statistics that mean something; never the
+ * default because parity with the reference is the contract. They run in the oracle-order kernels (any mode; the register kernel
+ * and the large-map mode implement the reference's behaviour only). */
+enum
+{
+    NUSLAM_OPT_WRAP_INNOVATION = 1,     /* bearing innovation wrapped to (-pi, pi] in update and associateLandmark (reference: :229-231, :272 do not) */
+    NUSLAM_OPT_JOSEPH = 2,              /* Sigma <- (I-KH) Sigma (I-KH)^T + K R K^T, then (Sigma + Sigma^T)/2 (reference: (I-KH) Sigma, :279) */
+    NUSLAM_OPT_PRE_MOTION_JACOBIAN = 4  /* getA evaluated at theta BEFORE the motion update (reference: after it, :129) */
+};
 
 /* Q = 0.1 I, R = 0.001 I (nuslam/config/slam_params.yaml:2-3), thresholds 0.01 / 60, STRICT mode */
 void nuslam_ekf_default_config(nuslam_ekf_config * cfg, int32_t n_landmarks);

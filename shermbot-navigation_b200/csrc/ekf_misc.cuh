@@ -10,7 +10,7 @@ namespace nuslam
 // INT_MAX on the landmark diagonal, seen = 0. One thread per Sigma element.
 __global__ void k_ekf_init(int64_t batch, int len, const double * __restrict__ robot, const double * __restrict__ map,
                            double * __restrict__ x, double * __restrict__ sigma, int32_t * __restrict__ seen,
-                           int32_t * __restrict__ status)
+                           int32_t * __restrict__ status, double prior)
 {
     const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t len2 = (int64_t) len * len;
@@ -18,7 +18,7 @@ __global__ void k_ekf_init(int64_t batch, int len, const double * __restrict__ r
     const int64_t b = t / len2;
     const int e = (int) (t - b * len2);
     const int j = e / len, i = e - j * len;
-    sigma[t] = (i == j && i >= 3) ? kLandmarkPrior : 0.0;
+    sigma[t] = (i == j && i >= 3) ? prior : 0.0;   // INT_MAX by default (slam_library.cpp:30)
     if (j == 0)
     {
         double v;

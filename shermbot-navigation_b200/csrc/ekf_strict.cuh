@@ -22,6 +22,7 @@ __host__ __device__ constexpr int strict_smem_doubles(int len) { return len * le
 struct WarpFilter
 {
     int len, n, lane;
+    unsigned opt = 0u;   // NUSLAM_OPT_* (0 = the reference's behaviour)
     double * S;    // len x len, column-major
     double * x;    // len
     double * R5;   // 5 x len: rows {0,1,2,c,c+1} of Sigma before the update, R5[k*len + j]
@@ -86,18 +87,19 @@ struct WarpFilter
             x[1] = x1;
             x[2] = y1;
         }
-        // getA :127-148 -- theta read AFTER predictEstimate (:129)
+        // getA :127-148 -- theta read AFTER predictEstimate (:129); the opt-in variant linearises where the motion started
+        const double thJ = (opt & kOptPreMotionJacobian) ? theta : th1;
         double b10, b20;
         if (dth == 0.0)
         {
-            b10 = mul_(-dx, sin(th1));
-            b20 = mul_(dx, cos(th1));
+            b10 = mul_(-dx, sin(thJ));
+            b20 = mul_(dx, cos(thJ));
         }
         else
         {
             const double q = div_(dx, dth);
-            b10 = add_(mul_(-q, cos(th1)), mul_(q, cos(add_(th1, dth))));
-            b20 = add_(mul_(-q, sin(th1)), mul_(q, sin(add_(th1, dth))));
+            b10 = add_(mul_(-q, cos(thJ)), mul_(q, cos(add_(thJ, dth))));
+            b20 = add_(mul_(-q, sin(thJ)), mul_(q, sin(add_(thJ, dth))));
         }
         // T = A * Sigma: rows 1 and 2 (k = 0 term first, then the unit diagonal term)
         for (int j = lane; j < len; j += kWarp)
@@ -201,7 +203,9 @@ struct WarpFilter
             singular = true;
             return 0.0;
         }
-        const double dz0 = sub_(z0, zr), dz1 = sub_(z1, zb);   // no angle wrap (:229-231)
+        double dz1 = sub_(z1, zb);   // no angle wrap (:229-231) unless opted in
+        if (opt & kOptWrapInnovation) dz1 = normalize_angle(dz1);
+        const double dz0 = sub_(z0, zr);
         // (dz.t() * psi.i()) * dz
         const double t0 = add_(mul_(dz0, i00), mul_(dz1, i10));
         const double t1 = add_(mul_(dz0, i01), mul_(dz1, i11));
@@ -314,7 +318,9 @@ struct WarpFilter
             __syncwarp();
             return;
         }
-        const double dz0 = sub_(z0, zr), dz1 = sub_(z1, zb);   // :272, no wrap
+        double dz1 = sub_(z1, zb);   // :272, no wrap unless opted in
+        if (opt & kOptWrapInnovation) dz1 = normalize_angle(dz1);
+        const double dz0 = sub_(z0, zr);
         // P = Sigma * H.t(); K = P * inv(psi); x += K * dz; columns of M = I - K*H
         for (int i = lane; i < len; i += kWarp)
         {
@@ -332,6 +338,11 @@ struct WarpFilter
             const double k0 = add_(mul_(pa, i00), mul_(pb, i10));
             const double k1 = add_(mul_(pa, i01), mul_(pb, i11));
             x[i] = add_(x[i], add_(mul_(k0, dz0), mul_(k1, dz1)));   // :275
+            if (opt & kOptJoseph)
+            {
+                K[0 * len + i] = k0;
+                K[1 * len + i] = k1;
+            }
             // (K*H)(i,j) = K(i,0)*H(0,j) + K(i,1)*H(1,j);  M = eye - K*H
             const double kh0 = -k1;   // K(i,0)*0 + K(i,1)*(-1)
             const double kh1 = add_(mul_(k0, H.h01), mul_(k1, H.h11));
@@ -362,6 +373,45 @@ struct WarpFilter
             S[e] = acc;
         }
         __syncwarp();
+        if (opt & kOptJoseph)
+        {
+            // Joseph form on top of T = (I - K H) Sigma (now in S): Sigma' = T (I - K H)^T + K R K^T = T - (T H^T) K^T + K R K^T,
+            // then the symmetric part. T H^T (len x 2) goes to the first two rows of R5 (dead after the pass above).
+            for (int i = lane; i < len; i += kWarp)
+            {
+                const double t0 = S[i + 0 * len], t1 = S[i + 1 * len], t2 = S[i + 2 * len];
+                const double tc = S[i + c * len], tc1 = S[i + (c + 1) * len];
+                R5[0 * len + i] = fma(t1, H.h01, fma(t2, H.h02, fma(tc, H.h0c, tc1 * H.h0c1)));
+                R5[1 * len + i] = fma(t1, H.h11, fma(t2, H.h12, fma(tc, H.h1c, fma(tc1, H.h1c1, -t0))));
+            }
+            __syncwarp();
+            for (int e = lane; e < len2; e += kWarp)
+            {
+                const int j = e / len;
+                const int i = e - j * len;
+                const double k0j = K[0 * len + j], k1j = K[1 * len + j];
+                const double rk0 = fma(R[0], k0j, R[2] * k1j), rk1 = fma(R[1], k0j, R[3] * k1j);   // (R K^T)(:, j), R column-major
+                double acc = S[e];
+                acc = fma(-R5[0 * len + i], k0j, acc);
+                acc = fma(-R5[1 * len + i], k1j, acc);
+                acc = fma(K[0 * len + i], rk0, acc);
+                acc = fma(K[1 * len + i], rk1, acc);
+                S[e] = acc;
+            }
+            __syncwarp();
+            for (int e = lane; e < len2; e += kWarp)
+            {
+                const int j = e / len;
+                const int i = e - j * len;
+                if (i < j)
+                {
+                    const double a = 0.5 * (S[i + j * len] + S[j + i * len]);
+                    S[i + j * len] = a;
+                    S[j + i * len] = a;
+                }
+            }
+            __syncwarp();
+        }
     }
 };
 
@@ -385,6 +435,7 @@ struct EkfParams
     const double * twists;   // B x 3
     const double * z;        // B x m x 2
     const int32_t * ids;     // B x m or null
+    unsigned options;        // NUSLAM_OPT_* (0 = the reference's behaviour)
     const int32_t * m_valid; // B or null: filter b uses only its first m_valid[b] (<= m) measurements (fused scan step)
     int32_t * ids_out;       // B x m or null
     double Q[9], R[4];
@@ -397,6 +448,7 @@ __device__ __forceinline__ void strict_filter(const EkfParams & p, const int64_t
 {
     WarpFilter f;
     f.carve(smem_warp, p.len, p.n, lane);
+    f.opt = p.options;
     double * gx = p.x + b * p.len;
     double * gS = p.sigma + b * (int64_t) p.len * p.len;
     int status = p.status[b];

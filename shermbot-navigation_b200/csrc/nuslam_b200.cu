@@ -159,6 +159,7 @@ nuslam::EkfParams make_params(nuslam_ekf * h)
     memcpy(p.R, h->cfg.R, sizeof(p.R));
     p.amin = h->cfg.assoc_min;
     p.amax = h->cfg.assoc_max;
+    p.options = h->cfg.options;
     return p;
 }
 
@@ -264,6 +265,8 @@ void nuslam_ekf_default_config(nuslam_ekf_config * cfg, int32_t n_landmarks)
     cfg->R[0] = cfg->R[3] = 0.001;             // nuslam/config/slam_params.yaml:2
     cfg->assoc_min = 0.01;                     // slam_library.cpp:193
     cfg->assoc_max = 60;                       // slam_library.cpp:194
+    cfg->options = 0;                          // the reference's behaviour
+    cfg->landmark_prior = nuslam::kLandmarkPrior;   // INT_MAX, slam_library.cpp:30
 }
 
 int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, void * cuda_stream, nuslam_ekf ** out)
@@ -271,6 +274,8 @@ int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, 
     if (!cfg || !out) return fail(NUSLAM_ERR_INVALID, "null config or output pointer");
     if (cfg->n_landmarks < 1 || batch < 1) return fail(NUSLAM_ERR_INVALID, "n_landmarks and batch must be >= 1");
     if (cfg->mode != NUSLAM_MODE_STRICT && cfg->mode != NUSLAM_MODE_FAST && cfg->mode != NUSLAM_MODE_LARGE) return fail(NUSLAM_ERR_INVALID, "unknown mode");
+    if (cfg->options & ~(uint32_t) (NUSLAM_OPT_WRAP_INNOVATION | NUSLAM_OPT_JOSEPH | NUSLAM_OPT_PRE_MOTION_JACOBIAN)) return fail(NUSLAM_ERR_INVALID, "unknown option bit");
+    if (!(cfg->landmark_prior > 0.0)) return fail(NUSLAM_ERR_INVALID, "landmark_prior must be positive (default config sets INT_MAX)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount (this engine has no CPU path)");
@@ -291,6 +296,11 @@ int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, 
     h->strict_warps = 4;
     while (h->strict_warps > 1 && h->strict_smem * h->strict_warps > 200 * 1024) h->strict_warps /= 2;
     if (cfg->mode == NUSLAM_MODE_LARGE || h->strict_smem * h->strict_warps > (size_t) prop.sharedMemPerBlockOptin) h->large = true;
+    if (h->large && cfg->options != 0)
+    {
+        delete h;
+        return fail(NUSLAM_ERR_UNSUPPORTED, "the NUSLAM_OPT_* variants run in the oracle-order kernels only (state too long / large-map mode)");
+    }
     if (!h->large && cfg->mode == NUSLAM_MODE_FAST && !nuslam::fast_supported(cfg->n_landmarks))
     {
         delete h;
@@ -433,7 +443,7 @@ int nuslam_ekf_init(nuslam_ekf * h, const double * robot_state, const double * m
     const int64_t total = h->batch * (int64_t) h->len * h->len;
     const int threads = 256;
     const int64_t blocks = (total + threads - 1) / threads;
-    nuslam::k_ekf_init<<<(unsigned) blocks, threads, 0, h->stream>>>(h->batch, h->len, d_robot, d_map, h->x, h->sigma, h->seen, h->status);
+    nuslam::k_ekf_init<<<(unsigned) blocks, threads, 0, h->stream>>>(h->batch, h->len, d_robot, d_map, h->x, h->sigma, h->seen, h->status, h->cfg.landmark_prior);
     CU(cudaGetLastError());
     return finish(h, mem);
 }
@@ -542,7 +552,7 @@ int nuslam_ekf_update(nuslam_ekf * h, const double * z, const int32_t * id, int 
         if (rc) return rc;
         return finish(h, mem);
     }
-    if (h->cfg.mode == NUSLAM_MODE_FAST)
+    if (h->cfg.mode == NUSLAM_MODE_FAST && h->cfg.options == 0)
     {
         p.twists = nullptr;   // update only
         rc = launch_fast_then_strict<nuslam::kOpUpdate>(h, p, /*do_predict=*/false);
@@ -606,7 +616,7 @@ int step_device(nuslam_ekf * h, const nuslam::EkfParams & p)
         if (p.ids_out && m > 0) CU(cudaMemcpyAsync(p.ids_out, p.ids, sizeof(int32_t) * h->batch * m, cudaMemcpyDeviceToDevice, h->stream));
         return NUSLAM_OK;
     }
-    if (h->cfg.mode == NUSLAM_MODE_FAST && m <= nuslam::kFastMMax)
+    if (h->cfg.mode == NUSLAM_MODE_FAST && h->cfg.options == 0 && m <= nuslam::kFastMMax)
         // known correspondence, or on-device association (ids == NULL): the register kernel, then the strict kernel over the
         // filters it handed over (first touches, new landmarks)
         return launch_fast_then_strict<nuslam::kOpStep>(h, p, /*do_predict=*/true);

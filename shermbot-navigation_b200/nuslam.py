@@ -39,13 +39,17 @@ EXPORTS = [
 ]
 
 
+OPT_WRAP_INNOVATION, OPT_JOSEPH, OPT_PRE_MOTION_JACOBIAN = 1, 2, 4   # include/nuslam_b200.h NUSLAM_OPT_*
+
+
 class NuslamError(RuntimeError):
     pass
 
 
 class EkfConfig(C.Structure):
     _fields_ = [("n_landmarks", C.c_int32), ("mode", C.c_int32), ("Q", C.c_double * 9), ("R", C.c_double * 4),
-                ("assoc_min", C.c_double), ("assoc_max", C.c_double)]
+                ("assoc_min", C.c_double), ("assoc_max", C.c_double), ("options", C.c_uint32), ("reserved", C.c_uint32),
+                ("landmark_prior", C.c_double)]
 
 
 _lib = None
@@ -126,7 +130,7 @@ class BatchedExtendedKalman:
     """B independent ``slam_library::ExtendedKalman`` filters on one B200."""
 
     def __init__(self, robotState, mapState=None, Q=None, R=None, n_landmarks=None, mode="strict", device=0,
-                 stream=None, assoc_min=0.01, assoc_max=60.0):
+                 stream=None, assoc_min=0.01, assoc_max=60.0, options=0, landmark_prior=None):
         l = lib()
         robot = np.atleast_2d(np.asarray(robotState, dtype=np.float64))
         self.batch = robot.shape[0]
@@ -149,6 +153,9 @@ class BatchedExtendedKalman:
         if R is not None:
             cfg.R[:] = list(np.asarray(R, dtype=np.float64).reshape(2, 2).T.ravel())
         cfg.assoc_min, cfg.assoc_max = float(assoc_min), float(assoc_max)
+        cfg.options = int(options)   # OPT_* bit mask: opt-in departures from the reference, 0 = reference behaviour
+        if landmark_prior is not None:
+            cfg.landmark_prior = float(landmark_prior)
         self.mode = mode
         h = C.c_void_p()
         _check(l.nuslam_ekf_create(C.byref(cfg), self.batch, self.device, stream, C.byref(h)), "nuslam_ekf_create")

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/nuslam_b200.h but not exported"
     assert sorted(cuda_lib.EXPORTS) == syms
-    assert lib.nuslam_version() == 100
+    assert lib.nuslam_version() == 101
 
 
 def test_library_is_sm100a_only(cuda_lib):
