@@ -177,42 +177,102 @@ __device__ __forceinline__ LargeModel large_model(const double * xl)
     return mdl;
 }
 
-// W_i = H Sigma_i (2 x len) and P_i = Sigma_i H^T (len x 2) for update slot i of the pass; thread j owns index j.
-__device__ __forceinline__ void large_wp(const LargeParams & p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
-                                         const int32_t * __restrict__ seen_snapshot, const double * __restrict__ x_cur)
+// One delayed update (slot i of the pass), thread j owns state index j: W_i = H Sigma_i (row j of V), P_i = Sigma_i H^T, the 2 x 2
+// innovation covariance, K_i = P_i S^-1 (row j of U) and x_new = x + K_i dz (slam_library.cpp:263-276) in ONE phase. Sigma_i is the
+// current covariance, formed on the fly from Sigma_0 and the earlier updates of the pass (rows / columns {theta, x, y, c, c+1}
+// only). The 2 x 2 part needs W_i at those five columns, i.e. the 5 x 5 sub-block of Sigma_i: every block forms it for itself
+// (25 entries, same operation order as the owner threads use, so the values are bit-identical), which removes the grid-wide
+// hand-over between "W, P" and "K, x" -- one grid barrier (or kernel boundary) per measurement instead of two.
+__device__ __forceinline__ void large_update(const LargeParams & p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
+                                             const double * __restrict__ x_old, double * __restrict__ x_new,
+                                             const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen)
 {
     const int b = blockIdx.y;
     const int len = p.len;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int id = ids[b * m + i];
-    if (id < 1 || id > p.n) return;
-    const int c = 3 + 2 * (id - 1);
-    const double * x = x_cur + (int64_t) b * len;
+    const double * x = x_old + (int64_t) b * len;
+    double * xo = x_new + (int64_t) b * len;
     const double * S = p.sigma + (int64_t) b * len * len;
-    const double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
+    double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
     double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
-    double * P = p.P + (int64_t) b * 2 * len;
+    if (id < 1 || id > p.n)   // block-uniform
+    {
+        // no measurement in this slot: K = 0, W = 0 contribute nothing to the pass (U, V of the slot were cleared at its start)
+        if (j < len) xo[j] = x[j];
+        if (j == 0 && id > p.n) p.status[b] |= kStatusBadId;
+        return;
+    }
+    const int c = 3 + 2 * (id - 1);
     const int idx[5] = {0, 1, 2, c, c + 1};
-    // K_u at the five rows and W_u at the five columns of every earlier update of the pass: shared by the block
-    __shared__ double ku[2 * kLargeMMax][5], wu[2 * kLargeMMax][5];
+    // this thread's entries of the five rows / columns of Sigma_0 and its local state: issued first, so that their latency overlaps
+    // the staging of the shared operands below (the strided row gather is the longest load of the update)
+    double row[5], col[5];   // Sigma_i(idx[q], j) and Sigma_i(j, idx[q])
+    if (j < len)
+    {
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+        {
+            row[q] = S[idx[q] + (int64_t) j * len];
+            col[q] = S[j + (int64_t) idx[q] * len];
+        }
+    }
+    double xl[5];
+    const bool init = large_local_state(x, c, id, z + (int64_t) (b * m + i) * 2, seen_snapshot, b, xl);
+    const double x_own = (j < len) ? x[j] : 0.0;
+    // K_u at the five rows and W_u at the five columns of every earlier update of the pass, and the 5 x 5 sub-block of Sigma_0
+    __shared__ double ku[2 * kLargeMMax][5], wu[2 * kLargeMMax][5], blk[5][5];
     for (int k = threadIdx.x; k < 2 * i * 5; k += blockDim.x)
     {
         const int r = k / 5, q = k % 5;
         ku[r][q] = U[(int64_t) r * len + idx[q]];
         wu[r][q] = V[(int64_t) r * len + idx[q]];
     }
-    __syncthreads();
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= len) return;
-    double xl[5];
-    large_local_state(x, c, id, z + (int64_t) (b * m + i) * 2, seen_snapshot, b, xl);
-    const LargeModel mdl = large_model(xl);
-    double row[5], col[5];   // Sigma_i(idx[q], j) and Sigma_i(j, idx[q])
-#pragma unroll
-    for (int q = 0; q < 5; ++q)
+    if (threadIdx.x < 25)
     {
-        row[q] = S[idx[q] + (int64_t) j * len];
-        col[q] = S[j + (int64_t) idx[q] * len];
+        const int r = threadIdx.x / 5, q = threadIdx.x % 5;
+        blk[r][q] = S[idx[r] + (int64_t) idx[q] * len];
     }
+    __syncthreads();
+    if (threadIdx.x < 25)
+    {
+        // Sigma_i(idx[r], idx[q]): what the owner of column idx[q] computes as row[r] below, term for term
+        const int r = threadIdx.x / 5, q = threadIdx.x % 5;
+        double v = blk[r][q];
+        for (int u = 0; u < 2 * i; ++u) v = fma(-ku[u][r], wu[u][q], v);
+        blk[r][q] = v;
+    }
+    __syncthreads();
+    const LargeModel mdl = large_model(xl);
+    // S = W_i[:, idx] H^T + R from the block's copy of the sub-block
+    double s[2][2];
+    {
+        double w5[2][5];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+            {
+                double w = 0.0;
+#pragma unroll
+                for (int r = 0; r < 5; ++r) w = fma(mdl.h[a][r], blk[r][q], w);
+                w5[a][q] = w;
+            }
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+            {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) acc = fma(w5[a][q], mdl.h[e][q], acc);
+                s[a][e] = acc + p.R[a + 2 * e];
+            }
+    }
+    if (j >= len) return;
+    const double xj = (init && j == c) ? xl[3] : (init && j == c + 1) ? xl[4] : x_own;   // x after initializeLandmark
+    if (j == 0 && seen && id > seen[b]) seen[b] = id;                                      // what associateLandmark would have done to `seen`
+#pragma unroll 4
     for (int r = 0; r < 2 * i; ++r)
     {
         const double wj = V[(int64_t) r * len + j], kj = U[(int64_t) r * len + j];
@@ -223,6 +283,7 @@ __device__ __forceinline__ void large_wp(const LargeParams & p, const double * _
             col[q] = fma(-kj, wu[r][q], col[q]);
         }
     }
+    double pj[2];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
     {
@@ -234,56 +295,8 @@ __device__ __forceinline__ void large_wp(const LargeParams & p, const double * _
             pp = fma(col[q], mdl.h[a][q], pp);
         }
         V[(int64_t) (2 * i + a) * len + j] = w;
-        P[(int64_t) a * len + j] = pp;
+        pj[a] = pp;
     }
-}
-
-// K_i = P_i S^-1, x_new = x + K_i dz (slam_library.cpp:270-276); thread j owns index j, every thread forms the 2 x 2 part.
-__global__ void __launch_bounds__(256) k_large_wp(const LargeParams p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
-                                                  const int32_t * __restrict__ seen_snapshot)
-{
-    large_wp(p, z, ids, m, i, seen_snapshot, p.x);
-}
-
-__device__ __forceinline__ void large_gain(const LargeParams & p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
-                                           const double * __restrict__ x_old, double * __restrict__ x_new,
-                                           const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen)
-{
-    const int b = blockIdx.y;
-    const int len = p.len;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= len) return;
-    const int id = ids[b * m + i];
-    const double * x = x_old + (int64_t) b * len;
-    double * xo = x_new + (int64_t) b * len;
-    double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
-    const double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
-    const double * P = p.P + (int64_t) b * 2 * len;
-    if (id < 1 || id > p.n)
-    {
-        // no measurement in this slot: K = 0, W = 0 contribute nothing to the pass
-        xo[j] = x[j];   // U, V of the slot were cleared at the start of the pass
-        if (j == 0 && id > p.n) p.status[b] |= kStatusBadId;
-        return;
-    }
-    const int c = 3 + 2 * (id - 1);
-    const int idx[5] = {0, 1, 2, c, c + 1};
-    double xl[5];
-    const bool init = large_local_state(x, c, id, z + (int64_t) (b * m + i) * 2, seen_snapshot, b, xl);
-    const double xj = (init && j == c) ? xl[3] : (init && j == c + 1) ? xl[4] : x[j];   // x after initializeLandmark
-    if (j == 0 && seen && id > seen[b]) seen[b] = id;                                     // what associateLandmark would have done to `seen`
-    const LargeModel mdl = large_model(xl);
-    double s[2][2];
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-        {
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < 5; ++q) acc = fma(V[(int64_t) (2 * i + a) * len + idx[q]], mdl.h[e][q], acc);
-            s[a][e] = acc + p.R[a + 2 * e];
-        }
     const double det = s[0][0] * s[1][1] - s[0][1] * s[1][0];
     if (det == 0.0)
     {
@@ -294,8 +307,7 @@ __device__ __forceinline__ void large_gain(const LargeParams & p, const double *
         return;
     }
     const double i00 = s[1][1] / det, i01 = -s[0][1] / det, i10 = -s[1][0] / det, i11 = s[0][0] / det;
-    const double p0 = P[j], p1 = P[(int64_t) len + j];
-    const double k0 = p0 * i00 + p1 * i10, k1 = p0 * i01 + p1 * i11;
+    const double k0 = pj[0] * i00 + pj[1] * i10, k1 = pj[0] * i01 + pj[1] * i11;
     U[(int64_t) (2 * i) * len + j] = k0;
     U[(int64_t) (2 * i + 1) * len + j] = k1;
     const double dz0 = z[(int64_t) (b * m + i) * 2] - mdl.zr, dz1 = z[(int64_t) (b * m + i) * 2 + 1] - mdl.zb;   // :272, no wrap
@@ -304,15 +316,15 @@ __device__ __forceinline__ void large_gain(const LargeParams & p, const double *
     xo[j] = xn;
 }
 
-__global__ void __launch_bounds__(256) k_large_gain(const LargeParams p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
-                                                    const double * __restrict__ x_old, double * __restrict__ x_new,
-                                                    const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen)
+__global__ void __launch_bounds__(256) k_large_update(const LargeParams p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
+                                                      const double * __restrict__ x_old, double * __restrict__ x_new,
+                                                      const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen)
 {
-    large_gain(p, z, ids, m, i, x_old, x_new, seen_snapshot, seen);
+    large_update(p, z, ids, m, i, x_old, x_new, seen_snapshot, seen);
 }
 
-// all `cnt` delayed updates of a pass in ONE cooperative launch: the two phases of an update are separated by grid barriers
-// (~2 us) instead of kernel boundaries (~12 us of dependent-launch latency each). x ping-pongs between p.x and p.x2.
+// all `cnt` delayed updates of a pass in ONE cooperative launch: consecutive updates are separated by a grid barrier (~2 us) instead
+// of a kernel boundary (~12 us of dependent-launch latency). x ping-pongs between p.x and p.x2.
 __global__ void __launch_bounds__(64) k_large_updates_coop(const LargeParams p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int cnt,
                                                           const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen)
 {
@@ -321,9 +333,7 @@ __global__ void __launch_bounds__(64) k_large_updates_coop(const LargeParams p, 
     double * xn = p.x2;
     for (int k = 0; k < cnt; ++k)
     {
-        large_wp(p, z, ids, m, k, seen_snapshot, xc);
-        grid.sync();
-        large_gain(p, z, ids, m, k, xc, xn, seen_snapshot, seen);
+        large_update(p, z, ids, m, k, xc, xn, seen_snapshot, seen);
         grid.sync();
         const double * t = xc;
         xc = xn;
@@ -476,8 +486,7 @@ inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const
     for (int k = 0; k < cnt; ++k)
     {
         // slot k of the pass holds measurement i0 + k: the kernels index ids / z with (b * m + k) from the shifted base pointers
-        k_large_wp<<<grid, threads, 0, st>>>(p, z + 2 * (int64_t) i0, ids + i0, m, k, seen_snapshot);
-        k_large_gain<<<grid, threads, 0, st>>>(p, z + 2 * (int64_t) i0, ids + i0, m, k, p.x, p.x2, seen_snapshot, seen);
+        k_large_update<<<grid, threads, 0, st>>>(p, z + 2 * (int64_t) i0, ids + i0, m, k, p.x, p.x2, seen_snapshot, seen);
         double * tmp = p.x;
         p.x = p.x2;
         p.x2 = tmp;
