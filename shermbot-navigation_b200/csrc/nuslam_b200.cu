@@ -301,11 +301,9 @@ int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, 
         delete h;
         return fail(NUSLAM_ERR_UNSUPPORTED, "the NUSLAM_OPT_* variants run in the oracle-order kernels only (state too long / large-map mode)");
     }
-    if (!h->large && cfg->mode == NUSLAM_MODE_FAST && !nuslam::fast_supported(cfg->n_landmarks))
-    {
-        delete h;
-        return fail(NUSLAM_ERR_UNSUPPORTED, "FAST mode is instantiated for n_landmarks in {6, 12} only");
-    }
+    // the register kernel is instantiated for n_landmarks in {6, 12}; any other map size runs the oracle-order CUDA kernels
+    // (same results to the last bit of the reference's arithmetic, lower throughput) -- a FAST request never fails for its size
+    if (!h->large && cfg->mode == NUSLAM_MODE_FAST && !nuslam::fast_supported(cfg->n_landmarks)) h->cfg.mode = NUSLAM_MODE_STRICT;
     if (cuda_stream)
     {
         h->stream = static_cast<cudaStream_t>(cuda_stream);

@@ -345,11 +345,12 @@ def test_diffdrive_matches_oracle(cuda_lib, orc):
         assert np.array_equal(u[b], orc.convert_twist(0.16, 0.033, tws[b, 0], tws[b, 1]))
 
 
-@pytest.mark.parametrize("B,n,m,dropout", [(1, 12, 12, 0.0), (3, 12, 5, 0.0), (33, 12, 12, 0.3), (7, 6, 6, 0.0), (5, 6, 3, 0.2), (9, 12, 16, 0.0), (2, 12, 1, 0.0)])
+@pytest.mark.parametrize("B,n,m,dropout", [(1, 12, 12, 0.0), (3, 12, 5, 0.0), (33, 12, 12, 0.3), (7, 6, 6, 0.0), (5, 6, 3, 0.2), (9, 12, 16, 0.0), (2, 12, 1, 0.0), (4, 3, 3, 0.0), (2, 20, 20, 0.1)])
 def test_fast_step_shapes(cuda_lib, orc, B, n, m, dropout):
     """FAST kernel corner cases: odd batch sizes (the bulk-copy window of the last filter is clamped), fewer / more measurements than
     landmarks (odd m: half-empty rank-4 chunk; m = 16: repeated landmarks inside a step), dropped measurements (id 0), n = 6
-    (padded fragments). Warm start after the first-touch step, then free running; <= 1e-9 against the oracle."""
+    (padded fragments), map sizes without a register-kernel instantiation (n = 3, n = 20: the FAST handle runs the oracle-order kernels).
+    Warm start after the first-touch step, then free running; <= 1e-9 against the oracle."""
     T = 8
     sc = synth.ekf_scenario(B, T, n=n, seed=100 + B + m, dropout=0.0)
     rng = np.random.default_rng(B * 131 + m)
