@@ -456,6 +456,14 @@ struct ClusterFit
 };
 constexpr int kFitNMax = 32;        // clusters up to this many points are fitted one per THREAD (work matrix interleaved in shared memory)
 constexpr int kFitThreads = 64;
+#ifndef NUSLAM_FIT_SMALL
+#define NUSLAM_FIT_SMALL 12
+#endif
+#ifndef NUSLAM_FIT_CTAS
+#define NUSLAM_FIT_CTAS 8
+#endif
+constexpr int kFitCtas = NUSLAM_FIT_CTAS;     // CTAs of the first class per SM
+constexpr int kFitSmall = NUSLAM_FIT_SMALL;   // largest cluster of the first size class (work matrix kFitSmall x 4 doubles per thread)
 constexpr int kMaxFastClusters = 32;   // scans returning more clusters than this take the one-warp-per-scan path
 
 struct ScanPipe
@@ -463,7 +471,7 @@ struct ScanPipe
     ClusterDesc * desc;      // chunk * kMaxFastClusters
     ClusterFit * fit;        // same
     int32_t * big;           // indices into desc of clusters with more than kFitNMax points
-    int32_t * mid;           // indices into desc of clusters with 17 .. kFitNMax points
+    int32_t * mid;           // indices into desc of clusters with kFitSmall + 1 .. kFitNMax points
     int32_t * slow;          // scans (global index) with more than kMaxFastClusters clusters
     int32_t * scan_base;     // per scan of the chunk: first entry in desc, -1 for slow / UB scans
     int32_t * counters;      // [0] entries in desc, [1] entries in big, [2] entries in slow, [3] entries in mid
@@ -632,7 +640,7 @@ k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_ran
                     d.q = lane;
                     pipe.desc[base + lane] = d;
                     if (n > kFitNMax) pipe.big[atomicAdd(&pipe.counters[1], 1)] = base + lane;
-                    else if (n > 16) pipe.mid[atomicAdd(&pipe.counters[3], 1)] = base + lane;
+                    else if (n > kFitSmall) pipe.mid[atomicAdd(&pipe.counters[3], 1)] = base + lane;
                 }
             }
             if (lane == 0)
@@ -779,8 +787,9 @@ __device__ __forceinline__ void classify_and_publish(int n, const WorkMatrix Z, 
     }
 }
 
-// stage 2: one THREAD per cluster; work matrices interleaved over the CTA's threads in shared memory. Two instantiations: up to 16
-// points straight from the work list (most tube clusters; 32 KB per CTA) and 17..32 points from their own dense list.
+// stage 2: one THREAD per cluster; work matrices interleaved over the CTA's threads in shared memory. Two instantiations: up to
+// kFitSmall = 12 points straight from the work list (most tube clusters; 24 KB per CTA, 8 CTAs = 16 warps per SM: measured best
+// of 8 / 10 / 12 / 16) and 13..32 points from their own dense list.
 template <int NMAX, bool FROM_LIST>
 __global__ void __launch_bounds__(kFitThreads) k_scan_fit_small(const float * __restrict__ ranges, double min_range, double max_range, ScanPipe pipe)
 {
@@ -1105,7 +1114,7 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
     cudaError_t e = scan_tables_init(device);
     if (e != cudaSuccess) return e;
     const size_t smem = sizeof(ScanSmem) * kScanWarps;
-    const size_t fit_smem16 = sizeof(double) * 4 * 16 * kFitThreads, fit_smem32 = sizeof(double) * 4 * kFitNMax * kFitThreads;
+    const size_t fit_smem16 = sizeof(double) * 4 * kFitSmall * kFitThreads, fit_smem32 = sizeof(double) * 4 * kFitNMax * kFitThreads;
     static bool configured_dev[kMaxDevices] = {false};
     bool & configured = configured_dev[(device >= 0 && device < kMaxDevices) ? device : 0];
     if (!configured)
@@ -1177,7 +1186,7 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
         if (e == cudaSuccess) e = cudaStreamWaitEvent(side.s1, side.fork, 0);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(side.s2, side.fork, 0);
         if (e != cudaSuccess) return e;
-        k_scan_fit_small<16, false><<<(unsigned) (sm_count * 6), kFitThreads, fit_smem16, stream>>>(ranges, min_range, max_range, pipe);
+        k_scan_fit_small<kFitSmall, false><<<(unsigned) (sm_count * kFitCtas), kFitThreads, fit_smem16, stream>>>(ranges, min_range, max_range, pipe);
         k_scan_fit_small<kFitNMax, true><<<(unsigned) (sm_count * 3), kFitThreads, fit_smem32, side.s1>>>(ranges, min_range, max_range, pipe);
         k_scan_fit_big<<<(unsigned) (sm_count * 5), 64, 0, side.s2>>>(ranges, min_range, max_range, pipe);
         // scans with more than kMaxFastClusters clusters: the one-warp-per-scan kernel over their list (it writes those scans' outputs itself)
