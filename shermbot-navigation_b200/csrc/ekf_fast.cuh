@@ -19,14 +19,17 @@
 //   Pt = Sigma Ht^T (lane i = row i), Wt = Ht Sigma (lane j = column j), M = Wt Ht^T + D^-1 R D^-1.
 //   (A) the landmark's two rows and two columns are published from the fragments through shared memory into
 //       vector layout; (B) lanes form Pt, Wt and exchange Wt; every lane evaluates the 2 x 2 part (M, one
-//       reciprocal, sqrt d, atan2, innovation) redundantly -- no cross-warp synchronisation anywhere in the kernel, the
-//       ~20 resident warps of an SM hide each other's dependency chains; (C) lanes form Kt = Pt Minv, update x, the
-//       replicated pose and the 6 robot vectors with plain FMAs;
+//       reciprocal, sqrt d from a one-Newton rsqrt, a division-free atan2 of the unit vector, innovation) redundantly -- no
+//       cross-warp synchronisation anywhere in the kernel, the 16 resident warps of an SM hide each other's dependency
+//       chains; (C) lanes form Kt = Pt Minv, update x, the replicated pose and the 6 robot vectors with plain FMAs;
 //   (D) updates are applied to the fragments LAZILY in chunks of 2: the second update of a chunk takes its
 //       landmark rows / columns from the stale fragments and corrects them in vector layout with the first update
 //       (4 vectors x 2 FMAs), then ONE rank-4 DMMA pass (9 mma.m8n8k4 at N = 12, k = 4 fully used) applies both.
 //
-// Arithmetic: predict uses the oracle's operation order (it is O(len)). A filter-step that contains a landmark's
+// Both triangles of Sigma are kept: the reference's Sigma is NOT symmetric (its INT_MAX first touches leave |Sigma - Sigma^T| at
+// ~1e-6 relative and (I - KH) Sigma never restores it), and rows and columns enter the update separately.
+// Arithmetic: predict uses the oracle's operation order on the covariance (it is O(len)), one library sincos plus the
+// addition theorems for the three angles. A filter-step that contains a landmark's
 // FIRST TOUCH (INT_MAX prior, slam_library.cpp:28-31, where only the reference's own operation order reproduces its
 // catastrophic cancellation) or an initializeLandmark is not evaluated here: the filter is
 // appended to a work list that the STRICT kernel (ekf_strict.cuh) processes right after on the same stream.
