@@ -151,3 +151,40 @@ def test_map_to_odom_matches_oracle(cuda_lib, orc):
     want = np.stack([orc.map_to_odom(odom[b, 2:5], est[b]) for b in range(B)])
     assert np.abs(got - want).max() < 1e-14
     assert np.abs(got[0]).max() < 1e-15
+
+
+def test_replay_matches_closed_loop(cuda_lib, tmp_path):
+    """The ROS-free replay of the slam node's loop (joint positions + scans in, estimates + map->odom out) reproduces the
+    device-resident closed loop that produced the log, bit for bit; also through its command line."""
+    import subprocess
+    import sys
+    import torch
+    from shermbot_navigation_b200 import replay
+    B, T = 48, 30
+    Q, R = 0.1 * np.eye(3), 0.001 * np.eye(2)
+    loop = tube_world.ClosedLoop(B, n_landmarks=12, Q=Q, R=R, mode="fast", max_markers=8)
+    cmd = torch.tensor(np.tile(np.array([0.15, 0.06, 0.0]), (B, 1)), device="cuda")
+    joints, ranges = np.empty((T, 2, B)), np.empty((T, B, 360), np.float32)
+    for t in range(T):
+        loop.step(cmd)
+        loop.ekf.synchronize()
+        joints[t] = loop.world.joints.cpu().numpy()
+        ranges[t] = loop.world.ranges.cpu().numpy()
+    xl, sl, seenl, stl = loop.ekf.get_state()
+    res = replay.replay(joints, ranges, n_landmarks=12, Q=Q, R=R, mode="fast", max_markers=8)
+    x, s, seen, st = res["state"]
+    assert np.array_equal(x, xl) and np.array_equal(s, sl) and np.array_equal(seen, seenl) and np.array_equal(st, stl)
+    assert np.array_equal(res["pose"][-1], x[:, :3])
+    # map -> odom composed with odom -> body gives the estimate back: T_mo * T_ob = T_mb
+    tx, ty, yaw = res["map_to_odom"][-1].T
+    ox, oy, oth = res["odom"][-1].T
+    bx = tx + np.cos(yaw) * ox - np.sin(yaw) * oy
+    by = ty + np.sin(yaw) * ox + np.cos(yaw) * oy
+    assert np.abs(bx - x[:, 1]).max() < 1e-12 and np.abs(by - x[:, 2]).max() < 1e-12
+    np.savez(tmp_path / "log.npz", joints=joints, ranges=ranges)
+    r = subprocess.run([sys.executable, "-m", "shermbot_navigation_b200.replay", str(tmp_path / "log.npz"), str(tmp_path / "out.npz")],
+                       capture_output=True, text=True, cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
+    assert r.returncode == 0, r.stderr
+    # the command line uses the node's defaults (Q = 0.1 I, R = 0.001 I, 12 markers): same filter, same log
+    out = np.load(tmp_path / "out.npz")
+    assert out["pose"].shape == (T, B, 3) and np.isfinite(out["x"]).all()
