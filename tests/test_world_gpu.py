@@ -188,3 +188,53 @@ def test_replay_matches_closed_loop(cuda_lib, tmp_path):
     # the command line uses the node's defaults (Q = 0.1 I, R = 0.001 I, 12 markers): same filter, same log
     out = np.load(tmp_path / "out.npz")
     assert out["pose"].shape == (T, B, 3) and np.isfinite(out["x"]).all()
+
+
+def test_closed_loop_free_running_vs_oracle(cuda_lib, orc):
+    """L2-style check of the whole fused stack: the device-resident closed loop against the SAME loop built from oracle calls
+    (world step -> DiffDrive odometry -> scan_detect -> cartesian2polar -> associate / initialize / update), free running from
+    scratch for 80 steps. First touches amplify rounding, so the bound is loose; association sequences
+    and tracking quality must agree."""
+    import torch
+    B, T, n, m = 24, 80, 12, 8
+    g = np.random.default_rng(17)
+    cmd = np.stack([g.uniform(0.1, 0.3, B), np.full(B, 0.07), np.zeros(B)], axis=1)
+    Q, R = 0.1 * np.eye(3), 0.001 * np.eye(2)
+    loop = tube_world.ClosedLoop(B, n_landmarks=n, Q=Q, R=R, mode="fast", max_markers=m)
+    cmd_d = torch.tensor(cmd, device="cuda")
+    # oracle side
+    world = np.zeros((B, 9))
+    world[:, 0], world[:, 1] = tube_world.WHEEL_BASE, tube_world.WHEEL_RAD
+    odom = world[:, :7].copy()
+    filt = [orc.ekf(n, np.zeros(3), np.zeros(2 * n), Q, R) for _ in range(B)]
+    same_ids = np.ones(B, dtype=bool)
+    for t in range(T):
+        loop.step(cmd_d)
+        ranges = orc.world_step(world, cmd, None, 0.1, tube_world.TUBES, tube_world.TUBE_RADIUS, tube_world.ROBOT_RADIUS, 1.0)
+        det = orc.scan_detect_batch(ranges, tube_world.MIN_RANGE, tube_world.MAX_RANGE, kmax=m)
+        for b, f in enumerate(filt):
+            odom[b], tw = orc.diffdrive_step(odom[b], world[b, 7], world[b, 8])
+            _, _, snapshot = f.get()
+            f.predict(tw[0], tw[1], tw[2])
+            for i in range(min(max(det["n_circles"][b], 0), m)):
+                z = orc.cartesian2polar(det["circles"][b, i, 0], det["circles"][b, i, 1])
+                j = f.associate(z)
+                if j > snapshot:
+                    f.init_landmark(z, j)
+                elif j < 0:
+                    continue
+                f.update(z, j)
+    loop.ekf.synchronize()
+    x, s, seen, status = loop.ekf.get_state()
+    xo = np.stack([f.get()[0] for f in filt])
+    seeno = np.array([f.get()[2] for f in filt])
+    true = world[:, 2:5]
+    assert rel_max(loop.world.world.cpu().numpy(), world) < 1e-12          # the simulators agree
+    err_gpu = np.abs(x[:, 1:3] - true[:, 0:2]).max(axis=1)
+    err_orc = np.abs(xo[:, 1:3] - true[:, 0:2]).max(axis=1)
+    diff = np.abs(x[:, :3] - xo[:, :3]).max(axis=1)
+    agree = (seen == seeno) & (diff < 1e-3)
+    print(f"[closed loop vs oracle] {T} steps: robots agreeing {agree.sum()}/{B}, worst pose difference among them {diff[agree].max():.2e}; "
+          f"tracking error median gpu {np.median(err_gpu):.2e} / oracle {np.median(err_orc):.2e}, max gpu {err_gpu.max():.2e} / oracle {err_orc.max():.2e}")
+    assert agree.sum() >= 0.9 * B and not status.any()
+    assert abs(np.median(err_gpu) - np.median(err_orc)) < 1e-3
