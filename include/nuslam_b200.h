@@ -61,7 +61,7 @@ enum
  * keeps Sigma in registers; it falls back to the STRICT arithmetic for any update whose landmark still
  * carries its INT_MAX prior (first touch, slam_library.cpp:28-31), where the reference's
  * (I-KH)*Sigma cancels catastrophically and only the same operation order reproduces its result.
- * The register kernel exists for n_landmarks in {6, 12} and m <= 16; a FAST handle of any other size runs the STRICT kernels. */
+ * The register kernel covers n_landmarks <= 12 and m <= 16; a FAST handle of any other size runs the STRICT kernels. */
 enum
 {
     NUSLAM_MODE_STRICT = 0,

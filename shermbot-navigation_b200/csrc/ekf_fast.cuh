@@ -56,12 +56,17 @@ constexpr bool kFastSingleStage = NUSLAM_FAST_SINGLE_STAGE != 0;
 constexpr int kFastCtasPerSm = NUSLAM_FAST_CTAS;   // 16 single-warp CTAs / SM at 128 registers (20 at 96 registers spill; measured slower)
 constexpr int kFastMMax = 16;                      // measurements per step handled by this kernel
 
+// N > 0: the number of landmarks is a compile-time constant (the BASELINE sizes 12 and 6: every index folds). N < 0: a GENERIC
+// instantiation for any n with ceil(2 n / 8) = -N fragment blocks per side (n read from the parameters at run time; n <= 4, 8, 12
+// for -N = 1, 2, 3), so that FAST mode covers every map of up to 12 landmarks.
 template <int N>
 struct FastGeom
 {
-    static constexpr int LEN = 3 + 2 * N;     // state length
+    static constexpr bool FIXED = N > 0;
+    static constexpr int NB = FIXED ? (2 * N + 7) / 8 : -N;   // 8 x 8 fragment blocks per side of the landmark block
+    static constexpr int NMAX = FIXED ? N : 4 * NB;           // most landmarks this instantiation serves
+    static constexpr int LEN = 3 + 2 * NMAX;                  // (largest) state length
     static constexpr int SIG = LEN * LEN;
-    static constexpr int NB = (2 * N + 7) / 8;   // 8 x 8 fragment blocks per side of the landmark block
     static constexpr int TP = 8 * NB;         // padded landmark-block side
     static constexpr int VP = 3 + TP;         // padded vector length (state index space)
     static_assert(VP <= 32, "vector layout needs one lane per state index");
@@ -159,11 +164,16 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm)
 k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ worklist, int32_t * __restrict__ wl_count)
 {
     using G = FastGeom<N>;
-    constexpr int LEN = G::LEN, SIG = G::SIG, NB = G::NB;
+    constexpr int NB = G::NB;
+    // sizes: compile-time constants in a fixed-N instantiation, read from the parameters in a generic one
+    const int NL = G::FIXED ? G::NMAX : p.n;            // landmarks
+    const int LEN = G::FIXED ? G::LEN : p.len;          // state length
+    const int SIG = LEN * LEN;
     constexpr unsigned kFull = 0xffffffffu;
-    constexpr int kImg = SIG * 8;                                   // bytes of one Sigma
-    constexpr int kWin = ((kImg + 8 + 15) / 16) * 16;               // 16-byte aligned window that covers it at either alignment
-    constexpr int kStage = ((kWin > (int) sizeof(FastSmem<N>) ? kWin : (int) sizeof(FastSmem<N>)) + 127) / 128 * 128;
+    constexpr int kImgMax = G::SIG * 8;                             // bytes of the largest Sigma this instantiation serves
+    constexpr int kWinMax = ((kImgMax + 8 + 15) / 16) * 16;         // 16-byte aligned window that covers it at either alignment
+    const int kWin = ((SIG * 8 + 8 + 15) / 16) * 16;
+    constexpr int kStage = ((kWinMax > (int) sizeof(FastSmem<N>) ? kWinMax : (int) sizeof(FastSmem<N>)) + 127) / 128 * 128;
     constexpr int kStages = (BULK && !kFastSingleStage) ? 2 : 1;
     __shared__ __align__(128) unsigned char stage[kStages][kStage];
     __shared__ uint64_t full_bar;
@@ -304,8 +314,10 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         }
         if (ASSOC)
         {
-            // an empty map: the first measurement opens landmark 1 (slam_library.cpp:196-200) -> strict kernel
-            if (seen0 == 0 && m > 0)
+            // an empty map: the first measurement opens landmark 1 (slam_library.cpp:196-200); a FULL map: associateLandmark writes
+            // temp(3 + 2 seen) out of bounds and Armadillo throws before any candidate is examined (:204-207).
+            // Both belong to the strict kernel.
+            if (m > 0 && (seen0 == 0 || 3 + 2 * seen0 >= LEN))
             {
                 if (lane == 0) worklist[atomicAdd(wl_count, 1)] = (int32_t) bf;
                 leave();
@@ -314,7 +326,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         }
         else
         {
-            const bool idok = (unsigned) (my_id - 1) < (unsigned) N;
+            const bool idok = (unsigned) (my_id - 1) < (unsigned) NL;
             const int c = idok ? 1 + 2 * my_id : 3;
             const double d0 = __shfl_sync(kFull, diag, c), d1 = __shfl_sync(kFull, diag, c + 1);
             // first touch (INT_MAX prior) or initializeLandmark (slam.cpp:295-297): the strict kernel takes this filter-step
@@ -353,11 +365,11 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         unsigned idlo = 0u, idhi = 0u;
         if (!ASSOC)
         {
-            static_assert(N <= 15 && kFastMMax <= 16, "4-bit id codes in two 32-bit words");
-            const unsigned code = ((unsigned) (my_id - 1) < (unsigned) N) ? (unsigned) my_id : 0u;
+            static_assert(G::NMAX <= 15 && kFastMMax <= 16, "4-bit id codes in two 32-bit words");
+            const unsigned code = ((unsigned) (my_id - 1) < (unsigned) NL) ? (unsigned) my_id : 0u;
             idlo = __reduce_or_sync(kFull, lane < 8 ? code << (4 * lane) : 0u);
             idhi = __reduce_or_sync(kFull, (lane >= 8 && lane < 16) ? code << (4 * (lane - 8)) : 0u);
-            if (__any_sync(kFull, my_id > N)) status |= kStatusBadId;
+            if (__any_sync(kFull, my_id > NL)) status |= kStatusBadId;
         }
         unsigned idw = idlo;
         if (lane < 2 * m) f.z[lane] = my_z;
@@ -557,7 +569,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     id = (int) (idw & 15u);
                     idw >>= 4;
                 }
-                const bool live = ASSOC ? ((unsigned) (id - 1) < (unsigned) N) : (id != 0);   // warp-uniform
+                const bool live = ASSOC ? ((unsigned) (id - 1) < (unsigned) NL) : (id != 0);   // warp-uniform
                 cc[s] = live ? 1 + 2 * id : -1;
                 if (live)
                 {
@@ -788,8 +800,8 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             __syncwarp();
             if (lane == 0)
             {
-                constexpr int kInner = ((SIG - 1) * 8) / 16 * 16;   // bytes of the aligned interior (SIG is odd: SIG - 1 elements)
-                static_assert((SIG & 1) == 1 && kInner == (SIG - 1) * 8, "a filter's Sigma is an odd number of doubles");
+                const int kInner = (SIG - 1) * 8;   // bytes of the aligned interior: SIG = (3 + 2n)^2 is odd, SIG - 1 elements = a multiple of 16 bytes
+                static_assert((G::SIG & 1) == 1, "a filter's Sigma is an odd number of doubles");
                 bulk_s2g(gw + odd, img + odd, kInner);
                 const int edge = odd ? 0 : SIG - 1;
                 gw[edge] = img[edge];
@@ -839,7 +851,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
 #endif
 }
 
-inline bool fast_supported(int n) { return n == 12 || n == 6; }
+inline bool fast_supported(int n) { return n >= 1 && n <= 12; }
 
 template <int N>
 int launch_fast_n(const EkfParams & p, bool do_predict, int sm_count, int32_t * worklist, int32_t * wl_count, cudaStream_t stream)
@@ -884,6 +896,10 @@ inline int launch_fast(int n, const EkfParams & p, bool do_predict, int sm_count
     if ((reinterpret_cast<uintptr_t>(p.sigma) & 7) || (reinterpret_cast<uintptr_t>(p.x) & 7)) return -1;
     if (n == 12) return launch_fast_n<12>(p, do_predict, sm_count, worklist, wl_count, stream);
     if (n == 6) return launch_fast_n<6>(p, do_predict, sm_count, worklist, wl_count, stream);
+    // any other map of up to 12 landmarks: the generic instantiation with the same number of fragment blocks
+    if (n >= 1 && n <= 4) return launch_fast_n<-1>(p, do_predict, sm_count, worklist, wl_count, stream);
+    if (n <= 8) return launch_fast_n<-2>(p, do_predict, sm_count, worklist, wl_count, stream);
+    if (n <= 12) return launch_fast_n<-3>(p, do_predict, sm_count, worklist, wl_count, stream);
     return -1;
 }
 

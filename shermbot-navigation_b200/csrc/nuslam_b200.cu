@@ -186,7 +186,7 @@ template <int OP>
 int launch_fast_then_strict(nuslam_ekf * h, const nuslam::EkfParams & p, bool do_predict)
 {
     int rc = nuslam::launch_fast(h->cfg.n_landmarks, p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream);
-    if (rc == -1) return fail(NUSLAM_ERR_UNSUPPORTED, "FAST mode covers n_landmarks in {6, 12}, m <= 16 and known correspondence");
+    if (rc == -1) return fail(NUSLAM_ERR_UNSUPPORTED, "FAST mode covers n_landmarks <= 12, m <= 16");
     if (rc) return cuda_fail((cudaError_t) rc, "fast kernel launch");
     const int warps = h->strict_warps;
     const size_t smem = h->strict_smem * warps;
@@ -301,7 +301,7 @@ int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, 
         delete h;
         return fail(NUSLAM_ERR_UNSUPPORTED, "the NUSLAM_OPT_* variants run in the oracle-order kernels only (state too long / large-map mode)");
     }
-    // the register kernel is instantiated for n_landmarks in {6, 12}; any other map size runs the oracle-order CUDA kernels
+    // the register kernel covers n_landmarks <= 12; any larger map (that still fits on chip) runs the oracle-order CUDA kernels
     // (same results to the last bit of the reference's arithmetic, lower throughput) -- a FAST request never fails for its size
     if (!h->large && cfg->mode == NUSLAM_MODE_FAST && !nuslam::fast_supported(cfg->n_landmarks)) h->cfg.mode = NUSLAM_MODE_STRICT;
     if (cuda_stream)
