@@ -181,11 +181,12 @@ def test_map_full_status(cuda_lib, orc):
     assert rel_max(x[0], xo) < TOL and rel_max(s[0], so) < TOL and seen[0] == no
 
 
-@pytest.mark.parametrize("mode", ["strict", "fast"])
-def test_step_free_running_after_first_touch(cuda_lib, orc, mode):
+@pytest.mark.parametrize("mode,B,T", [("strict", 16, 151), ("fast", 16, 151), ("fast", 4, 2001)])
+def test_step_free_running_after_first_touch(cuda_lib, orc, mode, B, T):
     """L1: the engine is warm-started from the oracle's state after step 1 (every landmark touched once),
-    then both run freely for 150 fused steps; benign geometry. <= 1e-9."""
-    B, T, n = 16, 151, 12
+    then both run freely for 150 fused steps -- and for the 2 000 steps of BASELINE config 1 (more than six laps of the
+    circle: the heading crosses +-pi a dozen times); benign geometry. <= 1e-9."""
+    n = 12
     sc = synth.ekf_scenario(B, T, n=n, geometry="benign", seed=11)
     first = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][:1], sc["z"][:1], sc["ids"][:1])
     full = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"], sc["z"], sc["ids"], trace=True)
