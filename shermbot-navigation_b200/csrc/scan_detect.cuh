@@ -456,6 +456,10 @@ struct ClusterFit
 };
 constexpr int kFitNMax = 32;        // clusters up to this many points are fitted one per THREAD (work matrix interleaved in shared memory)
 constexpr int kFitThreads = 64;
+#ifndef NUSLAM_BIGS_CTAS
+#define NUSLAM_BIGS_CTAS 5   // resident CTAs (of 4 warps) per SM of the first warp-per-cluster class (96 registers per thread; measured best of 4 / 5)
+#endif
+constexpr int kFitBigSmall = 126;   // largest cluster of the first warp-per-cluster class
 #ifndef NUSLAM_FIT_SMALL
 #define NUSLAM_FIT_SMALL 12
 #endif
@@ -470,11 +474,12 @@ struct ScanPipe
 {
     ClusterDesc * desc;      // chunk * kMaxFastClusters
     ClusterFit * fit;        // same
-    int32_t * big;           // indices into desc of clusters with more than kFitNMax points
+    int32_t * big;           // indices into desc of clusters with more than kFitBigSmall points
+    int32_t * big_s;         // indices into desc of clusters with kFitNMax + 1 .. kFitBigSmall points
     int32_t * mid;           // indices into desc of clusters with kFitSmall + 1 .. kFitNMax points
     int32_t * slow;          // scans (global index) with more than kMaxFastClusters clusters
     int32_t * scan_base;     // per scan of the chunk: first entry in desc, -1 for slow / UB scans
-    int32_t * counters;      // [0] entries in desc, [1] entries in big, [2] entries in slow, [3] entries in mid
+    int32_t * counters;      // [0] entries in desc, [1] entries in big, [2] entries in slow, [3] entries in mid, [4] entries in big_s
     int64_t scan0;           // first scan of the chunk
 };
 
@@ -639,7 +644,8 @@ k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_ran
                     d.n_wrap = n | (wr ? 1 << 16 : 0);
                     d.q = lane;
                     pipe.desc[base + lane] = d;
-                    if (n > kFitNMax) pipe.big[atomicAdd(&pipe.counters[1], 1)] = base + lane;
+                    if (n > kFitBigSmall) pipe.big[atomicAdd(&pipe.counters[1], 1)] = base + lane;
+                    else if (n > kFitNMax) pipe.big_s[atomicAdd(&pipe.counters[4], 1)] = base + lane;
                     else if (n > kFitSmall) pipe.mid[atomicAdd(&pipe.counters[3], 1)] = base + lane;
                 }
             }
@@ -887,41 +893,51 @@ __device__ inline void svd_n4_warp(double * A, int m, double * prod, int lane, d
         norms[j] = sqrt(__shfl_sync(kFull, acc, 0));
         __syncwarp();
     }
-    int order[4] = {0, 1, 2, 3};
+    // stable insertion sort, descending, by selects (registers only; same permutation as svd_n4)
 #pragma unroll
     for (int a = 1; a < 4; ++a)
     {
 #pragma unroll
         for (int b = a; b > 0; --b)
         {
-            const bool sw = norms[order[b - 1]] < norms[order[b]];
-            const int o0 = order[b - 1], o1 = order[b];
-            order[b - 1] = sw ? o1 : o0;
-            order[b] = sw ? o0 : o1;
+            const bool sw = norms[b - 1] < norms[b];
+            const double k0 = norms[b - 1], k1 = norms[b];
+            norms[b - 1] = sw ? k1 : k0;
+            norms[b] = sw ? k0 : k1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                const double w0 = W[i + (b - 1) * 4], w1 = W[i + b * 4];
+                W[i + (b - 1) * 4] = sw ? w1 : w0;
+                W[i + b * 4] = sw ? w0 : w1;
+            }
         }
     }
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
     {
-        s[jj] = norms[order[jj]];
+        s[jj] = norms[jj];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) V[i + jj * 4] = W[i + order[jj] * 4];
+        for (int i = 0; i < 4; ++i) V[i + jj * 4] = W[i + jj * 4];
     }
 }
 
 // stage 2b: clusters with more than 32 points (walls, very close tubes): one warp per cluster. classifyCluster's inscribed angles
 // (one atan2 each) and the Jacobi SVD's products / rotations are spread over the lanes; every sum is accumulated by lane 0 in the
 // reference's order, so the results are bit-identical to the sequential evaluation. The 4 x 4 tail (eig, solve) is replicated.
-__global__ void __launch_bounds__(64) k_scan_fit_big(const float * __restrict__ ranges, double min_range, double max_range, ScanPipe pipe)
+// Two capacities: up to kFitBigSmall points (7 KB of shared memory per warp: four times the resident warps, which is what hides the
+// ordered sums' latency) and up to a whole scan.
+template <int CAP, int WARPS, bool SMALL_LIST>
+__global__ void __launch_bounds__(32 * WARPS, SMALL_LIST ? NUSLAM_BIGS_CTAS : 5) k_scan_fit_big(const float * __restrict__ ranges, double min_range, double max_range, ScanPipe pipe)
 {
-    __shared__ double zbuf[2][4 * (kBeams + 2)];
-    __shared__ double angbuf[2][3 * (kBeams + 2)];
+    __shared__ double zbuf[WARPS][4 * CAP];
+    __shared__ double angbuf[WARPS][3 * CAP];
     constexpr unsigned kFull = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total = pipe.counters[1];
-    for (int w = blockIdx.x * 2 + warp; w < total; w += gridDim.x * 2)
+    const int total = SMALL_LIST ? pipe.counters[4] : pipe.counters[1];
+    for (int w = blockIdx.x * WARPS + warp; w < total; w += gridDim.x * WARPS)
     {
-        const int idx = pipe.big[w];
+        const int idx = SMALL_LIST ? pipe.big_s[w] : pipe.big[w];
         const ClusterDesc d = pipe.desc[idx];
         const int n = d.n_wrap & 0xffff;
         double * Zp = zbuf[warp];
@@ -972,7 +988,7 @@ __global__ void __launch_bounds__(64) k_scan_fit_big(const float * __restrict__ 
         }
         __syncwarp();
         // mean and population variance (:229-241): the quotients and squares by all lanes, the SUMS by lane 0 in the reference's order
-        double * q1 = tmp + (kBeams + 2);
+        double * q1 = tmp + CAP;
         double sd = 0.0;
         {
             const int na = n - 2;
@@ -1004,7 +1020,7 @@ __global__ void __launch_bounds__(64) k_scan_fit_big(const float * __restrict__ 
         {
             // circleFit (circle_fit_library.cpp:15-134): centroid and z_bar by lane 0 (sequential sums), Z by all lanes
             double x_hat = 0.0, y_hat = 0.0, z_bar = 0.0;
-            double * q2 = tmp + 2 * (kBeams + 2);
+            double * q2 = tmp + 2 * CAP;
             for (int i = lane; i < n; i += 32)
             {
                 q1[i] = div_(Z(i, 1), (double) n);
@@ -1146,7 +1162,7 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
     const int64_t chunk_max = n_scans < kScanChunk ? n_scans : kScanChunk;
     const size_t n_desc = (size_t) chunk_max * kMaxFastClusters;
     auto al = [](size_t v) { return (v + 255) & ~(size_t) 255; };
-    const size_t need = al(n_desc * sizeof(ClusterDesc)) + al(n_desc * sizeof(ClusterFit)) + 2 * al(n_desc * sizeof(int32_t)) +
+    const size_t need = al(n_desc * sizeof(ClusterDesc)) + al(n_desc * sizeof(ClusterFit)) + 3 * al(n_desc * sizeof(int32_t)) +
                         al((size_t) chunk_max * sizeof(int32_t)) * 2 + 256;
     if (sc.bytes < need)
     {
@@ -1165,6 +1181,8 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
     q += al(n_desc * sizeof(ClusterFit));
     pipe.big = reinterpret_cast<int32_t *>(q);
     q += al(n_desc * sizeof(int32_t));
+    pipe.big_s = reinterpret_cast<int32_t *>(q);
+    q += al(n_desc * sizeof(int32_t));
     pipe.mid = reinterpret_cast<int32_t *>(q);
     q += al(n_desc * sizeof(int32_t));
     pipe.slow = reinterpret_cast<int32_t *>(q);
@@ -1176,7 +1194,7 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
     {
         const int64_t chunk = (n_scans - s0 < kScanChunk) ? n_scans - s0 : kScanChunk;
         pipe.scan0 = s0;
-        e = cudaMemsetAsync(pipe.counters, 0, 4 * sizeof(int32_t), stream);
+        e = cudaMemsetAsync(pipe.counters, 0, 8 * sizeof(int32_t), stream);
         if (e != cudaSuccess) return e;
         int64_t blocks = (chunk + kScanWarps - 1) / kScanWarps;
         if (blocks > resident) blocks = resident;
@@ -1188,7 +1206,8 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
         if (e != cudaSuccess) return e;
         k_scan_fit_small<kFitSmall, false><<<(unsigned) (sm_count * kFitCtas), kFitThreads, fit_smem16, stream>>>(ranges, min_range, max_range, pipe);
         k_scan_fit_small<kFitNMax, true><<<(unsigned) (sm_count * 3), kFitThreads, fit_smem32, side.s1>>>(ranges, min_range, max_range, pipe);
-        k_scan_fit_big<<<(unsigned) (sm_count * 5), 64, 0, side.s2>>>(ranges, min_range, max_range, pipe);
+        k_scan_fit_big<kFitBigSmall + 2, 4, true><<<(unsigned) (sm_count * NUSLAM_BIGS_CTAS), 128, 0, side.s2>>>(ranges, min_range, max_range, pipe);
+        k_scan_fit_big<kBeams + 2, 2, false><<<(unsigned) (sm_count * 5), 64, 0, side.s2>>>(ranges, min_range, max_range, pipe);
         // scans with more than kMaxFastClusters clusters: the one-warp-per-scan kernel over their list (it writes those scans' outputs itself)
         k_scan_detect<true><<<(unsigned) sm_count, 32 * kScanWarps, smem, side.s2>>>(ranges, n_scans, min_range, max_range, cluster_of_beam, n_clusters,
                                                                                   n_circles, circles, max_circles, scan_ub, pipe.slow, pipe.counters + 2, pipe);
