@@ -357,20 +357,31 @@ struct WarpFilter
         }
         __syncwarp();
         if (lane == 0) x[0] = normalize_angle(x[0]);   // :276
-        // Sigma = M * Sigma (:279): ascending-k merge of {0,1,2,c,c+1} with the unit diagonal term k = i
+        // Sigma = M * Sigma (:279): ascending-k merge of {0,1,2,c,c+1} with the unit diagonal term k = i. Every element is an
+        // independent expression, so the traversal is free: lane = row i (its five M entries stay in registers), loop over the
+        // columns j (the five R5 entries of a column are one broadcast read each) -- a third of the shared-memory traffic of a
+        // flat element loop, the same arithmetic per element.
         const int len2 = len * len;
-        for (int e = lane; e < len2; e += kWarp)
+        for (int i0 = 0; i0 < len; i0 += kWarp)
         {
-            const int j = e / len;
-            const int i = e - j * len;
-            double acc = mul_(M5[0 * len + i], R5[0 * len + j]);
-            acc = add_(acc, mul_(M5[1 * len + i], R5[1 * len + j]));
-            acc = add_(acc, mul_(M5[2 * len + i], R5[2 * len + j]));
-            if (i >= 3 && i < c) acc = add_(acc, S[e]);
-            acc = add_(acc, mul_(M5[3 * len + i], R5[3 * len + j]));
-            acc = add_(acc, mul_(M5[4 * len + i], R5[4 * len + j]));
-            if (i > c + 1) acc = add_(acc, S[e]);
-            S[e] = acc;
+            const int i = i0 + lane;
+            if (i < len)
+            {
+                const double m0 = M5[0 * len + i], m1 = M5[1 * len + i], m2 = M5[2 * len + i], m3 = M5[3 * len + i], m4 = M5[4 * len + i];
+                const bool mid = i >= 3 && i < c, hi = i > c + 1;
+                for (int j = 0; j < len; ++j)
+                {
+                    const int e = i + j * len;
+                    double acc = mul_(m0, R5[0 * len + j]);
+                    acc = add_(acc, mul_(m1, R5[1 * len + j]));
+                    acc = add_(acc, mul_(m2, R5[2 * len + j]));
+                    if (mid) acc = add_(acc, S[e]);
+                    acc = add_(acc, mul_(m3, R5[3 * len + j]));
+                    acc = add_(acc, mul_(m4, R5[4 * len + j]));
+                    if (hi) acc = add_(acc, S[e]);
+                    S[e] = acc;
+                }
+            }
         }
         __syncwarp();
         if (opt & kOptJoseph)
