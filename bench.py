@@ -391,7 +391,17 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="ekf", choices=["ekf", "scan", "assoc", "large", "closed_loop"],
+                    help="ekf (default): the headline line of BASELINE.json configs[1]; the others run the per-config benches under tools/ "
+                         "(config 3 scans, config 4 shard with on-device association, config 5 large map, the device-resident closed loop) "
+                         "on one GPU and print their own JSON line")
     args = ap.parse_args()
+    if args.config != "ekf":
+        import runpy
+        tool = {"scan": "bench_scan.py", "assoc": "bench_assoc.py", "large": "bench_large.py", "closed_loop": "bench_closed_loop.py"}[args.config]
+        sys.argv = [str(ROOT / "tools" / tool)]
+        runpy.run_path(str(ROOT / "tools" / tool), run_name="__main__")
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:
