@@ -468,3 +468,39 @@ def test_config4_subsample_4096_filters(cuda_lib, orc):
               f"x rel {ex:.2e} ({int(late.sum())} filters with a late first touch: {ex_late:.2e}), filters the reference froze (map full) {frozen}")
         assert mism == 0 and np.array_equal(seen, full["seen"]) and np.array_equal(status != 0, full["status"] != 0)
         assert ex < TOL and ex_late < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_empty_and_single_inputs(cuda_lib, orc, mode):
+    """Edge sizes: a step without measurements is a predict (m = 0, z = None or an empty array), a batch of one filter, and a step
+    whose measurements are all 'no measurement' (id 0)."""
+    n = 12
+    sc = synth.ekf_scenario(3, 4, n=n, seed=9)
+    first = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][:1], sc["z"][:1], sc["ids"][:1])
+    # m = 0
+    a = make_engine(cuda_lib, sc, mode)
+    b = make_engine(cuda_lib, sc, mode)
+    c = make_engine(cuda_lib, sc, mode)
+    for e in (a, b, c):
+        e.set_state(first["x"], first["sigma"], first["seen"])
+    a.predict(sc["twists"][1])
+    b.step(sc["twists"][1], None, None)
+    c.step(sc["twists"][1], np.zeros((3, 0, 2)), np.zeros((3, 0), dtype=np.int32))
+    xa, sa, na, _ = a.get_state()
+    for e in (b, c):
+        x, s, nn, st = e.get_state()
+        assert rel_max(x, xa) < 1e-15 and max(rel_max(s[k], sa[k]) for k in range(3)) < 1e-15 and np.array_equal(nn, na) and not st.any()
+    # every slot empty (id 0): again a predict
+    d = make_engine(cuda_lib, sc, mode)
+    d.set_state(first["x"], first["sigma"], first["seen"])
+    got = d.step(sc["twists"][1], sc["z"][1], np.zeros_like(sc["ids"][1]), return_ids=True)
+    x, s, nn, st = d.get_state()
+    assert not got.any() and rel_max(x, xa) < 1e-15 and max(rel_max(s[k], sa[k]) for k in range(3)) < 1e-15
+    # batch of one, against the oracle
+    one = cuda_lib.BatchedExtendedKalman(sc["robot0"][:1], sc["map0"][:1], sc["Q"], sc["R"], mode=mode)
+    one.set_state(first["x"][:1], first["sigma"][:1], first["seen"][:1])
+    for t in range(1, 4):
+        one.step(sc["twists"][t, :1], sc["z"][t, :1], sc["ids"][t, :1])
+    ref = orc.ekf_run(n, sc["robot0"][:1], sc["map0"][:1], sc["Q"], sc["R"], sc["twists"][:, :1], sc["z"][:, :1], sc["ids"][:, :1])
+    x, s, _, st = one.get_state()
+    assert rel_max(x, ref["x"]) < TOL and rel_max(s[0], ref["sigma"][0]) < TOL and not st.any()
