@@ -69,7 +69,9 @@ enum
     /* LARGE-MAP mode (BASELINE.json config 5): Sigma stays in HBM; the m updates of a step are DELAYED -- each needs only
      * rows / columns {theta, x, y, c, c+1} of the current Sigma, formed on the fly from Sigma_0 and the stored K_u, W_u -- and
      * applied in ONE rank-2m pass on the fp64 tensor pipe: one read + one write of Sigma per scan whatever m is. Selected
-     * automatically when the state is too long for the on-chip kernels (n_landmarks > ~70); known correspondence only. */
+     * automatically when the state is too long for the on-chip kernels (n_landmarks > ~70). nuslam_ekf_step takes known or unknown correspondence
+     * (associateLandmark: one thread per candidate landmark against the pass's current covariance); the single-call
+     * nuslam_ekf_associate and the fused scan step are not offered in this mode. */
     NUSLAM_MODE_LARGE = 2
 };
 

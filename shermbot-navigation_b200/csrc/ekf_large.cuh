@@ -43,6 +43,15 @@ __global__ void k_large_predict_pose(const LargeParams p, const double * __restr
     if (b >= p.batch) return;
     double * x = p.x + (int64_t) b * p.len;
     double * scratch = p.P + (int64_t) b * 2 * p.len;
+    if (p.status[b] & (kStatusMapFull | kStatusSingular))
+    {
+        // the reference process died on an earlier scan: the filter stays as it was (zero Jacobian entries = identity covariance step)
+        scratch[0] = 0.0;
+        scratch[1] = 0.0;
+        scratch[2] = 1.0;   // frozen marker: no process noise either
+        return;
+    }
+    scratch[2] = 0.0;
     const double dth = twists[3 * b], dx = twists[3 * b + 1];
     const double theta = x[0];
     double s0, c0, th1, x1, y1, b10, b20;
@@ -83,6 +92,7 @@ __global__ void k_large_predict_cov(const LargeParams p)
     double * S = p.sigma + (int64_t) b * len * len;
     const double * scratch = p.P + (int64_t) b * 2 * len;
     const double b10 = scratch[0], b20 = scratch[1];
+    if (scratch[2] != 0.0) return;   // frozen filter (k_large_predict_pose): covariance untouched
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= 3 && j < len)
     {
@@ -323,6 +333,134 @@ __global__ void __launch_bounds__(256) k_large_update(const LargeParams p, const
     large_update(p, z, ids, m, i, x_old, x_new, seen_snapshot, seen);
 }
 
+// ---- associateLandmark (slam_library.cpp:188-253) against the CURRENT covariance of a delayed pass ----
+// One thread per candidate landmark k <= seen: the 5 x 5 sub-block of Sigma_i at {theta, x, y, c_k, c_k+1} from Sigma_0 and the
+// pass's earlier updates, H and z_hat at the current state, the Mahalanobis distance with the unwrapped innovation. The reference's
+// in-order early exit ("the first k whose distance decides") becomes an atomicMin over the keys (k << 2 | kind) of the deciding
+// candidates. k_large_assoc_finalize then turns the winner into the id of slam.cpp:291 (and into `seen`, the status bits, the id
+// slot the update kernel reads). kind: 0 = inv(psi) throws, 1 = match (d < 0.01), 2 = ambiguous (0.01 < d < 60).
+__global__ void __launch_bounds__(128) k_large_associate(const LargeParams p, const double * __restrict__ z, int m, int i_meas, int i_pass,
+                                                         const double * __restrict__ x_cur, const int32_t * __restrict__ seen,
+                                                         int32_t * __restrict__ result, double amin, double amax)
+{
+    const int b = blockIdx.y;
+    const int len = p.len;
+    const int sn = seen[b];
+    if (p.status[b] & (kStatusMapFull | kStatusSingular)) return;   // the reference process died on an earlier measurement
+    if (sn == 0 || 3 + 2 * sn >= len) return;                        // first landmark / full map: decided without any candidate
+    const double * S = p.sigma + (int64_t) b * len * len;
+    const double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
+    const double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
+    const double * x = x_cur + (int64_t) b * len;
+    // robot rows / columns of the earlier updates: shared by every candidate
+    __shared__ double ku3[2 * kLargeMMax][3], wu3[2 * kLargeMMax][3];
+    for (int t = threadIdx.x; t < 2 * i_pass * 3; t += blockDim.x)
+    {
+        ku3[t / 3][t % 3] = U[(int64_t) (t / 3) * len + t % 3];
+        wu3[t / 3][t % 3] = V[(int64_t) (t / 3) * len + t % 3];
+    }
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (k > sn) return;
+    const int c = 3 + 2 * (k - 1);
+    const int idx[5] = {0, 1, 2, c, c + 1};
+    double B5[5][5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int q = 0; q < 5; ++q) B5[r][q] = S[idx[r] + (int64_t) idx[q] * len];
+    for (int u = 0; u < 2 * i_pass; ++u)
+    {
+        const double kc = U[(int64_t) u * len + c], kc1 = U[(int64_t) u * len + c + 1];
+        const double wc = V[(int64_t) u * len + c], wc1 = V[(int64_t) u * len + c + 1];
+        const double kr[5] = {ku3[u][0], ku3[u][1], ku3[u][2], kc, kc1};
+        const double wq[5] = {wu3[u][0], wu3[u][1], wu3[u][2], wc, wc1};
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) B5[r][q] = fma(-kr[r], wq[q], B5[r][q]);
+    }
+    const double xl[5] = {x[0], x[1], x[2], x[c], x[c + 1]};
+    const LargeModel mdl = large_model(xl);
+    double w5[2][5];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+        {
+            double w = 0.0;
+#pragma unroll
+            for (int r = 0; r < 5; ++r) w = fma(mdl.h[a][r], B5[r][q], w);
+            w5[a][q] = w;
+        }
+    double psi[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+        {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) acc = fma(w5[a][q], mdl.h[e][q], acc);
+            psi[a][e] = acc + p.R[a + 2 * e];
+        }
+    const double det = psi[0][0] * psi[1][1] - psi[0][1] * psi[1][0];
+    const double z0 = z[(int64_t) (b * m + i_meas) * 2], z1 = z[(int64_t) (b * m + i_meas) * 2 + 1];
+    int kind = -1;
+    if (det == 0.0 || !(fabs(det) < 1.0e300) || !(fabs(1.0 / det) < 1.0e300)) kind = 0;
+    else
+    {
+        const double i00 = psi[1][1] / det, i01 = -psi[0][1] / det, i10 = -psi[1][0] / det, i11 = psi[0][0] / det;
+        const double dz0 = z0 - mdl.zr, dz1 = z1 - mdl.zb;   // no angle wrap (:229-231)
+        const double t0 = dz0 * i00 + dz1 * i10, t1 = dz0 * i01 + dz1 * i11;
+        const double d = t0 * dz0 + t1 * dz1;
+        if (d < amin) kind = 1;
+        else if (d > amin && d < amax) kind = 2;
+    }
+    if (kind >= 0) atomicMin(&result[b], (k << 2) | kind);
+}
+
+// slam.cpp:291 for every filter: the id associateLandmark returns, its side effect on `seen`, and the status bits where it throws.
+// ids_slot: B x m scratch the update kernel reads (id <= 0: no update); ids_out: B x m or null.
+__global__ void k_large_assoc_finalize(const LargeParams p, int m, int i_meas, int32_t * __restrict__ seen, int32_t * __restrict__ result,
+                                       int32_t * __restrict__ ids_slot, int32_t * __restrict__ ids_out)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.batch) return;
+    int id;
+    const int st = p.status[b];
+    const int sn = seen[b];
+    if (st & (kStatusMapFull | kStatusSingular)) id = 0;
+    else if (sn == 0)
+    {
+        seen[b] = 1;   // :196-200
+        id = 1;
+    }
+    else if (3 + 2 * sn >= p.len)
+    {
+        p.status[b] = st | kStatusMapFull;   // temp(3 + 2 seen) out of bounds: Armadillo throws (:204-207)
+        id = kIdException;
+    }
+    else
+    {
+        const int r = result[b];
+        if (r >= 0x7f000000)   // untouched (any fill above the largest key (n << 2 | 3))
+        {
+            seen[b] = sn + 1;   // no candidate decided: a new landmark (:251)
+            id = sn + 1;
+        }
+        else if ((r & 3) == 0)
+        {
+            p.status[b] = st | kStatusSingular;
+            id = kIdException;
+        }
+        else id = ((r & 3) == 1) ? (r >> 2) : -1;
+    }
+    result[b] = 0x7fffffff;
+    ids_slot[(int64_t) b * m + i_meas] = id;
+    if (ids_out) ids_out[(int64_t) b * m + i_meas] = id;
+}
+
 // all `cnt` delayed updates of a pass in ONE cooperative launch: consecutive updates are separated by a grid barrier (~2 us) instead
 // of a kernel boundary (~12 us of dependent-launch latency). x ping-pongs between p.x and p.x2.
 __global__ void __launch_bounds__(64) k_large_updates_coop(const LargeParams p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int cnt,
@@ -445,13 +583,39 @@ __global__ void k_large_init_landmark(const LargeParams p, const double * __rest
 }
 
 // host: one delayed pass over measurements [i0, i0 + cnt) of the step (cnt <= kLargeMMax); x ping-pongs between p.x and p.x2
+// association of a pass: unknown correspondence (ids written measurement by measurement into ids_slot by the association kernels)
+struct LargeAssoc
+{
+    int32_t * ids_slot = nullptr;   // B x m
+    int32_t * result = nullptr;     // B, initialised to INT_MAX
+    int32_t * ids_out = nullptr;    // B x m or null
+    double amin = 0.01, amax = 60.0;
+};
+
 inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const int32_t * ids, int m, int i0, int cnt,
-                                        const int32_t * seen_snapshot, int32_t * seen, cudaStream_t st)
+                                        const int32_t * seen_snapshot, int32_t * seen, cudaStream_t st, const LargeAssoc * assoc = nullptr)
 {
     const int threads = 64;   // ~130 small blocks at len 8195: every SM takes part in the latency-bound row / column gathers
     const dim3 grid((p.len + threads - 1) / threads, (unsigned) p.batch);
     const int kk = (2 * cnt + 3) & ~3;
     k_large_clear_w<<<dim3((unsigned) (((int64_t) kk * p.len + threads - 1) / threads), (unsigned) p.batch), threads, 0, st>>>(p, kk / 2);
+    if (assoc)
+    {
+        // unknown correspondence: per measurement associate (one thread per candidate) -> finalize -> update
+        for (int k = 0; k < cnt; ++k)
+        {
+            k_large_associate<<<dim3((unsigned) ((p.n + 127) / 128), (unsigned) p.batch), 128, 0, st>>>(p, z, m, i0 + k, k, p.x, seen, assoc->result,
+                                                                                                     assoc->amin, assoc->amax);
+            k_large_assoc_finalize<<<(unsigned) ((p.batch + 63) / 64), 64, 0, st>>>(p, m, i0 + k, seen, assoc->result, assoc->ids_slot, assoc->ids_out);
+            k_large_update<<<grid, threads, 0, st>>>(p, z + 2 * (int64_t) i0, assoc->ids_slot + i0, m, k, p.x, p.x2, seen_snapshot, seen);
+            double * tmp = p.x;
+            p.x = p.x2;
+            p.x2 = tmp;
+        }
+        const unsigned tiles = (p.len + kLargeTile - 1) / kLargeTile;
+        k_large_rank_update<<<dim3(tiles, tiles, (unsigned) p.batch), 128, 0, st>>>(p, kk);
+        return cudaGetLastError();
+    }
     // one cooperative launch when the whole grid is co-resident (it is for a few large maps), else two launches per update
     static int coop_dev[kMaxDevices];
     static bool coop_known[kMaxDevices] = {false};

@@ -107,6 +107,7 @@ struct nuslam_ekf
     double * lg_V = nullptr;
     double * lg_P = nullptr;
     int32_t * lg_seen_snap = nullptr;
+    DevBuf lg_ids_slot, lg_assoc_result;   // unknown correspondence in large-map mode
     int32_t * worklist = nullptr;   // batch entries
     int32_t * wl_count = nullptr;   // [0] = entries, [1] = finished blocks of the list kernel
     size_t strict_smem = 0;   // per-warp shared memory of the strict kernels, bytes
@@ -226,15 +227,29 @@ nuslam::LargeParams make_large_params(nuslam_ekf * h)
 
 // LARGE-MAP mode: m measurements in delayed passes of at most kLargeMMax; `step_protocol` adds slam.cpp:295-297
 // (initializeLandmark for ids above the scan's seen snapshot, seen = max(seen, id))
-int large_updates(nuslam_ekf * h, const double * z, const int32_t * ids, int m, bool step_protocol)
+int large_updates(nuslam_ekf * h, const double * z, const int32_t * ids, int m, bool step_protocol, int32_t * ids_out = nullptr)
 {
     nuslam::LargeParams p = make_large_params(h);
+    nuslam::LargeAssoc assoc;
+    if (!ids)
+    {
+        // unknown correspondence: associateLandmark per measurement against the pass's current covariance
+        int rc = h->lg_ids_slot.reserve(sizeof(int32_t) * h->batch * (m > 0 ? m : 1));
+        if (!rc) rc = h->lg_assoc_result.reserve(sizeof(int32_t) * h->batch);
+        if (rc) return rc;
+        assoc.ids_slot = static_cast<int32_t *>(h->lg_ids_slot.p);
+        assoc.result = static_cast<int32_t *>(h->lg_assoc_result.p);
+        assoc.ids_out = ids_out;
+        assoc.amin = h->cfg.assoc_min;
+        assoc.amax = h->cfg.assoc_max;
+        CU(cudaMemsetAsync(assoc.result, 0x7f, sizeof(int32_t) * h->batch, h->stream));   // any value >= every key; finalize resets to INT_MAX
+    }
     if (step_protocol) CU(cudaMemcpyAsync(h->lg_seen_snap, h->seen, sizeof(int32_t) * h->batch, cudaMemcpyDeviceToDevice, h->stream));
     for (int i0 = 0; i0 < m; i0 += nuslam::kLargeMMax)
     {
         const int cnt = (m - i0 < nuslam::kLargeMMax) ? m - i0 : nuslam::kLargeMMax;
         cudaError_t e = nuslam::launch_large_updates(p, z, ids, m, i0, cnt, step_protocol ? h->lg_seen_snap : nullptr,
-                                                     step_protocol ? h->seen : nullptr, h->stream);
+                                                     step_protocol ? h->seen : nullptr, h->stream, ids ? nullptr : &assoc);
         if (e != cudaSuccess) return cuda_fail(e, "large-map update pass");
     }
     // x ping-pongs between the state buffer and the scratch: leave the result in the state buffer
@@ -384,6 +399,8 @@ int nuslam_ekf_destroy(nuslam_ekf * h)
     if (h->lg_V) cudaFree(h->lg_V);
     if (h->lg_P) cudaFree(h->lg_P);
     if (h->lg_seen_snap) cudaFree(h->lg_seen_snap);
+    h->lg_ids_slot.release();
+    h->lg_assoc_result.release();
     if (h->worklist) cudaFree(h->worklist);
     if (h->wl_count) cudaFree(h->wl_count);
     h->s_tw.release();
@@ -493,7 +510,7 @@ int nuslam_ekf_predict(nuslam_ekf * h, const double * twists, int mem)
 int nuslam_ekf_associate(nuslam_ekf * h, const double * z, int32_t * id_out, int mem)
 {
     if (!h || !z || !id_out) return fail(NUSLAM_ERR_INVALID, "null argument");
-    if (h->large) return fail(NUSLAM_ERR_UNSUPPORTED, "large-map mode covers known correspondence only (associateLandmark is not built yet)");
+    if (h->large) return fail(NUSLAM_ERR_UNSUPPORTED, "large-map mode associates inside nuslam_ekf_step (ids == NULL); the single-call form is not offered");
     if (select_device(h)) return NUSLAM_ERR_CUDA;
     nuslam::EkfParams p = make_params(h);
     p.m = 1;
@@ -602,16 +619,15 @@ int step_device(nuslam_ekf * h, const nuslam::EkfParams & p)
     const int m = p.m;
     if (h->large)
     {
-        if (!p.ids || p.m_valid)
-            return fail(NUSLAM_ERR_UNSUPPORTED, "large-map mode covers known correspondence only (associateLandmark is not built yet)");
+        if (p.m_valid) return fail(NUSLAM_ERR_UNSUPPORTED, "large-map mode takes a uniform measurement count");
         cudaError_t e = nuslam::launch_large_predict(make_large_params(h), p.twists, h->stream);
         if (e != cudaSuccess) return cuda_fail(e, "large-map predict");
         if (m > 0)
         {
-            int rc = large_updates(h, p.z, p.ids, m, /*step_protocol=*/true);
+            int rc = large_updates(h, p.z, p.ids, m, /*step_protocol=*/true, p.ids_out);
             if (rc) return rc;
         }
-        if (p.ids_out && m > 0) CU(cudaMemcpyAsync(p.ids_out, p.ids, sizeof(int32_t) * h->batch * m, cudaMemcpyDeviceToDevice, h->stream));
+        if (p.ids && p.ids_out && m > 0) CU(cudaMemcpyAsync(p.ids_out, p.ids, sizeof(int32_t) * h->batch * m, cudaMemcpyDeviceToDevice, h->stream));
         return NUSLAM_OK;
     }
     if (h->cfg.mode == NUSLAM_MODE_FAST && h->cfg.options == 0 && m <= nuslam::kFastMMax)
@@ -656,7 +672,7 @@ int nuslam_ekf_scan_step(nuslam_ekf * h, const double * twists, const float * ra
 {
     if (!h || !twists || !ranges) return fail(NUSLAM_ERR_INVALID, "null handle, twists or ranges");
     if (m < 1) return fail(NUSLAM_ERR_INVALID, "m < 1");
-    if (h->large) return fail(NUSLAM_ERR_UNSUPPORTED, "large-map mode covers known correspondence only");
+    if (h->large) return fail(NUSLAM_ERR_UNSUPPORTED, "the fused scan step is not offered in large-map mode");
     if (select_device(h)) return NUSLAM_ERR_CUDA;
     const size_t B = (size_t) h->batch;
     nuslam::EkfParams p = make_params(h);

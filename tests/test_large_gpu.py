@@ -130,3 +130,38 @@ def test_4096_landmarks_delayed_equals_sequential(cuda_lib):
     assert int(states[0][3][0]) == 0 and torch.isfinite(states[0][1]).all()
     for e in engs:
         e.close()
+
+
+@pytest.mark.parametrize("n,m,B", [(12, 12, 3), (64, 10, 2), (128, 20, 1)])
+def test_large_mode_unknown_association(cuda_lib, orc, n, m, B):
+    """associateLandmark in large-map mode (one thread per candidate against the pass's CURRENT covariance, in-order early exit as an
+    atomic minimum): every scan teacher-forced from the oracle's state; ids identical, state <= 1e-9 on scans without a first touch."""
+    T = 6
+    sc = synth.ekf_scenario(B, T, n=n, seed=71, geometry="benign", shuffle_order=True)
+    pick = np.linspace(0, n - 1, m).astype(int)
+    z = np.ascontiguousarray(sc["z"][:, :, pick])
+    eng = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="large")
+    state = None
+    decisions = matched = opened = 0
+    for t in range(T):
+        r = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][t:t + 1], z[t:t + 1], None, init=state)
+        if state is not None:
+            eng.set_state(state[0], state[1], state[2])
+        got = eng.step(sc["twists"][t], z[t], None, return_ids=True)
+        x, s, seen, status = eng.get_state()
+        assert np.array_equal(got, r["ids_out"][0]), f"ids differ at scan {t}"
+        assert np.array_equal(seen, r["seen"]) and np.array_equal(status != 0, r["status"] != 0)
+        new = int((r["seen"] - (state[2] if state is not None else 0)).sum())
+        if new == 0:   # no first touch in this scan: tight bound
+            assert rel_max(x, r["x"]) < TOL
+            touched = np.concatenate([[0, 1, 2]] + [[3 + 2 * (k - 1), 4 + 2 * (k - 1)] for k in range(1, int(r["seen"].max()) + 1)])
+            for b in range(B):
+                assert rel_max(s[b][np.ix_(touched, touched)], r["sigma"][b][np.ix_(touched, touched)]) < TOL
+        else:
+            assert rel_max(x, r["x"]) < 1e-3
+        decisions += got.size
+        matched += int((got > 0).sum())
+        opened += new
+        state = (r["x"], r["sigma"], r["seen"])
+    print(f"[large association n={n} m={m}] {decisions} decisions, {matched} with an id, {opened} landmarks opened: ids identical")
+    assert matched > 0
