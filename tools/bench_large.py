@@ -48,8 +48,39 @@ def main(n=4096, steps=30, warmup=5):
         ms = e0.elapsed_time(e1) / steps
         nbytes = 16.0 * length * length
         out.append(dict(m=m, ms_per_scan=ms, scans_per_s=1e3 / ms, achieved_gbs=nbytes / (ms * 1e-3) / 1e9, frac_of_hbm=nbytes / (ms * 1e-3) / 1e9 / peak))
+    # unknown correspondence: associateLandmark against 4 000 seen landmarks per measurement (a full map would throw, as the
+    # reference does), exact measurements so that every one matches its landmark
+    # a precise sensor (R = 1e-6 I), a converged map (variances 1e-8) and next to no process noise keep the other 3 999 landmarks outside
+    # the ambiguity gate (with the node's Q = 0.1 I every landmark within 2.4 m would be "ambiguous" after one predict)
+    eng.close()
+    eng = nuslam.BatchedExtendedKalman(robot, lm.reshape(1, -1), 1e-10 * np.eye(3), 1e-6 * np.eye(2), mode="large", stream=stream.cuda_stream)
+    xs.copy_(torch.tensor(np.concatenate([robot[0], lm.ravel()])[None], device=dev))
+    sig.zero_()
+    sig[0].diagonal().fill_(1e-8)
+    status.zero_()
+    eng.bind_state(xs, sig, seen, status)
+    seen.fill_(n - 96)
+    assoc = []
+    for m in (1, 12):
+        pick = rng.choice(n - 96, size=m, replace=False)
+        dl = lm[pick]
+        z = torch.tensor(np.stack([np.hypot(dl[:, 0], dl[:, 1]), np.arctan2(dl[:, 1], dl[:, 0])], axis=1)[None], device=dev)
+        tw = torch.tensor([[0.0, 0.0, 0.0]], device=dev, dtype=torch.float64)
+        got = None
+        for _ in range(warmup):
+            got = eng.step(tw, z, None, return_ids=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(steps):
+            eng.step(tw, z, None)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        assoc.append(dict(m=m, ms_per_scan=ms, scans_per_s=1e3 / ms, ids_matching_truth=int((got[0].cpu().numpy() == pick + 1).sum())))
     print(json.dumps({"workload": "config 5: 4096 landmarks, len 8195, Sigma 537 MB, delayed rank-2m DMMA pass", "algorithmic_bytes_per_scan": 16.0 * length * length,
-                      "hbm_peak_gbs": peak, "results": out, "status": int(status[0]), "finite": bool(torch.isfinite(sig).all())}))
+                      "hbm_peak_gbs": peak, "results": out, "unknown_association_4000_candidates": assoc, "status": int(status[0]),
+                      "finite": bool(torch.isfinite(sig).all())}))
 
 
 if __name__ == "__main__":
