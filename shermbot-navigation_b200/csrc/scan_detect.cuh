@@ -34,18 +34,27 @@ constexpr double kPiRef = 3.14159265358979323846;   // rigid2d.hpp:16
 __device__ double c_beam_cos[kBeams];
 __device__ double c_beam_sin[kBeams];
 
-struct ScanSmem
+// clustering state of one scan (one warp); the point and work-matrix arrays follow it only in the instantiation that also fits
+struct ScanSmemHead
 {
-    double px[kBeams + 2];        // points in the reference's stored order (flat over the pre-erase clusters); [361] = wrap point
-    double py[kBeams + 2];
-    double A[4 * (kBeams + 2)];   // Jacobi work matrices of the clusters being fitted (disjoint slices)
     float r[kBeams + 8];
     short cend[kBeams + 2];       // flat position of the last point of pre-erase cluster k
     short cbeam[kBeams + 2];      // beam index of that point (the closer)
     short newidx[kBeams + 2];     // index after the erase loop, -1 when erased
     short kept[kBeams + 2];       // pre-erase index of kept cluster q
     int nk;
+    int pad[3];
 };
+struct ScanSmem : ScanSmemHead
+{
+    double px[kBeams + 2];        // points in the reference's stored order (flat over the pre-erase clusters); [361] = wrap point
+    double py[kBeams + 2];
+    double A[4 * (kBeams + 2)];   // Jacobi work matrices of the clusters being fitted (disjoint slices)
+};
+static_assert(sizeof(ScanSmemHead) % 16 == 0, "per-warp slices stay 16-byte aligned");
+// per-warp shared-memory footprint: 4.4 KB for clustering only (22 resident warps per SM, register-bound), 21.8 KB with the fits
+template <bool INLINE_FIT>
+constexpr size_t scan_smem_stride() { return INLINE_FIT ? sizeof(ScanSmem) : sizeof(ScanSmemHead); }
 
 // view of an m x 4 work matrix: element (i, c) at p[(i + c * ld) * stride] (stride > 1: interleaved over the threads of a CTA)
 struct WorkMatrix
@@ -493,7 +502,8 @@ k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_ran
               const int32_t * __restrict__ list, const int32_t * __restrict__ list_count, ScanPipe pipe)
 {
     extern __shared__ __align__(16) unsigned char scan_smem_raw[];
-    ScanSmem & sm = reinterpret_cast<ScanSmem *>(scan_smem_raw)[threadIdx.x >> 5];
+    // the clustering-only instantiation never touches px / py / A: its slices are ScanSmemHead-sized
+    ScanSmem & sm = *reinterpret_cast<ScanSmem *>(scan_smem_raw + (threadIdx.x >> 5) * scan_smem_stride<INLINE_FIT>());
     const int lane = threadIdx.x & 31;
     constexpr unsigned kFull = 0xffffffffu;
     constexpr int kChunks = (kBeams + 31) / 32;   // 12
@@ -557,9 +567,12 @@ k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_ran
             my_clu[k] = clu_base + __popc(clo_m[k] & lt);
             if (inr)
             {
-                const double r = (double) sm.r[i];
-                sm.px[my_pos[k]] = mul_(r, __ldg(&c_beam_cos[i]));   // :162-163
-                sm.py[my_pos[k]] = mul_(r, __ldg(&c_beam_sin[i]));
+                if (INLINE_FIT)
+                {
+                    const double r = (double) sm.r[i];
+                    sm.px[my_pos[k]] = mul_(r, __ldg(&c_beam_cos[i]));   // :162-163
+                    sm.py[my_pos[k]] = mul_(r, __ldg(&c_beam_sin[i]));
+                }
                 if (clo)
                 {
                     sm.cend[my_clu[k]] = (short) my_pos[k];
@@ -569,7 +582,7 @@ k_scan_detect(const float * __restrict__ ranges, int64_t n_scans, double min_ran
             pos_base += __popc(inr_m[k]);
             clu_base += __popc(clo_m[k]);
         }
-        if (wrap && lane == 0)
+        if (INLINE_FIT && wrap && lane == 0)
         {
             const double r = (double) sm.r[kBeams - 1];
             sm.px[kBeams + 1] = mul_(r, __ldg(&c_beam_cos[kBeams - 1]));
@@ -1129,19 +1142,19 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
 {
     cudaError_t e = scan_tables_init(device);
     if (e != cudaSuccess) return e;
-    const size_t smem = sizeof(ScanSmem) * kScanWarps;
+    const size_t smem = sizeof(ScanSmem) * kScanWarps, smem_cluster = sizeof(ScanSmemHead) * kScanWarps;
     const size_t fit_smem16 = sizeof(double) * 4 * kFitSmall * kFitThreads, fit_smem32 = sizeof(double) * 4 * kFitNMax * kFitThreads;
     static bool configured_dev[kMaxDevices] = {false};
     bool & configured = configured_dev[(device >= 0 && device < kMaxDevices) ? device : 0];
     if (!configured)
     {
         e = cudaFuncSetAttribute(k_scan_detect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan_detect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan_fit_small<kFitNMax, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fit_smem32);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int64_t resident = (int64_t) sm_count * 5;
+    const int64_t resident_cluster = (int64_t) sm_count * 11;   // clustering only: 90 registers x 64 threads, 8.8 KB of shared memory per CTA
     ScanPipe none;
     memset(&none, 0, sizeof(none));
     if (n_scans <= 256)
@@ -1197,8 +1210,8 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
         e = cudaMemsetAsync(pipe.counters, 0, 8 * sizeof(int32_t), stream);
         if (e != cudaSuccess) return e;
         int64_t blocks = (chunk + kScanWarps - 1) / kScanWarps;
-        if (blocks > resident) blocks = resident;
-        k_scan_detect<false><<<(unsigned) blocks, 32 * kScanWarps, smem, stream>>>(ranges, chunk, min_range, max_range, cluster_of_beam, n_clusters,
+        if (blocks > resident_cluster) blocks = resident_cluster;
+        k_scan_detect<false><<<(unsigned) blocks, 32 * kScanWarps, smem_cluster, stream>>>(ranges, chunk, min_range, max_range, cluster_of_beam, n_clusters,
                                                                                 n_circles, circles, max_circles, scan_ub, nullptr, nullptr, pipe);
         e = cudaEventRecord(side.fork, stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(side.s1, side.fork, 0);
