@@ -856,17 +856,15 @@ __device__ inline void svd_n4_warp(double * A, int m, double * prod, int lane, d
                     prod[2 * m + i] = mul_(ap, aq);
                 }
                 __syncwarp();
-                double alpha = 0.0, beta = 0.0, gamma = 0.0;
-                if (lane == 0)
-                    for (int i = 0; i < m; ++i)
-                    {
-                        alpha = add_(alpha, prod[i]);
-                        beta = add_(beta, prod[m + i]);
-                        gamma = add_(gamma, prod[2 * m + i]);
-                    }
-                alpha = __shfl_sync(kFull, alpha, 0);
-                beta = __shfl_sync(kFull, beta, 0);
-                gamma = __shfl_sync(kFull, gamma, 0);
+                // the three ordered sums side by side: lane 0 alpha, lane 1 beta, lane 2 gamma (each in the reference's order)
+                double acc3 = 0.0;
+                if (lane < 3)
+                {
+                    const double * pr = prod + lane * m;
+#pragma unroll 4
+                    for (int i = 0; i < m; ++i) acc3 = add_(acc3, pr[i]);
+                }
+                const double alpha = __shfl_sync(kFull, acc3, 0), beta = __shfl_sync(kFull, acc3, 1), gamma = __shfl_sync(kFull, acc3, 2);
                 const bool skip = (gamma == 0.0) || (fabs(gamma) <= 1e-300) ||
                                   (fabs(gamma) <= mul_(2.220446049250313e-16, sqrt(mul_(alpha, beta))));
                 if (!skip)
@@ -895,15 +893,17 @@ __device__ inline void svd_n4_warp(double * A, int m, double * prod, int lane, d
         if (!rotated) break;
     }
     double norms[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
     {
-        for (int i = lane; i < m; i += 32) prod[i] = mul_(A[i + j * m], A[i + j * m]);
-        __syncwarp();
+        // the four column norms side by side: lane j squares and sums column j in the reference's order
         double acc = 0.0;
-        if (lane == 0)
-            for (int i = 0; i < m; ++i) acc = add_(acc, prod[i]);
-        norms[j] = sqrt(__shfl_sync(kFull, acc, 0));
+        if (lane < 4)
+        {
+            const double * col = A + lane * m;
+#pragma unroll 4
+            for (int i = 0; i < m; ++i) acc = add_(acc, mul_(col[i], col[i]));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) norms[j] = sqrt(__shfl_sync(kFull, acc, j));
         __syncwarp();
     }
     // stable insertion sort, descending, by selects (registers only; same permutation as svd_n4)
@@ -1040,14 +1040,17 @@ __global__ void __launch_bounds__(32 * WARPS, SMALL_LIST ? NUSLAM_BIGS_CTAS : 5)
                 q2[i] = div_(Z(i, 2), (double) n);
             }
             __syncwarp();
-            if (lane == 0)
-                for (int i = 0; i < n; ++i)
+            {
+                double acc = 0.0;
+                if (lane < 2)
                 {
-                    x_hat = add_(x_hat, q1[i]);
-                    y_hat = add_(y_hat, q2[i]);
+                    const double * qq = lane == 0 ? q1 : q2;
+#pragma unroll 4
+                    for (int i = 0; i < n; ++i) acc = add_(acc, qq[i]);
                 }
-            x_hat = __shfl_sync(kFull, x_hat, 0);
-            y_hat = __shfl_sync(kFull, y_hat, 0);
+                x_hat = __shfl_sync(kFull, acc, 0);
+                y_hat = __shfl_sync(kFull, acc, 1);
+            }
             __syncwarp();
             for (int j = lane; j < n; j += 32)
             {
