@@ -60,3 +60,37 @@ def test_default_config(cuda_lib):
     assert cfg.n_landmarks == 12 and cfg.mode == 0
     assert list(cfg.Q) == [0.1, 0, 0, 0, 0.1, 0, 0, 0, 0.1] and list(cfg.R) == [0.001, 0, 0, 0.001]
     assert cfg.assoc_min == 0.01 and cfg.assoc_max == 60
+
+
+def build_abi_main(tmp_path, cuda_lib):
+    import subprocess
+    exe = tmp_path / "abi_main"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(ROOT / "tests" / "abi_main.c"), "-o", str(exe),
+           str(cuda_lib.LIB_PATH), f"-Wl,-rpath,{cuda_lib.LIB_PATH.parent}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_every_entry_point_links(cuda_lib, tmp_path):
+    """The boundary is a C ABI: include/nuslam_b200.h compiles as C99 (-pedantic -Werror), a C program links every declared entry point,
+    and the calls that need no device behave (version, default config, refusal of a null config)."""
+    import subprocess
+    exe = build_abi_main(tmp_path, cuda_lib)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = dict(line.split(" ", 1) for line in r.stdout.strip().splitlines())
+    assert out["VERSION"] == "101" and int(out["ENTRY_POINTS"]) == len(declared_symbols())
+    assert "n=12 mode=0 Q00=0.1 R00=0.001 amin=0.01 amax=60 options=0 prior=2147483647.0" in out["DEFAULT"]
+    assert "null config" in out["NULLCFG"]
+
+
+@pytest.mark.gpu
+def test_c_program_runs_the_batched_loop(cuda_lib, tmp_path):
+    """INTEGRATION.md section 3 from plain C: create, init, three fused steps with host buffers, get_state."""
+    import subprocess
+    exe = build_abi_main(tmp_path, cuda_lib)
+    r = subprocess.run([str(exe), "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    state = [ln for ln in r.stdout.splitlines() if ln.startswith("STATE")][0].split()
+    assert state[-1] == "0" and abs(float(state[1]) - 0.06) < 0.05

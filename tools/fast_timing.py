@@ -30,7 +30,7 @@ for t in range(3, 3 + K):
 eng.synchronize()
 lib.nuslam_debug_fast_timing(out, 0)
 v = np.array(list(out), dtype=np.float64)
-nblk = 148 * int(os.environ.get("NUSLAM_FAST_CTAS_PER_SM", "20"))
+nblk = 148 * int(os.environ.get("NUSLAM_FAST_CTAS_PER_SM", "16"))
 filters = K * ((B + nblk - 1) // nblk)   # filters processed by block 0 / warp 0
 names = ["load", "predict", "publish", "pre (Pt,Wt)", "2x2 part + Kt", "post (x, robot)", "dmma", "store"]
 tot = v[:8].sum()
