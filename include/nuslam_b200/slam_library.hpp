@@ -25,6 +25,11 @@
 #include <armadillo>
 #endif
 
+#ifdef NUSLAM_B200_USE_RIGID2D
+// inside the reference's workspace the geometry value types stay rigid2d's own (slam.cpp also uses Vector2D, Transform2D and
+// DiffDrive from it): only slam_library / circle_fit_library are replaced
+#include "rigid2d/rigid2d.hpp"
+#else
 namespace rigid2d
 {
 struct Twist2D   // rigid2d.hpp:150-155: that field order
@@ -38,6 +43,7 @@ inline double normalize_angle(double rad)   // rigid2d.cpp:9-13, evaluated on th
     return out;
 }
 }   // namespace rigid2d
+#endif
 
 namespace slam_library
 {

@@ -24,6 +24,20 @@ def test_facade_compiles_and_links(cuda_lib):
     assert EXE.exists()
 
 
+def test_facade_compiles_against_the_references_rigid2d(cuda_lib, tmp_path):
+    """Inside the reference's workspace the facade takes Twist2D / normalize_angle from rigid2d itself (-DNUSLAM_B200_USE_RIGID2D; the
+    node keeps using Vector2D, Transform2D and DiffDrive from it): the same caller compiles against the reference's header and links
+    its rigid2d.cpp next to libnuslam_b200. Needs /root/reference (absent on the GPU box)."""
+    ref = Path("/root/reference/rigid2d")
+    if not ref.exists():
+        pytest.skip("reference sources not present")
+    libdir = cuda_lib.LIB_PATH.parent
+    cmd = ["g++", "-std=c++17", "-O1", "-DNUSLAM_B200_USE_RIGID2D", f"-I{ROOT / 'include'}", f"-I{ref / 'include'}", "-o", str(tmp_path / "facade_rigid2d"),
+           str(ROOT / "tests" / "facade_main.cpp"), str(ref / "src" / "rigid2d.cpp"), f"-L{libdir}", "-lnuslam_b200", f"-Wl,-rpath,{libdir}"]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+
+
 @pytest.mark.gpu
 def test_facade_matches_oracle(cuda_lib, orc):
     build_facade(cuda_lib)
