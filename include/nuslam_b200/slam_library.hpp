@@ -25,6 +25,12 @@
 #include <armadillo>
 #endif
 
+#ifdef NUSLAM_B200_USE_ROS
+// the message types the landmarks node passes around (circle_fit_library.hpp:8-9)
+#include <geometry_msgs/Point.h>
+#include <visualization_msgs/Marker.h>
+#endif
+
 #ifdef NUSLAM_B200_USE_RIGID2D
 // inside the reference's workspace the geometry value types stay rigid2d's own (slam.cpp also uses Vector2D, Transform2D and
 // DiffDrive from it): only slam_library / circle_fit_library are replaced

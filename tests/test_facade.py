@@ -38,6 +38,16 @@ def test_facade_compiles_against_the_references_rigid2d(cuda_lib, tmp_path):
     assert out.returncode == 0, out.stderr
 
 
+def test_facade_compiles_with_ros_message_types(cuda_lib, tmp_path):
+    """-DNUSLAM_B200_USE_ROS: Point / Marker are geometry_msgs::Point / visualization_msgs::Marker, as in the landmarks node. ROS is
+    not in this image: the message stubs of the oracle's shim stand in for the headers (compile and link check)."""
+    libdir = cuda_lib.LIB_PATH.parent
+    cmd = ["g++", "-std=c++17", "-O1", "-DNUSLAM_B200_USE_ROS", f"-I{ROOT / 'include'}", f"-I{ROOT / 'oracle' / 'shim'}", "-o", str(tmp_path / "facade_ros"),
+           str(ROOT / "tests" / "facade_main.cpp"), f"-L{libdir}", "-lnuslam_b200", f"-Wl,-rpath,{libdir}"]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+
+
 @pytest.mark.gpu
 def test_facade_matches_oracle(cuda_lib, orc):
     build_facade(cuda_lib)
