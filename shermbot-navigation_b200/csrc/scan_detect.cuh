@@ -1113,7 +1113,10 @@ __global__ void k_scan_publish(int64_t chunk, int32_t * __restrict__ n_clusters,
     n_circles[s] = published;
 }
 
-constexpr int64_t kScanChunk = 65536;   // scans per pipeline pass (bounds the scratch: 65536 x 32 x 48 B = 100 MB)
+#ifndef NUSLAM_SCAN_CHUNK
+#define NUSLAM_SCAN_CHUNK 262144
+#endif
+constexpr int64_t kScanChunk = NUSLAM_SCAN_CHUNK;   // scans per pipeline pass (bounds the scratch: 262144 x 32 x 60 B = 0.5 GB of the 180 GB; fewer, longer launches: measured best of 64 K / 128 K / 256 K)
 
 struct ScanScratch
 {
