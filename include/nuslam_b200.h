@@ -210,6 +210,10 @@ int nuslam_normalize_angle(const double * rad_in, double * rad_out, int64_t coun
 int nuslam_diffdrive_step(double * state7, const double * thL_new, const double * thR_new, double * twists_out, int64_t count, int mem,
                           int device, void * cuda_stream);
 
+/* rigid2d::integrateTwist (rigid2d/src/rigid2d.cpp:294-328), batched: twists count x 3 (dth, dx, dy) -> transforms count x 4
+ * (cos theta, sin theta, x, y), the Transform2D the twist reaches in unit time (T_bs * T_ss' * T_sb, pure translation for dth == 0). */
+int nuslam_integrate_twist(const double * twists, double * transforms_out, int64_t count, int mem, int device, void * cuda_stream);
+
 /* DiffDrive::convertTwist (diff_drive.cpp:66-78), batched: twists count x 3 -> wheel velocities count x 2 (uL, uR). */
 int nuslam_diffdrive_convert_twist(double wheel_base, double wheel_rad, const double * twists, double * wheel_vel_out, int64_t count, int mem,
                                    int device, void * cuda_stream);

@@ -145,6 +145,18 @@ __device__ __forceinline__ Tf2D integrate_twist(double dth, double dx, double dy
     return tf_mul(tf_mul(tf_inv(T_sb), T_ss), T_sb);   // operator* is left-associative (rigid2d.cpp:211-214,325)
 }
 
+// rigid2d::integrateTwist (rigid2d.cpp:294-328), batched: twists count x 3 (dth, dx, dy) -> transforms count x 4 (cos, sin, x, y)
+__global__ void k_integrate_twist(const double * __restrict__ twists, double * __restrict__ out, int64_t count)
+{
+    const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= count) return;
+    const Tf2D T = integrate_twist(twists[3 * b], twists[3 * b + 1], twists[3 * b + 2]);
+    out[4 * b] = T.c;
+    out[4 * b + 1] = T.s;
+    out[4 * b + 2] = T.x;
+    out[4 * b + 3] = T.y;
+}
+
 __global__ void k_diffdrive_step(double * __restrict__ state, const double * __restrict__ thL, const double * __restrict__ thR,
                                  double * __restrict__ twists, int64_t count)
 {

@@ -819,7 +819,8 @@ int elementwise_io(const double * in, double * out, int64_t count, int in_width,
     const int threads = 256;
     const int64_t blocks = (count + threads - 1) / threads;
     if (which == 0) nuslam::k_cartesian2polar<<<(unsigned) blocks, threads, 0, st>>>(d_in, d_out, count);
-    else nuslam::k_normalize_angle<<<(unsigned) blocks, threads, 0, st>>>(d_in, d_out, count);
+    else if (which == 1) nuslam::k_normalize_angle<<<(unsigned) blocks, threads, 0, st>>>(d_in, d_out, count);
+    else nuslam::k_integrate_twist<<<(unsigned) blocks, threads, 0, st>>>(d_in, d_out, count);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && mem == NUSLAM_HOST)
     {
@@ -840,6 +841,11 @@ int nuslam_cartesian2polar(const double * xy, double * rb, int64_t count, int me
 int nuslam_normalize_angle(const double * rad_in, double * rad_out, int64_t count, int mem, int device, void * cuda_stream)
 {
     return elementwise_io(rad_in, rad_out, count, 1, 1, mem, device, cuda_stream, 1);
+}
+
+int nuslam_integrate_twist(const double * twists, double * transforms_out, int64_t count, int mem, int device, void * cuda_stream)
+{
+    return elementwise_io(twists, transforms_out, count, 3, 4, mem, device, cuda_stream, 2);
 }
 
 int nuslam_diffdrive_step(double * state7, const double * thL_new, const double * thR_new, double * twists_out, int64_t count, int mem,

@@ -35,7 +35,7 @@ EXPORTS = [
     "nuslam_ekf_update", "nuslam_ekf_measurement_model", "nuslam_ekf_step", "nuslam_ekf_step_async", "nuslam_ekf_wait_async",
     "nuslam_ekf_scan_step", "nuslam_ekf_map_to_odom", "nuslam_ekf_synchronize",
     "nuslam_cartesian2polar", "nuslam_normalize_angle", "nuslam_scan_detect", "nuslam_classify_and_fit",
-    "nuslam_diffdrive_step", "nuslam_diffdrive_convert_twist", "nuslam_world_step",
+    "nuslam_diffdrive_step", "nuslam_diffdrive_convert_twist", "nuslam_world_step", "nuslam_integrate_twist",
 ]
 
 
@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
         l.nuslam_scan_detect.argtypes = [vp, i64, C.c_double, C.c_double, vp, vp, vp, vp, i32, C.c_int, C.c_int, vp]
         l.nuslam_classify_and_fit.argtypes = [vp, vp, vp, i64, vp, vp, C.c_int, C.c_int, vp]
         l.nuslam_diffdrive_step.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.c_int, vp]
+        l.nuslam_integrate_twist.argtypes = [vp, vp, i64, C.c_int, C.c_int, vp]
         l.nuslam_diffdrive_convert_twist.argtypes = [C.c_double, C.c_double, vp, vp, i64, C.c_int, C.c_int, vp]
         _lib = l
     return _lib

@@ -8,6 +8,15 @@ import numpy as np
 from .nuslam import NUSLAM_HOST, _check, lib
 
 
+def integrateTwist(twists, device=0):
+    """rigid2d::integrateTwist (rigid2d.cpp:294-328), batched: twists [N,3] (dth, dx, dy) -> [N,4] = (cos, sin, x, y) of the
+    Transform2D the twist reaches in unit time."""
+    tw = np.ascontiguousarray(np.atleast_2d(np.asarray(twists, dtype=np.float64)))
+    out = np.empty((tw.shape[0], 4))
+    _check(lib().nuslam_integrate_twist(tw.ctypes.data, out.ctypes.data, tw.shape[0], NUSLAM_HOST, device, None), "nuslam_integrate_twist")
+    return out
+
+
 class DiffDrive:
     """B differential-drive robots. ``config`` rows are (x, y, th); wheel angles start at (thL, thR) = 0 unless given."""
 

@@ -318,6 +318,19 @@ def test_pipelined_host_steps_match_synchronous(cuda_lib):
     assert np.array_equal(xa, xb) and np.array_equal(sa, sb) and np.array_equal(na, nb)
 
 
+def test_integrate_twist_matches_oracle(cuda_lib, orc):
+    """rigid2d::integrateTwist (rigid2d.cpp:294-328): pure translations (dth == 0 exactly), rotations, general twists."""
+    from shermbot_navigation_b200 import rigid2d
+    g = np.random.default_rng(12)
+    tw = g.uniform(-2, 2, (300, 3))
+    tw[:40, 0] = 0.0
+    tw[40:60, 1:] = 0.0
+    got = rigid2d.integrateTwist(tw)
+    want = np.stack([orc.integrate_twist(*t) for t in tw])
+    assert np.abs(got - want).max() < 1e-14
+    assert np.array_equal(got[:40], np.column_stack([np.ones(40), np.zeros(40), tw[:40, 1], tw[:40, 2]]))
+
+
 def test_diffdrive_matches_oracle(cuda_lib, orc):
     """rigid2d::DiffDrive getTwist + operator() and convertTwist (diff_drive.cpp:66-146), batched on the device, against the oracle:
     the arithmetic is + - * / in the reference's order, so everything but sin / cos / atan rounding is bit-identical."""
