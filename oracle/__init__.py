@@ -219,6 +219,11 @@ class OracleLib:
                             _d(tr) if trace else None, 1 if init is not None else 0, int(nthreads))
         return dict(x=x, sigma=np.transpose(s, (0, 2, 1)).copy(), seen=seen, status=status, ids_out=ids_out, trace=tr)
 
+    def ekf_stepper(self, n, robot0, map0, Q, R, nthreads=1):
+        """A persistent batch of B reference filters advanced one slam.cpp:262-319 iteration per call, state kept in the library's own
+        layout between calls (no per-step copies or transposes on the Python side): what bench.py's reference arm times."""
+        return _Stepper(self, n, robot0, map0, Q, R, nthreads)
+
     def map_to_odom(self, odom3, est3):
         """EKFSlam::broadcast_map2odom_tf (slam.cpp:175-210): (tx, ty, yaw) of the map -> odom transform."""
         o, e, out = _f64(odom3), _f64(est3), np.empty(3)
@@ -283,6 +288,30 @@ class OracleLib:
         self._c.orc_scan_detect_batch(S, r.ctypes.data_as(_fp), float(min_range), float(max_range),
                                       cob.ctypes.data_as(_sp), _i(ncl), _i(nci), _d(circ), kmax, int(nthreads))
         return dict(cluster_of_beam=cob, n_clusters=ncl, n_circles=nci, circles=circ)
+
+
+class _Stepper:
+    def __init__(self, lib, n, robot0, map0, Q, R, nthreads):
+        self.lib, self.n, self.nthreads = lib, int(n), int(nthreads)
+        self.robot0 = _f64(np.atleast_2d(robot0))
+        self.B = self.robot0.shape[0]
+        ln = 3 + 2 * self.n
+        self.map0 = _f64(np.broadcast_to(map0, (self.B, 2 * self.n)))
+        self.Qc = _f64(np.asarray(Q, dtype=np.float64).reshape(3, 3).T)
+        self.Rc = _f64(np.asarray(R, dtype=np.float64).reshape(2, 2).T)
+        self.x = np.zeros((self.B, ln))
+        self.s = np.zeros((self.B, ln, ln))   # the library's layout (column-major per filter)
+        self.seen = np.zeros(self.B, dtype=np.int32)
+        self.status = np.zeros(self.B, dtype=np.int32)
+        self.started = False
+
+    def step(self, twists, z, ids):
+        """twists (B,3) f64, z (B,m,2) f64, ids (B,m) int32: all C-contiguous."""
+        assert twists.flags["C_CONTIGUOUS"] and z.flags["C_CONTIGUOUS"] and ids.flags["C_CONTIGUOUS"] and ids.dtype == np.int32
+        m = z.shape[1]
+        self.lib._c.orc_ekf_run(self.n, self.B, 1, m, _d(self.robot0), _d(self.map0), _d(self.Qc), _d(self.Rc), _d(twists), _d(z), _i(ids),
+                                _d(self.x), _d(self.s), _i(self.seen), _i(self.status), None, None, 1 if self.started else 0, self.nthreads)
+        self.started = True
 
 
 _cache: dict[str, OracleLib] = {}
