@@ -178,7 +178,7 @@ int nuslam_ekf_measurement_model(nuslam_ekf * h, const int32_t * j, double * zha
 int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, const int32_t * ids, int32_t m,
                     int32_t * ids_out, int mem);
 
-/* Pipelined form of nuslam_ekf_step for HOST buffers (known correspondence): the call enqueues (1) the host->device copy of this
+/* Pipelined form of nuslam_ekf_step for HOST buffers (ids may be NULL: unknown correspondence): the call enqueues (1) the host->device copy of this
  * step's twists / z / ids, (2) the fused step, (3) the device->host copy of the resulting state vector into x_out (B x len f64),
  * on three streams chained by events, and returns at once; up to three steps are in flight, so the copies of steps t+1 and t-1
  * overlap the kernel of step t. All host pointers should be page-locked and must stay untouched until a later call has

@@ -716,7 +716,7 @@ int nuslam_ekf_scan_step(nuslam_ekf * h, const double * twists, const float * ra
 
 int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * z, const int32_t * ids, int32_t m, double * x_out)
 {
-    if (!h || !twists || !ids || !x_out) return fail(NUSLAM_ERR_INVALID, "null argument (the pipelined step takes known correspondence)");
+    if (!h || !twists || !x_out) return fail(NUSLAM_ERR_INVALID, "null argument");
     if (m < 0 || (m > 0 && !z)) return fail(NUSLAM_ERR_INVALID, "m < 0 or null z");
     if (select_device(h)) return NUSLAM_ERR_CUDA;
     if (!h->s_in)
@@ -736,7 +736,7 @@ int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * 
     const size_t B = (size_t) h->batch, l = (size_t) h->len;
     int rc = sl.tw.reserve(sizeof(double) * 3 * B);
     if (!rc) rc = sl.z.reserve(sizeof(double) * 2 * B * (m > 0 ? m : 1));
-    if (!rc) rc = sl.ids.reserve(sizeof(int32_t) * B * (m > 0 ? m : 1));
+    if (!rc && ids) rc = sl.ids.reserve(sizeof(int32_t) * B * (m > 0 ? m : 1));
     if (!rc) rc = sl.xsnap.reserve(sizeof(double) * l * B);
     if (rc) return rc;
     // stage 1 (copy-in stream): host -> device
@@ -744,13 +744,13 @@ int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * 
     if (m > 0)
     {
         CU(cudaMemcpyAsync(sl.z.p, z, sizeof(double) * 2 * B * m, cudaMemcpyHostToDevice, h->s_in));
-        CU(cudaMemcpyAsync(sl.ids.p, ids, sizeof(int32_t) * B * m, cudaMemcpyHostToDevice, h->s_in));
+        if (ids) CU(cudaMemcpyAsync(sl.ids.p, ids, sizeof(int32_t) * B * m, cudaMemcpyHostToDevice, h->s_in));
     }
     CU(cudaEventRecord(sl.h2d_done, h->s_in));
     // stage 2 (compute stream): the step on device buffers, then a snapshot of x so that the next step may start at once
     CU(cudaStreamWaitEvent(h->stream, sl.h2d_done, 0));
-    rc = nuslam_ekf_step(h, static_cast<const double *>(sl.tw.p), static_cast<const double *>(sl.z.p), static_cast<const int32_t *>(sl.ids.p), m,
-                         nullptr, NUSLAM_DEVICE);
+    rc = nuslam_ekf_step(h, static_cast<const double *>(sl.tw.p), static_cast<const double *>(sl.z.p),
+                         ids ? static_cast<const int32_t *>(sl.ids.p) : nullptr, m, nullptr, NUSLAM_DEVICE);
     if (rc) return rc;
     CU(cudaMemcpyAsync(sl.xsnap.p, h->x, sizeof(double) * l * B, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaEventRecord(sl.kernel_done, h->stream));

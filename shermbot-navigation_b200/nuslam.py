@@ -316,9 +316,12 @@ class BatchedExtendedKalman:
         """Pipelined host-buffer step (nuslam_ekf_step_async): numpy views of page-locked buffers; ``x_out`` [B,len] receives the state
         vector once the step has left the pipeline (three calls later, or after ``wait_async``)."""
         for a, dt in ((twists, np.float64), (z, np.float64), (ids, np.int32), (x_out, np.float64)):
+            if a is None and dt == np.int32:
+                continue   # unknown correspondence: associateLandmark on the device
             if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"]):
                 raise NuslamError("step_async takes contiguous numpy arrays of the exact dtype (no hidden copies in a pipelined call)")
-        _check(lib().nuslam_ekf_step_async(self._h, twists.ctypes.data, z.ctypes.data, ids.ctypes.data, int(z.shape[1]), x_out.ctypes.data),
+        _check(lib().nuslam_ekf_step_async(self._h, twists.ctypes.data, z.ctypes.data, ids.ctypes.data if ids is not None else None, int(z.shape[1]),
+                                           x_out.ctypes.data),
                "nuslam_ekf_step_async")
 
     def wait_async(self):

@@ -297,8 +297,10 @@ def test_cartesian2polar_and_normalize(cuda_lib, orc):
     assert np.abs(got - np.array([orc.normalize_angle(v) for v in a])).max() < 1e-14
 
 
-def test_pipelined_host_steps_match_synchronous(cuda_lib):
-    """nuslam_ekf_step_async (three streams, three steps in flight) gives exactly the states of the synchronous host-buffer steps."""
+@pytest.mark.parametrize("known", [True, False])
+def test_pipelined_host_steps_match_synchronous(cuda_lib, known):
+    """nuslam_ekf_step_async (three streams, three steps in flight) gives exactly the states of the synchronous host-buffer steps,
+    with known correspondence and with associateLandmark on the device (ids = None)."""
     B, T, n = 512, 9, 12
     sc = synth.ekf_scenario(B, T, n=n, seed=71)
     a = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="fast")
@@ -306,7 +308,7 @@ def test_pipelined_host_steps_match_synchronous(cuda_lib):
     outs = [np.zeros((B, 27)) for _ in range(T)]
     tw = [np.ascontiguousarray(sc["twists"][t]) for t in range(T)]
     zz = [np.ascontiguousarray(sc["z"][t]) for t in range(T)]
-    ii = [np.ascontiguousarray(sc["ids"][t]) for t in range(T)]
+    ii = [np.ascontiguousarray(sc["ids"][t]) if known else None for t in range(T)]
     for t in range(T):
         a.step_async(tw[t], zz[t], ii[t], outs[t])
     a.wait_async()
