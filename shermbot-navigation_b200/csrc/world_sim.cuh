@@ -8,8 +8,8 @@
 //   :405-471  simulate_lidar_scanner 54 one-degree rays around each tube's bearing, ray / circle intersection, min per beam
 // and rigid2d/src/diff_drive.cpp:66-78 (convertTwist), :111-146 (operator()), :154-159 (changeConfig).
 //
-// One warp per robot. The motion update is a few dozen flops (every lane evaluates it, lane 0 stores); the scan is 54 rays x T tubes
-// spread over the lanes, reduced per beam with a shared-memory atomicMin on the float bit pattern (ranges are non-negative; the
+// Two launches: the motion update with one thread per robot (it is a few dozen scalar operations with libm calls), then the scan
+// with one warp per robot, 54 rays x T tubes spread over the lanes, reduced per beam with a shared-memory atomicMin on the float bit pattern (ranges are non-negative; the
 // reference's `if (distance < ranges[ind]) ranges[ind] = distance` is order-independent: the result is float(min)), then written as
 // one coalesced 1 440-byte row. Arithmetic is the reference's operation order, unfused; cos / sin of the integer-degree ray
 // directions come from a host-libm table like the detector's (bit-identical to the oracle); atan2 / sincos of the pose from the
@@ -97,12 +97,10 @@ __device__ __forceinline__ double world_ray(double x1, double y1, double c, doub
     return add_(max_range, 1.0);
 }
 
-__global__ void __launch_bounds__(32 * kWorldWarps) k_world_step(const WorldParams p)
+// stage 1: the motion update, one THREAD per robot (a few dozen scalar operations with libm calls: one lane's worth of work)
+__global__ void __launch_bounds__(128) k_world_motion(const WorldParams p)
 {
-    __shared__ int s_r[kWorldWarps][360];
-    __shared__ int s_ta[kWorldWarps][kWorldMaxTubes];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t b = (int64_t) blockIdx.x * kWorldWarps + warp;
+    const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.count) return;
     double * w = p.world + 9 * b;
     const double wheelBase = w[0], wheelRad = w[1];
@@ -145,7 +143,6 @@ __global__ void __launch_bounds__(32 * kWorldWarps) k_world_step(const WorldPara
         x = add_(x, dq_x);
         y = add_(y, dq_y);
     }
-    if (lane == 0)
     {
         w[2] = x;
         w[3] = y;
@@ -160,6 +157,18 @@ __global__ void __launch_bounds__(32 * kWorldWarps) k_world_step(const WorldPara
             p.joints[p.count + b] = jR;
         }
     }
+}
+
+// stage 2: simulate_lidar_scanner :405-471, one WARP per robot: 54 rays x T tubes spread over the lanes
+__global__ void __launch_bounds__(32 * kWorldWarps) k_world_scan(const WorldParams p)
+{
+    __shared__ int s_r[kWorldWarps][360];
+    __shared__ int s_ta[kWorldWarps][kWorldMaxTubes];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b = (int64_t) blockIdx.x * kWorldWarps + warp;
+    if (b >= p.count) return;
+    const double * w = p.world + 9 * b;
+    const double x = w[2], y = w[3], th = w[4];   // the configuration after the motion update
     // simulate_lidar_scanner :405-471
     const float fill = (float) add_(p.max_range, 1.0);   // :416
     for (int k = lane; k < 360; k += 32) s_r[warp][k] = __float_as_int(fill);
@@ -195,7 +204,8 @@ inline cudaError_t launch_world_step(const WorldParams & p, int device, cudaStre
     cudaError_t e = world_tables_init(device);
     if (e != cudaSuccess) return e;
     const int64_t blocks = (p.count + kWorldWarps - 1) / kWorldWarps;
-    k_world_step<<<(unsigned) blocks, 32 * kWorldWarps, 0, stream>>>(p);
+    k_world_motion<<<(unsigned) ((p.count + 127) / 128), 128, 0, stream>>>(p);
+    k_world_scan<<<(unsigned) blocks, 32 * kWorldWarps, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
