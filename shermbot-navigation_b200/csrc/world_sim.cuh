@@ -68,9 +68,14 @@ __device__ __forceinline__ double world_ray(double x1, double y1, double c, doub
     const double x2 = add_(x1, mul_(max_range, c));
     const double y2 = add_(y1, mul_(max_range, s));
     const double dx = sub_(x2, x1), dy = sub_(y2, y1);
-    const double dr = sqrt(add_(mul_(dx, dx), mul_(dy, dy)));
     const double det = sub_(mul_(x1, y2), mul_(x2, y1));
-    const double rr = mul_(tube_rad, tube_rad), dr2 = mul_(dr, dr);
+    const double rr = mul_(tube_rad, tube_rad);
+    // Most rays of the 54-degree window pass the tube far away. dr^2 equals max_range^2 to ~1e-15 (a unit direction times
+    // max_range), so det^2 above r^2 max_range^2 with a 1e-9 margin plus the reference's 1e-5 tangency band means dis < -1e-5 for
+    // certain: the reference's last branch, without the square root. Everything closer takes the reference's own expressions.
+    if (det * det > fma(rr * (max_range * max_range), 1.0 + 1e-9, 2e-5)) return add_(max_range, 1.0);
+    const double dr = sqrt(add_(mul_(dx, dx), mul_(dy, dy)));
+    const double dr2 = mul_(dr, dr);
     const double dis = sub_(mul_(rr, dr2), mul_(det, det));
     if (fabs(dis) < 1e-5)
     {
