@@ -309,6 +309,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         if (st0 & (kStatusMapFull | kStatusSingular))   // the reference process died on an earlier scan
         {
             if (p.ids_out && lane < p.m) p.ids_out[bf * p.m + lane] = 0;
+            if (p.x_snap && vlane) p.x_snap[bf * LEN + lane] = x;
             leave();
             continue;
         }
@@ -795,6 +796,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     img[2 * LEN + lane] = Cy;
                 }
                 p.x[bf * LEN + lane] = x;
+                if (p.x_snap) p.x_snap[bf * LEN + lane] = x;
             }
             fence_proxy_async();
             __syncwarp();
@@ -839,6 +841,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     __stcs(gw + 2 * LEN + lane, Cy);
                 }
                 p.x[bf * LEN + lane] = x;
+                if (p.x_snap) p.x_snap[bf * LEN + lane] = x;
             }
             if (lane == 0 && status != st0) p.status[bf] = status;
         }

@@ -449,6 +449,8 @@ struct EkfParams
     unsigned options;        // NUSLAM_OPT_* (0 = the reference's behaviour)
     const int32_t * m_valid; // B or null: filter b uses only its first m_valid[b] (<= m) measurements (fused scan step)
     int32_t * ids_out;       // B x m or null
+    double * x_snap;         // B x len or null: a second copy of the state vector after the step (pipelined host path: the snapshot the
+                             // device -> host copy reads while the next step already runs)
     double Q[9], R[4];
     double amin, amax;
 };
@@ -509,6 +511,8 @@ __device__ __forceinline__ void strict_filter(const EkfParams & p, const int64_t
         {
             if (p.ids_out)
                 for (int i = lane; i < p.m; i += kWarp) p.ids_out[mb + i] = 0;
+            if (p.x_snap)
+                for (int e = lane; e < p.len; e += kWarp) p.x_snap[b * p.len + e] = f.x[e];
             return;
         }
         const int seen_snapshot = seen;                               // slam.cpp:251
@@ -546,6 +550,8 @@ __device__ __forceinline__ void strict_filter(const EkfParams & p, const int64_t
             f.update(z0, z1, id, status, p.R);                              // slam.cpp:318
         }
         f.store(gx, gS, true);
+        if (p.x_snap)
+            for (int e = lane; e < p.len; e += kWarp) p.x_snap[b * p.len + e] = f.x[e];
         if (lane == 0)
         {
             p.seen[b] = seen;

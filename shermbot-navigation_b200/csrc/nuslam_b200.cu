@@ -108,6 +108,7 @@ struct nuslam_ekf
     double * lg_P = nullptr;
     int32_t * lg_seen_snap = nullptr;
     DevBuf lg_ids_slot, lg_assoc_result;   // unknown correspondence in large-map mode
+    double * x_snap_next = nullptr;        // pipelined host path: where the next step's kernels also write the state vector
     int32_t * worklist = nullptr;   // batch entries
     int32_t * wl_count = nullptr;   // [0] = entries, [1] = finished blocks of the list kernel
     size_t strict_smem = 0;   // per-warp shared memory of the strict kernels, bytes
@@ -161,6 +162,7 @@ nuslam::EkfParams make_params(nuslam_ekf * h)
     p.amin = h->cfg.assoc_min;
     p.amax = h->cfg.assoc_max;
     p.options = h->cfg.options;
+    p.x_snap = h->x_snap_next;
     return p;
 }
 
@@ -749,10 +751,15 @@ int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * 
     CU(cudaEventRecord(sl.h2d_done, h->s_in));
     // stage 2 (compute stream): the step on device buffers, then a snapshot of x so that the next step may start at once
     CU(cudaStreamWaitEvent(h->stream, sl.h2d_done, 0));
+    // the step kernels write the snapshot themselves (216 B per filter next to the state store) where they can; the large-map
+    // kernels do not: a device-to-device copy stands in
+    const bool in_kernel_snapshot = !h->large;
+    h->x_snap_next = in_kernel_snapshot ? static_cast<double *>(sl.xsnap.p) : nullptr;
     rc = nuslam_ekf_step(h, static_cast<const double *>(sl.tw.p), static_cast<const double *>(sl.z.p),
                          ids ? static_cast<const int32_t *>(sl.ids.p) : nullptr, m, nullptr, NUSLAM_DEVICE);
+    h->x_snap_next = nullptr;
     if (rc) return rc;
-    CU(cudaMemcpyAsync(sl.xsnap.p, h->x, sizeof(double) * l * B, cudaMemcpyDeviceToDevice, h->stream));
+    if (!in_kernel_snapshot) CU(cudaMemcpyAsync(sl.xsnap.p, h->x, sizeof(double) * l * B, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaEventRecord(sl.kernel_done, h->stream));
     // stage 3 (copy-out stream): device -> host
     CU(cudaStreamWaitEvent(h->s_out, sl.kernel_done, 0));
