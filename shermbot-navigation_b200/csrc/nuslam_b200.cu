@@ -15,6 +15,7 @@
 #include "ekf_strict.cuh"
 #include "ekf_misc.cuh"
 #include "ekf_fast.cuh"
+#include "ekf_pair.cuh"
 #include "scan_detect.cuh"
 #include "ekf_large.cuh"
 #include "world_sim.cuh"
@@ -188,7 +189,10 @@ int launch_strict(nuslam_ekf * h, const nuslam::EkfParams & p)
 template <int OP>
 int launch_fast_then_strict(nuslam_ekf * h, const nuslam::EkfParams & p, bool do_predict)
 {
-    int rc = nuslam::launch_fast(h->cfg.n_landmarks, p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream);
+    // known correspondence at the BASELINE map size: two filters per warp (ekf_pair.cuh); everything else one filter per warp
+    int rc = (nuslam::pair_supported(h->cfg.n_landmarks, p) && !(p.ids == nullptr && !do_predict))
+                 ? nuslam::launch_pair_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
+                 : nuslam::launch_fast(h->cfg.n_landmarks, p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream);
     if (rc == -1) return fail(NUSLAM_ERR_UNSUPPORTED, "FAST mode covers n_landmarks <= 12, m <= 16");
     if (rc) return cuda_fail((cudaError_t) rc, "fast kernel launch");
     const int warps = h->strict_warps;

@@ -257,6 +257,7 @@ def test_step_unknown_association_teacher_forced(cuda_lib, orc, mode):
             state = (o["x"], o["sigma"], o["seen"])
         print(f"[step/unknown {geometry}/{mode}] id mismatches {mism} of {B * T * n}, worst x rel {worst:.3e}")
         assert mism == 0
+        assert worst < TOL
 
 
 def test_full_size_batch_consistency(cuda_lib, orc):
@@ -401,6 +402,35 @@ def test_fast_step_shapes(cuda_lib, orc, B, n, m, dropout):
     xo, so, _ = oracle_state(fs)
     x, s, _, _ = eng.get_state()
     assert rel_max(x, xo) < TOL and max(rel_max(s[b], so[b]) for b in range(B)) < TOL
+
+
+@pytest.mark.parametrize("B,m,dropout", [(64, 12, 0.0), (33, 12, 0.3), (7, 5, 0.0), (1, 12, 0.0), (6, 16, 0.1)])
+def test_pair_kernel_matches_single_filter_kernel(cuda_lib, orc, B, m, dropout, monkeypatch):
+    """The two-filters-per-warp kernel (ekf_pair.cuh) evaluates the statements of the one-filter-per-warp kernel (ekf_fast.cuh) in a
+    different lane layout: the same scenario through both (NUSLAM_PAIR=0 selects the latter, read at every call) must agree to
+    rounding, odd batches (a pair with one filter), dropped measurements and odd / repeated measurement counts included, and both
+    sit within 1e-9 of the oracle (test_fast_step_shapes checks that for whichever kernel is the default)."""
+    n, T = 12, 10
+    sc = synth.ekf_scenario(B, T, n=n, seed=300 + B + m)
+    rng = np.random.default_rng(B * 17 + m)
+    sel = np.stack([np.stack([rng.permutation(n)[:m] if m <= n else rng.integers(0, n, m) for _ in range(B)]) for _ in range(T)])
+    z = np.ascontiguousarray(np.take_along_axis(sc["z"], sel[..., None], axis=2))
+    ids = np.take_along_axis(sc["ids"], sel, axis=2).astype(np.int32)
+    ids[1:][rng.random(ids[1:].shape) < dropout] = 0
+    first = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][:1], sc["z"][:1], sc["ids"][:1])
+    out = {}
+    for pair in ("1", "0"):
+        monkeypatch.setenv("NUSLAM_PAIR", pair)
+        eng = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="fast")
+        eng.set_state(first["x"], first["sigma"], first["seen"])
+        for t in range(1, T):
+            eng.step(sc["twists"][t], z[t], ids[t])
+        out[pair] = eng.get_state()
+    (x1, s1, n1, st1), (x0, s0, n0, st0) = out["1"], out["0"]
+    assert np.array_equal(n1, n0) and np.array_equal(st1, st0) and not st1.any()
+    ex, es = rel_max(x1, x0), max(rel_max(s1[b], s0[b]) for b in range(B))
+    print(f"[pair vs single, B={B} m={m}] x rel {ex:.2e}, Sigma rel {es:.2e}")
+    assert ex < 1e-13 and es < 1e-13
 
 
 @pytest.mark.parametrize("B,n", [(64, 12), (16, 6), (12, 8), (10, 3), (9, 10)])
