@@ -5,8 +5,10 @@
  * (nuslam/include/nuslam/slam_library.hpp:18-113, nuslam/include/nuslam/circle_fit_library.hpp:18-28)
  * and `librigid2d`. Every entry point below is the batched (B filters / S scans per call) form of one
  * of those functions and cites the interface it replaces; the B = 1 C++ facade that keeps the
- * reference's class and function names lives in include/nuslam_b200/ (slam_library.hpp,
- * circle_fit_library.hpp, rigid2d.hpp, diff_drive.hpp).
+ * reference's class and function names is include/nuslam_b200/slam_library.hpp (namespaces slam_library
+ * and circle_fit), with forwarding headers include/nuslam_b200/compat/nuslam/{slam_library,
+ * circle_fit_library}.hpp for unmodified callers. rigid2d stays the caller's own host library (it has no
+ * third-party arithmetic); its functions on the path have batched entry points below.
  *
  * Conventions (all inherited from the reference):
  *   - state vector x = [theta, x, y, m1x, m1y, ...], length len = 3 + 2n   (slam_library.cpp:46-59)
@@ -194,6 +196,9 @@ int nuslam_ekf_wait_async(nuslam_ekf * h);
 int nuslam_ekf_map_to_odom(nuslam_ekf * h, const double * odom_state7, double * out, int mem);
 
 int nuslam_ekf_synchronize(nuslam_ekf * h);
+/* The cudaStream_t every NUSLAM_DEVICE call of this handle enqueues on (the one given to nuslam_ekf_create, or the handle's own
+ * non-blocking stream): a caller that produces inputs / consumes outputs on another stream orders the two with events on it. */
+int nuslam_ekf_get_stream(nuslam_ekf * h, void ** cuda_stream_out);
 
 /* slam_library::cartesian2polar(x, y), slam_library.cpp:16-22, batched: xy count x 2 -> rb count x 2. */
 int nuslam_cartesian2polar(const double * xy, double * rb, int64_t count, int mem, int device,
@@ -250,6 +255,19 @@ int nuslam_world_step(double * world, const double * cmd, const double * noise, 
 int nuslam_scan_detect(const float * ranges, int64_t n_scans, double min_range, double max_range,
                        int16_t * cluster_of_beam, int32_t * n_clusters, int32_t * n_circles,
                        double * circles, int32_t max_circles, int mem, int device, void * cuda_stream);
+
+/* Arithmetic of circleFit (circle_fit_library.cpp:15-134) on the batched paths (nuslam_scan_detect, nuslam_ekf_scan_step):
+ *   NUSLAM_FIT_MOMENT (default): the Hyper fit from warp-shuffle moment reductions, one fused kernel per call; circles agree with
+ *                                the reference to <= 1e-9 relative (measured ~1e-13), every integer output is exact; a scan whose
+ *                                decisions could hinge on rounding is re-run in NUSLAM_FIT_JACOBI arithmetic
+ *   NUSLAM_FIT_JACOBI:           SVD -> eig_sym -> solve in the operation order the oracle defines for Armadillo's calls
+ * Process-wide; returns the previous mode (any other value only queries). The environment variable NUSLAM_SCAN_FIT=jacobi selects
+ * the second at start-up. nuslam_scan_last_fallbacks: how many scans of the calling thread's last NUSLAM_FIT_MOMENT call on
+ * `device` were re-run (diagnostics; synchronises the device), -1 if none was made. */
+#define NUSLAM_FIT_MOMENT 0
+#define NUSLAM_FIT_JACOBI 1
+int nuslam_scan_set_fit(int mode);
+int nuslam_scan_last_fallbacks(int device);
 
 /* circle_fit::classifyCluster / circleFit on explicit point lists: C clusters, cluster c owns points
  * offsets[c] .. offsets[c+1]-1 of px/py. is_circle: C (0/1); fit: C x 4 (marker.id, cx, cy, R). */

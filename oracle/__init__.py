@@ -39,10 +39,16 @@ def build(verbose: bool = False) -> None:
         print(out.stdout, out.stderr)
     if out.returncode != 0:
         raise RuntimeError("oracle build failed")
+    # the reference's own circle-fit test against the B200 facade (needs /root/reference and the built CUDA library; a no-op otherwise)
+    out = subprocess.run(["make", "-C", str(HERE), "facade_tests"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout, out.stderr)
+    if out.returncode != 0:
+        raise RuntimeError("facade_tests build failed")
 
 
 def lib_path(kind: str) -> Path:
-    return {"ref": HERE / "_ref" / "libnuslam_ref.so", "port": HERE / "libnuslam_oracle.so",
+    return {"ref": HERE / "_ref" / "libnuslam_ref.so", "port": HERE / "libnuslam_oracle.so", "ref_blas": HERE / "_ref" / "libnuslam_ref_blas.so",
             "ref_det": HERE / "_ref" / "libnuslam_ref_det.so", "port_det": HERE / "libnuslam_oracle_det.so"}[kind]
 
 

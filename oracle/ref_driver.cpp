@@ -37,6 +37,14 @@ namespace
     {
         Silence() { std::cout.setstate(std::ios::badbit); }
     } silence_instance;
+#ifdef ORACLE_SHIM_BLAS
+    // timing variant: one BLAS thread per calling thread (the driver's own std::thread pool partitions the filters)
+    extern "C" void ORACLE_SHIM_SET_THREADS(int);
+    struct BlasThreads
+    {
+        BlasThreads() { ORACLE_SHIM_SET_THREADS(1); }
+    } blas_threads_instance;
+#endif
 
     arma::mat to_mat(const double * p, int r, int c)
     {

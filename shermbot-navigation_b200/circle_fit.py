@@ -15,6 +15,19 @@ import numpy as np
 from .nuslam import NUSLAM_DEVICE, NUSLAM_HOST, SCAN_UB, NuslamError, _check, _is_torch, lib
 
 BEAMS = 360
+FIT_MOMENT, FIT_JACOBI = 0, 1   # NUSLAM_FIT_* of include/nuslam_b200.h
+
+
+def set_fit(mode) -> int:
+    """Arithmetic of circleFit on the batched paths: ``"moment"`` (default: Hyper fit from warp-shuffle moment reductions, circles
+    within 1e-9 of the reference) or ``"jacobi"`` (SVD -> eig_sym -> solve in the oracle's operation order). Returns the previous mode."""
+    code = {"moment": FIT_MOMENT, "jacobi": FIT_JACOBI}.get(mode, mode)
+    return int(lib().nuslam_scan_set_fit(int(code)))
+
+
+def last_fallbacks(device=0) -> int:
+    """Scans of this thread's last moment-mode call that were re-run by the oracle-order kernel (-1: no such call)."""
+    return int(lib().nuslam_scan_last_fallbacks(int(device)))
 
 
 def scan_detect(ranges, min_range, max_range, max_circles=16, want_cluster_of_beam=True, device=0, stream=None):

@@ -553,6 +553,17 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     break;
                 }
                 assoc_id = ((hitA >> (__ffs(any) - 1)) & 1u) ? __ffs(any) : -1;
+                if (assoc_id > 0)
+                {
+                    // a landmark that is counted in `seen` but still carries the INT_MAX prior (set_state, or associate without update):
+                    // its first touch belongs to the oracle-order kernel, exactly as with known correspondence
+                    const double d0 = __shfl_sync(kFull, diag, 1 + 2 * assoc_id), d1 = __shfl_sync(kFull, diag, 2 + 2 * assoc_id);
+                    if (d0 > kFirstTouchVariance || d1 > kFirstTouchVariance)
+                    {
+                        handed_over = true;
+                        break;
+                    }
+                }
                 if (p.ids_out && lane == 0) p.ids_out[bf * p.m + i0] = assoc_id;
                 __syncwarp();
             }

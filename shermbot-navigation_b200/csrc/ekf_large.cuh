@@ -206,11 +206,12 @@ __device__ __forceinline__ void large_update(const LargeParams & p, const double
     const double * S = p.sigma + (int64_t) b * len * len;
     double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
     double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
-    if (id < 1 || id > p.n)   // block-uniform
+    if (id < 1 || id > p.n || (p.status[b] & (kStatusMapFull | kStatusSingular)))   // block-uniform
     {
+        // (a filter the reference's process would have died on stays frozen, as in the STRICT and FAST kernels)
         // no measurement in this slot: K = 0, W = 0 contribute nothing to the pass (U, V of the slot were cleared at its start)
         if (j < len) xo[j] = x[j];
-        if (j == 0 && id > p.n) p.status[b] |= kStatusBadId;
+        if (j == 0 && id > p.n && !(p.status[b] & (kStatusMapFull | kStatusSingular))) p.status[b] |= kStatusBadId;
         return;
     }
     const int c = 3 + 2 * (id - 1);

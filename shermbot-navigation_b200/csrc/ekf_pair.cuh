@@ -26,8 +26,12 @@ namespace nuslam
 {
 
 #ifndef NUSLAM_PAIR_CTAS
-#define NUSLAM_PAIR_CTAS 12
+#define NUSLAM_PAIR_CTAS 8
 #endif
+#ifndef NUSLAM_PAIR_STAGES
+#define NUSLAM_PAIR_STAGES 2   // 2: buffer A prefetches the next pair while buffer B is exchange area / output image; 1: one buffer
+#endif
+constexpr int kPairStages = NUSLAM_PAIR_STAGES;
 constexpr int kPairCtasPerSm = NUSLAM_PAIR_CTAS;
 // registers per thread: the 64 K registers of an SM over kPairCtasPerSm single-warp CTAs, in the allocation granule of 8
 #ifndef NUSLAM_PAIR_REGS
@@ -41,16 +45,92 @@ struct __align__(16) PairSmem
     double2 wt[2][36];        // Wt of the chunk's two updates (DMMA B operand)
     double rho[2][2][40];     // per chunk slot: landmark rows c, c+1, entry j at [j + 1]
     double2 kap[2][32];       // per chunk slot: landmark columns (c, c+1) interleaved, entry i
-    double xs[34];            // state broadcast copy, x_i at [i + 1]
     double z[2 * kFastMMax];  // this step's measurements
 };
 
+// shared-memory copy of the atan2 tables (fastmath.cuh): the two halves of a warp index them with different entries, which the
+// constant cache serialises at a long latency -- and the bearing chain is the critical path of an update
+struct PairTables
+{
+    AtanEntry unit[65];
+    AtanOctant oct[8];
+};
+
+__device__ __forceinline__ double atan2_unit_tab(double y, double x, double rs, const PairTables & T)
+{
+    const double ax = abs_bits(x), ay = abs_bits(y);
+    const bool sw = gt_nonneg(ay, ax);
+    const double mx = sw ? ay : ax, mn = sw ? ax : ay;
+    const int idx = (sw ? 1 : 0) | (sign_bit(x) ? 2 : 0) | (sign_bit(y) ? 4 : 0);
+    const float tf = __fdividef((float) mn, (float) mx);
+    const int k = max(0, min(64, __float2int_rn(tf * 64.0f)));
+    const AtanEntry t = T.unit[k];
+    const AtanOctant oc = T.oct[idx];
+    const double u = mn * rs, v = mx * rs;
+    const double e = fma(u, t.c, -(v * t.s));
+    const double e2 = e * e;
+    const double pl = fma(fma(fma(kFastK2[0], e2, kFastK2[1]), e2, kFastK2[2]), e2 * e, e);   // asin(e)
+    const double a = t.hi + (pl + t.lo);
+    return oc.hi + fma(oc.s, a, oc.lo);
+}
+
+// (A) publish landmark rows / columns c, c+1 (slot-space update i, chunk slot s) of either filter from its fragments into vector
+// layout; after inlining into the unrolled update loop s, i and everything derived from them are constants
+template <int NB>
+__device__ __forceinline__ void pair_publish(const double (&C)[2][NB][NB][2], const double (&Rt)[2], const double (&Rx)[2], const double (&Ry)[2],
+                                             const double (&Ct)[2], const double (&Cx)[2], const double (&Cy)[2], PairSmem * const (&EF)[2],
+                                             PairSmem & E, const unsigned live_w, const int g, const int t, const int q, const int s, const int i)
+{
+    const int c = 3 + 2 * i;
+    const int bsel = (2 * i) >> 3, sel = ((2 * i) & 7) >> 1;
+    const bool rsel = (g >> 1) == sel;   // this lane holds row c or c+1
+    const bool csel = t == sel;          // this lane holds columns c, c+1
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+    {
+        if ((live_w >> (16 * f + i)) & 1u)   // warp-uniform
+        {
+            PairSmem & F = *EF[f];
+            double * const rdst = &F.rho[s][g & 1][4 + 2 * t];
+            double2 * const cdst = &F.kap[s][3 + g];
+#pragma unroll
+            for (int qq = 0; qq < NB; ++qq)
+            {
+                if (rsel) *reinterpret_cast<double2 *>(rdst + 8 * qq) = make_double2(C[f][bsel][qq][0], C[f][bsel][qq][1]);
+                if (csel) cdst[8 * qq] = make_double2(C[f][qq][bsel][0], C[f][qq][bsel][1]);
+            }
+        }
+    }
+    // robot part of rows / columns c, c+1: the lanes that own those indices, for their own filter (both filters at once)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+    {
+        const int sl = (c + e) >> 4;
+        if (q == ((c + e) & 15))
+        {
+            E.rho[s][e][1] = Ct[sl];
+            E.rho[s][e][2] = Cx[sl];
+            E.rho[s][e][3] = Cy[sl];
+            double * kd = reinterpret_cast<double *>(&E.kap[s][0]) + e;
+            kd[0] = Rt[sl];
+            kd[2] = Rx[sl];
+            kd[4] = Ry[sl];
+        }
+    }
+}
+
+// slot space: the pair kernel works on P Sigma P^T, x' = P x with the landmarks permuted so that measurement slot j of THIS step is
+// landmark slot j (state indices 3 + 2 j, 4 + 2 j): the update loop is fully unrolled and every register index, shared-memory offset
+// and lane predicate of update i is a compile-time constant (no id decode, no fragment-selection ladder, no address arithmetic).
+// perm[j] = landmark (1-based) held by slot j; orig index of slot-space index i' >= 3: 1 + 2 perm[(i' - 3) / 2] + (i' - 3) % 2.
+// The permutation exists when the step's ids are distinct valid landmarks (slots without a measurement -- id 0, or m < n -- take the
+// unmeasured landmarks); a step with a repeated or out-of-range id goes to the strict work list.
 template <int N>
 __global__ void __maxnreg__(NUSLAM_PAIR_REGS)
 k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ worklist, int32_t * __restrict__ wl_count)
 {
     using G = FastGeom<N>;
-    static_assert(G::FIXED && G::LEN > 16 && G::LEN <= 32, "pair layout: two slots of 16 state indices");
+    static_assert(G::FIXED && G::LEN > 16 && G::LEN <= 32 && 2 * N == 8 * G::NB, "pair layout: two slots of 16 state indices, unpadded fragments");
     constexpr int NB = G::NB, NL = N, LEN = G::LEN, SIG = G::SIG;
     constexpr unsigned kFull = 0xffffffffu;
     constexpr int kImg = SIG * 8;                 // bytes of one Sigma
@@ -59,13 +139,19 @@ k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
     constexpr int kEOff = kImg16 > (int) sizeof(PairSmem) ? kImg16 : (int) sizeof(PairSmem);   // exchange area of filter 1
     constexpr int kNeed = (kPairBytes > kEOff + (int) sizeof(PairSmem)) ? kPairBytes : kEOff + (int) sizeof(PairSmem);
     constexpr int kBuf = (kNeed + 127) / 128 * 128;
-    __shared__ __align__(128) unsigned char buf[kBuf];
+    __shared__ __align__(128) unsigned char stage[kPairStages][kBuf];
+    __shared__ __align__(16) PairTables tabs;
     __shared__ uint64_t full_bar;
+    __shared__ int perm_s[2][16];
+    unsigned char * const buf = stage[0];                    // input images (bulk-loaded)
+    unsigned char * const xbuf = stage[kPairStages - 1];     // exchange areas, then output images
     const int lane = threadIdx.x;
     const int h = lane >> 4, q = lane & 15;       // vector / scalar domain: filter of this lane, index inside the half
     const int g = lane >> 2, t = lane & 3;        // fragment domain
-    PairSmem & E = *reinterpret_cast<PairSmem *>(buf + h * kEOff);                  // this lane's filter
-    PairSmem * const EF[2] = {reinterpret_cast<PairSmem *>(buf), reinterpret_cast<PairSmem *>(buf + kEOff)};
+    PairSmem & E = *reinterpret_cast<PairSmem *>(xbuf + h * kEOff);                  // this lane's filter
+    PairSmem * const EF[2] = {reinterpret_cast<PairSmem *>(xbuf), reinterpret_cast<PairSmem *>(xbuf + kEOff)};
+    for (int k = lane; k < (int) (sizeof(PairTables) / 8); k += 32)
+        reinterpret_cast<double *>(&tabs)[k] = (k < 260) ? reinterpret_cast<const double *>(kAtanUnit)[k] : reinterpret_cast<const double *>(kAtanOct)[k - 260];
     const int64_t npairs = (p.batch + 1) >> 1;
     const int m = p.m;
 
@@ -77,6 +163,10 @@ k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         bulk_g2s(buf, src, bytes, &full_bar);
     };
     uint32_t full_parity = 0;
+#ifdef NUSLAM_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#endif
     if (lane == 0)
     {
         mbar_init(&full_bar, 1);
@@ -99,88 +189,130 @@ k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             prefetch_l2_bulk(p.sigma + 2 * pn * SIG, bytes);
         }
         // ---- small inputs: plain loads, issued before anything waits ----
-        double x[2];
-        x[0] = p.x[bfc * LEN + q];
-        x[1] = (16 + q < LEN) ? p.x[bfc * LEN + 16 + q] : 0.0;
         const int st0 = p.status[bfc], seen0 = p.seen[bfc];
         const int my_id = (q < m) ? p.ids[bfc * m + q] : 0;
         const double my_z0 = (q < m) ? p.z[bfc * m * 2 + 2 * q] : 0.0;
         const double my_z1 = (q < m) ? p.z[bfc * m * 2 + 2 * q + 1] : 0.0;
         const double my_tw = (do_predict && q < 2) ? p.twists[bfc * 3 + q] : 0.0;
+        // ---- the step's permutation: slot q <- landmark lq ----
+        const bool idok = (unsigned) (my_id - 1) < (unsigned) NL;
+        const bool meas = q < m && idok;                                    // slot q carries a measurement
+        const unsigned bits = meas ? (1u << my_id) : 0u;
+        const unsigned maskA = __reduce_or_sync(kFull, h ? 0u : bits), maskB = __reduce_or_sync(kFull, h ? bits : 0u);
+        const unsigned mymask = h ? maskB : maskA;
+        const unsigned meas_w = __ballot_sync(kFull, meas);
+        const unsigned bad_w = __ballot_sync(kFull, q < m && my_id != 0 && !idok);   // an id outside 1..N (negative ids included)
+        const unsigned meas_h = (meas_w >> (16 * h)) & 0xffffu;
+        // a repeated landmark or a bad id: no permutation; the oracle-order kernel runs this filter-step (and flags the bad id)
+        const bool generic = __popc(meas_h) != __popc(mymask) || ((bad_w >> (16 * h)) & 0xffffu) != 0u;
+        int lq = my_id;
+        if (!meas)
+        {
+            const unsigned unmeas = ~mymask & (((1u << NL) - 1u) << 1);
+            const int before = __popc(~meas_h & ((1u << q) - 1u));          // slots without a measurement below this one
+            lq = (int) __fns(unmeas, 0, before + 1);                        // the (before + 1)-th unmeasured landmark
+        }
+        if (q < NL) perm_s[h][q] = ((unsigned) (lq - 1) < (unsigned) NL) ? lq : 1;   // (garbage stays addressable when `generic`)
 
         // ---- Sigma: staging buffer -> registers ----
-        double C[2][NB][NB][2];
-        double Rt[2], Rx[2], Ry[2], Ct[2], Cx[2], Cy[2];
+        mbar_wait(&full_bar, full_parity);
+        full_parity ^= 1;
+        if (2 * pr + 1 >= p.batch && lane == 0) reinterpret_cast<double *>(buf)[SIG - 1] = p.sigma[2 * pr * SIG + SIG - 1];
+        __syncwarp();
         bool need;
         {
-            mbar_wait(&full_bar, full_parity);
-            full_parity ^= 1;
-            if (2 * pr + 1 >= p.batch && lane == 0) reinterpret_cast<double *>(buf)[SIG - 1] = p.sigma[2 * pr * SIG + SIG - 1];
-            __syncwarp();
-#pragma unroll
-            for (int f = 0; f < 2; ++f)
-            {
-                const double * img = reinterpret_cast<const double *>(buf + f * kImg);
-#pragma unroll
-                for (int br = 0; br < NB; ++br)
-#pragma unroll
-                    for (int bc = 0; bc < NB; ++bc)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e)
-                        {
-                            const int row = 3 + 8 * br + g, col = 3 + 8 * bc + 2 * t + e;
-                            C[f][br][bc][e] = (row < LEN && col < LEN) ? img[col * LEN + row] : 0.0;
-                        }
-            }
-            const double * img = reinterpret_cast<const double *>(buf + h * kImg);
-#pragma unroll
-            for (int sl = 0; sl < 2; ++sl)
-            {
-                const int i = 16 * sl + q;
-                const bool v = i < LEN;
-                Ct[sl] = v ? img[i] : 0.0;
-                Cx[sl] = v ? img[LEN + i] : 0.0;
-                Cy[sl] = v ? img[2 * LEN + i] : 0.0;
-                Rt[sl] = v ? img[i * LEN] : 0.0;
-                Rx[sl] = v ? img[i * LEN + 1] : 0.0;
-                Ry[sl] = v ? img[i * LEN + 2] : 0.0;
-            }
             // first touch (INT_MAX prior) or initializeLandmark (slam.cpp:295-297): the strict kernel takes this filter-step
-            const bool idok = (unsigned) (my_id - 1) < (unsigned) NL;
+            const double * img = reinterpret_cast<const double *>(buf + h * kImg);
             const int c = idok ? 1 + 2 * my_id : 3;
             const double d0 = img[c * (LEN + 1)], d1 = img[(c + 1) * (LEN + 1)];
-            need = has && idok && ((do_predict && my_id > seen0) || d0 > kFirstTouchVariance || d1 > kFirstTouchVariance);
-            __syncwarp();   // the images are dead from here on: the buffer becomes the exchange areas
+            need = has && meas && ((do_predict && my_id > seen0) || d0 > kFirstTouchVariance || d1 > kFirstTouchVariance);
         }
         const unsigned need_w = __ballot_sync(kFull, need);
         const bool stat_dead = (st0 & (kStatusMapFull | kStatusSingular)) != 0;   // the reference process died on an earlier scan
-        const bool need_h = ((need_w >> (16 * h)) & 0xffffu) != 0u;
-        const bool dead = !has || stat_dead || need_h;
+        const bool to_strict = has && !stat_dead && (generic || ((need_w >> (16 * h)) & 0xffffu) != 0u);
+        const bool dead = !has || stat_dead || to_strict;
+        // orig state index of this lane's two vector slots
+        int o[2];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl)
+        {
+            const int i = 16 * sl + q;
+            const int j = (i >= 3 && i < LEN) ? (i - 3) >> 1 : 0;
+            o[sl] = (i < 3) ? i : (i < LEN) ? 1 + 2 * perm_s[h][j] + ((i - 3) & 1) : 0;
+        }
+        double x[2];
+        x[0] = p.x[bfc * LEN + o[0]];
+        x[1] = (16 + q < LEN) ? p.x[bfc * LEN + o[1]] : 0.0;
         if (has && stat_dead)
         {
             if (p.ids_out && q < m) p.ids_out[bf * m + q] = 0;
             if (p.x_snap)
             {
-                p.x_snap[bf * LEN + q] = x[0];
-                if (16 + q < LEN) p.x_snap[bf * LEN + 16 + q] = x[1];
+                p.x_snap[bf * LEN + o[0]] = x[0];
+                if (16 + q < LEN) p.x_snap[bf * LEN + o[1]] = x[1];
             }
         }
-        else if (has && need_h && q == 0)
+        else if (to_strict && q == 0)
             worklist[atomicAdd(wl_count, 1)] = (int32_t) bf;
         const unsigned dead_w = __ballot_sync(kFull, dead);
         const bool deadA = (dead_w & 1u) != 0u, deadB = (dead_w & 0x10000u) != 0u;
         if (deadA && deadB)
         {
+            __syncwarp();   // the images have been read (first-touch test)
             if (lane == 0 && next) issue_load(pr + gridDim.x);
             continue;
         }
+        NUSLAM_T(0)
+        double C[2][NB][NB][2];
+        double Rt[2], Rx[2], Ry[2], Ct[2], Cx[2], Cy[2];
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+        {
+            const double * img = reinterpret_cast<const double *>(buf + f * kImg);
+            int ro[NB], co[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+            {
+                ro[b] = 1 + 2 * perm_s[f][4 * b + (g >> 1)] + (g & 1);
+                co[b] = (1 + 2 * perm_s[f][4 * b + t]) * LEN;
+            }
+#pragma unroll
+            for (int br = 0; br < NB; ++br)
+#pragma unroll
+                for (int bc = 0; bc < NB; ++bc)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) C[f][br][bc][e] = img[co[bc] + e * LEN + ro[br]];
+        }
+        {
+            const double * img = reinterpret_cast<const double *>(buf + h * kImg);
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+            {
+                const bool v = 16 * sl + q < LEN;
+                Ct[sl] = v ? img[o[sl]] : 0.0;
+                Cx[sl] = v ? img[LEN + o[sl]] : 0.0;
+                Cy[sl] = v ? img[2 * LEN + o[sl]] : 0.0;
+                Rt[sl] = v ? img[o[sl] * LEN] : 0.0;
+                Rx[sl] = v ? img[o[sl] * LEN + 1] : 0.0;
+                Ry[sl] = v ? img[o[sl] * LEN + 2] : 0.0;
+            }
+        }
+        __syncwarp();   // the images are dead from here on
+        if (kPairStages > 1)
+        {
+            // buffer A is free again: prefetch this CTA's next pair while the current one is computed; buffer B held the previous
+            // pair's output images: wait until the bulk store has read them
+            if (lane == 0)
+            {
+                if (next) issue_load(pr + gridDim.x);
+                bulk_wait_read();
+            }
+            __syncwarp();
+        }
         int status = st0;
         if (!dead && p.ids_out && q < m) p.ids_out[bf * m + q] = my_id > 0 ? my_id : 0;
-        {
-            // an id above N flags the whole filter (sticky)
-            const unsigned bad_w = __ballot_sync(kFull, !dead && my_id > NL);
-            if (!dead && ((bad_w >> (16 * h)) & 0xffffu) != 0u) status |= kStatusBadId;
-        }
+        // measurement slots of the live filters: bit i (filter 0), bit 16 + i (filter 1)
+        const unsigned live_w = __ballot_sync(kFull, meas && !dead);
         // exchange entries that belong to no state index are zero
         if (16 + q >= LEN)
         {
@@ -271,102 +403,42 @@ k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 Cy[0] = add_(Cy[0], p.Q[q + 3 * 2]);
             }
         }
-        E.xs[q + 1] = x[0];
-        E.xs[16 + q + 1] = x[1];
         __syncwarp();
+        NUSLAM_T(1)
 
-        // ---- m sequential updates in chunks of 2 (slam.cpp:279-319, known correspondence) ----
-#pragma unroll 1
-        for (int i0 = 0; i0 < m; i0 += 2)
+        // ---- m sequential updates in chunks of 2 (slam.cpp:279-319), slot space: update i works on state indices 3 + 2 i, 4 + 2 i ----
+        // Shared-memory hand-overs per update: rows / columns -> (sync) -> Pt, Wt -> (sync) -> 2 x 2 part, -Kt -> (sync) -> pose, robot rows.
+        // Everything that depends on the state alone (sqrt d, the bearing, the innovation) is evaluated BEFORE the first hand-over, and
+        // the chunk's second publish is issued behind the first update's Wt hand-over, so that both overlap the waiting.
+#pragma unroll
+        for (int ch = 0; ch < (NL + 1) / 2; ++ch)
         {
-            // the chunk's ids: per filter (fragment domain, warp-uniform) and of this lane's filter
-            int cF[2][2], cc[2];
-            bool liveF[2][2], live[2];
+            if (2 * ch >= m) break;   // warp-uniform
+            double pW0[2], pW1[2], pK0[2], pK1[2];   // this lane's Wt and -Kt of the chunk's first update (lazy correction of the second)
 #pragma unroll
             for (int s = 0; s < 2; ++s)
             {
-                const bool in = i0 + s < m;
-                const int src = in ? i0 + s : 0;
-                const int idA = __shfl_sync(kFull, my_id, src), idB = __shfl_sync(kFull, my_id, 16 + src);
-                liveF[0][s] = in && !deadA && (unsigned) (idA - 1) < (unsigned) NL;
-                liveF[1][s] = in && !deadB && (unsigned) (idB - 1) < (unsigned) NL;
-                cF[0][s] = liveF[0][s] ? 1 + 2 * idA : 3;
-                cF[1][s] = liveF[1][s] ? 1 + 2 * idB : 3;
-                live[s] = h ? liveF[1][s] : liveF[0][s];
-                cc[s] = h ? cF[1][s] : cF[0][s];
-            }
-            // (A) publish the chunk's landmark rows / columns of either filter from its (stale) fragments into vector layout
-#pragma unroll
-            for (int f = 0; f < 2; ++f)
-#pragma unroll
-                for (int s = 0; s < 2; ++s)
-                {
-                    if (liveF[f][s])   // warp-uniform
-                    {
-                        PairSmem & F = *EF[f];
-                        const int c = cF[f][s];
-                        const int tau = c - 3;
-                        const int bsel = tau >> 3;
-                        const bool rsel = (g >> 1) == ((tau & 7) >> 1);   // this lane holds row c or c+1
-                        const bool csel = t == ((tau & 7) >> 1);          // this lane holds columns c, c+1
-                        double * const rdst = &F.rho[s][g & 1][4 + 2 * t];
-                        double2 * const cdst = &F.kap[s][3 + g];
-#define NUSLAM_PUBLISH(b)                                                                                                                  \
-    if constexpr (NB > b)                                                                                                                  \
-    {                                                                                                                                      \
-        _Pragma("unroll") for (int qq = 0; qq < NB; ++qq)                                                                                  \
-        {                                                                                                                                  \
-            if (rsel) *reinterpret_cast<double2 *>(rdst + 8 * qq) = make_double2(C[f][b < NB ? b : 0][qq][0], C[f][b < NB ? b : 0][qq][1]); \
-            if (csel) cdst[8 * qq] = make_double2(C[f][qq][b < NB ? b : 0][0], C[f][qq][b < NB ? b : 0][1]);                               \
-        }                                                                                                                                  \
-    }
-                        if (bsel == 0)
-                        {
-                            NUSLAM_PUBLISH(0)
-                        }
-                        else if (bsel == 1)
-                        {
-                            NUSLAM_PUBLISH(1)
-                        }
-                        else if (bsel == 2)
-                        {
-                            NUSLAM_PUBLISH(2)
-                        }
-                        else
-                        {
-                            NUSLAM_PUBLISH(3)
-                        }
-#undef NUSLAM_PUBLISH
-                        // robot part of rows / columns c, c+1: the lanes of half f that own those indices
-                        if (h == f)
-                        {
-#pragma unroll
-                            for (int sl = 0; sl < 2; ++sl)
-                            {
-                                const int e = 16 * sl + q - c;
-                                if (e == 0 || e == 1)
-                                {
-                                    F.rho[s][e][1] = Ct[sl];
-                                    F.rho[s][e][2] = Cx[sl];
-                                    F.rho[s][e][3] = Cy[sl];
-                                    double * kd = reinterpret_cast<double *>(&F.kap[s][0]) + e;
-                                    kd[0] = Rt[sl];
-                                    kd[2] = Rx[sl];
-                                    kd[4] = Ry[sl];
-                                }
-                            }
-                        }
-                    }
-                }
-            __syncwarp();
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-            {
-                const int c = cc[s];
-                const double2 mxy = *reinterpret_cast<const double2 *>(&E.xs[c + 1]);
-                const double2 zz = *reinterpret_cast<const double2 *>(&E.z[2 * ((i0 + s < m) ? i0 + s : 0)]);
-                const double dx = mxy.x - px, dy = mxy.y - py;
+                const int i = 2 * ch + s;
+                const int c = 3 + 2 * i;
+                const bool live = (live_w >> (16 * h + i)) & 1u;
+                if (s == 0) pair_publish<NB>(C, Rt, Rx, Ry, Ct, Cx, Cy, EF, E, live_w, g, t, q, 0, i);
+                // ---- state-only part: landmark position from the lanes that own it, sqrt d, bearing, innovation (:150-160, :272 no wrap) ----
+                const double mxv = __shfl_sync(kFull, x[c >> 4], 16 * h + (c & 15));
+                const double myv = __shfl_sync(kFull, x[(c + 1) >> 4], 16 * h + ((c + 1) & 15));
+                const double2 zz = *reinterpret_cast<const double2 *>(&E.z[2 * (i < kFastMMax ? i : 0)]);
+                const double dx = mxv - px, dy = myv - py;
                 const double d = fma(dx, dx, dy * dy);
+                const double rs = rsqrt_1(d);
+                double sq = d * rs;
+                sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);   // sqrt(d) to ~1 ulp
+                const double dsq = d * sq;
+                double zb = atan2_unit_tab(dy, dx, rs, tabs) - th;
+                if (__any_sync(kFull, abs_ge_hi(zb, kHiPi)))   // the wrap is the identity inside [-pi, pi]
+                    if (abs_ge_hi(zb, kHiPi)) zb = wrap_angle(zb);
+                double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);
+                const double r00 = d * p.R[0], r10 = dsq * p.R[1], r01 = dsq * p.R[2], r11 = (d * d) * p.R[3];   // D^-1 R D^-1
+                if (s == 0) __syncwarp();   // the chunk's first publish (the second one is ordered by the first update's hand-overs)
+                NUSLAM_T(2)
                 double P0[2], P1[2], W0[2], W1[2];
                 double2 ka, kb, wa2, wb2;
                 if (s == 1)
@@ -379,19 +451,18 @@ k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
 #pragma unroll
                 for (int sl = 0; sl < 2; ++sl)
                 {
-                    const int i = 16 * sl + q;
-                    // landmark rows c, c+1 (this lane = column i) and columns c, c+1 (this lane = row i)
-                    double rho0 = E.rho[s][0][i + 1], rho1 = E.rho[s][1][i + 1];
-                    const double2 kp = E.kap[s][i];
+                    const int ii = 16 * sl + q;
+                    // landmark rows c, c+1 (this lane = column ii) and columns c, c+1 (this lane = row ii)
+                    double rho0 = E.rho[s][0][ii + 1], rho1 = E.rho[s][1][ii + 1];
+                    const double2 kp = E.kap[s][ii];
                     double kap0 = kp.x, kap1 = kp.y;
                     if (s == 1)
                     {
                         // the fragments predate the chunk's first update: bring the four vectors up to date with it
-                        const double2 pW = E.wt[0][i], pK = E.kt[0][i];
-                        rho0 = fma(ka.x, pW.x, fma(ka.y, pW.y, rho0));
-                        rho1 = fma(kb.x, pW.x, fma(kb.y, pW.y, rho1));
-                        kap0 = fma(pK.x, wa2.x, fma(pK.y, wa2.y, kap0));
-                        kap1 = fma(pK.x, wb2.x, fma(pK.y, wb2.y, kap1));
+                        rho0 = fma(ka.x, pW0[sl], fma(ka.y, pW1[sl], rho0));
+                        rho1 = fma(kb.x, pW0[sl], fma(kb.y, pW1[sl], rho1));
+                        kap0 = fma(pK0[sl], wa2.x, fma(pK1[sl], wa2.y, kap0));
+                        kap1 = fma(pK0[sl], wb2.x, fma(pK1[sl], wb2.y, kap1));
                     }
                     // (B) Pt (row role) and Wt (column role)
                     const double pa = kap0 - Cx[sl], pb = kap1 - Cy[sl];
@@ -400,26 +471,20 @@ k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     P1[sl] = fma(dx, pb, fma(-dy, pa, -d * Ct[sl]));
                     W0[sl] = fma(dx, wa, dy * wb);
                     W1[sl] = fma(dx, wb, fma(-dy, wa, -d * Rt[sl]));
-                    E.wt[s][i] = make_double2(W0[sl], W1[sl]);
+                    E.wt[s][ii] = make_double2(W0[sl], W1[sl]);
                 }
                 __syncwarp();
-                // the 2 x 2 part of this lane's filter: M = Wt Ht^T + D^-1 R D^-1, Minv, innovation (:150-160, :272 no wrap)
+                NUSLAM_T(3)
+                if (s == 0 && 2 * ch + 1 < NL) pair_publish<NB>(C, Rt, Rx, Ry, Ct, Cx, Cy, EF, E, live_w, g, t, q, 1, i + 1);
+                // the 2 x 2 part of this lane's filter: M = Wt Ht^T + D^-1 R D^-1, Minv
                 const double2 g0 = E.wt[s][0], g1 = E.wt[s][1], g2 = E.wt[s][2], g3 = E.wt[s][c], g4 = E.wt[s][c + 1];
                 const double e0 = g3.x - g1.x, f0 = g4.x - g2.x, e1 = g3.y - g1.y, f1 = g4.y - g2.y;
-                const double s00 = fma(dx, e0, dy * f0), s01 = fma(dx, f0, fma(-dy, e0, -d * g0.x));
-                const double s10 = fma(dx, e1, dy * f1), s11 = fma(dx, f1, fma(-dy, e1, -d * g0.y));
-                const double rs = rsqrt_1(d);
-                double sq = d * rs;
-                sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);   // sqrt(d) to ~1 ulp
-                const double dsq = d * sq;
-                const double m00 = fma(d, p.R[0], s00), m10 = fma(dsq, p.R[1], s10), m01 = fma(dsq, p.R[2], s01), m11 = fma(d * d, p.R[3], s11);
+                const double m00 = fma(dx, e0, fma(dy, f0, r00)), m01 = fma(dx, f0, fma(-dy, e0, fma(-d, g0.x, r01)));
+                const double m10 = fma(dx, e1, fma(dy, f1, r10)), m11 = fma(dx, f1, fma(-dy, e1, fma(-d, g0.y, r11)));
                 const double det = fma(m00, m11, -m01 * m10);
                 const double idet = rcp_fast(det);
-                double zb = atan2_unit(dy, dx, rs) - th;
-                if (abs_ge_hi(zb, kHiPi)) zb = wrap_angle(zb);   // the identity inside [-pi, pi]
-                double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);
                 // |idet| < ~1e300: false for det = 0, inf or nan, where arma::inv throws (slam_library.cpp:270)
-                const bool ok = live[s] && !abs_ge_hi(idet, kHi1e300);
+                const bool ok = live && !abs_ge_hi(idet, kHi1e300);
                 const double i00 = m11 * idet, i01 = -m01 * idet, i10 = -m10 * idet, i11 = m00 * idet;
                 // (C) -Kt = -Pt Minv
                 double nk0[2], nk1[2];
@@ -434,7 +499,7 @@ k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     // a slot without a measurement (or a singular one) contributes nothing: its update is the identity
                     if (!ok)
                     {
-                        if (live[s]) status |= kStatusSingular;
+                        if (live) status |= kStatusSingular;
                         n0 = 0.0;
                         n1 = 0.0;
 #pragma unroll
@@ -457,25 +522,33 @@ k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     Cx[sl] = fma(nk0[sl], g1.x, fma(nk1[sl], g1.y, Cx[sl]));
                     Cy[sl] = fma(nk0[sl], g2.x, fma(nk1[sl], g2.y, Cy[sl]));
                     x[sl] = fma(-nk0[sl], n0, fma(-nk1[sl], n1, x[sl]));
+                    if (s == 0)
+                    {
+                        pW0[sl] = W0[sl];
+                        pW1[sl] = W1[sl];
+                        pK0[sl] = nk0[sl];
+                        pK1[sl] = nk1[sl];
+                    }
                 }
                 __syncwarp();
+                NUSLAM_T(4)
                 const double2 k0 = E.kt[s][0], k1 = E.kt[s][1], k2 = E.kt[s][2];
                 // replicated pose: what lanes q = 0..2 compute for their own x, evaluated identically by the whole half
                 th = fma(-k0.x, n0, fma(-k0.y, n1, th));
                 px = fma(-k1.x, n0, fma(-k1.y, n1, px));
                 py = fma(-k2.x, n0, fma(-k2.y, n1, py));
-                if (abs_ge_hi(th, kHiPi)) th = wrap_angle(th);   // slam_library.cpp:275-276 (the identity inside [-pi, pi])
+                if (__any_sync(kFull, abs_ge_hi(th, kHiPi)))   // slam_library.cpp:275-276 (the identity inside [-pi, pi])
+                    if (abs_ge_hi(th, kHiPi)) th = wrap_angle(th);
+                if (q == 0) x[0] = th;
 #pragma unroll
                 for (int sl = 0; sl < 2; ++sl)
                 {
-                    if (sl == 0 && q == 0) x[0] = th;
-                    E.xs[16 * sl + q + 1] = x[sl];
                     // robot rows: Sigma -= Kt Wt restricted to them
                     Rt[sl] = fma(k0.x, W0[sl], fma(k0.y, W1[sl], Rt[sl]));
                     Rx[sl] = fma(k1.x, W0[sl], fma(k1.y, W1[sl], Rx[sl]));
                     Ry[sl] = fma(k2.x, W0[sl], fma(k2.y, W1[sl], Ry[sl]));
                 }
-                __syncwarp();
+                NUSLAM_T(5)
             }
             // (D) one DMMA pass per filter applies the chunk to its fragments: C += (-Kt) Wt, k = (u0, u1, v0, v1)
 #pragma unroll
@@ -499,48 +572,52 @@ k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                         for (int bc = 0; bc < NB; ++bc) dmma884(C[f][br][bc][0], C[f][br][bc][1], a[br], b[bc]);
                 }
             }
-            __syncwarp();
+            NUSLAM_T(6)
         }
+        __syncwarp();
 
-        // ---- write back: registers -> output images in the staging buffer -> bulk store ----
+        // ---- write back: registers -> output images (orig order) in the staging buffer -> bulk store ----
 #pragma unroll
         for (int f = 0; f < 2; ++f)
         {
             if (f == 0 ? !deadA : !deadB)
             {
-                double * img = reinterpret_cast<double *>(buf + f * kImg);
+                double * img = reinterpret_cast<double *>(xbuf + f * kImg);
+                int ro[NB], co[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+                {
+                    ro[b] = 1 + 2 * perm_s[f][4 * b + (g >> 1)] + (g & 1);
+                    co[b] = (1 + 2 * perm_s[f][4 * b + t]) * LEN;
+                }
 #pragma unroll
                 for (int br = 0; br < NB; ++br)
 #pragma unroll
                     for (int bc = 0; bc < NB; ++bc)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e)
-                        {
-                            const int row = 3 + 8 * br + g, col = 3 + 8 * bc + 2 * t + e;
-                            if (row < LEN && col < LEN) img[col * LEN + row] = C[f][br][bc][e];
-                        }
+                        for (int e = 0; e < 2; ++e) img[co[bc] + e * LEN + ro[br]] = C[f][br][bc][e];
             }
         }
         if (!dead)
         {
-            double * img = reinterpret_cast<double *>(buf + h * kImg);
+            double * img = reinterpret_cast<double *>(xbuf + h * kImg);
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl)
             {
                 const int i = 16 * sl + q;
                 if (i < LEN)
                 {
-                    img[i * LEN] = Rt[sl];
-                    img[i * LEN + 1] = Rx[sl];
-                    img[i * LEN + 2] = Ry[sl];
+                    img[o[sl] * LEN] = Rt[sl];
+                    img[o[sl] * LEN + 1] = Rx[sl];
+                    img[o[sl] * LEN + 2] = Ry[sl];
                     if (i >= 3)
                     {
-                        img[i] = Ct[sl];
-                        img[LEN + i] = Cx[sl];
-                        img[2 * LEN + i] = Cy[sl];
+                        img[o[sl]] = Ct[sl];
+                        img[LEN + o[sl]] = Cx[sl];
+                        img[2 * LEN + o[sl]] = Cy[sl];
                     }
-                    p.x[bf * LEN + i] = x[sl];
-                    if (p.x_snap) p.x_snap[bf * LEN + i] = x[sl];
+                    p.x[bf * LEN + o[sl]] = x[sl];
+                    if (p.x_snap) p.x_snap[bf * LEN + o[sl]] = x[sl];
                 }
             }
             if (q == 0 && status != st0) p.status[bf] = status;
@@ -550,7 +627,7 @@ k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         if (lane == 0)
         {
             double * gw = p.sigma + 2 * pr * SIG;
-            double * img = reinterpret_cast<double *>(buf);
+            double * img = reinterpret_cast<double *>(xbuf);
             if (!deadA && !deadB)
                 bulk_s2g(gw, img, kPairBytes);
             else if (!deadA)
@@ -565,11 +642,20 @@ k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 gw[SIG] = img[SIG];
                 bulk_s2g(gw + SIG + 1, img + SIG + 1, kImg - 8);
             }
-            // the buffer receives the next pair as soon as the store has read it
-            bulk_wait_read();
-            if (next) issue_load(pr + gridDim.x);
+            if (kPairStages == 1)
+            {
+                // the buffer receives the next pair as soon as the store has read it
+                bulk_wait_read();
+                if (next) issue_load(pr + gridDim.x);
+            }
         }
+        __syncwarp();   // perm_s is rewritten by the next round
+        NUSLAM_T(7)
     }
+#ifdef NUSLAM_TIMING
+    if (blockIdx.x == 0 && lane == 0)
+        for (int k = 0; k < 8; ++k) atomicAdd((unsigned long long *) &g_fast_timing[k], (unsigned long long) tacc[k]);
+#endif
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the last bulk store
 }
 

@@ -532,6 +532,14 @@ __device__ __forceinline__ void strict_filter(const EkfParams & p, const int64_t
                     if (p.ids_out && lane == 0) p.ids_out[mb + i] = 0;
                     continue;
                 }
+                if (id > p.n)
+                {
+                    // not a landmark of this map: flagged and skipped like the FAST and LARGE paths do, `seen` untouched (the reference
+                    // would index its state out of bounds)
+                    status |= kStatusBadId;
+                    if (p.ids_out && lane == 0) p.ids_out[mb + i] = id;
+                    continue;
+                }
                 if (id > seen) seen = id;
             }
             else

@@ -16,6 +16,7 @@
 #include "ekf_misc.cuh"
 #include "ekf_fast.cuh"
 #include "ekf_pair.cuh"
+#include "scan_moment.cuh"
 #include "scan_detect.cuh"
 #include "ekf_large.cuh"
 #include "world_sim.cuh"
@@ -193,7 +194,9 @@ int launch_fast_then_strict(nuslam_ekf * h, const nuslam::EkfParams & p, bool do
     int rc = (nuslam::pair_supported(h->cfg.n_landmarks, p) && !(p.ids == nullptr && !do_predict))
                  ? nuslam::launch_pair_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
                  : nuslam::launch_fast(h->cfg.n_landmarks, p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream);
-    if (rc == -1) return fail(NUSLAM_ERR_UNSUPPORTED, "FAST mode covers n_landmarks <= 12, m <= 16");
+    // not covered by the register kernels (more than 16 measurements per step, ragged counts with known ids, a state pointer that
+    // is not 8-byte aligned): the oracle-order kernel runs the whole batch
+    if (rc == -1) return launch_strict<OP>(h, p);
     if (rc) return cuda_fail((cudaError_t) rc, "fast kernel launch");
     const int warps = h->strict_warps;
     const size_t smem = h->strict_smem * warps;
@@ -208,7 +211,13 @@ int launch_fast_then_strict(nuslam_ekf * h, const nuslam::EkfParams & p, bool do
     const int64_t resident = (int64_t) h->sm_count * 4;
     if (blocks > resident) blocks = resident;
     nuslam::k_ekf_strict_list<OP><<<(unsigned) blocks, warps * 32, smem, h->stream>>>(p, h->worklist, h->wl_count, h->wl_count + 1);
-    CU(cudaGetLastError());
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess)
+    {
+        // the list kernel resets the counters itself when it runs; it did not: the next call must not replay this call's entries
+        cudaMemsetAsync(h->wl_count, 0, sizeof(int32_t) * 2, h->stream);
+        return cuda_fail(le, "strict list kernel launch");
+    }
     return NUSLAM_OK;
 }
 
@@ -699,8 +708,9 @@ int nuslam_ekf_scan_step(nuslam_ekf * h, const double * twists, const float * ra
     double * d_z = static_cast<double *>(h->f_z.p);
     int32_t * d_mv = static_cast<int32_t *>(h->f_mv.p);
     // Landmarks::main_loop, landmarks.cpp:84-109: the first m markers of every scan, in detection order
-    cudaError_t e = nuslam::launch_scan_detect(d_ranges, (int64_t) B, min_range, max_range, nullptr, static_cast<int32_t *>(h->f_ncl.p), d_nci, d_circ, m,
-                                               NUSLAM_SCAN_UB, h->device, h->sm_count, h->stream);
+    cudaError_t e = (nuslam::scan_fit_mode() == nuslam::kFitMoment ? nuslam::launch_scan_moment : nuslam::launch_scan_detect)(
+        d_ranges, (int64_t) B, min_range, max_range, nullptr, static_cast<int32_t *>(h->f_ncl.p), d_nci, d_circ, m, NUSLAM_SCAN_UB, h->device,
+        h->sm_count, h->stream);
     if (e != cudaSuccess) return cuda_fail(e, "scan_detect");
     // slam.cpp:282-286: markers -> (range, bearing)
     const int64_t total = (int64_t) B * m;
@@ -800,6 +810,13 @@ int nuslam_debug_fast_timing(long long * out16, int reset)
     return 0;
 }
 #endif
+
+int nuslam_ekf_get_stream(nuslam_ekf * h, void ** cuda_stream_out)
+{
+    if (!h || !cuda_stream_out) return fail(NUSLAM_ERR_INVALID, "null handle or output");
+    *cuda_stream_out = static_cast<void *>(h->stream);
+    return NUSLAM_OK;
+}
 
 int nuslam_ekf_synchronize(nuslam_ekf * h)
 {
@@ -1010,6 +1027,19 @@ int nuslam_diffdrive_convert_twist(double wheel_base, double wheel_rad, const do
     return NUSLAM_OK;
 }
 
+int nuslam_scan_set_fit(int mode)
+{
+    const int prev = nuslam::scan_fit_mode();
+    if (mode == NUSLAM_FIT_MOMENT || mode == NUSLAM_FIT_JACOBI) nuslam::scan_fit_mode() = mode;
+    return prev;
+}
+
+int nuslam_scan_last_fallbacks(int device)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    return nuslam::scan_moment_fallbacks(device);
+}
+
 int nuslam_scan_detect(const float * ranges, int64_t n_scans, double min_range, double max_range, int16_t * cluster_of_beam,
                        int32_t * n_clusters, int32_t * n_circles, double * circles, int32_t max_circles, int mem, int device,
                        void * cuda_stream)
@@ -1045,8 +1075,9 @@ int nuslam_scan_detect(const float * ranges, int64_t n_scans, double min_range, 
     }
     int sm_count = 0;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
-    cudaError_t e = nuslam::launch_scan_detect(d_ranges, n_scans, min_range, max_range, cluster_of_beam ? d_cob : nullptr, d_ncl, d_nci,
-                                               d_circ, max_circles, NUSLAM_SCAN_UB, device, sm_count > 0 ? sm_count : 148, st);
+    cudaError_t e = (nuslam::scan_fit_mode() == nuslam::kFitMoment ? nuslam::launch_scan_moment : nuslam::launch_scan_detect)(
+        d_ranges, n_scans, min_range, max_range, cluster_of_beam ? d_cob : nullptr, d_ncl, d_nci, d_circ, max_circles, NUSLAM_SCAN_UB, device,
+        sm_count > 0 ? sm_count : 148, st);
     if (e == cudaSuccess && mem == NUSLAM_HOST)
     {
         if (cluster_of_beam) e = cudaMemcpyAsync(cluster_of_beam, d_cob, b_cob, cudaMemcpyDeviceToHost, st);

@@ -1,0 +1,452 @@
+// scan_moment.cuh -- the throughput path of the landmark detector: ONE fused kernel, one warp per 360-beam scan.
+//
+//   clusterPoints (circle_fit_library.cpp:136-206)  ballots + popcounts over the beams, as in scan_detect.cuh: cluster ids are
+//                                                   integer work and stay bit-exact, every quirk of SURVEY.md Appendix A-11 included;
+//                                                   the erase loop's two-state walk (:198-204) is evaluated in closed form (a run of
+//                                                   consecutive small clusters alternates erased / kept, starting with erased)
+//   classifyCluster (:208-250)                      one point per lane: inscribed angles, warp-shuffle segmented sums
+//   circleFit (:15-134)                             the Hyper algebraic fit (Al-Sharadqah / Chernov) from WARP-SHUFFLE MOMENT REDUCTIONS:
+//                                                   centroid, then the six centred moments of (x, y, z = x^2 + y^2), one lane per
+//                                                   cluster solves the characteristic polynomial by Newton's iteration from 0 (its
+//                                                   smallest non-negative root is the "smallest positive eigenvalue" of :91-101) and
+//                                                   forms centre and radius in closed form
+//   Landmarks::main_loop (landmarks.cpp:84-109)     id < 0 / R > 1 filters, circles in detection order
+//
+// The reference reaches the same A = argmin A^T M A / A^T H A through svd -> Y = V S V^T -> eig_sym(Y H^-1 Y) -> solve; on its own
+// kind of data the two routes agree to ~1e-13 relative (measured against oracle/_ref on 36 828 fits: worst published circle 8.4e-14,
+// no gate decision differs). Where a decision of the reference could hinge on rounding -- the classifier's std within 1e-6 of 10
+// degrees, R within 1e-6 of the 1 m gate, a non-finite result, Newton not converging, nearly collinear points that would still be
+// published -- the scan is handed to the oracle-order kernels of scan_detect.cuh (one-sided Jacobi SVD etc.) through a work list.
+// Tolerance on circles: 1e-9 relative (BASELINE.json north_star); cluster ids, cluster and circle counts: exact.
+#pragma once
+#include "scan_detect.cuh"
+
+namespace nuslam
+{
+
+constexpr int kMomWarps = 4;          // scans per CTA
+constexpr int kMomMaxClusters = 32;   // pre-erase clusters handled by the warp (one per lane); busier scans take the work list
+
+struct __align__(16) MomentSmem
+{
+    unsigned pb[kBeams + 8];                  // flat position (in-range beams in beam order) -> beam | pre-erase cluster << 16
+    double acc[kMomMaxClusters][10];          // per cluster: sums X, Y | XX, YY, XY, XZ, YZ, ZZ (centred) | angle, angle^2
+    double org[kMomMaxClusters][2];           // per cluster: its first point (local origin of the sums)
+    short cend[kMomMaxClusters + 8];          // flat position of the cluster's last point
+};
+
+// segmented inclusive scan over the lanes: lanes with equal `key` are contiguous; afterwards the LAST lane of a run holds its total
+template <int NV>
+__device__ __forceinline__ void seg_scan(double (&v)[NV], const int key, const int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const int kk = __shfl_up_sync(0xffffffffu, key, d);
+        const bool take = lane >= d && kk == key;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+        {
+            const double tv = __shfl_up_sync(0xffffffffu, v[k], d);
+            if (take) v[k] += tv;
+        }
+    }
+}
+
+struct ScanGate
+{
+    float max_f, min_f;   // r > max_range <=> r > max_f, r < min_range <=> r < min_f for every float r (the reference compares in double)
+};
+
+// largest float <= v / smallest float >= v (host side)
+inline float float_below(double v)
+{
+    float f = (float) v;
+    if ((double) f > v) f = nextafterf(f, -INFINITY);
+    return f;
+}
+inline float float_above(double v)
+{
+    float f = (float) v;
+    if ((double) f < v) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+__global__ void __launch_bounds__(32 * kMomWarps)
+k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const double min_range, const double max_range, const ScanGate gate,
+              int16_t * __restrict__ cluster_of_beam, int32_t * __restrict__ n_clusters, int32_t * __restrict__ n_circles,
+              double * __restrict__ circles, const int max_circles, const int scan_ub, int32_t * __restrict__ slow, int32_t * __restrict__ slow_count)
+{
+    __shared__ MomentSmem smem_all[kMomWarps];
+    MomentSmem & sm = smem_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    constexpr unsigned kFull = 0xffffffffu;
+    constexpr int kChunks = (kBeams + 31) / 32;   // 12
+    const unsigned lt = (1u << lane) - 1u;
+    for (int64_t s = (int64_t) blockIdx.x * kMomWarps + (threadIdx.x >> 5); s < n_scans; s += (int64_t) gridDim.x * kMomWarps)
+    {
+        const float * rs = ranges + s * kBeams;
+        float r[kChunks + 1];
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k) r[k] = (32 * k + lane < kBeams) ? __ldg(rs + 32 * k + lane) : 0.0f;
+        r[kChunks] = 0.0f;
+        const float r_first = __shfl_sync(kFull, r[0], 0);
+        // ---- per-beam predicates and their ballots (circle_fit_library.cpp:146-190) ----
+        unsigned inr_m[kChunks], clo_m[kChunks];
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k)
+        {
+            const int i = 32 * k + lane;
+            // the next beam's range: lane + 1 of this round, lane 0 of the next round for lane 31, beam 0 for beam 359
+            float nb = __shfl_sync(kFull, lane == 0 ? r[k + 1] : r[k], (lane + 1) & 31);
+            if (i == kBeams - 1) nb = r_first;
+            const float rv = r[k];
+            const bool inr = i < kBeams && !(rv > gate.max_f || rv < gate.min_f);   // :149, NaN counts as in range
+            // :166 |r_i - r_(i+1)| < 0.04 in double. The float difference is within an ulp of the exact one: decided in float unless
+            // it lies within 1e-5 of the threshold (or the ranges are huge), then in double like the reference
+            const float df = fabsf(rv - nb);
+            bool sim = df < 0.04f;
+            if (fabsf(df - 0.04f) < 1e-5f || !(fabsf(rv) < 64.0f) || !(fabsf(nb) < 64.0f)) sim = fabs((double) rv - (double) nb) < 0.04;
+            inr_m[k] = __ballot_sync(kFull, inr);
+            clo_m[k] = __ballot_sync(kFull, inr && !sim);
+        }
+        constexpr int kLastBit = (kBeams - 1) & 31;
+        const bool wrap = ((inr_m[kChunks - 1] >> kLastBit) & 1u) && !((clo_m[kChunks - 1] >> kLastBit) & 1u);
+        // beam 359 in range and similar to beam 0: it is not stored in the flat list but appended to cluster 0 (:170-174)
+        if (wrap) inr_m[kChunks - 1] &= ~(1u << kLastBit);
+        int nc = 0, npts = 0;
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k)
+        {
+            nc += __popc(clo_m[k]);
+            npts += __popc(inr_m[k]);
+        }
+        const int64_t sb = s * kBeams;
+        if (wrap && nc == 0)
+        {
+            // clusters[0].push_back on an empty vector (:173): undefined behaviour in the reference
+            if (cluster_of_beam)
+                for (int i = lane; i < kBeams; i += 32) cluster_of_beam[sb + i] = -1;
+            if (lane == 0)
+            {
+                n_clusters[s] = 0;
+                n_circles[s] = scan_ub;
+            }
+            continue;
+        }
+        if (nc > kMomMaxClusters)
+        {
+            if (lane == 0) slow[atomicAdd(slow_count, 1)] = (int32_t) s;   // the one-warp-per-scan kernel writes every output of this scan
+            continue;
+        }
+        // ---- flat positions, cluster ends ----
+        {
+            int pos_base = 0, clu_base = 0;
+#pragma unroll
+            for (int k = 0; k < kChunks; ++k)
+            {
+                if (inr_m[k] == 0u) continue;   // warp-uniform
+                const bool inr = (inr_m[k] >> lane) & 1u, clo = (clo_m[k] >> lane) & 1u;
+                const int pos = pos_base + __popc(inr_m[k] & lt), clu = clu_base + __popc(clo_m[k] & lt);
+                if (inr)
+                {
+                    sm.pb[pos] = (unsigned) (32 * k + lane) | ((unsigned) clu << 16);
+                    if (clo) sm.cend[clu] = (short) pos;
+                }
+                pos_base += __popc(inr_m[k]);
+                clu_base += __popc(clo_m[k]);
+            }
+        }
+        __syncwarp();
+        // ---- one cluster per lane: extent, erase loop (:198-204) in closed form ----
+        const int cend = (lane < nc) ? (int) sm.cend[lane] : -1;
+        int cstart = __shfl_up_sync(kFull, cend, 1) + 1;
+        if (lane == 0) cstart = 0;
+        const int csize = (lane < nc) ? cend - cstart + 1 + ((lane == 0 && wrap) ? 1 : 0) : 0;
+        const bool small = lane < nc && csize < 3;
+        const unsigned small_m = __ballot_sync(kFull, small);
+        const unsigned big_below = ~small_m & lt;
+        const int run = big_below ? lane - 1 - (31 - __clz((int) big_below)) : lane;   // consecutive small clusters right below this one
+        const bool erased = small && !(run & 1);   // a cluster following an erased one is never examined
+        const unsigned erased_m = __ballot_sync(kFull, erased);
+        const int newidx = (lane < nc && !erased) ? lane - __popc(erased_m & lt) : -1;
+        const int nk = nc - __popc(erased_m);
+        if (cluster_of_beam)
+        {
+            const int new0 = __shfl_sync(kFull, newidx, 0);
+            int clu_base = 0;
+#pragma unroll
+            for (int k = 0; k < kChunks; ++k)
+            {
+                const int i = 32 * k + lane;
+                const bool inr = (inr_m[k] >> lane) & 1u;
+                const int clu = clu_base + __popc(clo_m[k] & lt);
+                const int nidx = __shfl_sync(kFull, newidx, clu & 31);
+                int out = (inr && clu < nc) ? nidx : -1;
+                if (wrap && i == kBeams - 1) out = new0;
+                if (i < kBeams) cluster_of_beam[sb + i] = (int16_t) out;
+                clu_base += __popc(clo_m[k]);
+            }
+        }
+        // ---- points: one per lane, two passes of segmented warp sums (centroid, then centred moments and inscribed angles) ----
+        // a cluster is examined when it survives the erase loop and has at least 3 points (fewer: classifyCluster's std is 0/0 = NaN, :229-249)
+        const bool examined = lane < nc && !erased && csize >= 3;
+        const int ntot = npts + (wrap ? 1 : 0);
+        double ca = 0.0, cb = 0.0;   // centroid of this lane's cluster, relative to its first point
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass)
+        {
+#pragma unroll 1
+            for (int base = 0; base < ntot; base += 32)
+            {
+                const int j = base + lane;
+                const bool iswrap = wrap && j == npts;
+                const unsigned pbv = (j < npts) ? sm.pb[j] : 0u;
+                const int beam = iswrap ? kBeams - 1 : (int) (pbv & 0xffffu);
+                const int clu = iswrap ? 0 : (int) (pbv >> 16);
+                const int src = clu & 31;
+                const int cs = __shfl_sync(kFull, cstart, src), ce = __shfl_sync(kFull, cend, src);
+                const bool ex = __shfl_sync(kFull, examined ? 1 : 0, src) != 0;
+                const bool active = (j < npts || iswrap) && clu < nc && ex;
+                const bool wrapped_cluster = wrap && clu == 0;
+                const int b2 = active ? (int) (sm.pb[cs] & 0xffffu) : 0;
+                const int b3 = !active ? 0 : wrapped_cluster ? kBeams - 1 : (int) (sm.pb[ce] & 0xffffu);
+                // points = r (cos, sin)(deg2rad(beam)) (:161-163), relative to the cluster's first point
+                const double r1 = (double) __ldg(rs + beam), r2 = (double) __ldg(rs + b2), r3 = (double) __ldg(rs + b3);
+                const double x2 = r2 * __ldg(&c_beam_cos[b2]), y2 = r2 * __ldg(&c_beam_sin[b2]);
+                const double X = active ? fma(r1, __ldg(&c_beam_cos[beam]), -x2) : 0.0, Y = active ? fma(r1, __ldg(&c_beam_sin[beam]), -y2) : 0.0;
+                const int key = active ? (iswrap ? 32 : clu) : -1 - lane;
+                const bool tail = lane == 31 || __shfl_down_sync(kFull, key, 1) != key;
+                const bool first = cs >= base;   // the cluster's first contribution to its accumulators
+                if (pass == 0)
+                {
+                    double v[2] = {X, Y};
+                    seg_scan<2>(v, key, lane);
+                    if (tail && active && !iswrap)
+                    {
+                        sm.acc[clu][0] = first ? v[0] : sm.acc[clu][0] + v[0];
+                        sm.acc[clu][1] = first ? v[1] : sm.acc[clu][1] + v[1];
+                        sm.org[clu][0] = x2;
+                        sm.org[clu][1] = y2;
+                    }
+                    __syncwarp();
+                    if (active && iswrap)
+                    {
+                        sm.acc[0][0] += v[0];
+                        sm.acc[0][1] += v[1];
+                    }
+                    __syncwarp();
+                }
+                else
+                {
+                    const double a = __shfl_sync(kFull, ca, src), b = __shfl_sync(kFull, cb, src);
+                    const double Xc = X - a, Yc = Y - b;
+                    const double Z = fma(Xc, Xc, Yc * Yc);
+                    double v[8];
+                    v[0] = active ? Xc * Xc : 0.0;
+                    v[1] = active ? Yc * Yc : 0.0;
+                    v[2] = active ? Xc * Yc : 0.0;
+                    v[3] = active ? Xc * Z : 0.0;
+                    v[4] = active ? Yc * Z : 0.0;
+                    v[5] = active ? Z * Z : 0.0;
+                    // inscribed angle of an interior point P1 over the chord P2 (first) -> P3 (last as stored) (:211-224)
+                    const bool last = iswrap || (!wrapped_cluster && j == ce);
+                    const bool interior = active && j != cs && !last;
+                    double ang = 0.0;
+                    if (interior)
+                    {
+                        const double X3 = fma(r3, __ldg(&c_beam_cos[b3]), -x2), Y3 = fma(r3, __ldg(&c_beam_sin[b3]), -y2);
+                        const double num = fma(Y, X3, -(Y3 * X));
+                        const double den = -fma(X, X - X3, Y * (Y - Y3));
+                        ang = (180.0 / kPiRef) * atan2(num, den);
+                    }
+                    v[6] = ang;
+                    v[7] = ang * ang;
+                    seg_scan<8>(v, key, lane);
+                    if (tail && active && !iswrap)
+                    {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) sm.acc[clu][2 + k] = first ? v[k] : sm.acc[clu][2 + k] + v[k];
+                    }
+                    __syncwarp();
+                    if (active && iswrap)
+                    {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) sm.acc[0][2 + k] += v[k];
+                    }
+                    __syncwarp();
+                }
+            }
+            if (pass == 0 && examined)
+            {
+                const double inv_n = 1.0 / (double) csize;
+                ca = sm.acc[lane][0] * inv_n;
+                cb = sm.acc[lane][1] * inv_n;
+            }
+        }
+        // ---- one cluster per lane: classification, Hyper fit, gates ----
+        bool pub = false, fallback = false;
+        double cx = 0.0, cy = 0.0, R = 0.0;
+        if (examined)
+        {
+            const double inv_n = 1.0 / (double) csize, inv_na = 1.0 / (double) (csize - 2);
+            const double mean = sm.acc[lane][8] * inv_na;
+            const double var = fma(-mean, mean, sm.acc[lane][9] * inv_na);
+            const double sd = sqrt(fmax(var, 0.0));   // population std of the angles in degrees (:229-241); one angle: 0
+            if (!(fabs(sd - 10.0) > 1e-6)) fallback = true;   // too close to the gate (or not finite): the oracle-order kernel decides
+            const bool circle = sd < 10.0;                     // :243
+            if (circle && csize >= 4)                          // circleFit rejects N < 4 with id = -1 (:72-76)
+            {
+                const double Mxx = sm.acc[lane][2] * inv_n, Myy = sm.acc[lane][3] * inv_n, Mxy = sm.acc[lane][4] * inv_n;
+                const double Mxz = sm.acc[lane][5] * inv_n, Myz = sm.acc[lane][6] * inv_n, Mzz = sm.acc[lane][7] * inv_n;
+                const double Mz = Mxx + Myy;
+                const double Cov = fma(Mxx, Myy, -Mxy * Mxy);
+                const double Var = fma(-Mz, Mz, Mzz);
+                // characteristic polynomial of M A = eta H A (Hyper constraint), divided by its trivial factor
+                const double A2 = 4.0 * Cov - 3.0 * Mz * Mz - Mzz;
+                const double A1 = Var * Mz + 4.0 * Cov * Mz - Mxz * Mxz - Myz * Myz;
+                const double A0 = Mxz * (Mxz * Myy - Myz * Mxy) + Myz * (Myz * Mxx - Mxz * Mxy) - Var * Cov;
+                const double A22 = A2 + A2;
+                double eta = 0.0, yv = A0;
+                bool converged = false;
+#pragma unroll 1
+                for (int it = 0; it < 24; ++it)
+                {
+                    const double Dy = A1 + eta * (A22 + 16.0 * eta * eta);
+                    const double en = eta - yv / Dy;
+                    if (en == eta)
+                    {
+                        converged = true;
+                        break;
+                    }
+                    if (!(fabs(en) < 1e300)) break;
+                    const double yn = A0 + en * (A1 + en * (A2 + 4.0 * en * en));
+                    if (fabs(yn) >= fabs(yv))
+                    {
+                        converged = true;   // the residual no longer shrinks: eta is the root to rounding
+                        break;
+                    }
+                    eta = en;
+                    yv = yn;
+                }
+                const double DET = fma(eta, eta, fma(-eta, Mz, Cov));
+                const double hx = (Mxz * (Myy - eta) - Myz * Mxy) / DET * 0.5;
+                const double hy = (Myz * (Mxx - eta) - Mxz * Mxy) / DET * 0.5;
+                R = sqrt(fma(hx, hx, fma(hy, hy, Mz - eta - eta)));
+                cx = hx + ca + sm.org[lane][0];
+                cy = hy + cb + sm.org[lane][1];
+                pub = !(R > 1.0);   // landmarks.cpp:95; a NaN radius would pass the reference's gate: never decided here
+                if (!converged || !(fabs(R) < 1e300) || !(fabs(cx) < 1e300) || !(fabs(cy) < 1e300)) fallback = true;
+                if (fabs(R - 1.0) < 1e-6) fallback = true;
+                if (pub && !(Cov > 1e-9 * Mz * Mz)) fallback = true;   // nearly collinear yet published: conditioning too poor to promise 1e-9
+            }
+        }
+        if (__any_sync(kFull, fallback))
+        {
+            if (lane == 0) slow[atomicAdd(slow_count, 1)] = (int32_t) s;   // rewrites every output of this scan (cluster_of_beam stays the same)
+            continue;
+        }
+        // ---- publication in detection order (landmarks.cpp:84-109) ----
+        const unsigned pm = __ballot_sync(kFull, pub);
+        if (pub)
+        {
+            const int slot = __popc(pm & lt);
+            if (slot < max_circles)
+            {
+                double * cout = circles + (s * (int64_t) max_circles + slot) * 4;
+                cout[0] = cx;
+                cout[1] = cy;
+                cout[2] = R;
+                cout[3] = (double) newidx;
+            }
+        }
+        if (lane == 0)
+        {
+            n_clusters[s] = nk;
+            n_circles[s] = __popc(pm);
+        }
+        __syncwarp();
+    }
+}
+
+// circle-fit arithmetic of the throughput path: the moment route above (default) or the oracle-order Jacobi pipeline of scan_detect.cuh
+constexpr int kFitMoment = 0, kFitJacobi = 1;
+inline int & scan_fit_mode()
+{
+    static int mode = [] {
+        const char * e = getenv("NUSLAM_SCAN_FIT");
+        return (e && (e[0] == 'j' || e[0] == 'J' || e[0] == '1')) ? kFitJacobi : kFitMoment;
+    }();
+    return mode;
+}
+
+inline ScanScratch & moment_scratch(int device)
+{
+    static thread_local ScanScratch scratch[64];
+    return scratch[(device >= 0 && device < 64) ? device : 0];
+}
+
+inline cudaError_t launch_scan_moment(const float * ranges, int64_t n_scans, double min_range, double max_range, int16_t * cluster_of_beam,
+                                      int32_t * n_clusters, int32_t * n_circles, double * circles, int32_t max_circles, int scan_ub,
+                                      int device, int sm_count, cudaStream_t stream)
+{
+    cudaError_t e = scan_tables_init(device);
+    if (e != cudaSuccess) return e;
+    // work list of the scans that need the oracle-order kernel + its counter
+    ScanScratch & sc = moment_scratch(device);
+    size_t need = ((size_t) n_scans * sizeof(int32_t) + 255) / 256 * 256 + 256;
+    if (sc.bytes >= need) need = sc.bytes;   // the counter lives in the last 256 bytes of the allocation
+    if (sc.bytes < need)
+    {
+        if (sc.p) cudaFree(sc.p);
+        sc.p = nullptr;
+        sc.bytes = 0;
+        e = cudaMalloc(&sc.p, need);
+        if (e != cudaSuccess) return e;
+        sc.bytes = need;
+    }
+    int32_t * slow = static_cast<int32_t *>(sc.p);
+    int32_t * slow_count = reinterpret_cast<int32_t *>(static_cast<char *>(sc.p) + need - 256);
+    e = cudaMemsetAsync(slow_count, 0, sizeof(int32_t), stream);
+    if (e != cudaSuccess) return e;
+    ScanGate gate;
+    gate.max_f = float_below(max_range);
+    gate.min_f = float_above(min_range);
+    int64_t blocks = (n_scans + kMomWarps - 1) / kMomWarps;
+    const int64_t resident = (int64_t) sm_count * 8;
+    if (blocks > resident) blocks = resident;
+    if (blocks < 1) blocks = 1;
+    k_scan_moment<<<(unsigned) blocks, 32 * kMomWarps, 0, stream>>>(ranges, n_scans, min_range, max_range, gate, cluster_of_beam, n_clusters, n_circles,
+                                                                 circles, max_circles, scan_ub, slow, slow_count);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // the scans the moment route does not decide: oracle-order clustering + Jacobi fit, one warp per scan (usually an empty list)
+    const size_t smem = sizeof(ScanSmem) * kScanWarps;
+    static bool configured_dev[kMaxDevices] = {false};
+    bool & configured = configured_dev[(device >= 0 && device < kMaxDevices) ? device : 0];
+    if (!configured)
+    {
+        e = cudaFuncSetAttribute(k_scan_detect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    ScanPipe none;
+    memset(&none, 0, sizeof(none));
+    int64_t sblocks = (n_scans + kScanWarps - 1) / kScanWarps;
+    if (sblocks > sm_count) sblocks = sm_count;
+    k_scan_detect<true><<<(unsigned) sblocks, 32 * kScanWarps, smem, stream>>>(ranges, n_scans, min_range, max_range, cluster_of_beam, n_clusters, n_circles,
+                                                                            circles, max_circles, scan_ub, slow, slow_count, none);
+    return cudaGetLastError();
+}
+
+// number of scans the last launch_scan_moment of this thread on `device` handed to the oracle-order kernel (diagnostics; blocking copy)
+inline int scan_moment_fallbacks(int device)
+{
+    ScanScratch & sc = moment_scratch(device);
+    if (!sc.p || sc.bytes < 256) return -1;
+    int32_t v = -1;
+    if (cudaMemcpy(&v, static_cast<char *>(sc.p) + sc.bytes - 256, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int) v;
+}
+
+}   // namespace nuslam

@@ -36,6 +36,7 @@ EXPORTS = [
     "nuslam_ekf_scan_step", "nuslam_ekf_map_to_odom", "nuslam_ekf_synchronize",
     "nuslam_cartesian2polar", "nuslam_normalize_angle", "nuslam_scan_detect", "nuslam_classify_and_fit",
     "nuslam_diffdrive_step", "nuslam_diffdrive_convert_twist", "nuslam_world_step", "nuslam_integrate_twist",
+    "nuslam_ekf_get_stream", "nuslam_scan_set_fit", "nuslam_scan_last_fallbacks",
 ]
 
 
@@ -84,6 +85,9 @@ def lib() -> C.CDLL:
         l.nuslam_world_step.argtypes = [vp, vp, vp, C.c_double, vp, i32, C.c_double, C.c_double, C.c_double, vp, vp, i64, C.c_int, C.c_int, vp]
         l.nuslam_ekf_scan_step.argtypes = [vp, vp, vp, C.c_double, C.c_double, i32, vp, vp, vp, C.c_int]
         l.nuslam_ekf_step_async.argtypes = [vp, vp, vp, vp, i32, vp]
+        l.nuslam_scan_set_fit.argtypes = [C.c_int]
+        l.nuslam_ekf_get_stream.argtypes = [vp, C.POINTER(vp)]
+        l.nuslam_scan_last_fallbacks.argtypes = [C.c_int]
         l.nuslam_ekf_wait_async.argtypes = [vp]
         l.nuslam_ekf_synchronize.argtypes = [vp]
         l.nuslam_cartesian2polar.argtypes = [vp, vp, i64, C.c_int, C.c_int, vp]
@@ -163,9 +167,35 @@ class BatchedExtendedKalman:
         self._h = h
         self._keep = None
         self.stream_ptr = stream   # the cudaStream_t the handle launches on when the caller supplied one (None: the handle's own stream)
+        hs = C.c_void_p()
+        _check(l.nuslam_ekf_get_stream(self._h, C.byref(hs)), "nuslam_ekf_get_stream")
+        self._stream = hs.value or 0   # the stream every DEVICE call enqueues on
         robot = np.ascontiguousarray(robot)
         _check(l.nuslam_ekf_init(self._h, robot.ctypes.data, mp.ctypes.data if mp is not None else None, NUSLAM_HOST),
                "nuslam_ekf_init")
+
+    # ---- stream ordering for CUDA-tensor arguments ----
+    # A DEVICE call only enqueues work on the handle's stream. When that is not torch's current stream, the wrapper orders the two
+    # with events: the handle's stream first waits for everything queued on torch's current stream (the producers of the argument
+    # tensors), and torch's current stream afterwards waits for the call's kernels, so that tensors returned by the call (and the
+    # state tensors of bind_state) can be used by ordinary torch code without a manual synchronize. No host synchronisation.
+    def _order_begin(self, *args):
+        tens = [a for a in args if _is_torch(a) and a.is_cuda]
+        if not tens:
+            return None
+        import torch
+        dev = tens[0].device
+        cur = torch.cuda.current_stream(dev)
+        if cur.cuda_stream == self._stream:
+            return None   # same stream: program order
+        hs = torch.cuda.ExternalStream(self._stream, device=dev)
+        hs.wait_stream(cur)
+        return cur, hs
+
+    @staticmethod
+    def _order_end(tok):
+        if tok is not None:
+            tok[0].wait_stream(tok[1])
 
     def close(self):
         if getattr(self, "_h", None):
@@ -192,7 +222,9 @@ class BatchedExtendedKalman:
             sigma = np.ascontiguousarray(np.transpose(np.asarray(sigma, dtype=np.float64).reshape(self.batch, self.len, self.len), (0, 2, 1)))
         px, ps = _ptr(x, np.float64), _ptr(sigma, np.float64)
         pn, pt = _ptr(seen, np.int32), _ptr(status, np.int32)
+        tok = self._order_begin(x, sigma, seen, status)
         _check(lib().nuslam_ekf_set_state(self._h, px[0], ps[0], pn[0], pt[0], _mem_of(px, ps, pn, pt)), "nuslam_ekf_set_state")
+        self._order_end(tok)
 
     def get_state(self):
         x = np.empty((self.batch, self.len))
@@ -225,14 +257,18 @@ class BatchedExtendedKalman:
     # ---- ExtendedKalman members, batched ----
     def predict(self, twists):
         p = _ptr(twists, np.float64)
+        tok = self._order_begin(twists)
         _check(lib().nuslam_ekf_predict(self._h, p[0], p[2]), "nuslam_ekf_predict")
+        self._order_end(tok)
 
     def associateLandmark(self, z):
         pz = _ptr(z, np.float64)
         if pz[2] == NUSLAM_DEVICE:
             import torch
             out = torch.empty(self.batch, dtype=torch.int32, device=z.device)
+            tok = self._order_begin(z, out)
             _check(lib().nuslam_ekf_associate(self._h, pz[0], out.data_ptr(), NUSLAM_DEVICE), "nuslam_ekf_associate")
+            self._order_end(tok)
             return out
         out = np.empty(self.batch, dtype=np.int32)
         _check(lib().nuslam_ekf_associate(self._h, pz[0], out.ctypes.data, NUSLAM_HOST), "nuslam_ekf_associate")
@@ -240,12 +276,16 @@ class BatchedExtendedKalman:
 
     def initializeLandmark(self, z, ids):
         pz, pi = _ptr(z, np.float64), _ptr(ids, np.int32)
+        tok = self._order_begin(z, ids)
         _check(lib().nuslam_ekf_initialize_landmark(self._h, pz[0], pi[0], _mem_of(pz, pi)), "nuslam_ekf_initialize_landmark")
+        self._order_end(tok)
 
     def update(self, z, ids, twists=None):
         """``twists`` is accepted for signature parity with update(tw, z, id) and ignored, as in the reference."""
         pz, pi = _ptr(z, np.float64), _ptr(ids, np.int32)
+        tok = self._order_begin(z, ids)
         _check(lib().nuslam_ekf_update(self._h, pz[0], pi[0], _mem_of(pz, pi)), "nuslam_ekf_update")
+        self._order_end(tok)
 
     def computeTheoreticalMeasurement(self, j):
         j = np.ascontiguousarray(np.broadcast_to(np.asarray(j, dtype=np.int32), (self.batch,)))
@@ -274,7 +314,9 @@ class BatchedExtendedKalman:
             else:
                 out = np.empty((self.batch, m), dtype=np.int32)
                 optr = out.ctypes.data
+        tok = self._order_begin(twists, z, ids, out)
         _check(lib().nuslam_ekf_step(self._h, pt[0], pz[0], pi[0], m, optr, mem), "nuslam_ekf_step")
+        self._order_end(tok)
         return out
 
     def scan_step(self, twists, ranges, min_range, max_range, m, return_all=False):
@@ -294,8 +336,10 @@ class BatchedExtendedKalman:
             else:
                 outs = (np.empty((self.batch,), np.int32), np.empty((self.batch, m, 2), np.float64), np.empty((self.batch, m), np.int32))
                 ptrs = tuple(o.ctypes.data for o in outs)
+        tok = self._order_begin(twists, ranges, *outs)
         _check(lib().nuslam_ekf_scan_step(self._h, pt[0], pr[0], float(min_range), float(max_range), int(m), ptrs[0], ptrs[1], ptrs[2], mem),
                "nuslam_ekf_scan_step")
+        self._order_end(tok)
         return outs if return_all else None
 
     def map_to_odom(self, odom_state7):
@@ -309,7 +353,9 @@ class BatchedExtendedKalman:
         else:
             out = np.empty((self.batch, 3))
             optr = out.ctypes.data
+        tok = self._order_begin(odom_state7, out)
         _check(lib().nuslam_ekf_map_to_odom(self._h, po[0], optr, po[2]), "nuslam_ekf_map_to_odom")
+        self._order_end(tok)
         return out
 
     def step_async(self, twists, z, ids, x_out):

@@ -430,7 +430,8 @@ def test_pair_kernel_matches_single_filter_kernel(cuda_lib, orc, B, m, dropout, 
     assert np.array_equal(n1, n0) and np.array_equal(st1, st0) and not st1.any()
     ex, es = rel_max(x1, x0), max(rel_max(s1[b], s0[b]) for b in range(B))
     print(f"[pair vs single, B={B} m={m}] x rel {ex:.2e}, Sigma rel {es:.2e}")
-    assert ex < 1e-13 and es < 1e-13
+    tol = 1e-13 if m <= n else 1e-10   # m > n: repeated landmarks inside a step go to the oracle-order kernel
+    assert ex < tol and es < tol
 
 
 @pytest.mark.parametrize("B,n", [(64, 12), (16, 6), (12, 8), (10, 3), (9, 10)])

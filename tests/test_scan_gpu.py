@@ -74,19 +74,32 @@ def test_classify_and_fit_matches_oracle(cuda_lib, orc):
             assert (np.abs(fit[k][~nan] - want[~nan]) <= 1e-9 * np.maximum(np.abs(want[~nan]), 1e-3)).all(), (k, fit[k], want)
 
 
-@pytest.mark.parametrize("noise", [0.0, 0.001])
-def test_scan_detect_matches_oracle(cuda_lib, orc, noise):
+@pytest.fixture(params=["moment", "jacobi"])
+def fit_mode(request, cuda_lib):
+    """Both circle-fit arithmetics of the batched path: the moment route (default) and the oracle-order Jacobi pipeline."""
+    from shermbot_navigation_b200 import circle_fit
+    prev = circle_fit.set_fit(request.param)
+    yield request.param
+    circle_fit.set_fit(prev)
+
+
+@pytest.mark.parametrize("noise", [0.0, 0.001, 0.01])
+def test_scan_detect_matches_oracle(cuda_lib, orc, noise, fit_mode):
     from shermbot_navigation_b200 import circle_fit
     sd = synth.scan_scenario(4096, seed=41, noise_sigma=noise)
     want = orc.scan_detect_batch(sd["ranges"], sd["min_range"], sd["max_range"], nthreads=0)
     got = circle_fit.scan_detect(sd["ranges"], sd["min_range"], sd["max_range"])
     worst = compare_scans(got, want)
-    assert (want["n_circles"] > 0).mean() > 0.5
-    print(f"[scan_detect noise={noise}] 4096 scans: cluster ids / counts exact, circles worst rel {worst:.2e}, "
-          f"{int((want['n_circles'] == -2000).sum())} UB scans, mean circles {want['n_circles'].clip(0).mean():.2f}")
+    assert noise >= 0.01 or (want["n_circles"] > 0).mean() > 0.5
+    fb = circle_fit.last_fallbacks() if fit_mode == "moment" else 0
+    print(f"[scan_detect noise={noise} fit={fit_mode}] 4096 scans: cluster ids / counts exact, circles worst rel {worst:.2e}, "
+          f"{int((want['n_circles'] == -2000).sum())} UB scans, mean circles {want['n_circles'].clip(0).mean():.2f}, "
+          f"scans re-run in oracle order {fb}")
+    # the moment route must decide (almost) every scan itself: the work list is for decisions that hinge on rounding
+    assert fb <= 0.01 * 4096
 
 
-def test_scan_edge_cases(cuda_lib, oracle_libs):
+def test_scan_edge_cases(cuda_lib, oracle_libs, fit_mode):
     """Empty scan, everything in one cluster, wrap rule, wrap with no cluster (UB), short clusters and the erase-loop skip,
     NaN ranges (count as in range), every beam a closer."""
     from shermbot_navigation_b200 import circle_fit
@@ -100,7 +113,7 @@ def test_scan_edge_cases(cuda_lib, oracle_libs):
     assert got["n_clusters"][0] == 0 and got["n_circles"][0] == 0
 
 
-def test_scan_full_size_properties(cuda_lib, orc):
+def test_scan_full_size_properties(cuda_lib, orc, fit_mode):
     """BASELINE config 3 size on the device (262 144 scans here, 1 M in bench): the batch is 64 copies of 4096 distinct scans; every
     copy must equal its twin bit for bit, and the distinct ones must match the oracle."""
     import torch

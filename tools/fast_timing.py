@@ -31,8 +31,11 @@ eng.synchronize()
 lib.nuslam_debug_fast_timing(out, 0)
 v = np.array(list(out), dtype=np.float64)
 nblk = 148 * int(os.environ.get("NUSLAM_FAST_CTAS_PER_SM", "16"))
-filters = K * ((B + nblk - 1) // nblk)   # filters processed by block 0 / warp 0
+per_warp = int(os.environ.get("NUSLAM_FILTERS_PER_WARP", "1"))   # 2: the pair kernel
+filters = K * per_warp * ((B // per_warp + nblk - 1) // nblk)   # filters processed by block 0 / warp 0
 names = ["load", "predict", "publish", "pre (Pt,Wt)", "2x2 part + Kt", "post (x, robot)", "dmma", "store"]
+if per_warp == 2:
+    names = ["inputs + perm + wait", "load regs + predict", "publish", "V1 (Pt,Wt)", "2x2 part + Kt + cols", "pose + rows", "dmma", "store"]
 tot = v[:8].sum()
 print(f"block 0 / warp 0: {filters} filter-steps, {tot / filters:.0f} cycles per filter-step ({tot / filters / 12:.0f} per update)")
 for k, nm in enumerate(names):
