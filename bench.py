@@ -165,6 +165,50 @@ def bind_to_gpu_numa_node(index: int):
         return f"unchanged ({type(e).__name__})"
 
 
+def config_dict(world):
+    """The workload description shared verbatim by both arms (the driver compares them)."""
+    return {"workload": "BASELINE.json configs[1]: batched 64K independent EKF filters x 12 landmarks, known correspondence, fp64",
+            "filters_per_gpu": FILTERS_PER_GPU, "landmarks": N_LANDMARKS, "state_len": LEN,
+            "l2": f"inputs larger than L2: filter state {FILTERS_PER_GPU * (LEN + LEN * LEN) * 8 / 1e6:.0f} MB per GPU is streamed every step (L2 126 MB)",
+            "parallelism": f"filters sharded {world}x, no data-path collective; final NCCL all_gather of states + all_reduce of error statistics"}
+
+
+def e2e_leg(eng, torch, dist, world, dev, B, twists, zs, ids, t, K, dry):
+    """The same metric through the public host-buffer API (BatchedExtendedKalman.step_async = nuslam_ekf_step_async): pinned host buffers,
+    every step copies its twists / z / ids host -> device and its resulting state vector device -> host inside the timed region, three
+    steps in flight. dry = True: the same copies on the same streams with the kernels left out -- the ceiling the host side allows."""
+    nbuf = 3
+    h_tw = [torch.empty((B, 3), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
+    h_z = [torch.empty((B, N_LANDMARKS, 2), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
+    h_ids = ids.cpu().pin_memory()
+    h_x = [torch.empty((B, LEN), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
+    for k in range(nbuf):
+        h_tw[k].copy_(twists[t + k])
+        h_z[k].copy_(zs[t + k])
+    torch.cuda.synchronize(dev)
+    eng.async_dry_run(dry)
+    for k in range(6):   # warm the host path (staging buffers, streams, events)
+        eng.step_async(h_tw[k % nbuf].numpy(), h_z[k % nbuf].numpy(), h_ids.numpy(), h_x[k % nbuf].numpy())
+    eng.wait_async()
+    if world > 1:
+        dist.barrier()
+    checksum = 0.0
+    t0 = time.perf_counter()
+    for k in range(K):
+        eng.step_async(h_tw[k % nbuf].numpy(), h_z[k % nbuf].numpy(), h_ids.numpy(), h_x[k % nbuf].numpy())
+        # the host consumes the result of the step that has just left the pipeline (three calls back): robot pose of filter 0
+        if k >= nbuf:
+            checksum += float(h_x[k % nbuf][0, 1])
+    eng.wait_async()
+    secs = time.perf_counter() - t0
+    eng.async_dry_run(False)
+    tt = torch.tensor([secs], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return world * B * K / float(tt.item())
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -228,40 +272,19 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_max = float(ms_t.item())
-    bad = int((status != 0).sum().item()) + int((~torch.isfinite(xs)).any(dim=1).sum().item())
+    # K6: the shard's error statistics, reduced on the device (truth: the trajectory the measurements were generated from)
+    from shermbot_navigation_b200 import synth
+    poses = synth.true_trajectory(synth.wheel_twists(total_steps + 1, first_step_straight=True))
+    truth_pose = torch.tensor(np.ascontiguousarray(np.broadcast_to(poses[t - 1], (B, 3))), device=dev)
+    truth_map = torch.tensor(np.ascontiguousarray(synth.landmark_ring(N_LANDMARKS, 0.20)), device=dev)
+    stats = eng.error_stats(truth_pose=truth_pose, truth_map=truth_map)
+    bad_nonfinite = (~torch.isfinite(xs)).any(dim=1).sum().to(torch.float64)
 
-    # ---- end to end through the public API with HOST buffers (pinned): every step copies its twists / z / ids host -> device
-    # and its resulting state vector device -> host inside the timed region (BatchedExtendedKalman.step_async = the C ABI's
-    # nuslam_ekf_step_async: three streams, three steps in flight, so the copies of neighbouring steps overlap the kernel) ----
+    # ---- end to end through the public API with HOST buffers, and the copy-only ceiling of the same path ----
     Ke = max(3, min(K, args.e2e_steps))
-    nbuf = 3
-    h_tw = [torch.empty((B, 3), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
-    h_z = [torch.empty((B, N_LANDMARKS, 2), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
-    h_ids = ids.cpu().pin_memory()
-    h_x = [torch.empty((B, LEN), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
-    for k in range(nbuf):
-        h_tw[k].copy_(twists[t + k])
-        h_z[k].copy_(zs[t + k])
-    torch.cuda.synchronize(dev)
-    for k in range(6):   # warm the host path (staging buffers, streams, events)
-        eng.step_async(h_tw[k % nbuf].numpy(), h_z[k % nbuf].numpy(), h_ids.numpy(), h_x[k % nbuf].numpy())
-    eng.wait_async()
-    if world > 1:
-        dist.barrier()
-    checksum = 0.0
-    t0 = time.perf_counter()
-    for k in range(Ke):
-        eng.step_async(h_tw[k % nbuf].numpy(), h_z[k % nbuf].numpy(), h_ids.numpy(), h_x[k % nbuf].numpy())
-        # the host consumes the result of the step that has just left the pipeline (three calls back): robot pose of filter 0
-        if k >= nbuf:
-            checksum += float(h_x[k % nbuf][0, 1])
-    eng.wait_async()
-    e2e_s = time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * Ke / float(e2e_t.item())
+    e2e_runs = [e2e_leg(eng, torch, dist, world, dev, B, twists, zs, ids, t, Ke, dry=False) for _ in range(max(1, args.e2e_repeats))]
+    e2e_value = float(np.median(e2e_runs))
+    ceiling = e2e_leg(eng, torch, dist, world, dev, B, twists, zs, ids, t, Ke, dry=True)
     h2d = B * (3 * 8 + N_LANDMARKS * 2 * 8 + N_LANDMARKS * 4)
     d2h = B * LEN * 8
 
@@ -270,8 +293,10 @@ def run_ours(args):
         from shermbot_navigation_b200 import shard
         gathered = shard.gather_states(xs, world * B)
         assert gathered.shape == (world * B, LEN)
-        stats = shard.allreduce_stats(torch.tensor([float(bad)], device=dev, dtype=torch.float64))
-        bad = int(stats.item())
+        stats = shard.allreduce_stats(stats)
+        bad_nonfinite = shard.allreduce_stats(bad_nonfinite.reshape(1)).reshape(())
+    st = dict(zip(nuslam.BatchedExtendedKalman.STATS, [float(v) for v in stats.cpu().numpy()]))
+    bad = int(st["bad_status"]) + int(bad_nonfinite.item())
 
     out = None
     if rank == 0:
@@ -286,57 +311,110 @@ def run_ours(args):
             except Exception:
                 pass
         value = world * B * K / (ms_max / 1e3)
+        nf = max(st["filters"], 1.0)
+        launches = 2 if args.mode == "fast" else 1
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[1]: batched 64K independent EKF filters x 12 landmarks, known correspondence, fp64",
-                       "filters_per_gpu": B, "landmarks": N_LANDMARKS, "state_len": LEN, "mode": args.mode,
-                       "batched_steps_per_s": value / (world * B) if B else None,
-                       "l2": f"inputs larger than L2: filter state {B * (LEN + LEN * LEN) * 8 / 1e6:.0f} MB per GPU is streamed every step (L2 126 MB)",
-                       "parallelism": f"filters sharded {world}x, no data-path collective; final NCCL all_gather of states"},
-            "clocks": clocks, "gpu_launches": (2 * K if args.mode == "fast" else K), "bad_filters": bad,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(world),
+            "details": {"mode": args.mode, "filters_this_run": B, "batched_steps_per_s": value / (world * B) if B else None},
+            "clocks": clocks, "gpu_launches": launches * K, "bad_filters": bad,
+            "stats": {"reduced": "k_error_stats per rank" + (" + NCCL all_reduce(sum)" if world > 1 else ""), "filters": st["filters"],
+                      "rmse_position_m": (st["sq_position_error"] / nf) ** 0.5, "rmse_heading_rad": (st["sq_heading_error"] / nf) ** 0.5,
+                      "mean_nees_3dof": st["nees"] / nf, "rmse_landmark_m": (st["sq_landmark_error"] / max(st["landmarks"], 1.0)) ** 0.5,
+                      "bad_status": st["bad_status"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "api": "BatchedExtendedKalman.step_async (nuslam_ekf_step_async): pinned host buffers, H2D + fused step + D2H of the state vector per step, 3 steps in flight", "host_affinity": numa},
+                    "runs": e2e_runs, "copy_ceiling": ceiling, "frac_of_copy_ceiling": e2e_value / ceiling if ceiling else None,
+                    "copy_ceiling_note": "the same nuslam_ekf_step_async calls with the kernels left out: identical copies, streams and events",
+                    "api": "BatchedExtendedKalman.step_async (nuslam_ekf_step_async): pinned host buffers, H2D + fused step + D2H of the state vector per step, 3 steps in flight",
+                    "host_affinity": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_filter_step": BYTES_PER_FILTER_STEP,
-                         "kernel": "k_ekf_fast_step<12> (+ k_ekf_strict_list over the first-touch work list, empty in steady state)" if args.mode == "fast" else "k_ekf_strict<kOpStep>",
-                         "launch_us": per_launch_s * 1e6, "launches_per_step": 2 if args.mode == "fast" else 1},
+                         "kernel": "k_ekf_pair_step<12> (two filters per warp; + k_ekf_strict_list over the first-touch work list, empty in steady state)" if args.mode == "fast" else "k_ekf_strict<kOpStep>",
+                         "launch_us": per_launch_s * 1e6, "launches_per_step": launches},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     eng.close()
+    del xs, sig, zs, twists
+    torch.cuda.empty_cache()
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
+
+    # ---- the other BASELINE configurations, each with its own roofline and the reference's CPU path timed beside it ----
+    if not args.no_extras:
+        sys.path.insert(0, str(ROOT / "tools"))
+        import bench_assoc
+        cpu_s = 0.0 if args.no_cpu_baseline else args.cpu_seconds / 2
+        extra = {}
+        # config 4: 1 Mi filters over the ranks of the job (strong scaling), unknown association, statistics all-reduced over NCCL
+        a = bench_assoc.run(total=args.assoc_filters, steps=10, warmup=3, cpu_seconds=cpu_s if world == 1 else 0.0, world=world, rank=rank,
+                            dist=dist if world > 1 else None)
+        extra["assoc"] = a
+        if world == 1:
+            import bench_large
+            import bench_scan
+            extra["scan"] = bench_scan.run(cpu_seconds=cpu_s)
+            extra["large"] = bench_large.run(steps=20, warmup=3, cpu_seconds=cpu_s, assoc=False)
+        if out is not None:
+            out["extra"] = extra
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and out is not None:
+        out["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     if world > 1:
         dist.destroy_process_group()
     return out
 
 
-def cpu_reference_run(n_filters, n_steps, nthreads):
-    """Time the reference's own CPU implementation (oracle/_ref when built, else the C restatement) on a bounded
-    sample of the same workload: n_filters filters x n_steps fused steps after the first-touch step."""
-    import oracle
-    from shermbot_navigation_b200 import synth
-    orc = oracle.best()
-    sc = synth.ekf_scenario(n_filters, n_steps + 1, n=N_LANDMARKS, seed=4321)
-    first = orc.ekf_run(N_LANDMARKS, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][:1], sc["z"][:1], sc["ids"][:1], nthreads=nthreads)
-    t0 = time.perf_counter()
-    orc.ekf_run(N_LANDMARKS, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][1:], sc["z"][1:], sc["ids"][1:],
-                init=(first["x"], first["sigma"], first["seen"]), nthreads=nthreads)
-    dt = time.perf_counter() - t0
-    return n_filters * n_steps / dt, dt, ("reference" if orc.kind.startswith("ref") else "port")
+class CpuArm:
+    """The reference's own CPU implementation of the path (oracle/_ref: the unmodified sources; the C restatement only where that is
+    absent) as a persistent batch of filters: the state stays inside the oracle library between steps, so a timed step is the
+    reference's arithmetic on all host threads and nothing else. ONE protocol for `cpu_baseline` and `--impl reference`.
+    Variants: the parity build (naive-loop Armadillo shim) and the timing build BASELINE.md 4.1 asks for (matrix products above 4 x 4
+    through single-threaded OpenBLAS dgemm, as real Armadillo routes them); the faster one is the baseline, both are printed."""
+
+    def __init__(self):
+        import oracle
+        self.oracle = oracle
+        self.cores = os.cpu_count() or 1
+        self.kinds = [k for k in ("ref_blas", "ref") if oracle.available(k)] or ["port"]
+
+    def rate(self, kind, n_filters, n_steps, warmup=1):
+        from shermbot_navigation_b200 import synth
+        orc = self.oracle.load(kind)
+        sc = synth.ekf_scenario(n_filters, 2, n=N_LANDMARKS, seed=4321)
+        run = orc.ekf_stepper(N_LANDMARKS, sc["robot0"], sc["map0"], sc["Q"], sc["R"], nthreads=self.cores)
+        tw = [np.ascontiguousarray(sc["twists"][t]) for t in range(2)]
+        zz = [np.ascontiguousarray(sc["z"][t]) for t in range(2)]
+        ii = [np.ascontiguousarray(sc["ids"][t], dtype=np.int32) for t in range(2)]
+        run.step(tw[0], zz[0], ii[0])   # the first-touch step
+        times = []
+        for k in range(warmup + n_steps):
+            t0 = time.perf_counter()
+            run.step(tw[1], zz[1], ii[1])
+            if k >= warmup:
+                times.append(time.perf_counter() - t0)
+        return n_filters * n_steps / float(np.sum(times)), float(np.sum(times)), orc.flavour
+
+    def measure(self, n_steps, warmup, seconds_per_variant):
+        """Each variant on a sample sized for ~seconds_per_variant of wall time; returns (best, all)."""
+        results = []
+        for kind in self.kinds:
+            probe, _, _ = self.rate(kind, 64 * self.cores, 3, 1)
+            nf = int(max(self.cores, min(FILTERS_PER_GPU, probe * seconds_per_variant / max(1, n_steps + warmup))))
+            nf = max(self.cores, (nf // self.cores) * self.cores)
+            value, secs, flavour = self.rate(kind, nf, n_steps, warmup)
+            results.append({"value": value, "unit": UNIT, "cores": self.cores, "kind": "reference" if kind.startswith("ref") else "port",
+                            "variant": flavour, "filters_per_step": nf, "seconds": secs,
+                            "sample": f"{nf} of {FILTERS_PER_GPU} filters per step x {n_steps} steps on {self.cores} host threads, {secs:.1f} s "
+                                      f"({flavour}: " + ("unmodified reference sources, " if kind.startswith("ref") else "C restatement, ") +
+                                      ("matrix products above 4 x 4 through single-threaded OpenBLAS dgemm" if kind == "ref_blas" else "naive-loop Armadillo shim") + ", -O2)"})
+        best = max(results, key=lambda r: r["value"])
+        return best, results
 
 
 def cpu_baseline(target_seconds=12.0):
-    cores = os.cpu_count() or 1
-    # calibrate on a tiny run, then size the sample for ~target_seconds of wall time on all cores
-    rate, _, kind = cpu_reference_run(4 * cores, 10, cores)
-    n_steps = 50
-    n_filters = int(max(cores, min(FILTERS_PER_GPU, rate * target_seconds / n_steps)))
-    n_filters = max(cores, (n_filters // cores) * cores)
-    rate, dt, kind = cpu_reference_run(n_filters, n_steps, cores)
-    return {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{n_filters} filters x {n_steps} fused steps (12 landmarks, known correspondence) on {cores} threads, {dt:.1f} s; "
-                      "naive-loop Armadillo shim, -O2 -ffp-contract=off"}
+    arm = CpuArm()
+    best, allv = arm.measure(n_steps=20, warmup=1, seconds_per_variant=target_seconds / max(1, len(arm.kinds)))
+    out = dict(best)
+    out["variants"] = [{k: v[k] for k in ("variant", "value", "filters_per_step", "seconds")} for v in allv]
+    return out
 
 
 def run_reference(args):
@@ -344,41 +422,20 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return None
-    cores = os.cpu_count() or 1
     K, W = args.steps, args.warmup
-    # each "step" = one batched fused step over a bounded sample of the 64K-filter workload
-    rate, _, kind = cpu_reference_run(4 * cores, 5, cores)
-    per_step_budget = min(2.0, 150.0 / max(1, K + W))
-    n_filters = int(max(cores, min(FILTERS_PER_GPU, rate * per_step_budget)))
-    n_filters = max(cores, (n_filters // cores) * cores)
-    import oracle
-    from shermbot_navigation_b200 import synth
-    orc = oracle.best()
-    sc = synth.ekf_scenario(n_filters, 2, n=N_LANDMARKS, seed=4321)
-    # a persistent batch of reference filters: the state stays inside the oracle library between steps, so a timed step is the
-    # reference's arithmetic on all host threads and nothing else (no per-step copies on the Python side)
-    run = orc.ekf_stepper(N_LANDMARKS, sc["robot0"], sc["map0"], sc["Q"], sc["R"], nthreads=cores)
-    tw = [np.ascontiguousarray(sc["twists"][t]) for t in range(2)]
-    zz = [np.ascontiguousarray(sc["z"][t]) for t in range(2)]
-    ii = [np.ascontiguousarray(sc["ids"][t], dtype=np.int32) for t in range(2)]
-    run.step(tw[0], zz[0], ii[0])   # the first-touch step
-    times = []
-    for k in range(W + K):
-        t0 = time.perf_counter()
-        run.step(tw[1], zz[1], ii[1])
-        dt = time.perf_counter() - t0
-        if k >= W:
-            times.append(dt)
-    total = float(np.sum(times))
-    value = n_filters * K / total
-    sample = (f"{n_filters} of {FILTERS_PER_GPU} filters per step x {K} steps on {cores} host threads "
-              f"({'oracle/_ref: unmodified reference sources' if kind == 'reference' else 'oracle C restatement'}, naive-loop Armadillo shim, -O2)")
+    arm = CpuArm()
+    # each "step" = one batched fused step over a bounded sample of the 64K-filter workload; the whole run stays within minutes
+    budget = min(150.0, max(20.0, 0.4 * (K + W)))
+    best, allv = arm.measure(n_steps=K, warmup=W, seconds_per_variant=budget / max(1, len(arm.kinds)))
+    value = best["value"]
+    cb = dict(best)
+    cb["variants"] = [{k: v[k] for k in ("variant", "value", "filters_per_step", "seconds")} for v in allv]
     return {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": total / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1]: batched 64K independent EKF filters x 12 landmarks, known correspondence, fp64 "
-                               "(reference CPU implementation timed on a bounded sample)", "filters_per_step": n_filters, "landmarks": N_LANDMARKS},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "ms_per_step": best["seconds"] / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(world),
+        "details": {"filters_this_run": best["filters_per_step"], "note": "the reference's CPU implementation timed on a bounded sample of the workload; value = filter-steps/s"},
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -393,12 +450,14 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--filters", type=int, default=FILTERS_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--e2e-repeats", type=int, default=3, help="the end-to-end leg is repeated; the median is reported, all runs are listed")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 3 / 4 / 5 blocks (kernel A/B timing)")
+    ap.add_argument("--assoc-filters", type=int, default=1 << 20, help="config 4: filters of the WHOLE job (sharded over the ranks)")
     ap.add_argument("--config", default="ekf", choices=["ekf", "scan", "assoc", "large", "closed_loop"],
-                    help="ekf (default): the headline line of BASELINE.json configs[1]; the others run the per-config benches under tools/ "
-                         "(config 3 scans, config 4 shard with on-device association, config 5 large map, the device-resident closed loop) "
-                         "on one GPU and print their own JSON line")
+                    help="ekf (default): the headline line of BASELINE.json configs[1] with the other configurations under `extra`; "
+                         "the others run one per-config bench under tools/ on one GPU and print its own JSON line")
     args = ap.parse_args()
     if args.config != "ekf":
         import runpy

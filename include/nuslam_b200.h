@@ -195,7 +195,23 @@ int nuslam_ekf_wait_async(nuslam_ekf * h);
  * out: B x 3 = (translation x, translation y, yaw = normalize_angle(asin(T_mo.getSinTh()))). */
 int nuslam_ekf_map_to_odom(nuslam_ekf * h, const double * odom_state7, double * out, int mem);
 
+/* Measurement aid for the host-buffer path: while on, nuslam_ekf_step_async performs exactly its copies (host -> device inputs,
+ * device -> host state snapshot), stream hand-overs and events but launches no kernel, so that timing it gives the ceiling the
+ * host side (PCIe, pinned-memory bandwidth shared by the ranks of a box) allows for that path. The filters do not advance. */
+int nuslam_ekf_async_dry_run(nuslam_ekf * h, int on);
 int nuslam_ekf_synchronize(nuslam_ekf * h);
+/* Error statistics of the batch against a ground truth, reduced on the device (the Monte-Carlo driver's end-of-run numbers; the
+ * reference has no counterpart -- its nodes only draw rviz paths, slam.cpp:161-173). All pointers are DEVICE pointers; the call
+ * enqueues on the handle's stream. stats_out receives NUSLAM_STATS_COUNT doubles, SUMS over this handle's filters (so that shards
+ * add up under an all-reduce):
+ *   [0] squared robot position error   [1] squared heading error (wrapped)   [2] NEES e^T Sigma_rr^-1 e of the pose (3 dof)
+ *   [3] filters counted in [0..2]      [4] squared landmark position error   [5] landmarks counted in [4] (the first `seen` ones)
+ *   [6] filters with non-zero status   [7] entries of ids_got that differ from ids_want (both B x m, or both NULL)
+ * truth_pose: B x 3 (theta, x, y) or NULL; truth_map: n x 2 landmark positions shared by all filters, or NULL. */
+#define NUSLAM_STATS_COUNT 8
+int nuslam_ekf_error_stats(nuslam_ekf * h, const double * truth_pose, const double * truth_map, const int32_t * ids_got,
+                           const int32_t * ids_want, int32_t m, double * stats_out);
+
 /* The cudaStream_t every NUSLAM_DEVICE call of this handle enqueues on (the one given to nuslam_ekf_create, or the handle's own
  * non-blocking stream): a caller that produces inputs / consumes outputs on another stream orders the two with events on it. */
 int nuslam_ekf_get_stream(nuslam_ekf * h, void ** cuda_stream_out);

@@ -218,4 +218,72 @@ __global__ void k_diffdrive_convert_twist(double wheel_base, double wheel_rad, c
     u[2 * b + 1] = add_(mul_(div_(d, r), omg), div_(vbx, r));
 }
 
+// K6: error statistics of a Monte-Carlo batch, reduced on the device -- one thread per filter, warp-shuffle sums,
+// one atomicAdd per warp and statistic. The shard's eight sums are what the ranks all-reduce over NCCL at the end of a run.
+//   out[0] sum of squared robot position errors (m^2)      out[1] sum of squared heading errors (rad^2, wrapped)
+//   out[2] sum of NEES = e^T Sigma_rr^-1 e (3 dof)         out[3] filters counted in [0..2] (finite state, regular Sigma_rr)
+//   out[4] sum of squared landmark position errors (m^2)   out[5] landmarks counted in [4] (the first `seen` of every counted filter)
+//   out[6] filters with a non-zero status                  out[7] association ids differing from the expected ones
+constexpr int kStatsCount = 8;
+__global__ void __launch_bounds__(256)
+k_error_stats(const double * __restrict__ x, const double * __restrict__ sigma, const int32_t * __restrict__ seen, const int32_t * __restrict__ status,
+              int64_t batch, int len, int n, const double * __restrict__ truth_pose, const double * __restrict__ truth_map,
+              const int32_t * __restrict__ ids_got, const int32_t * __restrict__ ids_want, int m, double * __restrict__ out)
+{
+    const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    double v[kStatsCount] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (b < batch)
+    {
+        const double * xb = x + b * len;
+        const double * S = sigma + b * (int64_t) len * len;   // column-major
+        if (status[b] != 0) v[6] = 1.0;
+        if (truth_pose)
+        {
+            const double eth = normalize_angle(xb[0] - truth_pose[3 * b]), ex = xb[1] - truth_pose[3 * b + 1], ey = xb[2] - truth_pose[3 * b + 2];
+            // 3 x 3 robot block (order theta, x, y), inverse by cofactors
+            const double a00 = S[0], a10 = S[1], a20 = S[2], a01 = S[len], a11 = S[len + 1], a21 = S[len + 2], a02 = S[2 * len], a12 = S[2 * len + 1],
+                         a22 = S[2 * len + 2];
+            const double c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+            const double det = a00 * c00 + a01 * c01 + a02 * c02;
+            // solve Sigma_rr w = e by Cramer's rule
+            const double e0 = eth, e1 = ex, e2 = ey;
+            const double w0 = (e0 * c00 + a01 * (a12 * e2 - e1 * a22) + a02 * (e1 * a21 - a11 * e2)) / det;
+            const double w1 = (a00 * (e1 * a22 - a12 * e2) + e0 * c01 + a02 * (a10 * e2 - e1 * a20)) / det;
+            const double w2 = (a00 * (a11 * e2 - e1 * a21) + a01 * (e1 * a20 - a10 * e2) + e0 * c02) / det;
+            const double nees = e0 * w0 + e1 * w1 + e2 * w2;
+            if (fabs(nees) < 1e300 && fabs(ex) < 1e300 && fabs(ey) < 1e300)
+            {
+                v[0] = ex * ex + ey * ey;
+                v[1] = eth * eth;
+                v[2] = nees;
+                v[3] = 1.0;
+                if (truth_map)
+                {
+                    const int ns = min(n, max(0, seen[b]));
+                    for (int j = 0; j < ns; ++j)
+                    {
+                        const double lx = xb[3 + 2 * j] - truth_map[2 * j], ly = xb[4 + 2 * j] - truth_map[2 * j + 1];
+                        const double e = lx * lx + ly * ly;
+                        if (e < 1e300)
+                        {
+                            v[4] += e;
+                            v[5] += 1.0;
+                        }
+                    }
+                }
+            }
+        }
+        if (ids_got && ids_want)
+            for (int i = 0; i < m; ++i)
+                if (ids_got[b * m + i] != ids_want[b * m + i]) v[7] += 1.0;
+    }
+#pragma unroll
+    for (int k = 0; k < kStatsCount; ++k)
+    {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], d);
+        if ((threadIdx.x & 31) == 0 && v[k] != 0.0) atomicAdd(out + k, v[k]);
+    }
+}
+
 }   // namespace nuslam

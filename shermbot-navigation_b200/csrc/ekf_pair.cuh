@@ -204,7 +204,8 @@ k_ekf_pair_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         const unsigned bad_w = __ballot_sync(kFull, q < m && my_id != 0 && !idok);   // an id outside 1..N (negative ids included)
         const unsigned meas_h = (meas_w >> (16 * h)) & 0xffffu;
         // a repeated landmark or a bad id: no permutation; the oracle-order kernel runs this filter-step (and flags the bad id)
-        const bool generic = __popc(meas_h) != __popc(mymask) || ((bad_w >> (16 * h)) & 0xffffu) != 0u;
+        // (so is a measurement in a slot beyond the map size, m > n)
+        const bool generic = __popc(meas_h) != __popc(mymask) || ((bad_w >> (16 * h)) & 0xffffu) != 0u || (meas_h >> NL) != 0u;
         int lq = my_id;
         if (!meas)
         {
@@ -679,9 +680,7 @@ int launch_pair_n(const EkfParams & p, bool do_predict, int sm_count, int32_t * 
 // known correspondence, 16-byte aligned Sigma, the BASELINE map size: the pair kernel; everything else stays with ekf_fast.cuh
 inline bool pair_supported(int n, const EkfParams & p)
 {
-    // NUSLAM_PAIR=0 (read at every call) keeps the one-filter-per-warp kernel: A/B timing and the equality test
-    const char * e = getenv("NUSLAM_PAIR");
-    const bool enabled = !(e && e[0] == '0');
+    const bool enabled = true;
     return enabled && n == 12 && p.ids != nullptr && p.m_valid == nullptr && p.m >= 0 && p.m <= kFastMMax && p.batch >= 1 &&
            (reinterpret_cast<uintptr_t>(p.sigma) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 7) == 0;
 }

@@ -16,6 +16,7 @@
 #include "ekf_misc.cuh"
 #include "ekf_fast.cuh"
 #include "ekf_pair.cuh"
+#include "ekf_static.cuh"
 #include "scan_moment.cuh"
 #include "scan_detect.cuh"
 #include "ekf_large.cuh"
@@ -102,6 +103,7 @@ struct nuslam_ekf
     } slots[3];
     cudaStream_t s_in = nullptr, s_out = nullptr;
     uint64_t async_count = 0;
+    bool async_dry = false;   // nuslam_ekf_async_dry_run: step_async performs its copies and event chaining, no kernel (copy ceiling)
     // LARGE-MAP mode (state too long for the on-chip batched kernels): delayed-update scratch, see ekf_large.cuh
     bool large = false;
     double * lg_x2 = nullptr;
@@ -190,10 +192,13 @@ int launch_strict(nuslam_ekf * h, const nuslam::EkfParams & p)
 template <int OP>
 int launch_fast_then_strict(nuslam_ekf * h, const nuslam::EkfParams & p, bool do_predict)
 {
-    // known correspondence at the BASELINE map size: two filters per warp (ekf_pair.cuh); everything else one filter per warp
-    int rc = (nuslam::pair_supported(h->cfg.n_landmarks, p) && !(p.ids == nullptr && !do_predict))
-                 ? nuslam::launch_pair_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
-                 : nuslam::launch_fast(h->cfg.n_landmarks, p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream);
+    // known correspondence at the BASELINE map size: the static-schedule kernel (ekf_static.cuh; NUSLAM_KERNEL=pair / fast select the
+    // two-filters-per-warp kernel / the dynamic one for A/B timing); everything else: ekf_fast.cuh
+    const int which = nuslam::known_ids_kernel();
+    const bool special = which != 2 && nuslam::pair_supported(h->cfg.n_landmarks, p);
+    int rc = !special      ? nuslam::launch_fast(h->cfg.n_landmarks, p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
+             : which == 1 ? nuslam::launch_pair_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
+                          : nuslam::launch_static_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream);
     // not covered by the register kernels (more than 16 measurements per step, ragged counts with known ids, a state pointer that
     // is not 8-byte aligned): the oracle-order kernel runs the whole batch
     if (rc == -1) return launch_strict<OP>(h, p);
@@ -769,11 +774,12 @@ int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * 
     // kernels do not: a device-to-device copy stands in
     const bool in_kernel_snapshot = !h->large;
     h->x_snap_next = in_kernel_snapshot ? static_cast<double *>(sl.xsnap.p) : nullptr;
-    rc = nuslam_ekf_step(h, static_cast<const double *>(sl.tw.p), static_cast<const double *>(sl.z.p),
-                         ids ? static_cast<const int32_t *>(sl.ids.p) : nullptr, m, nullptr, NUSLAM_DEVICE);
+    rc = h->async_dry ? NUSLAM_OK
+                      : nuslam_ekf_step(h, static_cast<const double *>(sl.tw.p), static_cast<const double *>(sl.z.p),
+                                        ids ? static_cast<const int32_t *>(sl.ids.p) : nullptr, m, nullptr, NUSLAM_DEVICE);
     h->x_snap_next = nullptr;
     if (rc) return rc;
-    if (!in_kernel_snapshot) CU(cudaMemcpyAsync(sl.xsnap.p, h->x, sizeof(double) * l * B, cudaMemcpyDeviceToDevice, h->stream));
+    if (!in_kernel_snapshot && !h->async_dry) CU(cudaMemcpyAsync(sl.xsnap.p, h->x, sizeof(double) * l * B, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaEventRecord(sl.kernel_done, h->stream));
     // stage 3 (copy-out stream): device -> host
     CU(cudaStreamWaitEvent(h->s_out, sl.kernel_done, 0));
@@ -781,6 +787,13 @@ int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * 
     CU(cudaEventRecord(sl.d2h_done, h->s_out));
     sl.busy = true;
     h->async_count++;
+    return NUSLAM_OK;
+}
+
+int nuslam_ekf_async_dry_run(nuslam_ekf * h, int on)
+{
+    if (!h) return fail(NUSLAM_ERR_INVALID, "null handle");
+    h->async_dry = on != 0;
     return NUSLAM_OK;
 }
 
@@ -810,6 +823,20 @@ int nuslam_debug_fast_timing(long long * out16, int reset)
     return 0;
 }
 #endif
+
+int nuslam_ekf_error_stats(nuslam_ekf * h, const double * truth_pose, const double * truth_map, const int32_t * ids_got, const int32_t * ids_want,
+                           int32_t m, double * stats_out)
+{
+    if (!h || !stats_out) return fail(NUSLAM_ERR_INVALID, "null handle or output");
+    if ((ids_got == nullptr) != (ids_want == nullptr) || m < 0) return fail(NUSLAM_ERR_INVALID, "ids_got and ids_want go together");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    CU(cudaMemsetAsync(stats_out, 0, sizeof(double) * nuslam::kStatsCount, h->stream));
+    const int64_t blocks = (h->batch + 255) / 256;
+    nuslam::k_error_stats<<<(unsigned) blocks, 256, 0, h->stream>>>(h->x, h->sigma, h->seen, h->status, h->batch, h->len, h->cfg.n_landmarks, truth_pose,
+                                                                 truth_map, ids_got, ids_want, m, stats_out);
+    CU(cudaGetLastError());
+    return NUSLAM_OK;
+}
 
 int nuslam_ekf_get_stream(nuslam_ekf * h, void ** cuda_stream_out)
 {

@@ -21,6 +21,15 @@
 #pragma once
 #include "scan_detect.cuh"
 
+#ifdef NUSLAM_SCAN_DEBUG
+#include <cstdio>
+#define NUSLAM_DBG(...) do { if (lane == 0) printf(__VA_ARGS__); } while (0)
+#define NUSLAM_CHK(cond, code) do { if (!(cond)) printf("CHECK %d failed: lane %d\n", code, lane); } while (0)
+#else
+#define NUSLAM_DBG(...)
+#define NUSLAM_CHK(cond, code)
+#endif
+
 namespace nuslam
 {
 
@@ -122,6 +131,7 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
             npts += __popc(inr_m[k]);
         }
         const int64_t sb = s * kBeams;
+        NUSLAM_DBG("[scan %lld] nc %d npts %d wrap %d\n", (long long) s, nc, npts, (int) wrap);
         if (wrap && nc == 0)
         {
             // clusters[0].push_back on an empty vector (:173): undefined behaviour in the reference
@@ -171,6 +181,7 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
         const unsigned erased_m = __ballot_sync(kFull, erased);
         const int newidx = (lane < nc && !erased) ? lane - __popc(erased_m & lt) : -1;
         const int nk = nc - __popc(erased_m);
+        NUSLAM_DBG("[scan %lld] nk %d erased %x\n", (long long) s, nk, erased_m);
         if (cluster_of_beam)
         {
             const int new0 = __shfl_sync(kFull, newidx, 0);
@@ -200,6 +211,7 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
             for (int base = 0; base < ntot; base += 32)
             {
                 const int j = base + lane;
+                NUSLAM_DBG("[scan %lld] pass %d base %d of %d\n", (long long) s, pass, base, ntot);
                 const bool iswrap = wrap && j == npts;
                 const unsigned pbv = (j < npts) ? sm.pb[j] : 0u;
                 const int beam = iswrap ? kBeams - 1 : (int) (pbv & 0xffffu);
@@ -211,12 +223,14 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
                 const bool wrapped_cluster = wrap && clu == 0;
                 const int b2 = active ? (int) (sm.pb[cs] & 0xffffu) : 0;
                 const int b3 = !active ? 0 : wrapped_cluster ? kBeams - 1 : (int) (sm.pb[ce] & 0xffffu);
+                NUSLAM_CHK((unsigned) beam < 360u && (unsigned) b2 < 360u && (unsigned) b3 < 360u, 2);
                 // points = r (cos, sin)(deg2rad(beam)) (:161-163), relative to the cluster's first point
                 const double r1 = (double) __ldg(rs + beam), r2 = (double) __ldg(rs + b2), r3 = (double) __ldg(rs + b3);
                 const double x2 = r2 * __ldg(&c_beam_cos[b2]), y2 = r2 * __ldg(&c_beam_sin[b2]);
                 const double X = active ? fma(r1, __ldg(&c_beam_cos[beam]), -x2) : 0.0, Y = active ? fma(r1, __ldg(&c_beam_sin[beam]), -y2) : 0.0;
                 const int key = active ? (iswrap ? 32 : clu) : -1 - lane;
-                const bool tail = lane == 31 || __shfl_down_sync(kFull, key, 1) != key;
+                const int key_next = __shfl_down_sync(kFull, key, 1);   // (every lane takes part: no collective behind a short-circuit)
+                const bool tail = lane == 31 || key_next != key;
                 const bool first = cs >= base;   // the cluster's first contribution to its accumulators
                 if (pass == 0)
                 {
@@ -262,7 +276,9 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
                     }
                     v[6] = ang;
                     v[7] = ang * ang;
+                    NUSLAM_DBG("[scan %lld] angles done\n", (long long) s);
                     seg_scan<8>(v, key, lane);
+                    NUSLAM_DBG("[scan %lld] seg_scan done\n", (long long) s);
                     if (tail && active && !iswrap)
                     {
 #pragma unroll
@@ -285,6 +301,7 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
             }
         }
         // ---- one cluster per lane: classification, Hyper fit, gates ----
+        NUSLAM_DBG("[scan %lld] solve\n", (long long) s);
         bool pub = false, fallback = false;
         double cx = 0.0, cy = 0.0, R = 0.0;
         if (examined)
@@ -341,6 +358,7 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
                 if (pub && !(Cov > 1e-9 * Mz * Mz)) fallback = true;   // nearly collinear yet published: conditioning too poor to promise 1e-9
             }
         }
+        NUSLAM_DBG("[scan %lld] solved\n", (long long) s);
         if (__any_sync(kFull, fallback))
         {
             if (lane == 0) slow[atomicAdd(slow_count, 1)] = (int32_t) s;   // rewrites every output of this scan (cluster_of_beam stays the same)
@@ -420,6 +438,10 @@ inline cudaError_t launch_scan_moment(const float * ranges, int64_t n_scans, dou
                                                                  circles, max_circles, scan_ub, slow, slow_count);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+#ifdef NUSLAM_SCAN_DEBUG
+    e = cudaStreamSynchronize(stream);
+    fprintf(stderr, "[launch_scan_moment] k_scan_moment done: %s\n", cudaGetErrorString(e));
+#endif
     // the scans the moment route does not decide: oracle-order clustering + Jacobi fit, one warp per scan (usually an empty list)
     const size_t smem = sizeof(ScanSmem) * kScanWarps;
     static bool configured_dev[kMaxDevices] = {false};

@@ -36,7 +36,7 @@ EXPORTS = [
     "nuslam_ekf_scan_step", "nuslam_ekf_map_to_odom", "nuslam_ekf_synchronize",
     "nuslam_cartesian2polar", "nuslam_normalize_angle", "nuslam_scan_detect", "nuslam_classify_and_fit",
     "nuslam_diffdrive_step", "nuslam_diffdrive_convert_twist", "nuslam_world_step", "nuslam_integrate_twist",
-    "nuslam_ekf_get_stream", "nuslam_scan_set_fit", "nuslam_scan_last_fallbacks",
+    "nuslam_ekf_get_stream", "nuslam_scan_set_fit", "nuslam_scan_last_fallbacks", "nuslam_ekf_error_stats", "nuslam_ekf_async_dry_run",
 ]
 
 
@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
         l.nuslam_ekf_step_async.argtypes = [vp, vp, vp, vp, i32, vp]
         l.nuslam_scan_set_fit.argtypes = [C.c_int]
         l.nuslam_ekf_get_stream.argtypes = [vp, C.POINTER(vp)]
+        l.nuslam_ekf_async_dry_run.argtypes = [vp, C.c_int]
+        l.nuslam_ekf_error_stats.argtypes = [vp, vp, vp, vp, vp, i32, vp]
         l.nuslam_scan_last_fallbacks.argtypes = [C.c_int]
         l.nuslam_ekf_wait_async.argtypes = [vp]
         l.nuslam_ekf_synchronize.argtypes = [vp]
@@ -358,6 +360,25 @@ class BatchedExtendedKalman:
         self._order_end(tok)
         return out
 
+    STATS = ("sq_position_error", "sq_heading_error", "nees", "filters", "sq_landmark_error", "landmarks", "bad_status", "id_mismatches")
+
+    def error_stats(self, truth_pose=None, truth_map=None, ids_got=None, ids_want=None):
+        """K6: error statistics of this shard against a ground truth, reduced on the device (nuslam_ekf_error_stats): a CUDA tensor
+        of 8 SUMS (see ``STATS``) that the ranks add up with one NCCL all-reduce. All arguments are CUDA tensors (or None)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        out = torch.zeros(8, dtype=torch.float64, device=dev)
+        m = int(ids_got.shape[1]) if ids_got is not None else 0
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        for t, dt in ((truth_pose, torch.float64), (truth_map, torch.float64), (ids_got, torch.int32), (ids_want, torch.int32)):
+            if t is not None and (t.dtype != dt or not t.is_cuda or not t.is_contiguous()):
+                raise NuslamError(f"error_stats takes contiguous CUDA tensors ({dt})")
+        tok = self._order_begin(out, truth_pose, truth_map, ids_got, ids_want)
+        _check(lib().nuslam_ekf_error_stats(self._h, ptr(truth_pose), ptr(truth_map), ptr(ids_got), ptr(ids_want), m, out.data_ptr()),
+               "nuslam_ekf_error_stats")
+        self._order_end(tok)
+        return out
+
     def step_async(self, twists, z, ids, x_out):
         """Pipelined host-buffer step (nuslam_ekf_step_async): numpy views of page-locked buffers; ``x_out`` [B,len] receives the state
         vector once the step has left the pipeline (three calls later, or after ``wait_async``)."""
@@ -369,6 +390,10 @@ class BatchedExtendedKalman:
         _check(lib().nuslam_ekf_step_async(self._h, twists.ctypes.data, z.ctypes.data, ids.ctypes.data if ids is not None else None, int(z.shape[1]),
                                            x_out.ctypes.data),
                "nuslam_ekf_step_async")
+
+    def async_dry_run(self, on: bool):
+        """Measurement aid: while on, step_async performs its copies and stream hand-overs without launching kernels (copy ceiling)."""
+        _check(lib().nuslam_ekf_async_dry_run(self._h, 1 if on else 0), "nuslam_ekf_async_dry_run")
 
     def wait_async(self):
         _check(lib().nuslam_ekf_wait_async(self._h), "nuslam_ekf_wait_async")

@@ -2,18 +2,56 @@
 """BASELINE.json config 5: one 4096-landmark map (len 8195, Sigma 537 MB), m measurements per scan folded into one delayed
 rank-2m pass. Prints scan-updates/s and achieved GB/s against the 16 len^2-byte minimum (one read + one write of Sigma)."""
 import json
+import os
 import sys
+import time
 from pathlib import Path
 
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-import torch  # noqa: E402
-from shermbot_navigation_b200 import nuslam, synth  # noqa: E402
+from shermbot_navigation_b200 import synth  # noqa: E402
 
 
-def main(n=4096, steps=30, warmup=5):
+def cpu_large(m=12, seconds=8.0):
+    """The reference's own predict + m updates (dense O(len^3), slam_library.cpp:104,279) at len 27 / 131 / 259 on ONE thread, and the
+    cubic fitted through them evaluated at len 8195 -- an extrapolation, labelled as such (one update at 8195 is ~1.1 TFLOP: not run)."""
+    import oracle
+    kind = "ref_blas" if oracle.available("ref_blas") else ("ref" if oracle.available("ref") else "port")
+    orc = oracle.load(kind)
+    pts = []
+    t_budget = time.perf_counter() + seconds
+    for n in (12, 64, 128):
+        length = 3 + 2 * n
+        sc = synth.ekf_scenario(1, 3, n=n, seed=5)
+        mm = min(m, n)
+        first = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][:1], sc["z"][:1], sc["ids"][:1])
+        z, ids = np.ascontiguousarray(sc["z"][1:2, :, :mm]), np.ascontiguousarray(sc["ids"][1:2, :, :mm])
+        reps, dt = 0, 0.0
+        while reps < 3 or (dt < 0.3 and time.perf_counter() < t_budget):
+            t0 = time.perf_counter()
+            orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][1:2], z, ids, init=(first["x"], first["sigma"], first["seen"]))
+            dt += time.perf_counter() - t0
+            reps += 1
+            if reps >= 200:
+                break
+        pts.append((length, dt / reps))
+        if time.perf_counter() > t_budget and len(pts) >= 2:
+            break
+    lens = np.array([p[0] for p in pts], dtype=np.float64)
+    secs = np.array([p[1] for p in pts])
+    a = float((secs * lens ** 3).sum() / (lens ** 6).sum())   # least squares for t = a len^3
+    t8195 = a * 8195.0 ** 3
+    return {"value": 1.0 / t8195, "unit": "scans/s", "cores": 1, "kind": "reference" if kind.startswith("ref") else "port", "variant": orc.flavour,
+            "extrapolated": True,
+            "sample": f"predict + {m} updates measured at len " + ", ".join(f"{int(l)}: {t * 1e3:.2f} ms" for l, t in pts) +
+                      f"; t = {a:.3e} len^3 s fitted, evaluated at len 8195 ({t8195:.0f} s per scan) -- an extrapolation, one update there is ~1.1 TFLOP"}
+
+
+def run(n=4096, steps=30, warmup=5, cpu_seconds=8.0, assoc=True):
+    import torch
+    from shermbot_navigation_b200 import nuslam
     length = 3 + 2 * n
     rng = np.random.default_rng(11)
     lm = rng.uniform(-3, 3, size=(n, 2))
@@ -53,6 +91,9 @@ def main(n=4096, steps=30, warmup=5):
     # a precise sensor (R = 1e-6 I), a converged map (variances 1e-8) and next to no process noise keep the other 3 999 landmarks outside
     # the ambiguity gate (with the node's Q = 0.1 I every landmark within 2.4 m would be "ambiguous" after one predict)
     eng.close()
+    assoc_res = []
+    if not assoc:
+        return finish(length, peak, out, assoc_res, status, sig, cpu_seconds)
     eng = nuslam.BatchedExtendedKalman(robot, lm.reshape(1, -1), 1e-10 * np.eye(3), 1e-6 * np.eye(2), mode="large", stream=stream.cuda_stream)
     xs.copy_(torch.tensor(np.concatenate([robot[0], lm.ravel()])[None], device=dev))
     sig.zero_()
@@ -60,7 +101,6 @@ def main(n=4096, steps=30, warmup=5):
     status.zero_()
     eng.bind_state(xs, sig, seen, status)
     seen.fill_(n - 96)
-    assoc = []
     for m in (1, 12):
         pick = rng.choice(n - 96, size=m, replace=False)
         dl = lm[pick]
@@ -77,11 +117,25 @@ def main(n=4096, steps=30, warmup=5):
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        assoc.append(dict(m=m, ms_per_scan=ms, scans_per_s=1e3 / ms, ids_matching_truth=int((got[0].cpu().numpy() == pick + 1).sum())))
-    print(json.dumps({"workload": "config 5: 4096 landmarks, len 8195, Sigma 537 MB, delayed rank-2m DMMA pass", "algorithmic_bytes_per_scan": 16.0 * length * length,
-                      "hbm_peak_gbs": peak, "results": out, "unknown_association_4000_candidates": assoc, "status": int(status[0]),
-                      "finite": bool(torch.isfinite(sig).all())}))
+        assoc_res.append(dict(m=m, ms_per_scan=ms, scans_per_s=1e3 / ms, ids_matching_truth=int((got[0].cpu().numpy() == pick + 1).sum())))
+    eng.close()
+    return finish(length, peak, out, assoc_res, status, sig, cpu_seconds)
+
+
+def finish(length, peak, out, assoc_res, status, sig, cpu_seconds):
+    import torch
+    m12 = next(r for r in out if r["m"] == 12)
+    res = {"workload": "BASELINE.json configs[4]: single map of 4096 landmarks (len 8195, Sigma 537 MB), m measurements per scan folded into one delayed rank-2m DMMA pass",
+           "value": m12["scans_per_s"], "unit": "scans/s (m = 12 measurements per scan)", "target_hz": 100.0,
+           "roofline": {"bound": "hbm", "achieved": m12["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": m12["frac_of_hbm"], "traffic": None,
+                        "algorithmic_bytes_per_scan": 16.0 * length * length, "kernel": "k_large_rank_update (fp64 DMMA m8n8k4) + k_large_updates_coop"},
+           "per_m": out, "unknown_association_4000_candidates": assoc_res, "status": int(status[0]), "finite": bool(torch.isfinite(sig).all())}
+    if cpu_seconds > 0:
+        res["cpu_baseline"] = cpu_large(12, cpu_seconds)
+    del sig
+    torch.cuda.empty_cache()
+    return res
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(run()))
