@@ -173,29 +173,42 @@ def config_dict(world):
             "parallelism": f"filters sharded {world}x, no data-path collective; final NCCL all_gather of states + all_reduce of error statistics"}
 
 
-def e2e_leg(eng, torch, dist, world, dev, B, twists, zs, ids, t, K, dry):
-    """The same metric through the public host-buffer API (BatchedExtendedKalman.step_async = nuslam_ekf_step_async): pinned host buffers,
-    every step copies its twists / z / ids host -> device and its resulting state vector device -> host inside the timed region, three
-    steps in flight. dry = True: the same copies on the same streams with the kernels left out -- the ceiling the host side allows."""
+def e2e_leg(eng, torch, dist, world, dev, B, twists, zs, ids, t, K, dry, packed):
+    """The same metric through the public host-buffer API: pinned host buffers, every step copies its inputs host -> device and its
+    resulting state vector device -> host inside the timed region, three steps in flight.
+      packed = True : BatchedExtendedKalman.step_async_packed (nuslam_ekf_step_async_packed): ONE packed buffer [twists | z] per step,
+                      the known-correspondence ids kept on the device by set_ids (they are the same every step)
+      packed = False: BatchedExtendedKalman.step_async (nuslam_ekf_step_async): three buffers (twists, z, ids) per step
+    dry = True: the same calls with the kernels left out -- the ceiling the host side allows for that path."""
     nbuf = 3
-    h_tw = [torch.empty((B, 3), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
-    h_z = [torch.empty((B, N_LANDMARKS, 2), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
-    h_ids = ids.cpu().pin_memory()
     h_x = [torch.empty((B, LEN), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
-    for k in range(nbuf):
-        h_tw[k].copy_(twists[t + k])
-        h_z[k].copy_(zs[t + k])
+    if packed:
+        total, off_z, _ = eng.packed_layout(N_LANDMARKS, False)
+        h_p = [torch.empty(total, dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
+        for k in range(nbuf):
+            h_p[k][:off_z].view(torch.float64).view(B, 3).copy_(twists[t + k])
+            h_p[k][off_z:].view(torch.float64).view(B, N_LANDMARKS, 2).copy_(zs[t + k])
+        eng.set_ids(ids)
+        step = lambda k: eng.step_async_packed(h_p[k % nbuf].numpy(), N_LANDMARKS, eng.IDS_CACHED, h_x[k % nbuf].numpy())
+    else:
+        h_tw = [torch.empty((B, 3), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
+        h_z = [torch.empty((B, N_LANDMARKS, 2), dtype=torch.float64).pin_memory() for _ in range(nbuf)]
+        h_ids = ids.cpu().pin_memory()
+        for k in range(nbuf):
+            h_tw[k].copy_(twists[t + k])
+            h_z[k].copy_(zs[t + k])
+        step = lambda k: eng.step_async(h_tw[k % nbuf].numpy(), h_z[k % nbuf].numpy(), h_ids.numpy(), h_x[k % nbuf].numpy())
     torch.cuda.synchronize(dev)
     eng.async_dry_run(dry)
     for k in range(6):   # warm the host path (staging buffers, streams, events)
-        eng.step_async(h_tw[k % nbuf].numpy(), h_z[k % nbuf].numpy(), h_ids.numpy(), h_x[k % nbuf].numpy())
+        step(k)
     eng.wait_async()
     if world > 1:
         dist.barrier()
     checksum = 0.0
     t0 = time.perf_counter()
     for k in range(K):
-        eng.step_async(h_tw[k % nbuf].numpy(), h_z[k % nbuf].numpy(), h_ids.numpy(), h_x[k % nbuf].numpy())
+        step(k)
         # the host consumes the result of the step that has just left the pipeline (three calls back): robot pose of filter 0
         if k >= nbuf:
             checksum += float(h_x[k % nbuf][0, 1])
@@ -282,10 +295,13 @@ def run_ours(args):
 
     # ---- end to end through the public API with HOST buffers, and the copy-only ceiling of the same path ----
     Ke = max(3, min(K, args.e2e_steps))
-    e2e_runs = [e2e_leg(eng, torch, dist, world, dev, B, twists, zs, ids, t, Ke, dry=False) for _ in range(max(1, args.e2e_repeats))]
+    leg = lambda dry, packed: e2e_leg(eng, torch, dist, world, dev, B, twists, zs, ids, t, Ke, dry=dry, packed=packed)
+    e2e_runs = [leg(False, True) for _ in range(max(1, args.e2e_repeats))]
     e2e_value = float(np.median(e2e_runs))
-    ceiling = e2e_leg(eng, torch, dist, world, dev, B, twists, zs, ids, t, Ke, dry=True)
-    h2d = B * (3 * 8 + N_LANDMARKS * 2 * 8 + N_LANDMARKS * 4)
+    ceiling = leg(True, True)
+    sep_value, sep_ceiling = leg(False, False), leg(True, False)
+    h2d = B * (3 * 8 + N_LANDMARKS * 2 * 8)
+    h2d_sep = h2d + B * N_LANDMARKS * 4
     d2h = B * LEN * 8
 
     # ---- the only communication of the whole run: gather final states + error statistics (NCCL over NVLink) ----
@@ -325,12 +341,16 @@ def run_ours(args):
                       "bad_status": st["bad_status"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "runs": e2e_runs, "copy_ceiling": ceiling, "frac_of_copy_ceiling": e2e_value / ceiling if ceiling else None,
-                    "copy_ceiling_note": "the same nuslam_ekf_step_async calls with the kernels left out: identical copies, streams and events",
-                    "api": "BatchedExtendedKalman.step_async (nuslam_ekf_step_async): pinned host buffers, H2D + fused step + D2H of the state vector per step, 3 steps in flight",
+                    "copy_ceiling_note": "the same calls with the kernels left out (nuslam_ekf_async_dry_run): identical copies, streams and events",
+                    "api": "BatchedExtendedKalman.step_async_packed (nuslam_ekf_step_async_packed): one pinned packed buffer [twists | z] per step "
+                           "(one H2D copy), known-correspondence ids kept on the device by set_ids, fused step, D2H of the FULL state vector per step, "
+                           "3 steps in flight",
+                    "separate_buffers": {"value": sep_value, "copy_ceiling": sep_ceiling, "h2d_bytes_per_step": h2d_sep, "d2h_bytes_per_step": d2h,
+                                         "api": "BatchedExtendedKalman.step_async (nuslam_ekf_step_async): twists, z and ids as three host buffers per step"},
                     "host_affinity": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_filter_step": BYTES_PER_FILTER_STEP,
-                         "kernel": "k_ekf_pair_step<12> (two filters per warp; + k_ekf_strict_list over the first-touch work list, empty in steady state)" if args.mode == "fast" else "k_ekf_strict<kOpStep>",
+                         "kernel": "k_ekf_fast_step<12, BULK> (+ k_ekf_strict_list over the first-touch work list, empty in steady state)" if args.mode == "fast" else "k_ekf_strict<kOpStep>",
                          "launch_us": per_launch_s * 1e6, "launches_per_step": launches},
         }
     eng.close()

@@ -187,6 +187,20 @@ int nuslam_ekf_step(nuslam_ekf * h, const double * twists, const double * z, con
  * recycled the slot (three calls later) or nuslam_ekf_wait_async has returned. Same semantics and results as the synchronous
  * call: one iteration of nuslam/src/slam.cpp:262-319 per filter, followed by getStateVector(). */
 int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * z, const int32_t * ids, int32_t m, double * x_out);
+
+/* The same pipelined step with fewer, larger copies (the host-buffer path is bound by the copies, not by the kernel):
+ *   nuslam_ekf_set_ids          keeps the B x m known-correspondence ids on the device (a map with fixed landmark order sends the
+ *                               same ids every step); the buffer is free on return
+ *   nuslam_ekf_step_async_packed  takes ONE page-locked host buffer [twists B x 3 f64][z B x m x 2 f64][ids B x m i32 if
+ *                               NUSLAM_IDS_PACKED], copied by a single cudaMemcpyAsync. ids_mode: NUSLAM_IDS_NONE = unknown
+ *                               correspondence (associateLandmark on the device), NUSLAM_IDS_PACKED = ids travel in the buffer,
+ *                               NUSLAM_IDS_CACHED = the ids given to nuslam_ekf_set_ids (same m).
+ * x_out and the pipeline semantics are those of nuslam_ekf_step_async. */
+#define NUSLAM_IDS_NONE 0
+#define NUSLAM_IDS_PACKED 1
+#define NUSLAM_IDS_CACHED 2
+int nuslam_ekf_set_ids(nuslam_ekf * h, const int32_t * ids, int32_t m, int mem);
+int nuslam_ekf_step_async_packed(nuslam_ekf * h, const void * packed, int32_t m, int ids_mode, double * x_out);
 int nuslam_ekf_wait_async(nuslam_ekf * h);
 
 /* EKFSlam::broadcast_map2odom_tf, nuslam/src/slam.cpp:175-210 (the step after the path): T_mo = T_mb * T_ob.inv() with T_mb from

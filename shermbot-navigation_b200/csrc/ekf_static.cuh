@@ -40,8 +40,9 @@ struct __align__(16) StaticSmem
     double z[2 * kFastMMax];
 };
 
-// (A) publish landmark rows / columns c, c+1 (slot-space update i, chunk slot s) from the fragments into vector layout; s and i
-// are constants after inlining into the unrolled update loop
+// (A) publish landmark rows / columns c, c+1 (slot-space update i, chunk slot s) from the fragments into vector layout. The update
+// loop is ROLLED (its fully unrolled form, 60 KB of code, lost more to instruction fetch than it saved: the instruction cache holds
+// 32 KB): i is a loop value, so the fragment block is picked by a three-way switch; everything else is warp-uniform arithmetic on i.
 template <int NB>
 __device__ __forceinline__ void static_publish(const double (&C)[NB][NB][2], const double Rt, const double Rx, const double Ry, const double Ct,
                                                const double Cx, const double Cy, StaticSmem & F, const int g, const int t, const int lane,
@@ -53,12 +54,25 @@ __device__ __forceinline__ void static_publish(const double (&C)[NB][NB][2], con
     const bool csel = t == sel;          // this lane holds columns c, c+1
     double * const rdst = &F.rho[s][g & 1][4 + 2 * t];
     double2 * const cdst = &F.kap[s][3 + g];
-#pragma unroll
-    for (int qq = 0; qq < NB; ++qq)
-    {
-        if (rsel) *reinterpret_cast<double2 *>(rdst + 8 * qq) = make_double2(C[bsel][qq][0], C[bsel][qq][1]);
-        if (csel) cdst[8 * qq] = make_double2(C[qq][bsel][0], C[qq][bsel][1]);
+#define NUSLAM_SPUB(b)                                                                                                       \
+    _Pragma("unroll") for (int qq = 0; qq < NB; ++qq)                                                                        \
+    {                                                                                                                        \
+        if (rsel) *reinterpret_cast<double2 *>(rdst + 8 * qq) = make_double2(C[b < NB ? b : 0][qq][0], C[b < NB ? b : 0][qq][1]); \
+        if (csel) cdst[8 * qq] = make_double2(C[qq][b < NB ? b : 0][0], C[qq][b < NB ? b : 0][1]);                           \
     }
+    if (bsel == 0)
+    {
+        NUSLAM_SPUB(0)
+    }
+    else if (bsel == 1)
+    {
+        NUSLAM_SPUB(1)
+    }
+    else
+    {
+        NUSLAM_SPUB(2)
+    }
+#undef NUSLAM_SPUB
     // robot part of rows / columns c, c+1: the two lanes that own those indices
     if (lane == c || lane == c + 1)
     {
@@ -294,7 +308,7 @@ k_ekf_static_step(const EkfParams p, const int do_predict, int32_t * __restrict_
         __syncwarp();
 
         // ---- m sequential updates in chunks of 2 (slam.cpp:279-319), slot space: update i works on state indices 3 + 2 i, 4 + 2 i ----
-#pragma unroll
+#pragma unroll 1
         for (int ch = 0; ch < (NL + 1) / 2; ++ch)
         {
             if (2 * ch >= m) break;   // warp-uniform

@@ -103,6 +103,8 @@ struct nuslam_ekf
     } slots[3];
     cudaStream_t s_in = nullptr, s_out = nullptr;
     uint64_t async_count = 0;
+    DevBuf ids_cache;          // nuslam_ekf_set_ids: B x ids_cache_m known-correspondence ids kept on the device
+    int32_t ids_cache_m = 0;
     bool async_dry = false;   // nuslam_ekf_async_dry_run: step_async performs its copies and event chaining, no kernel (copy ceiling)
     // LARGE-MAP mode (state too long for the on-chip batched kernels): delayed-update scratch, see ekf_large.cuh
     bool large = false;
@@ -735,10 +737,13 @@ int nuslam_ekf_scan_step(nuslam_ekf * h, const double * twists, const float * ra
     return finish(h, mem);
 }
 
-int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * z, const int32_t * ids, int32_t m, double * x_out)
+namespace
 {
-    if (!h || !twists || !x_out) return fail(NUSLAM_ERR_INVALID, "null argument");
-    if (m < 0 || (m > 0 && !z)) return fail(NUSLAM_ERR_INVALID, "m < 0 or null z");
+// one pipelined host-buffer step. Inputs either as three host arrays (twists, z, ids_host) or as ONE packed host buffer
+// [twists | z | ids] copied by a single cudaMemcpyAsync; ids may also come from the handle's device cache (ids_dev).
+int step_async_impl(nuslam_ekf * h, const double * twists, const double * z, const int32_t * ids_host, const int32_t * ids_dev, const void * packed,
+                    bool packed_has_ids, int32_t m, double * x_out)
+{
     if (select_device(h)) return NUSLAM_ERR_CUDA;
     if (!h->s_in)
     {
@@ -755,17 +760,39 @@ int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * 
     // the slot's previous step must have left: its kernel has consumed the staged inputs and its snapshot has reached the host
     if (sl.busy) CU(cudaEventSynchronize(sl.d2h_done));
     const size_t B = (size_t) h->batch, l = (size_t) h->len;
-    int rc = sl.tw.reserve(sizeof(double) * 3 * B);
-    if (!rc) rc = sl.z.reserve(sizeof(double) * 2 * B * (m > 0 ? m : 1));
-    if (!rc && ids) rc = sl.ids.reserve(sizeof(int32_t) * B * (m > 0 ? m : 1));
-    if (!rc) rc = sl.xsnap.reserve(sizeof(double) * l * B);
+    const size_t b_tw = sizeof(double) * 3 * B, b_z = sizeof(double) * 2 * B * (size_t) m, b_ids = sizeof(int32_t) * B * (size_t) m;
+    const double * d_tw = nullptr;
+    const double * d_z = nullptr;
+    const int32_t * d_ids = ids_dev;
+    int rc = sl.xsnap.reserve(sizeof(double) * l * B);
     if (rc) return rc;
     // stage 1 (copy-in stream): host -> device
-    CU(cudaMemcpyAsync(sl.tw.p, twists, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, h->s_in));
-    if (m > 0)
+    if (packed)
     {
-        CU(cudaMemcpyAsync(sl.z.p, z, sizeof(double) * 2 * B * m, cudaMemcpyHostToDevice, h->s_in));
-        if (ids) CU(cudaMemcpyAsync(sl.ids.p, ids, sizeof(int32_t) * B * m, cudaMemcpyHostToDevice, h->s_in));
+        // [twists B x 3 f64][z B x m x 2 f64][ids B x m i32]: one copy (every section starts 8-byte aligned)
+        const size_t total = b_tw + b_z + (packed_has_ids ? b_ids : 0);
+        rc = sl.tw.reserve(total);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(sl.tw.p, packed, total, cudaMemcpyHostToDevice, h->s_in));
+        d_tw = static_cast<const double *>(sl.tw.p);
+        d_z = reinterpret_cast<const double *>(static_cast<const char *>(sl.tw.p) + b_tw);
+        if (packed_has_ids) d_ids = reinterpret_cast<const int32_t *>(static_cast<const char *>(sl.tw.p) + b_tw + b_z);
+    }
+    else
+    {
+        rc = sl.tw.reserve(b_tw);
+        if (!rc) rc = sl.z.reserve(b_z > 0 ? b_z : 8);
+        if (!rc && ids_host) rc = sl.ids.reserve(b_ids > 0 ? b_ids : 8);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(sl.tw.p, twists, b_tw, cudaMemcpyHostToDevice, h->s_in));
+        if (m > 0)
+        {
+            CU(cudaMemcpyAsync(sl.z.p, z, b_z, cudaMemcpyHostToDevice, h->s_in));
+            if (ids_host) CU(cudaMemcpyAsync(sl.ids.p, ids_host, b_ids, cudaMemcpyHostToDevice, h->s_in));
+        }
+        d_tw = static_cast<const double *>(sl.tw.p);
+        d_z = static_cast<const double *>(sl.z.p);
+        if (ids_host) d_ids = static_cast<const int32_t *>(sl.ids.p);
     }
     CU(cudaEventRecord(sl.h2d_done, h->s_in));
     // stage 2 (compute stream): the step on device buffers, then a snapshot of x so that the next step may start at once
@@ -774,9 +801,7 @@ int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * 
     // kernels do not: a device-to-device copy stands in
     const bool in_kernel_snapshot = !h->large;
     h->x_snap_next = in_kernel_snapshot ? static_cast<double *>(sl.xsnap.p) : nullptr;
-    rc = h->async_dry ? NUSLAM_OK
-                      : nuslam_ekf_step(h, static_cast<const double *>(sl.tw.p), static_cast<const double *>(sl.z.p),
-                                        ids ? static_cast<const int32_t *>(sl.ids.p) : nullptr, m, nullptr, NUSLAM_DEVICE);
+    rc = h->async_dry ? NUSLAM_OK : nuslam_ekf_step(h, d_tw, d_z, d_ids, m, nullptr, NUSLAM_DEVICE);
     h->x_snap_next = nullptr;
     if (rc) return rc;
     if (!in_kernel_snapshot && !h->async_dry) CU(cudaMemcpyAsync(sl.xsnap.p, h->x, sizeof(double) * l * B, cudaMemcpyDeviceToDevice, h->stream));
@@ -788,6 +813,42 @@ int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * 
     sl.busy = true;
     h->async_count++;
     return NUSLAM_OK;
+}
+}   // namespace
+
+int nuslam_ekf_step_async(nuslam_ekf * h, const double * twists, const double * z, const int32_t * ids, int32_t m, double * x_out)
+{
+    if (!h || !twists || !x_out) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (m < 0 || (m > 0 && !z)) return fail(NUSLAM_ERR_INVALID, "m < 0 or null z");
+    return step_async_impl(h, twists, z, ids, nullptr, nullptr, false, m, x_out);
+}
+
+int nuslam_ekf_set_ids(nuslam_ekf * h, const int32_t * ids, int32_t m, int mem)
+{
+    if (!h || !ids || m < 1) return fail(NUSLAM_ERR_INVALID, "null argument or m < 1");
+    if (select_device(h)) return NUSLAM_ERR_CUDA;
+    const size_t bytes = sizeof(int32_t) * (size_t) h->batch * (size_t) m;
+    int rc = h->ids_cache.reserve(bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->ids_cache.p, ids, bytes, mem == NUSLAM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    if (mem == NUSLAM_HOST) CU(cudaStreamSynchronize(h->stream));   // the caller's buffer is free on return
+    h->ids_cache_m = m;
+    return NUSLAM_OK;
+}
+
+int nuslam_ekf_step_async_packed(nuslam_ekf * h, const void * packed, int32_t m, int ids_mode, double * x_out)
+{
+    if (!h || !packed || !x_out) return fail(NUSLAM_ERR_INVALID, "null argument");
+    if (m < 0) return fail(NUSLAM_ERR_INVALID, "m < 0");
+    const int32_t * cached = nullptr;
+    if (ids_mode == NUSLAM_IDS_CACHED)
+    {
+        if (h->ids_cache_m != m || !h->ids_cache.p) return fail(NUSLAM_ERR_INVALID, "NUSLAM_IDS_CACHED: call nuslam_ekf_set_ids with the same m first");
+        cached = static_cast<const int32_t *>(h->ids_cache.p);
+    }
+    else if (ids_mode != NUSLAM_IDS_PACKED && ids_mode != NUSLAM_IDS_NONE)
+        return fail(NUSLAM_ERR_INVALID, "ids_mode is NUSLAM_IDS_NONE, NUSLAM_IDS_PACKED or NUSLAM_IDS_CACHED");
+    return step_async_impl(h, nullptr, nullptr, nullptr, cached, packed, ids_mode == NUSLAM_IDS_PACKED, m, x_out);
 }
 
 int nuslam_ekf_async_dry_run(nuslam_ekf * h, int on)

@@ -35,31 +35,44 @@ namespace nuslam
 
 constexpr int kMomWarps = 4;          // scans per CTA
 constexpr int kMomMaxClusters = 32;   // pre-erase clusters handled by the warp (one per lane); busier scans take the work list
+constexpr int kMomSums = 10;          // per cluster: X, Y, XX, YY, XY, XZ, YZ, ZZ about its first point, angle, angle^2
 
 struct __align__(16) MomentSmem
 {
     unsigned pb[kBeams + 8];                  // flat position (in-range beams in beam order) -> beam | pre-erase cluster << 16
-    double acc[kMomMaxClusters][10];          // per cluster: sums X, Y | XX, YY, XY, XZ, YZ, ZZ (centred) | angle, angle^2
+    double acc[kMomMaxClusters][kMomSums];    // per cluster: the sums above
     double org[kMomMaxClusters][2];           // per cluster: its first point (local origin of the sums)
     short cend[kMomMaxClusters + 8];          // flat position of the cluster's last point
+    unsigned char bclu[kBeams + 8];           // per beam: its pre-erase cluster, 255 when the beam is in no cluster
 };
 
-// segmented inclusive scan over the lanes: lanes with equal `key` are contiguous; afterwards the LAST lane of a run holds its total
-template <int NV>
-__device__ __forceinline__ void seg_scan(double (&v)[NV], const int key, const int lane)
+// the atan2 tables of fastmath.cuh in shared memory (the lanes index them with different entries, which the constant cache serialises)
+struct MomentTables
 {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1)
-    {
-        const int kk = __shfl_up_sync(0xffffffffu, key, d);
-        const bool take = lane >= d && kk == key;
-#pragma unroll
-        for (int k = 0; k < NV; ++k)
-        {
-            const double tv = __shfl_up_sync(0xffffffffu, v[k], d);
-            if (take) v[k] += tv;
-        }
-    }
+    double2 tab[65];
+    AtanOctant oct[8];
+};
+
+// atan2_fast (fastmath.cuh) on shared-memory tables: ~1e-16 absolute
+__device__ __forceinline__ double atan2_tab(double y, double x, const MomentTables & T)
+{
+    const double ax = fabs(x), ay = fabs(y);
+    const bool sw = ay > ax;
+    const double mx = sw ? ay : ax, mn = sw ? ax : ay;
+    const int idx = (sw ? 1 : 0) | (x < 0.0 ? 2 : 0) | (y < 0.0 ? 4 : 0);
+    const float tf = __fdividef((float) mn, (float) mx);
+    const int k = max(0, min(64, __float2int_rn(tf * 64.0f)));
+    const double tk = (double) k * 0.015625;
+    const double2 ak = T.tab[k];
+    const AtanOctant oc = T.oct[idx];
+    const double num = fma(-tk, mx, mn), den = fma(tk, mn, mx);
+    const double rc = rcp_fast(den);
+    double r = num * rc;
+    r = fma(fma(-den, r, num), rc, r);   // r = num / den to ~1 ulp
+    const double u = r * r;
+    const double pl = fma(fma(fma(kFastK[0], u, kFastK[1]), u, kFastK[2]), u * r, r);   // atan(r)
+    const double a = ak.x + (pl + ak.y);                                              // atan(mn / mx) in [0, pi/4]
+    return oc.hi + fma(oc.s, a, oc.lo);
 }
 
 struct ScanGate
@@ -87,11 +100,18 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
               double * __restrict__ circles, const int max_circles, const int scan_ub, int32_t * __restrict__ slow, int32_t * __restrict__ slow_count)
 {
     __shared__ MomentSmem smem_all[kMomWarps];
+    __shared__ __align__(16) MomentTables tabs;
     MomentSmem & sm = smem_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     constexpr unsigned kFull = 0xffffffffu;
     constexpr int kChunks = (kBeams + 31) / 32;   // 12
     const unsigned lt = (1u << lane) - 1u;
+    for (int k = threadIdx.x; k < 65 + 16; k += blockDim.x)
+    {
+        if (k < 65) tabs.tab[k] = kAtanTab[k];
+        else reinterpret_cast<double2 *>(tabs.oct)[k - 65] = reinterpret_cast<const double2 *>(kAtanOct)[k - 65];
+    }
+    __syncthreads();
     for (int64_t s = (int64_t) blockIdx.x * kMomWarps + (threadIdx.x >> 5); s < n_scans; s += (int64_t) gridDim.x * kMomWarps)
     {
         const float * rs = ranges + s * kBeams;
@@ -100,8 +120,10 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
         for (int k = 0; k < kChunks; ++k) r[k] = (32 * k + lane < kBeams) ? __ldg(rs + 32 * k + lane) : 0.0f;
         r[kChunks] = 0.0f;
         const float r_first = __shfl_sync(kFull, r[0], 0);
-        // ---- per-beam predicates and their ballots (circle_fit_library.cpp:146-190) ----
-        unsigned inr_m[kChunks], clo_m[kChunks];
+        // ---- per-beam predicates, their ballots (circle_fit_library.cpp:146-190), flat positions and cluster ends, in one sweep ----
+        // closer_i = in range and not similar to beam i + 1; the cluster of an in-range beam = closers before it
+        int nc = 0, npts = 0;
+        bool risky = false, wrap = false;
 #pragma unroll
         for (int k = 0; k < kChunks; ++k)
         {
@@ -111,27 +133,33 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
             if (i == kBeams - 1) nb = r_first;
             const float rv = r[k];
             const bool inr = i < kBeams && !(rv > gate.max_f || rv < gate.min_f);   // :149, NaN counts as in range
-            // :166 |r_i - r_(i+1)| < 0.04 in double. The float difference is within an ulp of the exact one: decided in float unless
-            // it lies within 1e-5 of the threshold (or the ranges are huge), then in double like the reference
+            // :166 |r_i - r_(i+1)| < 0.04 in double. The float difference is within an ulp of the exact one: decided in float; a scan
+            // where it lies within 1e-5 of the threshold (or a range is huge / NaN) goes to the oracle-order kernel, which compares
+            // in double like the reference
             const float df = fabsf(rv - nb);
-            bool sim = df < 0.04f;
-            if (fabsf(df - 0.04f) < 1e-5f || !(fabsf(rv) < 64.0f) || !(fabsf(nb) < 64.0f)) sim = fabs((double) rv - (double) nb) < 0.04;
-            inr_m[k] = __ballot_sync(kFull, inr);
-            clo_m[k] = __ballot_sync(kFull, inr && !sim);
-        }
-        constexpr int kLastBit = (kBeams - 1) & 31;
-        const bool wrap = ((inr_m[kChunks - 1] >> kLastBit) & 1u) && !((clo_m[kChunks - 1] >> kLastBit) & 1u);
-        // beam 359 in range and similar to beam 0: it is not stored in the flat list but appended to cluster 0 (:170-174)
-        if (wrap) inr_m[kChunks - 1] &= ~(1u << kLastBit);
-        int nc = 0, npts = 0;
-#pragma unroll
-        for (int k = 0; k < kChunks; ++k)
-        {
-            nc += __popc(clo_m[k]);
-            npts += __popc(inr_m[k]);
+            const bool sim = df < 0.04f;
+            risky = risky || (inr && (!(fabsf(df - 0.04f) >= 1e-5f) || !(fmaxf(fabsf(rv), fabsf(nb)) < 64.0f)));
+            unsigned inr_m = __ballot_sync(kFull, inr);
+            const unsigned clo_m = __ballot_sync(kFull, inr && !sim);
+            if (k == kChunks - 1)
+            {
+                constexpr int kLastBit = (kBeams - 1) & 31;
+                wrap = ((inr_m >> kLastBit) & 1u) && !((clo_m >> kLastBit) & 1u);
+                // beam 359 in range and similar to beam 0: it is not stored in the flat list but appended to cluster 0 (:170-174)
+                if (wrap) inr_m &= ~(1u << kLastBit);
+            }
+            const bool inr2 = (inr_m >> lane) & 1u;
+            const int pos = npts + __popc(inr_m & lt), clu = nc + __popc(clo_m & lt);
+            if (inr2)
+            {
+                sm.pb[pos] = (unsigned) i | ((unsigned) clu << 16);
+                if ((clo_m >> lane) & 1u) sm.cend[clu & (kMomMaxClusters - 1)] = (short) pos;
+            }
+            if (i < kBeams) sm.bclu[i] = inr2 ? (unsigned char) min(clu, 254) : (unsigned char) 255;
+            npts += __popc(inr_m);
+            nc += __popc(clo_m);
         }
         const int64_t sb = s * kBeams;
-        NUSLAM_DBG("[scan %lld] nc %d npts %d wrap %d\n", (long long) s, nc, npts, (int) wrap);
         if (wrap && nc == 0)
         {
             // clusters[0].push_back on an empty vector (:173): undefined behaviour in the reference
@@ -142,30 +170,14 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
                 n_clusters[s] = 0;
                 n_circles[s] = scan_ub;
             }
+            __syncwarp();
             continue;
         }
-        if (nc > kMomMaxClusters)
+        if (nc > kMomMaxClusters || __any_sync(kFull, risky))
         {
             if (lane == 0) slow[atomicAdd(slow_count, 1)] = (int32_t) s;   // the one-warp-per-scan kernel writes every output of this scan
+            __syncwarp();
             continue;
-        }
-        // ---- flat positions, cluster ends ----
-        {
-            int pos_base = 0, clu_base = 0;
-#pragma unroll
-            for (int k = 0; k < kChunks; ++k)
-            {
-                if (inr_m[k] == 0u) continue;   // warp-uniform
-                const bool inr = (inr_m[k] >> lane) & 1u, clo = (clo_m[k] >> lane) & 1u;
-                const int pos = pos_base + __popc(inr_m[k] & lt), clu = clu_base + __popc(clo_m[k] & lt);
-                if (inr)
-                {
-                    sm.pb[pos] = (unsigned) (32 * k + lane) | ((unsigned) clu << 16);
-                    if (clo) sm.cend[clu] = (short) pos;
-                }
-                pos_base += __popc(inr_m[k]);
-                clu_base += __popc(clo_m[k]);
-            }
         }
         __syncwarp();
         // ---- one cluster per lane: extent, erase loop (:198-204) in closed form ----
@@ -181,141 +193,123 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
         const unsigned erased_m = __ballot_sync(kFull, erased);
         const int newidx = (lane < nc && !erased) ? lane - __popc(erased_m & lt) : -1;
         const int nk = nc - __popc(erased_m);
-        NUSLAM_DBG("[scan %lld] nk %d erased %x\n", (long long) s, nk, erased_m);
         if (cluster_of_beam)
         {
             const int new0 = __shfl_sync(kFull, newidx, 0);
-            int clu_base = 0;
-#pragma unroll
+#pragma unroll 1
             for (int k = 0; k < kChunks; ++k)
             {
                 const int i = 32 * k + lane;
-                const bool inr = (inr_m[k] >> lane) & 1u;
-                const int clu = clu_base + __popc(clo_m[k] & lt);
-                const int nidx = __shfl_sync(kFull, newidx, clu & 31);
-                int out = (inr && clu < nc) ? nidx : -1;
+                const int bc = (i < kBeams) ? (int) sm.bclu[i] : 255;
+                const int nidx = __shfl_sync(kFull, newidx, bc & 31);
+                int out = (bc < nc) ? nidx : -1;   // beams behind the last closer form the open cluster the reference drops
                 if (wrap && i == kBeams - 1) out = new0;
                 if (i < kBeams) cluster_of_beam[sb + i] = (int16_t) out;
-                clu_base += __popc(clo_m[k]);
             }
         }
-        // ---- points: one per lane, two passes of segmented warp sums (centroid, then centred moments and inscribed angles) ----
-        // a cluster is examined when it survives the erase loop and has at least 3 points (fewer: classifyCluster's std is 0/0 = NaN, :229-249)
+        // ---- points: one per lane, ONE pass of segmented warp sums about the cluster's first point: the sums the Hyper fit needs and
+        // the inscribed angles of classifyCluster. A cluster is examined when it survives the erase loop and has at least 3 points
+        // (fewer: classifyCluster's std is 0/0 = NaN, :229-249)
         const bool examined = lane < nc && !erased && csize >= 3;
         const int ntot = npts + (wrap ? 1 : 0);
-        double ca = 0.0, cb = 0.0;   // centroid of this lane's cluster, relative to its first point
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass)
+        for (int base = 0; base < ntot; base += 32)
         {
+            const int j = base + lane;
+            const bool iswrap = wrap && j == npts;
+            const unsigned pbv = (j < npts) ? sm.pb[j] : 0u;
+            const int beam = iswrap ? kBeams - 1 : (int) (pbv & 0xffffu);
+            const int clu = iswrap ? 0 : (int) (pbv >> 16);
+            const int src = clu & 31;
+            const int cs = __shfl_sync(kFull, cstart, src), ce = __shfl_sync(kFull, cend, src);
+            const bool ex = __shfl_sync(kFull, examined ? 1 : 0, src) != 0;
+            const bool active = (j < npts || iswrap) && clu < nc && ex;
+            const bool wrapped_cluster = wrap && clu == 0;
+            const int b2 = active ? (int) (sm.pb[cs] & 0xffffu) : 0;
+            const int b3 = !active ? 0 : wrapped_cluster ? kBeams - 1 : (int) (sm.pb[ce] & 0xffffu);
+            // points = r (cos, sin)(deg2rad(beam)) (:161-163), relative to the cluster's first point
+            const double r1 = (double) __ldg(rs + beam), r2 = (double) __ldg(rs + b2), r3 = (double) __ldg(rs + b3);
+            const double x2 = r2 * __ldg(&c_beam_cos[b2]), y2 = r2 * __ldg(&c_beam_sin[b2]);
+            const double X = active ? fma(r1, __ldg(&c_beam_cos[beam]), -x2) : 0.0, Y = active ? fma(r1, __ldg(&c_beam_sin[beam]), -y2) : 0.0;
+            const double Z = fma(X, X, Y * Y);
+            double v[kMomSums];
+            v[0] = X;
+            v[1] = Y;
+            v[2] = X * X;
+            v[3] = Y * Y;
+            v[4] = X * Y;
+            v[5] = X * Z;
+            v[6] = Y * Z;
+            v[7] = Z * Z;
+            // inscribed angle of an interior point P1 over the chord P2 (first) -> P3 (last as stored) (:211-224), in degrees
+            const bool last = iswrap || (!wrapped_cluster && j == ce);
+            double ang = 0.0;
+            if (active && j != cs && !last)
+            {
+                const double X3 = fma(r3, __ldg(&c_beam_cos[b3]), -x2), Y3 = fma(r3, __ldg(&c_beam_sin[b3]), -y2);
+                const double num = fma(Y, X3, -(Y3 * X));
+                const double den = -fma(X, X - X3, Y * (Y - Y3));
+                ang = (180.0 / kPiRef) * atan2_tab(num, den, tabs);
+            }
+            v[8] = ang;
+            v[9] = ang * ang;
+            // segmented inclusive scan: lanes of one cluster are contiguous; as many doubling steps as the longest run in this batch needs
+            const int key = active ? (iswrap ? 32 : clu) : -1 - lane;
+            const int runpos = (active && !iswrap) ? j - max(cs, base) : 0;
+            const int maxrun = __reduce_max_sync(kFull, runpos);
 #pragma unroll 1
-            for (int base = 0; base < ntot; base += 32)
+            for (int d = 1; d <= maxrun; d <<= 1)
             {
-                const int j = base + lane;
-                NUSLAM_DBG("[scan %lld] pass %d base %d of %d\n", (long long) s, pass, base, ntot);
-                const bool iswrap = wrap && j == npts;
-                const unsigned pbv = (j < npts) ? sm.pb[j] : 0u;
-                const int beam = iswrap ? kBeams - 1 : (int) (pbv & 0xffffu);
-                const int clu = iswrap ? 0 : (int) (pbv >> 16);
-                const int src = clu & 31;
-                const int cs = __shfl_sync(kFull, cstart, src), ce = __shfl_sync(kFull, cend, src);
-                const bool ex = __shfl_sync(kFull, examined ? 1 : 0, src) != 0;
-                const bool active = (j < npts || iswrap) && clu < nc && ex;
-                const bool wrapped_cluster = wrap && clu == 0;
-                const int b2 = active ? (int) (sm.pb[cs] & 0xffffu) : 0;
-                const int b3 = !active ? 0 : wrapped_cluster ? kBeams - 1 : (int) (sm.pb[ce] & 0xffffu);
-                NUSLAM_CHK((unsigned) beam < 360u && (unsigned) b2 < 360u && (unsigned) b3 < 360u, 2);
-                // points = r (cos, sin)(deg2rad(beam)) (:161-163), relative to the cluster's first point
-                const double r1 = (double) __ldg(rs + beam), r2 = (double) __ldg(rs + b2), r3 = (double) __ldg(rs + b3);
-                const double x2 = r2 * __ldg(&c_beam_cos[b2]), y2 = r2 * __ldg(&c_beam_sin[b2]);
-                const double X = active ? fma(r1, __ldg(&c_beam_cos[beam]), -x2) : 0.0, Y = active ? fma(r1, __ldg(&c_beam_sin[beam]), -y2) : 0.0;
-                const int key = active ? (iswrap ? 32 : clu) : -1 - lane;
-                const int key_next = __shfl_down_sync(kFull, key, 1);   // (every lane takes part: no collective behind a short-circuit)
-                const bool tail = lane == 31 || key_next != key;
-                const bool first = cs >= base;   // the cluster's first contribution to its accumulators
-                if (pass == 0)
-                {
-                    double v[2] = {X, Y};
-                    seg_scan<2>(v, key, lane);
-                    if (tail && active && !iswrap)
-                    {
-                        sm.acc[clu][0] = first ? v[0] : sm.acc[clu][0] + v[0];
-                        sm.acc[clu][1] = first ? v[1] : sm.acc[clu][1] + v[1];
-                        sm.org[clu][0] = x2;
-                        sm.org[clu][1] = y2;
-                    }
-                    __syncwarp();
-                    if (active && iswrap)
-                    {
-                        sm.acc[0][0] += v[0];
-                        sm.acc[0][1] += v[1];
-                    }
-                    __syncwarp();
-                }
-                else
-                {
-                    const double a = __shfl_sync(kFull, ca, src), b = __shfl_sync(kFull, cb, src);
-                    const double Xc = X - a, Yc = Y - b;
-                    const double Z = fma(Xc, Xc, Yc * Yc);
-                    double v[8];
-                    v[0] = active ? Xc * Xc : 0.0;
-                    v[1] = active ? Yc * Yc : 0.0;
-                    v[2] = active ? Xc * Yc : 0.0;
-                    v[3] = active ? Xc * Z : 0.0;
-                    v[4] = active ? Yc * Z : 0.0;
-                    v[5] = active ? Z * Z : 0.0;
-                    // inscribed angle of an interior point P1 over the chord P2 (first) -> P3 (last as stored) (:211-224)
-                    const bool last = iswrap || (!wrapped_cluster && j == ce);
-                    const bool interior = active && j != cs && !last;
-                    double ang = 0.0;
-                    if (interior)
-                    {
-                        const double X3 = fma(r3, __ldg(&c_beam_cos[b3]), -x2), Y3 = fma(r3, __ldg(&c_beam_sin[b3]), -y2);
-                        const double num = fma(Y, X3, -(Y3 * X));
-                        const double den = -fma(X, X - X3, Y * (Y - Y3));
-                        ang = (180.0 / kPiRef) * atan2(num, den);
-                    }
-                    v[6] = ang;
-                    v[7] = ang * ang;
-                    NUSLAM_DBG("[scan %lld] angles done\n", (long long) s);
-                    seg_scan<8>(v, key, lane);
-                    NUSLAM_DBG("[scan %lld] seg_scan done\n", (long long) s);
-                    if (tail && active && !iswrap)
-                    {
+                const int kk = __shfl_up_sync(kFull, key, d);
+                const bool take = lane >= d && kk == key;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) sm.acc[clu][2 + k] = first ? v[k] : sm.acc[clu][2 + k] + v[k];
-                    }
-                    __syncwarp();
-                    if (active && iswrap)
-                    {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) sm.acc[0][2 + k] += v[k];
-                    }
-                    __syncwarp();
+                for (int k = 0; k < kMomSums; ++k)
+                {
+                    const double tv = __shfl_up_sync(kFull, v[k], d);
+                    if (take) v[k] += tv;
                 }
             }
-            if (pass == 0 && examined)
+            const int key_next = __shfl_down_sync(kFull, key, 1);   // (every lane takes part: no collective behind a short-circuit)
+            const bool tail = lane == 31 || key_next != key;
+            const bool first = cs >= base;   // the cluster's first contribution to its accumulators
+            if (tail && active && !iswrap)
             {
-                const double inv_n = 1.0 / (double) csize;
-                ca = sm.acc[lane][0] * inv_n;
-                cb = sm.acc[lane][1] * inv_n;
+#pragma unroll
+                for (int k = 0; k < kMomSums; ++k) sm.acc[clu][k] = first ? v[k] : sm.acc[clu][k] + v[k];
+                sm.org[clu][0] = x2;
+                sm.org[clu][1] = y2;
             }
+            __syncwarp();
+            if (active && iswrap)
+            {
+#pragma unroll
+                for (int k = 0; k < kMomSums; ++k) sm.acc[0][k] += v[k];
+            }
+            __syncwarp();
         }
         // ---- one cluster per lane: classification, Hyper fit, gates ----
-        NUSLAM_DBG("[scan %lld] solve\n", (long long) s);
         bool pub = false, fallback = false;
         double cx = 0.0, cy = 0.0, R = 0.0;
         if (examined)
         {
-            const double inv_n = 1.0 / (double) csize, inv_na = 1.0 / (double) (csize - 2);
-            const double mean = sm.acc[lane][8] * inv_na;
-            const double var = fma(-mean, mean, sm.acc[lane][9] * inv_na);
-            const double sd = sqrt(fmax(var, 0.0));   // population std of the angles in degrees (:229-241); one angle: 0
-            if (!(fabs(sd - 10.0) > 1e-6)) fallback = true;   // too close to the gate (or not finite): the oracle-order kernel decides
-            const bool circle = sd < 10.0;                     // :243
-            if (circle && csize >= 4)                          // circleFit rejects N < 4 with id = -1 (:72-76)
+            const double n = (double) csize, inv_n = rcp_fast(n), inv_na = rcp_fast((double) (csize - 2));
+            const double * S = sm.acc[lane];
+            const double mean = S[8] * inv_na;
+            const double var = fma(-mean, mean, S[9] * inv_na);   // population variance of the angles in degrees (:229-241); one angle: 0
+            // std < 10 degrees <=> var < 100 (:243); within 1e-6 degrees of the gate (or not finite): the oracle-order kernel decides
+            if (!(fabs(var - 100.0) > 2e-5)) fallback = true;
+            const bool circle = var < 100.0;
+            if (circle && csize >= 4)   // circleFit rejects N < 4 with id = -1 (:72-76)
             {
-                const double Mxx = sm.acc[lane][2] * inv_n, Myy = sm.acc[lane][3] * inv_n, Mxy = sm.acc[lane][4] * inv_n;
-                const double Mxz = sm.acc[lane][5] * inv_n, Myz = sm.acc[lane][6] * inv_n, Mzz = sm.acc[lane][7] * inv_n;
+                // centroid (relative to the first point) and the centred moments from the sums about the first point
+                const double Sx = S[0], Sy = S[1], Sxx = S[2], Syy = S[3], Sxy = S[4], Sxz = S[5], Syz = S[6], Szz = S[7];
+                const double a = Sx * inv_n, b = Sy * inv_n, Sz = Sxx + Syy, q = fma(a, a, b * b);
+                const double Mxx = fma(-a, a, Sxx * inv_n), Myy = fma(-b, b, Syy * inv_n), Mxy = fma(-a, b, Sxy * inv_n);
+                const double Cxz = Sxz - 2.0 * a * Sxx - 2.0 * b * Sxy + q * Sx - a * Sz + 2.0 * a * a * Sx + 2.0 * a * b * Sy - a * q * n;
+                const double Cyz = Syz - 2.0 * b * Syy - 2.0 * a * Sxy + q * Sy - b * Sz + 2.0 * b * b * Sy + 2.0 * a * b * Sx - b * q * n;
+                const double Czz = Szz - 4.0 * a * Sxz - 4.0 * b * Syz + 2.0 * q * Sz + 4.0 * a * a * Sxx + 8.0 * a * b * Sxy + 4.0 * b * b * Syy -
+                                   4.0 * a * q * Sx - 4.0 * b * q * Sy + n * q * q;
+                const double Mxz = Cxz * inv_n, Myz = Cyz * inv_n, Mzz = Czz * inv_n;
                 const double Mz = Mxx + Myy;
                 const double Cov = fma(Mxx, Myy, -Mxy * Mxy);
                 const double Var = fma(-Mz, Mz, Mzz);
@@ -327,17 +321,17 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
                 double eta = 0.0, yv = A0;
                 bool converged = false;
 #pragma unroll 1
-                for (int it = 0; it < 24; ++it)
+                for (int it = 0; it < 16; ++it)
                 {
-                    const double Dy = A1 + eta * (A22 + 16.0 * eta * eta);
-                    const double en = eta - yv / Dy;
-                    if (en == eta)
+                    const double Dy = fma(eta, fma(16.0 * eta, eta, A22), A1);
+                    const double en = fma(-yv, rcp_fast(Dy), eta);
+                    if (!(fabs(en) < 1e300)) break;
+                    if (fabs(en - eta) <= 4e-16 * fabs(en))
                     {
                         converged = true;
                         break;
                     }
-                    if (!(fabs(en) < 1e300)) break;
-                    const double yn = A0 + en * (A1 + en * (A2 + 4.0 * en * en));
+                    const double yn = fma(en, fma(en, fma(4.0 * en, en, A2), A1), A0);
                     if (fabs(yn) >= fabs(yv))
                     {
                         converged = true;   // the residual no longer shrinks: eta is the root to rounding
@@ -347,21 +341,22 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
                     yv = yn;
                 }
                 const double DET = fma(eta, eta, fma(-eta, Mz, Cov));
-                const double hx = (Mxz * (Myy - eta) - Myz * Mxy) / DET * 0.5;
-                const double hy = (Myz * (Mxx - eta) - Mxz * Mxy) / DET * 0.5;
+                const double hdet = 0.5 * rcp_fast(DET);
+                const double hx = (Mxz * (Myy - eta) - Myz * Mxy) * hdet;
+                const double hy = (Myz * (Mxx - eta) - Mxz * Mxy) * hdet;
                 R = sqrt(fma(hx, hx, fma(hy, hy, Mz - eta - eta)));
-                cx = hx + ca + sm.org[lane][0];
-                cy = hy + cb + sm.org[lane][1];
+                cx = hx + a + sm.org[lane][0];
+                cy = hy + b + sm.org[lane][1];
                 pub = !(R > 1.0);   // landmarks.cpp:95; a NaN radius would pass the reference's gate: never decided here
                 if (!converged || !(fabs(R) < 1e300) || !(fabs(cx) < 1e300) || !(fabs(cy) < 1e300)) fallback = true;
                 if (fabs(R - 1.0) < 1e-6) fallback = true;
                 if (pub && !(Cov > 1e-9 * Mz * Mz)) fallback = true;   // nearly collinear yet published: conditioning too poor to promise 1e-9
             }
         }
-        NUSLAM_DBG("[scan %lld] solved\n", (long long) s);
         if (__any_sync(kFull, fallback))
         {
             if (lane == 0) slow[atomicAdd(slow_count, 1)] = (int32_t) s;   // rewrites every output of this scan (cluster_of_beam stays the same)
+            __syncwarp();
             continue;
         }
         // ---- publication in detection order (landmarks.cpp:84-109) ----

@@ -36,7 +36,7 @@ EXPORTS = [
     "nuslam_ekf_scan_step", "nuslam_ekf_map_to_odom", "nuslam_ekf_synchronize",
     "nuslam_cartesian2polar", "nuslam_normalize_angle", "nuslam_scan_detect", "nuslam_classify_and_fit",
     "nuslam_diffdrive_step", "nuslam_diffdrive_convert_twist", "nuslam_world_step", "nuslam_integrate_twist",
-    "nuslam_ekf_get_stream", "nuslam_scan_set_fit", "nuslam_scan_last_fallbacks", "nuslam_ekf_error_stats", "nuslam_ekf_async_dry_run",
+    "nuslam_ekf_get_stream", "nuslam_scan_set_fit", "nuslam_scan_last_fallbacks", "nuslam_ekf_error_stats", "nuslam_ekf_async_dry_run", "nuslam_ekf_set_ids", "nuslam_ekf_step_async_packed",
 ]
 
 
@@ -88,6 +88,8 @@ def lib() -> C.CDLL:
         l.nuslam_scan_set_fit.argtypes = [C.c_int]
         l.nuslam_ekf_get_stream.argtypes = [vp, C.POINTER(vp)]
         l.nuslam_ekf_async_dry_run.argtypes = [vp, C.c_int]
+        l.nuslam_ekf_set_ids.argtypes = [vp, vp, i32, C.c_int]
+        l.nuslam_ekf_step_async_packed.argtypes = [vp, vp, i32, C.c_int, vp]
         l.nuslam_ekf_error_stats.argtypes = [vp, vp, vp, vp, vp, i32, vp]
         l.nuslam_scan_last_fallbacks.argtypes = [C.c_int]
         l.nuslam_ekf_wait_async.argtypes = [vp]
@@ -390,6 +392,31 @@ class BatchedExtendedKalman:
         _check(lib().nuslam_ekf_step_async(self._h, twists.ctypes.data, z.ctypes.data, ids.ctypes.data if ids is not None else None, int(z.shape[1]),
                                            x_out.ctypes.data),
                "nuslam_ekf_step_async")
+
+    IDS_NONE, IDS_PACKED, IDS_CACHED = 0, 1, 2   # NUSLAM_IDS_* of include/nuslam_b200.h
+
+    def set_ids(self, ids):
+        """Keep the [B,m] known-correspondence ids on the device for ``step_async_packed(..., ids_mode=IDS_CACHED)``."""
+        p = _ptr(ids, np.int32)
+        tok = self._order_begin(ids)
+        _check(lib().nuslam_ekf_set_ids(self._h, p[0], int(ids.shape[1]), p[2]), "nuslam_ekf_set_ids")
+        self._order_end(tok)
+
+    def packed_layout(self, m, with_ids):
+        """(total bytes, offset of z, offset of ids) of the packed host buffer of ``step_async_packed``: [twists B x 3 f64][z B x m x 2 f64]
+        [ids B x m i32 when with_ids]."""
+        b_tw, b_z = 8 * 3 * self.batch, 8 * 2 * self.batch * m
+        return b_tw + b_z + (4 * self.batch * m if with_ids else 0), b_tw, b_tw + b_z
+
+    def step_async_packed(self, packed, m, ids_mode, x_out):
+        """Pipelined host-buffer step from ONE page-locked buffer (a uint8 numpy view laid out by ``packed_layout``), one host -> device
+        copy per step (nuslam_ekf_step_async_packed)."""
+        if not (isinstance(packed, np.ndarray) and packed.dtype == np.uint8 and packed.flags["C_CONTIGUOUS"]):
+            raise NuslamError("step_async_packed takes a contiguous uint8 numpy view of the packed buffer")
+        need = self.packed_layout(m, ids_mode == self.IDS_PACKED)[0]
+        if packed.size < need:
+            raise NuslamError(f"packed buffer holds {packed.size} bytes, the step needs {need}")
+        _check(lib().nuslam_ekf_step_async_packed(self._h, packed.ctypes.data, int(m), int(ids_mode), x_out.ctypes.data), "nuslam_ekf_step_async_packed")
 
     def async_dry_run(self, on: bool):
         """Measurement aid: while on, step_async performs its copies and stream hand-overs without launching kernels (copy ceiling)."""

@@ -26,6 +26,11 @@ def main():
         r = ref.ekf_run(12, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"], sc["z"], ids, trace=True)
         for k in ("x", "sigma", "seen", "ids_out", "trace"):
             out[f"{tag}_{k}"] = r[k]
+        # the state after the first step (every landmark's first touch lies behind it): the warm start from which a GPU path can be
+        # held to 1e-9 without sharing the reference's libm (gate L1)
+        r1 = ref.ekf_run(12, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][:1], sc["z"][:1], None if ids is None else ids[:1])
+        for k in ("x", "sigma", "seen"):
+            out[f"{tag}_{k}1"] = r1[k]
     s = synth.scan_scenario(64, seed=4242, noise_sigma=0.001)
     sd = ref.scan_detect_batch(s["ranges"], s["min_range"], s["max_range"])
     out["ranges"] = s["ranges"]

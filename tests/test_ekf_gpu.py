@@ -321,6 +321,40 @@ def test_pipelined_host_steps_match_synchronous(cuda_lib, known):
     assert np.array_equal(xa, xb) and np.array_equal(sa, sb) and np.array_equal(na, nb)
 
 
+@pytest.mark.parametrize("ids_mode", ["packed", "cached", "none"])
+def test_packed_pipelined_steps_match_synchronous(cuda_lib, ids_mode):
+    """nuslam_ekf_step_async_packed (ONE packed host buffer per step, ids in the buffer / cached on the device by set_ids / absent =
+    associateLandmark on the device) gives exactly the states of the synchronous host-buffer steps."""
+    B, T, n = 300, 8, 12
+    sc = synth.ekf_scenario(B, T, n=n, seed=72)
+    a = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="fast")
+    b = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="fast")
+    mode = {"packed": a.IDS_PACKED, "cached": a.IDS_CACHED, "none": a.IDS_NONE}[ids_mode]
+    total, off_z, off_ids = a.packed_layout(n, ids_mode == "packed")
+    bufs, outs = [], [np.zeros((B, 27)) for _ in range(T)]
+    for t in range(T):
+        pk = np.zeros(total, dtype=np.uint8)
+        pk[:off_z].view(np.float64)[:] = sc["twists"][t].ravel()
+        pk[off_z:off_ids].view(np.float64)[:] = sc["z"][t].ravel()
+        if ids_mode == "packed":
+            pk[off_ids:].view(np.int32)[:] = sc["ids"][t].ravel()
+        bufs.append(pk)
+    if ids_mode == "cached":
+        a.set_ids(np.ascontiguousarray(sc["ids"][0]))   # the scenario measures landmarks 1..12 in that order at every step
+        assert all(np.array_equal(sc["ids"][t], sc["ids"][0]) for t in range(T))
+    for t in range(T):
+        a.step_async_packed(bufs[t], n, mode, outs[t])
+    a.wait_async()
+    for t in range(T):
+        b.step(np.ascontiguousarray(sc["twists"][t]), np.ascontiguousarray(sc["z"][t]), None if ids_mode == "none" else np.ascontiguousarray(sc["ids"][t]))
+        assert np.array_equal(outs[t], b.getStateVector()), t
+    xa, sa, na, _ = a.get_state()
+    xb, sb, nb, _ = b.get_state()
+    assert np.array_equal(xa, xb) and np.array_equal(sa, sb) and np.array_equal(na, nb)
+    with pytest.raises(cuda_lib.NuslamError):
+        b.step_async_packed(bufs[0], n, b.IDS_CACHED, outs[0])   # no ids were cached on this handle
+
+
 def test_integrate_twist_matches_oracle(cuda_lib, orc):
     """rigid2d::integrateTwist (rigid2d.cpp:294-328): pure translations (dth == 0 exactly), rotations, general twists."""
     from shermbot_navigation_b200 import rigid2d
@@ -602,3 +636,31 @@ def test_error_stats_match_numpy(cuda_lib):
     print("[error stats]", dict(zip(cuda_lib.BatchedExtendedKalman.STATS, st)))
     assert np.allclose(st, want, rtol=1e-9, atol=1e-12), (st, want)
     assert want[7] == len(range(0, B, 7))
+
+
+GOLDEN = __import__("pathlib").Path(__file__).resolve().parent / "golden" / "ekf_golden.npz"
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+@pytest.mark.parametrize("tag", ["known", "unknown"])
+def test_against_committed_golden_vectors(cuda_lib, mode, tag):
+    """The CUDA path against tests/golden/ekf_golden.npz directly -- vectors written by tests/golden/make_golden.py from the UNMODIFIED
+    reference sources (oracle/_ref) in the container that holds /root/reference -- so that parity does not rest on the restatement
+    on a box without _ref. Warm start from the golden state after the first step (every first touch lies behind it), 24 free-running
+    steps: association ids bit-exact, final state and covariance <= 1e-9."""
+    g = np.load(GOLDEN)
+    n = int(g["n"])
+    eng = cuda_lib.BatchedExtendedKalman(g["robot0"], g["map0"], g["Q"], g["R"], mode=mode)
+    eng.set_state(g[f"{tag}_x1"], g[f"{tag}_sigma1"], g[f"{tag}_seen1"])
+    T = g["twists"].shape[0]
+    mism = 0
+    for t in range(1, T):
+        ids = np.ascontiguousarray(g["ids"][t]) if tag == "known" else None
+        got = eng.step(np.ascontiguousarray(g["twists"][t]), np.ascontiguousarray(g["z"][t]), ids, return_ids=True)
+        mism += int((got != g[f"{tag}_ids_out"][t]).sum())
+    x, s, seen, status = eng.get_state()
+    B = x.shape[0]
+    ex, es = rel_max(x, g[f"{tag}_x"]), max(rel_max(s[b], g[f"{tag}_sigma"][b]) for b in range(B))
+    print(f"[golden {tag}/{mode}] ids mismatching {mism}, x rel {ex:.2e}, Sigma rel {es:.2e}")
+    assert n == 12 and mism == 0 and np.array_equal(seen, g[f"{tag}_seen"]) and not status.any()
+    assert ex < TOL and es < TOL

@@ -131,3 +131,15 @@ def test_scan_full_size_properties(cuda_lib, orc, fit_mode):
     assert np.array_equal(circ, np.broadcast_to(circ[0], circ.shape), equal_nan=True)
     first = dict(cluster_of_beam=cob[0], n_clusters=got["n_clusters"].cpu().numpy()[:4096], n_circles=nci[0], circles=circ[0].reshape(4096, -1, 4))
     compare_scans(first, want)
+
+
+def test_scan_against_committed_golden_vectors(cuda_lib, fit_mode):
+    """Both circle-fit arithmetics against tests/golden/ekf_golden.npz (64 scans through the unmodified reference sources, written by
+    tests/golden/make_golden.py): cluster ids and counts exact, circles <= 1e-9."""
+    from pathlib import Path
+    from shermbot_navigation_b200 import circle_fit
+    g = np.load(Path(__file__).resolve().parent / "golden" / "ekf_golden.npz")
+    got = circle_fit.scan_detect(g["ranges"], synth.MIN_RANGE, synth.MAX_RANGE)
+    want = dict(cluster_of_beam=g["scan_cluster_of_beam"], n_clusters=g["scan_n_clusters"], n_circles=g["scan_n_circles"], circles=g["scan_circles"])
+    worst = compare_scans(got, want)
+    print(f"[golden scans, fit={fit_mode}] worst circle rel {worst:.2e}")
