@@ -320,6 +320,46 @@ class _Stepper:
         self.started = True
 
 
+class TubeWorldRef:
+    """oracle/_ref/libtube_world_ref.so: the UNMODIFIED simulator node nuturtlesim/src/tube_world.cpp, compiled against the roscpp
+    stand-ins of oracle/shim_ros and driven by oracle/tube_world_driver.cpp. Pins oracle/world_oracle.h (tests/test_oracle.py)."""
+
+    PATH = HERE / "_ref" / "libtube_world_ref.so"
+
+    def __init__(self):
+        if not self.PATH.exists():
+            raise FileNotFoundError(f"{self.PATH} missing: run oracle.build() where /root/reference is present")
+        self._c = c = C.CDLL(str(self.PATH))
+        c.twref_flavour.restype = C.c_char_p
+        c.twref_lidar.argtypes = [C.c_double, C.c_double, C.c_double, _dp, C.c_double, C.c_double, _fp]
+        c.twref_run.argtypes = [C.c_int, _dp, C.c_double, C.c_double, C.c_double, _dp, C.c_double, C.c_double, C.c_double, _dp, _dp, _fp, _dp]
+
+    @staticmethod
+    def available() -> bool:
+        return TubeWorldRef.PATH.exists()
+
+    def lidar(self, x, y, th, tubes6, tube_rad, max_scan_range):
+        """TubeWorld::simulate_lidar_scanner (tube_world.cpp:405-471) at robot configuration (x, y, th): 360 float ranges."""
+        tubes = _f64(tubes6)
+        assert tubes.shape == (6, 2)
+        out = np.empty(360, dtype=np.float32)
+        rc = self._c.twref_lidar(float(x), float(y), float(th), _d(tubes), float(tube_rad), float(max_scan_range), out.ctypes.data_as(_fp))
+        assert rc == 0
+        return out
+
+    def run(self, cmd, wheel_base, wheel_rad, slip, tubes6, tube_rad, robot_rad, max_scan_range):
+        """TubeWorld::main_loop (tube_world.cpp:473-544) for the T commanded twists `cmd` (T,3) from the origin, noise-free (the node's
+        generator is seeded from random_device): returns poses (T,3) = (x, y, th), joints (T,2), scans (T,360), dt."""
+        cmd = _f64(cmd)
+        tubes = _f64(tubes6)
+        T = cmd.shape[0]
+        poses, joints, scans, dt = np.empty((T, 3)), np.empty((T, 2)), np.empty((T, 360), dtype=np.float32), np.zeros(1)
+        rc = self._c.twref_run(T, _d(cmd), float(wheel_base), float(wheel_rad), float(slip), _d(tubes), float(tube_rad), float(robot_rad),
+                               float(max_scan_range), _d(poses), _d(joints), scans.ctypes.data_as(_fp), _d(dt))
+        assert rc == 0
+        return poses, joints, scans, float(dt[0])
+
+
 _cache: dict[str, OracleLib] = {}
 
 

@@ -1,6 +1,7 @@
 /* oracle/world_oracle.h -- TEST INFRASTRUCTURE ONLY: plain-C restatement of the simulator node's per-step arithmetic,
- * /root/reference/nuturtlesim/src/tube_world.cpp (a roscpp node: it cannot be compiled here, so this slice is a restatement in
- * BOTH oracle flavours -- "parity unpinned": the reference holds no test, golden vector or fixture for it). The DiffDrive calls go
+ * /root/reference/nuturtlesim/src/tube_world.cpp (a roscpp node; the restatement serves BOTH oracle flavours and is PINNED bit
+ * for bit to the unmodified node compiled against roscpp stand-ins: oracle/tube_world_driver.cpp + oracle/shim_ros ->
+ * oracle/_ref/libtube_world_ref.so, checked by tests/test_oracle.py). The DiffDrive calls go
  * through the flavour's own orc_diffdrive_* (the unmodified rigid2d sources in oracle/_ref).
  *
  * One iteration of TubeWorld::main_loop (:512-537) for one robot:

@@ -208,3 +208,54 @@ def test_world_step_oracle_flavours_and_geometry(oracle_libs):
     assert r[0] == np.float32(2.0)
     assert abs(r[1] - (0.6 - 0.0381)) < 2e-3 and abs(r[359] - (0.6 - 0.0381)) < 2e-3
     assert (r < 1.5).sum() == 6 and set(np.nonzero(r < 1.5)[0]) == {1, 2, 3, 357, 358, 359}
+
+
+def test_world_oracle_pinned_to_the_compiled_simulator_node(oracle_libs):
+    """The simulator slice is PINNED: oracle/world_oracle.h (the restatement both oracle flavours -- and through them the GPU tests of
+    k_world_motion / k_world_scan -- rely on) against the UNMODIFIED nuturtlesim/src/tube_world.cpp compiled with roscpp stand-ins
+    (oracle/_ref/libtube_world_ref.so, recipe oracle/Makefile `tube_world`).
+      * simulate_lidar_scanner (:405-471) at 400 random robot configurations around the six reference tubes: all 360 beams bit-equal
+        (the +-27 degree window centred on atan2 of RELATIVE coordinates, the truncated heading offset, the fill value included);
+      * main_loop (:473-544) over a 300-step drive that runs into a tube (check_collision :371-389) with wheel slip: pose, encoder
+        readings and every scan bit-equal at every step (noise-free: the node seeds its generator from random_device)."""
+    import oracle
+    if not oracle.TubeWorldRef.available():
+        pytest.skip("oracle/_ref/libtube_world_ref.so not built (needs /root/reference at build time)")
+    ref = oracle.TubeWorldRef()
+    from shermbot_navigation_b200 import synth
+    tubes = np.ascontiguousarray(synth.TUBES[:6], dtype=np.float64)
+    rng = np.random.default_rng(5)
+    for flavour, o in oracle_libs.items():
+        # --- lidar at random configurations: world9 with the pose set, zero command, zero dt -> the step leaves the pose alone
+        worst = 0
+        for k in range(400):
+            x, y = rng.uniform(-1.2, 1.2, 2)
+            th = rng.uniform(-7.0, 7.0)
+            if np.hypot(*(tubes - [x, y]).T).min() <= 0.0381 + 1e-6:
+                continue   # inside a tube: world_step's check_collision would move the robot before the scan
+            want = ref.lidar(x, y, th, tubes, 0.0381, 1.0)
+            w = np.array([[0.16, 0.033, x, y, th, 0.0, 0.0, 0.0, 0.0]])
+            got = o.world_step(w, np.zeros(3), None, 0.0, tubes, 0.0381, 1e-9, 1.0)[0]   # robot radius ~ 0: no collision slip
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (flavour, k, x, y, th)
+            worst = max(worst, int((want < 1.5).sum()))
+        assert worst > 10   # the scans did see tubes
+        # --- main_loop: drive from the origin towards tube 1, collide, slide, keep turning; slip factor 0.02
+        T = 300
+        cmd = np.zeros((T, 3))
+        cmd[:, 1] = 0.22
+        cmd[:, 0] = 0.3 * np.sin(np.arange(T) / 17.0)
+        dirn = np.arctan2(tubes[0, 1], tubes[0, 0])
+        cmd[:40, 0] = dirn / (40 * 0.02)   # turn towards tube 1 first
+        cmd[:40, 1] = 0.0
+        poses, joints, scans, dt = ref.run(cmd, 0.16, 0.033, 0.02, tubes, 0.0381, 0.08, 1.0)
+        w = np.array([[0.16, 0.033, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]])
+        collided = False
+        for t in range(T):
+            before = w[0, 2:4].copy()
+            r = o.world_step(w, cmd[t], np.array([0.0, 0.0, 0.02, 0.02]), dt, tubes, 0.0381, 0.08, 1.0)[0]
+            assert np.array_equal(w[0, 2:5], poses[t]), (flavour, t, w[0, 2:5], poses[t])
+            assert np.array_equal(w[0, 7:9], joints[t]), (flavour, t)
+            assert np.array_equal(r.view(np.uint32), scans[t].view(np.uint32)), (flavour, t)
+            d = np.hypot(*(tubes - before).T).min()
+            collided = collided or d <= 0.0381 + 0.08
+        assert collided   # the drive did exercise check_collision
