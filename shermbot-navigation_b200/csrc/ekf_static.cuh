@@ -23,7 +23,7 @@ namespace nuslam
 {
 
 #ifndef NUSLAM_DEFAULT_KERNEL
-#define NUSLAM_DEFAULT_KERNEL 2   // 0 static, 1 pair, 2 fast
+#define NUSLAM_DEFAULT_KERNEL 2   // 0 static, 1 pair, 2 fast, 3 resident (ekf_res.cuh), 4 resident pair (ekf_res2.cuh)
 #endif
 #ifndef NUSLAM_STATIC_CTAS
 #define NUSLAM_STATIC_CTAS 16
@@ -512,6 +512,7 @@ inline int known_ids_kernel()
     if (e && e[0] == 'p') return 1;
     if (e && e[0] == 's') return 0;
     if (e && e[0] == 'f') return 2;
+    if (e && e[0] == 'r') return (e[1] && e[2] && e[3] == '2') ? 4 : 3;   // "res": ekf_res.cuh, "res2": ekf_res2.cuh
     return NUSLAM_DEFAULT_KERNEL;
 }
 

@@ -17,6 +17,8 @@
 #include "ekf_fast.cuh"
 #include "ekf_pair.cuh"
 #include "ekf_static.cuh"
+#include "ekf_res.cuh"
+#include "ekf_res2.cuh"
 #include "scan_moment.cuh"
 #include "scan_detect.cuh"
 #include "ekf_large.cuh"
@@ -199,6 +201,8 @@ int launch_fast_then_strict(nuslam_ekf * h, const nuslam::EkfParams & p, bool do
     const int which = nuslam::known_ids_kernel();
     const bool special = which != 2 && nuslam::pair_supported(h->cfg.n_landmarks, p);
     int rc = !special      ? nuslam::launch_fast(h->cfg.n_landmarks, p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
+             : which == 4 ? nuslam::launch_res2_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
+             : which == 3 ? nuslam::launch_res_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
              : which == 1 ? nuslam::launch_pair_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
                           : nuslam::launch_static_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream);
     // not covered by the register kernels (more than 16 measurements per step, ragged counts with known ids, a state pointer that

@@ -468,7 +468,7 @@ def test_known_ids_kernels_agree(cuda_lib, orc, B, m, dropout, monkeypatch):
     first = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][:1], sc["z"][:1], sc["ids"][:1])
     want = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"][1:], z[1:], ids[1:], init=(first["x"], first["sigma"], first["seen"]))
     out = {}
-    for kern in ("static", "pair", "fast"):
+    for kern in ("static", "pair", "res", "res2", "fast"):
         monkeypatch.setenv("NUSLAM_KERNEL", kern)
         eng = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="fast")
         eng.set_state(first["x"], first["sigma"], first["seen"])
@@ -479,7 +479,7 @@ def test_known_ids_kernels_agree(cuda_lib, orc, B, m, dropout, monkeypatch):
         assert not status.any() and np.array_equal(seen, want["seen"])
         assert rel_max(x, want["x"]) < TOL and max(rel_max(s[b], want["sigma"][b]) for b in range(B)) < TOL, kern
     x0, s0, _, _ = out["fast"]
-    for kern in ("static", "pair"):
+    for kern in ("static", "pair", "res", "res2"):
         x1, s1, _, _ = out[kern]
         ex, es = rel_max(x1, x0), max(rel_max(s1[b], s0[b]) for b in range(B))
         print(f"[{kern} vs fast, B={B} m={m} dropout={dropout}] x rel {ex:.2e}, Sigma rel {es:.2e}")
