@@ -30,6 +30,11 @@ N_LANDMARKS = 12
 FILTERS_PER_GPU = 65536
 LEN = 3 + 2 * N_LANDMARKS
 # algorithmic bytes per filter-step: read x 216 + Sigma 5832 + u 16 + z 192 + ids 48, write x 216 + Sigma 5832
+# known-correspondence kernels at 12 landmarks (NUSLAM_KERNEL selects; default: the resident pair kernel, csrc/ekf_static.cuh)
+KERNEL_NAMES = {"res2": "k_ekf_res2_step<12, 3> (two filters per warp, both Sigma images resident in shared memory, ekf_res2.cuh)",
+                "res": "k_ekf_res_step<12, 2> (one filter per warp, Sigma resident in shared memory, ekf_res.cuh)",
+                "fas": "k_ekf_fast_step<12, BULK> (register fragments, ekf_fast.cuh)", "pair": "k_ekf_pair_step<12> (ekf_pair.cuh)",
+                "sta": "k_ekf_static_step<12> (ekf_static.cuh)"}
 BYTES_PER_FILTER_STEP = 2 * 8 * (LEN + LEN * LEN) + 16 + 20 * N_LANDMARKS
 METRIC = "EKF predict+update filter-steps/s (64K filters x 12 landmarks per GPU, fp64, known correspondence)"
 UNIT = "filter-steps/s"
@@ -350,7 +355,8 @@ def run_ours(args):
                     "host_affinity": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_filter_step": BYTES_PER_FILTER_STEP,
-                         "kernel": "k_ekf_fast_step<12, BULK> (+ k_ekf_strict_list over the first-touch work list, empty in steady state)" if args.mode == "fast" else "k_ekf_strict<kOpStep>",
+                         "kernel": (KERNEL_NAMES.get((os.environ.get("NUSLAM_KERNEL") or "res2")[:4].rstrip("t"), KERNEL_NAMES["res2"]) +
+                                    " (+ k_ekf_strict_list over the first-touch work list, empty in steady state)") if args.mode == "fast" else "k_ekf_strict<kOpStep>",
                          "launch_us": per_launch_s * 1e6, "launches_per_step": launches},
         }
     eng.close()

@@ -27,42 +27,54 @@ namespace nuslam
 {
 
 #ifndef NUSLAM_RES2_CH
-#define NUSLAM_RES2_CH 4        // updates per delayed chunk (2 or 4)
+#define NUSLAM_RES2_CH 3        // updates per delayed chunk (2, 3 or 4)
 #endif
 #ifndef NUSLAM_RES2_CTAS
-#define NUSLAM_RES2_CTAS (NUSLAM_RES2_CH == 2 ? 12 : 10)
+#define NUSLAM_RES2_CTAS (NUSLAM_RES2_CH == 2 ? 12 : NUSLAM_RES2_CH == 3 ? 12 : 11)
 #endif
+#ifndef NUSLAM_RES2_WARPS
+#define NUSLAM_RES2_WARPS 1     // warps (= pairs in flight) per CTA; the warps of a CTA share nothing, a CTA of W warps only saves the
+#endif                          // 1 KB of shared memory the hardware reserves per CTA (W = 13, one CTA per SM: 13 pairs per SM instead of 12)
 constexpr int kRes2CtasPerSm = NUSLAM_RES2_CTAS;
+constexpr int kRes2Warps = NUSLAM_RES2_WARPS;
 
 template <int CH>
 struct __align__(16) Res2Smem
 {
-    double2 kt[2][CH][36];        // per filter: -Kt of the chunk's updates (DMMA A operand, pending corrections)
-    double2 wt[2][CH][36];        // per filter: Wt of the chunk's updates (DMMA B operand)
+    // slot stride 28 double2 = 56 doubles = 8 (mod 16): the operand loads of two slots hit disjoint banks; the lanes that own no state
+    // index store nothing
+    double2 kt[2][CH][28];        // per filter: -Kt of the chunk's updates (DMMA A operand, pending corrections)
+    double2 wt[2][CH][28];        // per filter: Wt of the chunk's updates (DMMA B operand)
     double z[2][2 * kFastMMax];   // per filter: this step's measurements
 };
 
 template <int N, int CH>
-__global__ void __launch_bounds__(32, kRes2CtasPerSm)
+__global__ void __launch_bounds__(32 * kRes2Warps, kRes2CtasPerSm)
 k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ worklist, int32_t * __restrict__ wl_count)
 {
     using G = FastGeom<N>;
     static_assert(G::FIXED && 2 * N == 8 * G::NB && G::LEN > 16 && G::LEN <= 32, "pair layout: two slots of 16 state indices, unpadded 8 x 8 tiles");
-    static_assert(CH == 2 || CH == 4, "chunks of 2 or 4 updates");
+    static_assert(CH >= 2 && CH <= 4, "chunks of 2, 3 or 4 updates");
+    constexpr int KS = (CH + 1) / 2;   // DMMA k-steps of a chunk's pass (an odd chunk leaves half of the last one empty)
     constexpr int NB = G::NB, NL = N, LEN = G::LEN, SIG = G::SIG;
     static_assert(NB == 3, "row permutation written for three row blocks");
     constexpr unsigned kFull = 0xffffffffu;
     constexpr int kImg = SIG * 8, kPairBytes = 2 * kImg;   // a pair is 16-byte aligned in HBM whenever the array is
-    __shared__ __align__(128) unsigned char stage[kPairBytes];
-    __shared__ __align__(16) Res2Smem<CH> f;
-    __shared__ uint64_t full_bar;
-    const int lane = threadIdx.x;
+    // per warp: [the pair's two images][exchange area][mbarrier]
+    extern __shared__ __align__(128) unsigned char res2_dyn[];
+    constexpr int kWarpBytes = kPairBytes + (int) sizeof(Res2Smem<CH>) + 16;
+    static_assert(kPairBytes % 16 == 0 && sizeof(Res2Smem<CH>) % 16 == 0, "16-byte aligned pieces");
+    unsigned char * const stage = res2_dyn + (threadIdx.x >> 5) * kWarpBytes;
+    Res2Smem<CH> & f = *reinterpret_cast<Res2Smem<CH> *>(stage + kPairBytes);
+    uint64_t & full_bar = *reinterpret_cast<uint64_t *>(stage + kPairBytes + sizeof(Res2Smem<CH>));
+    const int lane = threadIdx.x & 31;
+    const int64_t gw0 = (int64_t) blockIdx.x * kRes2Warps + (threadIdx.x >> 5), gwn = (int64_t) gridDim.x * kRes2Warps;   // this warp, all warps
     const int h = lane >> 4, q = lane & 15;   // vector / scalar domain: filter of this lane, index inside the half
     const int hb = 16 * h;                    // first lane of this half
     const int g = lane >> 2, t = lane & 3;    // tile domain of the in-place pass
     double * const img = reinterpret_cast<double *>(stage) + h * SIG;   // this lane's filter
-    double2(*const ktH)[36] = f.kt[h];
-    double2(*const wtH)[36] = f.wt[h];
+    double2(*const ktH)[28] = f.kt[h];
+    double2(*const wtH)[28] = f.wt[h];
     // state indices of this lane's two slots; a slot without a state entry re-reads what lanes q = 0..4 read for slot 1 (same address
     // inside the half-warp = broadcast: no bank conflict, no access outside the image); its results are never used
     const bool v1 = 16 + q < LEN;
@@ -86,19 +98,19 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
     {
         mbar_init(&full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if ((int64_t) blockIdx.x < npairs) issue_load(blockIdx.x);
+        if (gw0 < npairs) issue_load(gw0);
     }
     __syncwarp();
 
-    for (int64_t pr = blockIdx.x; pr < npairs; pr += gridDim.x)
+    for (int64_t pr = gw0; pr < npairs; pr += gwn)
     {
         const int64_t bf = 2 * pr + h;
         const bool has = bf < p.batch;
         const int64_t bfc = has ? bf : 2 * pr;   // safe addressing for the missing twin of an odd batch
-        const bool next = pr + gridDim.x < npairs;
-        if (lane == 0 && pr + 2 * (int64_t) gridDim.x < npairs)   // the pair after next: towards L2 while this one is computed
+        const bool next = pr + gwn < npairs;
+        if (lane == 0 && pr + 2 * gwn < npairs)   // the pair after next: towards L2 while this one is computed
         {
-            const int64_t pn = pr + 2 * (int64_t) gridDim.x;
+            const int64_t pn = pr + 2 * gwn;
             prefetch_l2_bulk(p.sigma + 2 * pn * SIG, (2 * pn + 1 < p.batch) ? (uint32_t) kPairBytes : (uint32_t) (kImg & ~15));
         }
         // ---- small inputs: plain loads, issued before anything waits ----
@@ -116,7 +128,7 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         __syncwarp();
         auto leave = [&]() {   // nothing is stored: the buffer is free at once
             __syncwarp();
-            if (lane == 0 && next) issue_load(pr + gridDim.x);
+            if (lane == 0 && next) issue_load(pr + gwn);
         };
         // ---- liveness, first touch ----
         const bool idok = (unsigned) (my_id - 1) < (unsigned) NL;
@@ -324,7 +336,7 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                         W1[sl] = fma(dx, wb, fma(-dy, wa, -d * Rt[sl]));
                     }
                     wtH[s][q] = make_double2(W0[0], W1[0]);
-                    wtH[s][16 + q] = make_double2(W0[1], W1[1]);
+                    if (v1) wtH[s][16 + q] = make_double2(W0[1], W1[1]);
                     __syncwarp();
                     // ---- the 2 x 2 part of this lane's filter: M = Wt Ht^T + D^-1 R D^-1, Minv ----
                     const double2 g0 = wtH[s][0], g1 = wtH[s][1], g2 = wtH[s][2], g3 = wtH[s][c], g4 = wtH[s][c + 1];
@@ -355,11 +367,11 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
 #pragma unroll
                             for (int sl = 0; sl < 2; ++sl) nk0[sl] = nk1[sl] = W0[sl] = W1[sl] = 0.0;
                             wtH[s][q] = make_double2(0.0, 0.0);
-                            wtH[s][16 + q] = make_double2(0.0, 0.0);
+                            if (v1) wtH[s][16 + q] = make_double2(0.0, 0.0);
                         }
                     }
                     ktH[s][q] = make_double2(nk0[0], nk1[0]);
-                    ktH[s][16 + q] = make_double2(nk0[1], nk1[1]);
+                    if (v1) ktH[s][16 + q] = make_double2(nk0[1], nk1[1]);
 #pragma unroll
                     for (int sl = 0; sl < 2; ++sl)
                     {
@@ -391,9 +403,9 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 {
                     // no filter of the pair has a measurement in this slot: it contributes nothing to the pass or to later corrections
                     ktH[s][q] = make_double2(0.0, 0.0);
-                    ktH[s][16 + q] = make_double2(0.0, 0.0);
+                    if (v1) ktH[s][16 + q] = make_double2(0.0, 0.0);
                     wtH[s][q] = make_double2(0.0, 0.0);
-                    wtH[s][16 + q] = make_double2(0.0, 0.0);
+                    if (v1) wtH[s][16 + q] = make_double2(0.0, 0.0);
                 }
                 if (s + 1 < CH)
                 {
@@ -417,14 +429,15 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 {
                     const double * const ka = reinterpret_cast<const double *>(&f.kt[ff][t >> 1][0]) + (t & 1);
                     const double * const wa = reinterpret_cast<const double *>(&f.wt[ff][t >> 1][3 + g]) + (t & 1);
-                    double a[CH / 2][NB], b[CH / 2][NB];
+                    double a[KS][NB], b[KS][NB];
 #pragma unroll
-                    for (int kk = 0; kk < CH / 2; ++kk)
+                    for (int kk = 0; kk < KS; ++kk)
 #pragma unroll
                         for (int bb = 0; bb < NB; ++bb)
                         {
-                            a[kk][bb] = ka[kk * 144 + 2 * rrow[bb]];
-                            b[kk][bb] = wa[kk * 144 + 16 * bb];
+                            const bool used = 2 * kk + 1 < CH || t < 2;   // slot 2 kk + (t >> 1) exists
+                            a[kk][bb] = used ? ka[kk * 112 + 2 * rrow[bb]] : 0.0;
+                            b[kk][bb] = used ? wa[kk * 112 + 16 * bb] : 0.0;
                         }
                     double * const tbase = reinterpret_cast<double *>(stage) + ff * SIG + (3 + 2 * t) * LEN;
                     double c0[NB][NB], c1[NB][NB];
@@ -438,7 +451,7 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                             c1[bc][br] = e0p[LEN];
                         }
 #pragma unroll
-                    for (int kk = 0; kk < CH / 2; ++kk)
+                    for (int kk = 0; kk < KS; ++kk)
 #pragma unroll
                         for (int bc = 0; bc < NB; ++bc)
 #pragma unroll
@@ -489,7 +502,7 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             }
             // the buffer receives the next pair as soon as the store has read it
             bulk_wait_read();
-            if (next) issue_load(pr + gridDim.x);
+            if (next) issue_load(pr + gwn);
         }
         __syncwarp();
     }
@@ -500,16 +513,19 @@ template <int N>
 int launch_res2_n(const EkfParams & p, bool do_predict, int sm_count, int32_t * worklist, int32_t * wl_count, cudaStream_t stream)
 {
     const int64_t npairs = (p.batch + 1) / 2;
-    int64_t blocks = npairs;
+    int64_t blocks = (npairs + kRes2Warps - 1) / kRes2Warps;
     if (blocks > kRes2CtasPerSm * (int64_t) sm_count) blocks = kRes2CtasPerSm * (int64_t) sm_count;
+    constexpr int kSmem = kRes2Warps * (2 * FastGeom<N>::SIG * 8 + (int) sizeof(Res2Smem<NUSLAM_RES2_CH>) + 16);
     static bool configured_dev[kMaxDevices] = {false};
     bool & configured = configured_dev[device_slot()];
     if (!configured)
     {
         cudaFuncSetAttribute(k_ekf_res2_step<N, NUSLAM_RES2_CH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        const cudaError_t e = cudaFuncSetAttribute(k_ekf_res2_step<N, NUSLAM_RES2_CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return (int) e;
         configured = true;
     }
-    k_ekf_res2_step<N, NUSLAM_RES2_CH><<<(unsigned) blocks, 32, 0, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
+    k_ekf_res2_step<N, NUSLAM_RES2_CH><<<(unsigned) blocks, 32 * kRes2Warps, kSmem, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
     return (int) cudaGetLastError();
 }
 

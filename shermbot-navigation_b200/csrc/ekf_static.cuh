@@ -23,7 +23,7 @@ namespace nuslam
 {
 
 #ifndef NUSLAM_DEFAULT_KERNEL
-#define NUSLAM_DEFAULT_KERNEL 2   // 0 static, 1 pair, 2 fast, 3 resident (ekf_res.cuh), 4 resident pair (ekf_res2.cuh)
+#define NUSLAM_DEFAULT_KERNEL 4   // 0 static, 1 pair, 2 fast, 3 resident (ekf_res.cuh), 4 resident pair (ekf_res2.cuh)
 #endif
 #ifndef NUSLAM_STATIC_CTAS
 #define NUSLAM_STATIC_CTAS 16
