@@ -32,6 +32,12 @@ namespace nuslam
 #ifndef NUSLAM_RES2_CTAS
 #define NUSLAM_RES2_CTAS (NUSLAM_RES2_CH == 2 ? 12 : NUSLAM_RES2_CH == 3 ? 12 : 11)
 #endif
+#ifndef NUSLAM_RES2_L2PREFETCH
+#define NUSLAM_RES2_L2PREFETCH 0   // 1: pull the pair after next towards L2 (measured: no faster, 1.5 x the DRAM reads)
+#endif
+#ifndef NUSLAM_RES2_BRANCHY
+#define NUSLAM_RES2_BRANCHY 0
+#endif
 #ifndef NUSLAM_RES2_WARPS
 #define NUSLAM_RES2_WARPS 1     // warps (= pairs in flight) per CTA; the warps of a CTA share nothing, a CTA of W warps only saves the
 #endif                          // 1 KB of shared memory the hardware reserves per CTA (W = 13, one CTA per SM: 13 pairs per SM instead of 12)
@@ -108,7 +114,7 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         const bool has = bf < p.batch;
         const int64_t bfc = has ? bf : 2 * pr;   // safe addressing for the missing twin of an odd batch
         const bool next = pr + gwn < npairs;
-        if (lane == 0 && pr + 2 * gwn < npairs)   // the pair after next: towards L2 while this one is computed
+        if (NUSLAM_RES2_L2PREFETCH && lane == 0 && pr + 2 * gwn < npairs)   // the pair after next: towards L2 while this one is computed
         {
             const int64_t pn = pr + 2 * gwn;
             prefetch_l2_bulk(p.sigma + 2 * pn * SIG, (2 * pn + 1 < p.batch) ? (uint32_t) kPairBytes : (uint32_t) (kImg & ~15));
@@ -122,6 +128,41 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         const double my_z0 = (q < m) ? p.z[bfc * m * 2 + 2 * q] : 0.0;
         const double my_z1 = (q < m) ? p.z[bfc * m * 2 + 2 * q + 1] : 0.0;
         const double my_tw = (do_predict && q < 2) ? p.twists[bfc * 3 + q] : 0.0;
+        // robot pose of this lane's filter, replicated over its half; lanes q = 0..2 own the same values in x[0]
+        double th = __shfl_sync(kFull, x[0], hb), px = __shfl_sync(kFull, x[0], hb + 1), py = __shfl_sync(kFull, x[0], hb + 2);
+
+        // ---- predict, scalar part (slam_library.cpp:71-94, :127-148): needs the state and the twist only -- evaluated while the bulk copy
+        //      of the images is still in flight ----
+        double b10 = 0.0, b20 = 0.0;
+        const double x0_in = x[0];   // a dead filter's snapshot is the state as it came
+        if (do_predict)
+        {
+            const double dth = __shfl_sync(kFull, my_tw, hb), dxx = __shfl_sync(kFull, my_tw, hb + 1);
+            double s0, c0;
+            sincos(th, &s0, &c0);
+            if (dth == 0.0)
+            {
+                px = add_(px, mul_(dxx, c0));
+                py = add_(py, mul_(dxx, s0));
+                th = add_(th, 0.0);
+                b10 = mul_(-dxx, s0);
+                b20 = mul_(dxx, c0);
+            }
+            else
+            {
+                const double qq = div_(dxx, dth);
+                double sd, cd;
+                sincos_small(dth, &sd, &cd);
+                const double s1 = fma(s0, cd, c0 * sd), c1 = fma(c0, cd, -s0 * sd);
+                const double s3 = fma(s1, cd, c1 * sd), c3 = fma(c1, cd, -s1 * sd);
+                px = add_(px, add_(mul_(-qq, s0), mul_(qq, s1)));
+                py = add_(py, sub_(mul_(qq, c0), mul_(qq, c1)));
+                th = add_(th, dth);
+                b10 = add_(mul_(-qq, c1), mul_(qq, c3));
+                b20 = add_(mul_(-qq, s1), mul_(qq, s3));
+            }
+            x[0] = (q == 0) ? th : (q == 1) ? px : (q == 2) ? py : x[0];
+        }
         mbar_wait(&full_bar, full_parity);
         full_parity ^= 1;
         if (2 * pr + 1 >= p.batch && lane == 0) reinterpret_cast<double *>(stage)[SIG - 1] = p.sigma[2 * pr * SIG + SIG - 1];
@@ -149,7 +190,7 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             if (p.ids_out && q < m) p.ids_out[bf * m + q] = 0;
             if (p.x_snap)
             {
-                p.x_snap[bf * LEN + q] = x[0];
+                p.x_snap[bf * LEN + q] = x0_in;
                 if (v1) p.x_snap[bf * LEN + 16 + q] = x[1];
             }
         }
@@ -176,37 +217,9 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         Rt[0] = img[q * LEN], Rx[0] = img[q * LEN + 1], Ry[0] = img[q * LEN + 2];
         Ct[1] = img[i1], Cx[1] = img[LEN + i1], Cy[1] = img[2 * LEN + i1];
         Rt[1] = img[i1 * LEN], Rx[1] = img[i1 * LEN + 1], Ry[1] = img[i1 * LEN + 2];
-        // robot pose of this lane's filter, replicated over its half; lanes q = 0..2 own the same values in x[0]
-        double th = __shfl_sync(kFull, x[0], hb), px = __shfl_sync(kFull, x[0], hb + 1), py = __shfl_sync(kFull, x[0], hb + 2);
-
-        // ---- predict (slam_library.cpp:65-108), oracle operation order, vector layout only ----
+        // ---- predict, covariance part (slam_library.cpp:96-108), oracle operation order, vector layout only ----
         if (do_predict)
         {
-            const double dth = __shfl_sync(kFull, my_tw, hb), dxx = __shfl_sync(kFull, my_tw, hb + 1);
-            double s0, c0, b10, b20;
-            sincos(th, &s0, &c0);
-            if (dth == 0.0)
-            {
-                px = add_(px, mul_(dxx, c0));
-                py = add_(py, mul_(dxx, s0));
-                th = add_(th, 0.0);
-                b10 = mul_(-dxx, s0);
-                b20 = mul_(dxx, c0);
-            }
-            else
-            {
-                const double qq = div_(dxx, dth);
-                double sd, cd;
-                sincos_small(dth, &sd, &cd);
-                const double s1 = fma(s0, cd, c0 * sd), c1 = fma(c0, cd, -s0 * sd);
-                const double s3 = fma(s1, cd, c1 * sd), c3 = fma(c1, cd, -s1 * sd);
-                px = add_(px, add_(mul_(-qq, s0), mul_(qq, s1)));
-                py = add_(py, sub_(mul_(qq, c0), mul_(qq, c1)));
-                th = add_(th, dth);
-                b10 = add_(mul_(-qq, c1), mul_(qq, c3));
-                b20 = add_(mul_(-qq, s1), mul_(qq, s3));
-            }
-            x[0] = (q == 0) ? th : (q == 1) ? px : (q == 2) ? py : x[0];
             // T = A * Sigma: rows x, y += b * row theta
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl)
@@ -301,8 +314,13 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);   // sqrt(d) to ~1 ulp
                     const double dsq = d * sq;
                     double zb = atan2_unit(dy, dx, rs) - th;
+#if NUSLAM_RES2_BRANCHY
                     if (__any_sync(kFull, abs_ge_hi(zb, kHiPi)))   // the wrap is the identity inside [-pi, pi]
                         if (abs_ge_hi(zb, kHiPi)) zb = wrap_angle(zb);
+#else
+                    zb = wrap_angle(zb);   // the identity inside [-pi, pi]; branch-free: the update stays ONE basic block, so that the
+                                           // state-only chain (rsqrt, atan2) and the covariance chain interleave
+#endif
                     double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);
                     // ---- landmark rows c, c+1 (lane = column) and columns c, c+1 (lane = row) as of the chunk's start, from the image;
                     //      brought up to date with the chunk's earlier updates (delayed-update algebra); Pt / Wt of this lane's slots ----
@@ -387,8 +405,12 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     th = fma(-k0.x, n0, fma(-k0.y, n1, th));
                     px = fma(-k1.x, n0, fma(-k1.y, n1, px));
                     py = fma(-k2.x, n0, fma(-k2.y, n1, py));
+#if NUSLAM_RES2_BRANCHY
                     if (__any_sync(kFull, abs_ge_hi(th, kHiPi)))   // slam_library.cpp:275-276 (the identity inside [-pi, pi])
                         if (abs_ge_hi(th, kHiPi)) th = wrap_angle(th);
+#else
+                    th = wrap_angle(th);   // slam_library.cpp:275-276 (the identity inside [-pi, pi])
+#endif
                     if (q == 0) x[0] = th;
 #pragma unroll
                     for (int sl = 0; sl < 2; ++sl)
