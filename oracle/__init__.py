@@ -133,6 +133,8 @@ class OracleLib:
         self.kind = kind
         self._c = c = C.CDLL(str(p))
         c.orc_flavour.restype = C.c_char_p
+        c.orc_eig_sym_full_sweeps.argtypes = [C.c_int]
+        c.orc_eig_sym_full_sweeps.restype = C.c_int
         c.orc_ekf_new.restype = C.c_void_p
         c.orc_ekf_new.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
         c.orc_ekf_free.argtypes = [C.c_void_p]
@@ -165,6 +167,11 @@ class OracleLib:
     @property
     def flavour(self) -> str:
         return self._c.orc_flavour().decode()
+
+    def eig_sym_full_sweeps(self, on: bool) -> bool:
+        """Test hook of the "ref" flavour: True = the shim's eig_sym runs to its criterion / 100-sweep cap instead of stopping at the fixed
+        point of its outputs (bit-identical results, tests/test_oracle.py). Returns the previous setting."""
+        return bool(self._c.orc_eig_sym_full_sweeps(1 if on else 0))
 
     # ---- EKF ----
     def ekf(self, n, robot, mapstate, Q, R) -> Ekf:

@@ -40,6 +40,7 @@
 #define ORC_PI 3.14159265358979323846 /* rigid2d/include/rigid2d/rigid2d.hpp:16 */
 
 const char * orc_flavour(void) { return ORC_FLAVOUR_STR; }
+int orc_eig_sym_full_sweeps(int on) { (void) on; return 1; }   /* the restatement always runs every sweep */
 
 /* ------------------------------------------------------------------ dense helpers (shim order) */
 

@@ -23,6 +23,9 @@ extern "C" {
 #define ORC_UB (-2000)
 
 const char * orc_flavour(void);
+/* test hook ("ref" flavour; a no-op in the restatement, which always runs every sweep): 1 = the shim's eig_sym runs to its criterion / 100-sweep
+ * cap instead of stopping at the fixed point of its outputs. Returns the previous setting. */
+int orc_eig_sym_full_sweeps(int on);
 
 /* ---- single-filter object API (slam_library.hpp:23-113); matrices column-major ---- */
 void * orc_ekf_new(int n, const double * robot3, const double * map2n, const double * Q9, const double * R4);

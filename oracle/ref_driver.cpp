@@ -64,6 +64,12 @@ namespace
 extern "C" {
 
 const char * orc_flavour(void) { return ORC_FLAVOUR; }
+int orc_eig_sym_full_sweeps(int on)
+{
+    const int was = arma::eig_sym_full_sweeps() ? 1 : 0;
+    arma::eig_sym_full_sweeps() = on != 0;
+    return was;
+}
 
 void * orc_ekf_new(int n, const double * robot3, const double * map2n, const double * Q9, const double * R4)
 {

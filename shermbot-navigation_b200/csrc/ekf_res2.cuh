@@ -108,6 +108,22 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
     }
     __syncwarp();
 
+    // the small inputs of a pair, carried one iteration ahead
+    double nx0 = 0.0, nx1 = 0.0, nz0 = 0.0, nz1 = 0.0, ntw = 0.0;
+    int nst = 0, nseen = 0, nid = 0;
+    auto load_small = [&](int64_t pr) {
+        const int64_t bfn = 2 * pr + h;
+        const int64_t b = bfn < p.batch ? bfn : 2 * pr;   // safe addressing for the missing twin of an odd batch
+        nx0 = p.x[b * LEN + q];
+        nx1 = v1 ? p.x[b * LEN + 16 + q] : 0.0;
+        nst = p.status[b];
+        nseen = p.seen[b];
+        nid = (q < m) ? p.ids[b * m + q] : 0;
+        nz0 = (q < m) ? p.z[b * m * 2 + 2 * q] : 0.0;
+        nz1 = (q < m) ? p.z[b * m * 2 + 2 * q + 1] : 0.0;
+        ntw = (do_predict && q < 2) ? p.twists[b * 3 + q] : 0.0;
+    };
+    if (gw0 < npairs) load_small(gw0);
     for (int64_t pr = gw0; pr < npairs; pr += gwn)
     {
         const int64_t bf = 2 * pr + h;
@@ -119,15 +135,11 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             const int64_t pn = pr + 2 * gwn;
             prefetch_l2_bulk(p.sigma + 2 * pn * SIG, (2 * pn + 1 < p.batch) ? (uint32_t) kPairBytes : (uint32_t) (kImg & ~15));
         }
-        // ---- small inputs: plain loads, issued before anything waits ----
-        double x[2];
-        x[0] = p.x[bfc * LEN + q];
-        x[1] = v1 ? p.x[bfc * LEN + 16 + q] : 0.0;
-        const int st0 = p.status[bfc], seen0 = p.seen[bfc];
-        const int my_id = (q < m) ? p.ids[bfc * m + q] : 0;
-        const double my_z0 = (q < m) ? p.z[bfc * m * 2 + 2 * q] : 0.0;
-        const double my_z1 = (q < m) ? p.z[bfc * m * 2 + 2 * q + 1] : 0.0;
-        const double my_tw = (do_predict && q < 2) ? p.twists[bfc * 3 + q] : 0.0;
+        // ---- small inputs: loaded one pair ahead (the loads of the next pair are in flight while this one is computed) ----
+        double x[2] = {nx0, nx1};
+        const int st0 = nst, seen0 = nseen, my_id = nid;
+        const double my_z0 = nz0, my_z1 = nz1, my_tw = ntw;
+        if (next) load_small(pr + gwn);
         // robot pose of this lane's filter, replicated over its half; lanes q = 0..2 own the same values in x[0]
         double th = __shfl_sync(kFull, x[0], hb), px = __shfl_sync(kFull, x[0], hb + 1), py = __shfl_sync(kFull, x[0], hb + 2);
 
