@@ -32,6 +32,8 @@ struct LargeParams
     double * V;        // B x (2 kLargeMMax) x len : W_u rows,    V[(2u+a) * len + j] = W_u(a, j)
     double * P;        // B x 2 x len              : P_i = Sigma_i H^T of the update in flight
     int32_t * status;
+    int32_t * strict_from;   // B or null: per filter, the first measurement slot of the pass in flight that the oracle-order tail takes
+                             // (k_large_strict_tail: a landmark's first touch / initializeLandmark); >= the pass's count: none
     double Q[9], R[4];
 };
 
@@ -206,12 +208,13 @@ __device__ __forceinline__ void large_update(const LargeParams & p, const double
     const double * S = p.sigma + (int64_t) b * len * len;
     double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
     double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
-    if (id < 1 || id > p.n || (p.status[b] & (kStatusMapFull | kStatusSingular)))   // block-uniform
+    const bool to_tail = p.strict_from != nullptr && i >= p.strict_from[b];   // this and every later measurement of the pass: oracle-order tail
+    if (to_tail || id < 1 || id > p.n || (p.status[b] & (kStatusMapFull | kStatusSingular)))   // block-uniform
     {
         // (a filter the reference's process would have died on stays frozen, as in the STRICT and FAST kernels)
         // no measurement in this slot: K = 0, W = 0 contribute nothing to the pass (U, V of the slot were cleared at its start)
         if (j < len) xo[j] = x[j];
-        if (j == 0 && id > p.n && !(p.status[b] & (kStatusMapFull | kStatusSingular))) p.status[b] |= kStatusBadId;
+        if (j == 0 && !to_tail && id > p.n && !(p.status[b] & (kStatusMapFull | kStatusSingular))) p.status[b] |= kStatusBadId;
         return;
     }
     const int c = 3 + 2 * (id - 1);
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(128) k_large_associate(const LargeParams p, co
     const int len = p.len;
     const int sn = seen[b];
     if (p.status[b] & (kStatusMapFull | kStatusSingular)) return;   // the reference process died on an earlier measurement
+    if (p.strict_from && p.strict_from[b] <= i_pass) return;         // this filter's measurements from i_pass on: oracle-order tail
     if (sn == 0 || 3 + 2 * sn >= len) return;                        // first landmark / full map: decided without any candidate
     const double * S = p.sigma + (int64_t) b * len * len;
     const double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
@@ -423,19 +427,27 @@ __global__ void __launch_bounds__(128) k_large_associate(const LargeParams p, co
 
 // slam.cpp:291 for every filter: the id associateLandmark returns, its side effect on `seen`, and the status bits where it throws.
 // ids_slot: B x m scratch the update kernel reads (id <= 0: no update); ids_out: B x m or null.
-__global__ void k_large_assoc_finalize(const LargeParams p, int m, int i_meas, int32_t * __restrict__ seen, int32_t * __restrict__ result,
+__global__ void k_large_assoc_finalize(const LargeParams p, int m, int i_meas, int i_pass, int32_t * __restrict__ seen, int32_t * __restrict__ result,
                                        int32_t * __restrict__ ids_slot, int32_t * __restrict__ ids_out)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.batch) return;
+    if (p.strict_from && p.strict_from[b] <= i_pass)   // already handed to the oracle-order tail (it writes ids_out itself)
+    {
+        result[b] = 0x7fffffff;
+        ids_slot[(int64_t) b * m + i_meas] = 0;
+        return;
+    }
     int id;
+    bool tail = false;   // the measurement opens a landmark or touches one for the first time: only the oracle's operation order reproduces
+                         // the reference there, so this and the pass's later measurements go to k_large_strict_tail
     const int st = p.status[b];
     const int sn = seen[b];
     if (st & (kStatusMapFull | kStatusSingular)) id = 0;
     else if (sn == 0)
     {
-        seen[b] = 1;   // :196-200
-        id = 1;
+        id = 1;   // :196-200
+        tail = true;
     }
     else if (3 + 2 * sn >= p.len)
     {
@@ -447,8 +459,8 @@ __global__ void k_large_assoc_finalize(const LargeParams p, int m, int i_meas, i
         const int r = result[b];
         if (r >= 0x7f000000)   // untouched (any fill above the largest key (n << 2 | 3))
         {
-            seen[b] = sn + 1;   // no candidate decided: a new landmark (:251)
-            id = sn + 1;
+            id = sn + 1;   // no candidate decided: a new landmark (:251)
+            tail = true;
         }
         else if ((r & 3) == 0)
         {
@@ -457,9 +469,116 @@ __global__ void k_large_assoc_finalize(const LargeParams p, int m, int i_meas, i
         }
         else id = ((r & 3) == 1) ? (r >> 2) : -1;
     }
+    if (!tail && id > 0 && p.strict_from)
+    {
+        const int c = 3 + 2 * (id - 1);
+        const double * S = p.sigma + (int64_t) b * p.len * p.len;
+        tail = S[c + (int64_t) c * p.len] > kFirstTouchVariance || S[c + 1 + (int64_t) (c + 1) * p.len] > kFirstTouchVariance;
+    }
     result[b] = 0x7fffffff;
+    if (tail && p.strict_from)
+    {
+        p.strict_from[b] = i_pass;   // `seen`, ids_out: the tail repeats this association in the oracle's order
+        ids_slot[(int64_t) b * m + i_meas] = 0;
+        return;
+    }
+    if (tail) seen[b] = id;   // (no tail scratch: the delayed path opens the landmark itself, as before)
     ids_slot[(int64_t) b * m + i_meas] = id;
     if (ids_out) ids_out[(int64_t) b * m + i_meas] = id;
+}
+
+// known correspondence: the first measurement slot of the pass [i0, i0 + cnt) that is a landmark's first touch (its variance still carries the
+// INT_MAX prior) or, under the step protocol, an initializeLandmark (id above the scan's `seen` snapshot, slam.cpp:295-297). ids == null
+// (unknown correspondence): none yet -- k_large_assoc_finalize finds it measurement by measurement.
+__global__ void k_large_first_touch(const LargeParams p, const int32_t * __restrict__ ids, int m, int i0, int cnt, const int32_t * __restrict__ seen_snapshot)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.batch) return;
+    int sf = cnt;
+    if (ids && !(p.status[b] & (kStatusMapFull | kStatusSingular)))
+    {
+        const double * S = p.sigma + (int64_t) b * p.len * p.len;
+        for (int i = 0; i < cnt; ++i)
+        {
+            const int id = ids[(int64_t) b * m + i0 + i];
+            if (id < 1 || id > p.n) continue;
+            const int c = 3 + 2 * (id - 1);
+            if ((seen_snapshot && id > seen_snapshot[b]) || S[c + (int64_t) c * p.len] > kFirstTouchVariance ||
+                S[c + 1 + (int64_t) (c + 1) * p.len] > kFirstTouchVariance)
+            {
+                sf = i;
+                break;
+            }
+        }
+    }
+    p.strict_from[b] = sf;
+}
+
+// The oracle-order tail of a pass: one warp per filter replays measurements [strict_from, cnt) of the pass with the STRICT arithmetic of
+// ekf_strict.cuh (WarpFilter working directly on the filter's Sigma in HBM; its 14 len doubles of scratch are the pass's U rows, free
+// once the rank update has run) -- associateLandmark / initializeLandmark / update exactly as EKFSlam::main_loop orders them
+// (slam.cpp:279-319). It exists for parity (a first touch costs one warp a full sweep over Sigma: ~30 ms at 4096 landmarks), the
+// steady state of a built map never takes it.
+__global__ void __launch_bounds__(32) k_large_strict_tail(const LargeParams p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i0,
+                                                          int cnt, double * __restrict__ x_cur, const int32_t * __restrict__ seen_snapshot,
+                                                          int32_t * __restrict__ seen, double amin, double amax, int32_t * __restrict__ ids_out)
+{
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int sf = p.strict_from[b];
+    if (sf >= cnt) return;
+    WarpFilter f;
+    f.len = p.len;
+    f.n = p.n;
+    f.lane = lane;
+    f.opt = 0u;
+    f.S = p.sigma + (int64_t) b * p.len * p.len;
+    f.x = x_cur + (int64_t) b * p.len;
+    double * scratch = p.U + (int64_t) b * 2 * kLargeMMax * p.len;
+    f.R5 = scratch;
+    f.M5 = scratch + 5 * (int64_t) p.len;
+    f.G = scratch + 10 * (int64_t) p.len;
+    f.K = scratch + 12 * (int64_t) p.len;
+    int status = p.status[b];
+    int sn = seen ? seen[b] : p.n;
+    const int snap = seen_snapshot ? seen_snapshot[b] : 0x7fffffff;   // no step protocol: never an initializeLandmark
+    const int64_t mb = (int64_t) b * m + i0;
+    for (int i = sf; i < cnt; ++i)
+    {
+        if (status & (kStatusMapFull | kStatusSingular)) break;   // the reference process has died
+        const double z0 = z[2 * (mb + i)], z1 = z[2 * (mb + i) + 1];
+        int id;
+        if (ids)
+        {
+            id = ids[mb + i];
+            if (id <= 0) continue;
+            if (id > p.n)
+            {
+                status |= kStatusBadId;
+                continue;
+            }
+            if (id > sn) sn = id;
+        }
+        else
+        {
+            id = f.associate(z0, z1, sn, status, p.R, amin, amax);   // slam.cpp:291
+            if (ids_out && lane == 0) ids_out[mb + i] = id;
+            if (id == kIdException)
+            {
+                if (ids_out)
+                    for (int r = i + 1 + lane; r < cnt; r += kWarp) ids_out[mb + r] = 0;
+                break;
+            }
+        }
+        if (id > snap) f.init_landmark(z0, z1, id, status);   // slam.cpp:295-297
+        else if (id < 0) continue;                            // slam.cpp:298-300
+        f.update(z0, z1, id, status, p.R);                    // slam.cpp:318
+    }
+    __syncwarp();
+    if (lane == 0)
+    {
+        if (seen) seen[b] = sn;
+        p.status[b] = status;
+    }
 }
 
 // all `cnt` delayed updates of a pass in ONE cooperative launch: consecutive updates are separated by a grid barrier (~2 us) instead
@@ -600,6 +719,13 @@ inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const
     const dim3 grid((p.len + threads - 1) / threads, (unsigned) p.batch);
     const int kk = (2 * cnt + 3) & ~3;
     k_large_clear_w<<<dim3((unsigned) (((int64_t) kk * p.len + threads - 1) / threads), (unsigned) p.batch), threads, 0, st>>>(p, kk / 2);
+    if (p.strict_from) k_large_first_touch<<<(unsigned) ((p.batch + 63) / 64), 64, 0, st>>>(p, ids, m, i0, cnt, seen_snapshot);
+    // after the pass: measurements the delayed path left to the oracle-order tail (first touches; usually none)
+    auto tail = [&]() {
+        if (p.strict_from)
+            k_large_strict_tail<<<(unsigned) p.batch, 32, 0, st>>>(p, z, ids, m, i0, cnt, p.x, seen_snapshot, seen, assoc ? assoc->amin : 0.0,
+                                                                assoc ? assoc->amax : 0.0, assoc ? assoc->ids_out : nullptr);
+    };
     if (assoc)
     {
         // unknown correspondence: per measurement associate (one thread per candidate) -> finalize -> update
@@ -607,7 +733,7 @@ inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const
         {
             k_large_associate<<<dim3((unsigned) ((p.n + 127) / 128), (unsigned) p.batch), 128, 0, st>>>(p, z, m, i0 + k, k, p.x, seen, assoc->result,
                                                                                                      assoc->amin, assoc->amax);
-            k_large_assoc_finalize<<<(unsigned) ((p.batch + 63) / 64), 64, 0, st>>>(p, m, i0 + k, seen, assoc->result, assoc->ids_slot, assoc->ids_out);
+            k_large_assoc_finalize<<<(unsigned) ((p.batch + 63) / 64), 64, 0, st>>>(p, m, i0 + k, k, seen, assoc->result, assoc->ids_slot, assoc->ids_out);
             k_large_update<<<grid, threads, 0, st>>>(p, z + 2 * (int64_t) i0, assoc->ids_slot + i0, m, k, p.x, p.x2, seen_snapshot, seen);
             double * tmp = p.x;
             p.x = p.x2;
@@ -615,6 +741,7 @@ inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const
         }
         const unsigned tiles = (p.len + kLargeTile - 1) / kLargeTile;
         k_large_rank_update<<<dim3(tiles, tiles, (unsigned) p.batch), 128, 0, st>>>(p, kk);
+        tail();
         return cudaGetLastError();
     }
     // one cooperative launch when the whole grid is co-resident (it is for a few large maps), else two launches per update
@@ -658,6 +785,7 @@ inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const
     }
     const unsigned tiles = (p.len + kLargeTile - 1) / kLargeTile;
     k_large_rank_update<<<dim3(tiles, tiles, (unsigned) p.batch), 128, 0, st>>>(p, kk);
+    tail();
     return cudaGetLastError();
 }
 

@@ -246,6 +246,7 @@ nuslam::LargeParams make_large_params(nuslam_ekf * h)
     p.V = h->lg_V;
     p.P = h->lg_P;
     p.status = h->status;
+    p.strict_from = h->lg_seen_snap ? h->lg_seen_snap + h->batch : nullptr;
     memcpy(p.Q, h->cfg.Q, sizeof(p.Q));
     memcpy(p.R, h->cfg.R, sizeof(p.R));
     return p;
@@ -381,7 +382,7 @@ int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, 
         cudaError_t l2 = cudaMalloc(&h->lg_U, sizeof(double) * 2 * nuslam::kLargeMMax * l * batch);
         cudaError_t l3 = cudaMalloc(&h->lg_V, sizeof(double) * 2 * nuslam::kLargeMMax * l * batch);
         cudaError_t l4 = cudaMalloc(&h->lg_P, sizeof(double) * 2 * l * batch);
-        cudaError_t l5 = cudaMalloc(&h->lg_seen_snap, sizeof(int32_t) * batch);
+        cudaError_t l5 = cudaMalloc(&h->lg_seen_snap, sizeof(int32_t) * 2 * batch);   // [0, B): seen snapshot of the scan, [B, 2B): strict_from of the pass
         if (l1 != cudaSuccess || l2 != cudaSuccess || l3 != cudaSuccess || l4 != cudaSuccess || l5 != cudaSuccess)
         {
             nuslam_ekf_destroy(h);

@@ -63,17 +63,60 @@ def test_large_mode_matches_oracle(cuda_lib, orc, n, m, T, B):
 
 
 def test_large_mode_initialises_new_landmarks(cuda_lib, orc):
-    """Step protocol from scratch (slam.cpp:295-297): landmarks are initialised inside the step; state matches loosely (first
-    touches), seen exactly."""
+    """Step protocol from scratch (slam.cpp:295-297): landmarks are initialised inside the step and their first touches run in the oracle's
+    operation order (k_large_strict_tail, the large-map counterpart of FAST -> STRICT). `seen` exact; the state equals the on-chip STRICT
+    kernel's to 1e-9. Against the oracle itself a from-scratch run is limited -- for STRICT and LARGE alike -- by the <= 2 ulp between CUDA's and
+    glibc's sin / cos in predict / initializeLandmark, which the INT_MAX first touch amplifies (2e9 x 1e-16 on entries of 1e-2): 1e-4 here;
+    the teacher-forced test below removes that input difference and holds the first touches themselves to the oracle."""
     n, B, T = 20, 2, 3
     sc = synth.ekf_scenario(B, T, n=n, seed=62)
     full = orc.ekf_run(n, sc["robot0"], sc["map0"], sc["Q"], sc["R"], sc["twists"], sc["z"], sc["ids"])
-    eng = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="large")
-    for t in range(T):
-        eng.step(sc["twists"][t], sc["z"][t], sc["ids"][t])     # m = 20 > 16: two delayed passes per step
-    x, s, seen, status = eng.get_state()
+    out = {}
+    for mode in ("large", "strict"):
+        eng = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode=mode)
+        for t in range(T):
+            eng.step(sc["twists"][t], sc["z"][t], sc["ids"][t])     # m = 20 > 16: two delayed passes per step
+        out[mode] = eng.get_state()
+    x, s, seen, status = out["large"]
+    xs, ss, _, _ = out["strict"]
     assert np.array_equal(seen, full["seen"]) and not status.any()
-    assert rel_max(x, full["x"]) < 1e-3
+    ex, es = rel_max(x, xs), max(rel_max(s[b], ss[b]) for b in range(B))
+    eo = rel_max(x, full["x"])
+    print(f"[large from scratch] vs STRICT kernel: x rel {ex:.2e}, Sigma rel {es:.2e}; vs oracle: x rel {eo:.2e} (STRICT vs oracle: {rel_max(xs, full['x']):.2e})")
+    assert ex < TOL and es < TOL
+    assert eo < 1e-4
+
+
+def test_large_mode_first_touch_teacher_forced(cuda_lib, orc):
+    """The first touch of a landmark (INT_MAX prior, non-Joseph update: catastrophic cancellation that only the reference's own operation
+    order reproduces) in LARGE mode, held to the oracle: before every single update both sides start from the oracle's
+    state bit for bit (after its predict and initializeLandmark), so no libm difference enters; the update of the never-touched landmark
+    then goes through k_large_strict_tail. Sigma after every first touch: <= 1e-12 of the oracle (STRICT is bit-identical there)."""
+    n, B = 40, 2
+    sc = synth.ekf_scenario(B, 2, n=n, seed=63)
+    fs = [orc.ekf(n, sc["robot0"][b], sc["map0"][b], sc["Q"], sc["R"]) for b in range(B)]
+    eng = cuda_lib.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="large")
+    for b, f in enumerate(fs):
+        f.predict(*sc["twists"][0, b])
+    worst_x = worst_s = 0.0
+    for i in range(12):
+        for b, f in enumerate(fs):
+            f.init_landmark(sc["z"][0][b, i], int(sc["ids"][0][b, i]))
+        xo = np.stack([f.get()[0] for f in fs])
+        so = np.stack([f.get()[1] for f in fs])
+        eng.set_state(xo, so, np.array([f.get()[2] for f in fs]))
+        eng.update(sc["z"][0][:, i], sc["ids"][0][:, i])        # first touch: landmark's variance is still INT_MAX
+        for b, f in enumerate(fs):
+            f.update(sc["z"][0][b, i], int(sc["ids"][0][b, i]))
+        x, s, _, status = eng.get_state()
+        assert not status.any()
+        xo = np.stack([f.get()[0] for f in fs])
+        so = np.stack([f.get()[1] for f in fs])
+        touched = np.concatenate([[0, 1, 2]] + [[3 + 2 * (int(k) - 1), 4 + 2 * (int(k) - 1)] for k in sc["ids"][0][0, :i + 1]])
+        worst_x = max(worst_x, rel_max(x, xo))
+        worst_s = max(worst_s, max(rel_max(s[b][np.ix_(touched, touched)], so[b][np.ix_(touched, touched)]) for b in range(B)))
+    print(f"[large first touch, teacher forced] 12 first touches: x rel {worst_x:.2e}, Sigma (touched block) rel {worst_s:.2e}")
+    assert worst_x < TOL and worst_s < 1e-12
 
 
 def test_4096_landmarks_delayed_equals_sequential(cuda_lib):
@@ -152,13 +195,13 @@ def test_large_mode_unknown_association(cuda_lib, orc, n, m, B):
         assert np.array_equal(got, r["ids_out"][0]), f"ids differ at scan {t}"
         assert np.array_equal(seen, r["seen"]) and np.array_equal(status != 0, r["status"] != 0)
         new = int((r["seen"] - (state[2] if state is not None else 0)).sum())
-        if new == 0:   # no first touch in this scan: tight bound
-            assert rel_max(x, r["x"]) < TOL
-            touched = np.concatenate([[0, 1, 2]] + [[3 + 2 * (k - 1), 4 + 2 * (k - 1)] for k in range(1, int(r["seen"].max()) + 1)])
-            for b in range(B):
-                assert rel_max(s[b][np.ix_(touched, touched)], r["sigma"][b][np.ix_(touched, touched)]) < TOL
-        else:
-            assert rel_max(x, r["x"]) < 1e-3
+        # a scan that opens landmarks runs their first touches in the oracle's order (k_large_strict_tail); what remains against the oracle
+        # is the <= 2 ulp of CUDA's sin / cos in initializeLandmark amplified by the INT_MAX first touch (same for the STRICT kernel)
+        tol = TOL if new == 0 else 1e-4
+        assert rel_max(x, r["x"]) < tol, (t, new)
+        touched = np.concatenate([[0, 1, 2]] + [[3 + 2 * (k - 1), 4 + 2 * (k - 1)] for k in range(1, int(r["seen"].max()) + 1)])
+        for b in range(B):
+            assert rel_max(s[b][np.ix_(touched, touched)], r["sigma"][b][np.ix_(touched, touched)]) < tol, (t, b, new)
         decisions += got.size
         matched += int((got > 0).sum())
         opened += new
