@@ -44,6 +44,7 @@ struct __align__(16) MomentSmem
     double org[kMomMaxClusters][2];           // per cluster: its first point (local origin of the sums)
     short cend[kMomMaxClusters + 8];          // flat position of the cluster's last point
     unsigned char bclu[kBeams + 8];           // per beam: its pre-erase cluster, 255 when the beam is in no cluster
+    short nidx[kMomMaxClusters];              // pre-erase cluster -> index among the returned clusters (-1: erased)
 };
 
 // the atan2 tables of fastmath.cuh in shared memory (the lanes index them with different entries, which the constant cache serialises)
@@ -124,6 +125,7 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
         // closer_i = in range and not similar to beam i + 1; the cluster of an in-range beam = closers before it
         int nc = 0, npts = 0;
         bool risky = false, wrap = false;
+        const bool big_gate = !(gate.max_f <= 32.0f);   // warp-uniform
 #pragma unroll
         for (int k = 0; k < kChunks; ++k)
         {
@@ -138,7 +140,9 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
             // in double like the reference
             const float df = fabsf(rv - nb);
             const bool sim = df < 0.04f;
-            risky = risky || (inr && (!(fabsf(df - 0.04f) >= 1e-5f) || !(fmaxf(fabsf(rv), fabsf(nb)) < 64.0f)));
+            // (an in-range beam is below max_f; when that is at most 32 m a neighbour of 64 m or more is nowhere near the threshold, and a
+            // NaN fails the first test by itself: the magnitude test is needed only for range gates beyond 32 m)
+            risky = risky || (inr && (!(fabsf(df - 0.04f) >= 1e-5f) || (big_gate && !(fmaxf(fabsf(rv), fabsf(nb)) < 64.0f))));
             unsigned inr_m = __ballot_sync(kFull, inr);
             const unsigned clo_m = __ballot_sync(kFull, inr && !sim);
             if (k == kChunks - 1)
@@ -195,16 +199,27 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
         const int nk = nc - __popc(erased_m);
         if (cluster_of_beam)
         {
+            // two beams per lane and pass: the pre-erase cluster of a beam -> its index among the returned clusters through a 32-entry
+            // table, both ids in one 32-bit store (a scan's ids start at a multiple of 4 bytes whenever the array does)
             const int new0 = __shfl_sync(kFull, newidx, 0);
+            sm.nidx[lane] = (short) newidx;
+            __syncwarp();
+            const bool pair_ok = (reinterpret_cast<uintptr_t>(cluster_of_beam) & 3) == 0;
 #pragma unroll 1
-            for (int k = 0; k < kChunks; ++k)
+            for (int i = 2 * lane; i < kBeams; i += 64)
             {
-                const int i = 32 * k + lane;
-                const int bc = (i < kBeams) ? (int) sm.bclu[i] : 255;
-                const int nidx = __shfl_sync(kFull, newidx, bc & 31);
-                int out = (bc < nc) ? nidx : -1;   // beams behind the last closer form the open cluster the reference drops
-                if (wrap && i == kBeams - 1) out = new0;
-                if (i < kBeams) cluster_of_beam[sb + i] = (int16_t) out;
+                const unsigned two = *reinterpret_cast<const unsigned short *>(&sm.bclu[i]);
+                const int bc0 = (int) (two & 0xffu), bc1 = (int) (two >> 8);
+                int o0 = (bc0 < nc) ? (int) sm.nidx[bc0 & (kMomMaxClusters - 1)] : -1;   // beams behind the last closer: the open cluster the reference drops
+                int o1 = (bc1 < nc) ? (int) sm.nidx[bc1 & (kMomMaxClusters - 1)] : -1;
+                if (wrap && i + 1 == kBeams - 1) o1 = new0;
+                if (pair_ok)
+                    *reinterpret_cast<unsigned *>(cluster_of_beam + sb + i) = ((unsigned) o0 & 0xffffu) | ((unsigned) o1 << 16);
+                else
+                {
+                    cluster_of_beam[sb + i] = (int16_t) o0;
+                    cluster_of_beam[sb + i + 1] = (int16_t) o1;
+                }
             }
         }
         // ---- points: one per lane, ONE pass of segmented warp sums about the cluster's first point: the sums the Hyper fit needs and
@@ -272,7 +287,18 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
             const int key_next = __shfl_down_sync(kFull, key, 1);   // (every lane takes part: no collective behind a short-circuit)
             const bool tail = lane == 31 || key_next != key;
             const bool first = cs >= base;   // the cluster's first contribution to its accumulators
-            if (tail && active && !iswrap)
+            const bool mine = tail && active && !iswrap;
+            if (__all_sync(kFull, !mine || first))   // usual case: every cluster of this batch starts in it -- plain stores
+            {
+                if (mine)
+                {
+#pragma unroll
+                    for (int k = 0; k < kMomSums; ++k) sm.acc[clu][k] = v[k];
+                    sm.org[clu][0] = x2;
+                    sm.org[clu][1] = y2;
+                }
+            }
+            else if (mine)
             {
 #pragma unroll
                 for (int k = 0; k < kMomSums; ++k) sm.acc[clu][k] = first ? v[k] : sm.acc[clu][k] + v[k];
