@@ -197,8 +197,11 @@ __device__ __forceinline__ LargeModel large_model(const double * xl)
 // hand-over between "W, P" and "K, x" -- one grid barrier (or kernel boundary) per measurement instead of two.
 __device__ __forceinline__ void large_update(const LargeParams & p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
                                              const double * __restrict__ x_old, double * __restrict__ x_new,
-                                             const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen)
+                                             const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen, double * own = nullptr)
 {
+    // own (cooperative single-launch pass only): this block's shared-memory copy of ITS threads' entries of the pass's K_u / W_u,
+    // own[(2 r + {0: W, 1: K}) * blockDim.x + threadIdx.x] -- the correction loop then reads no global memory at all; the global U / V
+    // rows are still written (the other blocks read five entries of them, the rank update all of them)
     const int b = blockIdx.y;
     const int len = p.len;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,6 +217,8 @@ __device__ __forceinline__ void large_update(const LargeParams & p, const double
         // (a filter the reference's process would have died on stays frozen, as in the STRICT and FAST kernels)
         // no measurement in this slot: K = 0, W = 0 contribute nothing to the pass (U, V of the slot were cleared at its start)
         if (j < len) xo[j] = x[j];
+        if (own)
+            for (int a = 0; a < 4; ++a) own[(4 * i + a) * blockDim.x + threadIdx.x] = 0.0;
         if (j == 0 && !to_tail && id > p.n && !(p.status[b] & (kStatusMapFull | kStatusSingular))) p.status[b] |= kStatusBadId;
         return;
     }
@@ -289,7 +294,8 @@ __device__ __forceinline__ void large_update(const LargeParams & p, const double
 #pragma unroll 4
     for (int r = 0; r < 2 * i; ++r)
     {
-        const double wj = V[(int64_t) r * len + j], kj = U[(int64_t) r * len + j];
+        const double wj = own ? own[(2 * r) * blockDim.x + threadIdx.x] : V[(int64_t) r * len + j];
+        const double kj = own ? own[(2 * r + 1) * blockDim.x + threadIdx.x] : U[(int64_t) r * len + j];
 #pragma unroll
         for (int q = 0; q < 5; ++q)
         {
@@ -309,6 +315,7 @@ __device__ __forceinline__ void large_update(const LargeParams & p, const double
             pp = fma(col[q], mdl.h[a][q], pp);
         }
         V[(int64_t) (2 * i + a) * len + j] = w;
+        if (own) own[(2 * (2 * i + a)) * blockDim.x + threadIdx.x] = w;
         pj[a] = pp;
     }
     const double det = s[0][0] * s[1][1] - s[0][1] * s[1][0];
@@ -316,6 +323,7 @@ __device__ __forceinline__ void large_update(const LargeParams & p, const double
     {
         U[(int64_t) (2 * i) * len + j] = 0.0;
         U[(int64_t) (2 * i + 1) * len + j] = 0.0;
+        if (own) own[(2 * (2 * i) + 1) * blockDim.x + threadIdx.x] = own[(2 * (2 * i + 1) + 1) * blockDim.x + threadIdx.x] = 0.0;
         xo[j] = xj;
         if (j == 0) p.status[b] |= kStatusSingular;
         return;
@@ -324,6 +332,11 @@ __device__ __forceinline__ void large_update(const LargeParams & p, const double
     const double k0 = pj[0] * i00 + pj[1] * i10, k1 = pj[0] * i01 + pj[1] * i11;
     U[(int64_t) (2 * i) * len + j] = k0;
     U[(int64_t) (2 * i + 1) * len + j] = k1;
+    if (own)
+    {
+        own[(2 * (2 * i) + 1) * blockDim.x + threadIdx.x] = k0;
+        own[(2 * (2 * i + 1) + 1) * blockDim.x + threadIdx.x] = k1;
+    }
     const double dz0 = z[(int64_t) (b * m + i) * 2] - mdl.zr, dz1 = z[(int64_t) (b * m + i) * 2 + 1] - mdl.zb;   // :272, no wrap
     double xn = xj + (k0 * dz0 + k1 * dz1);
     if (j == 0) xn = wrap_angle(xn);   // normalize_angle, slam_library.cpp:276
@@ -587,11 +600,38 @@ __global__ void __launch_bounds__(64) k_large_updates_coop(const LargeParams p, 
                                                           const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen)
 {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ double own[4 * kLargeMMax * 64];   // 32 KB: this block's entries of the pass's W_u / K_u (large_update)
     const double * xc = p.x;
     double * xn = p.x2;
+    // known correspondence: every update of the pass reads five rows and five columns of Sigma_0 whose indices are known now -- pull
+    // them towards L2 before the chain of dependent updates starts (the strided row gather from DRAM was its longest step)
+    {
+        const int b = blockIdx.y, len = p.len;
+        const int j = blockIdx.x * blockDim.x + threadIdx.x;
+        const double * S = p.sigma + (int64_t) b * len * len;
+        if (j < len)
+            for (int k = 0; k < cnt; ++k)
+            {
+                const int id = ids[b * m + k];
+                if (id < 1 || id > p.n) continue;
+                const int c = 3 + 2 * (id - 1);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(S + c + (int64_t) j * len));       // rows c, c + 1 at column j (one sector)
+                if ((j & 3) == 0)
+                {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(S + j + (int64_t) c * len));         // columns c, c + 1: 32-byte sectors
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(S + j + (int64_t) (c + 1) * len));
+                }
+            }
+        if (j < len)
+        {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(S + (int64_t) j * len));   // rows 0, 1, 2 at column j
+            if ((j & 3) == 0)
+                for (int q = 0; q < 3; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(S + j + (int64_t) q * len));
+        }
+    }
     for (int k = 0; k < cnt; ++k)
     {
-        large_update(p, z, ids, m, k, xc, xn, seen_snapshot, seen);
+        large_update(p, z, ids, m, k, xc, xn, seen_snapshot, seen, own);
         grid.sync();
         const double * t = xc;
         xc = xn;
