@@ -125,7 +125,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": reasons, "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
-def make_inputs_device(torch, dev, B, steps_total, seed):
+def make_inputs_device(torch, dev, B, steps_total, seed, radius=0.20):
     """Synthetic config-2 inputs generated on the device (data: synthetic): robot on the reference circle
     (d_theta 0.02, dx 0.007 per step), 12 landmarks on the benign ring, exact range/bearing + N(0, 0.01^2)."""
     from shermbot_navigation_b200 import synth
@@ -133,7 +133,7 @@ def make_inputs_device(torch, dev, B, steps_total, seed):
     g.manual_seed(seed)
     tw1 = synth.wheel_twists(steps_total + 1, first_step_straight=True)
     poses = synth.true_trajectory(tw1)
-    lm = synth.landmark_ring(N_LANDMARKS, 0.20)
+    lm = synth.landmark_ring(N_LANDMARKS, radius)
     dxl = lm[None, :, 0] - poses[:, None, 1]
     dyl = lm[None, :, 1] - poses[:, None, 2]
     rng_true = torch.tensor(np.sqrt(dxl * dxl + dyl * dyl), device=dev)                      # (T, n)
@@ -168,6 +168,28 @@ def bind_to_gpu_numa_node(index: int):
         return f"nvml ideal affinity: {after} of {before} cpus"
     except Exception as e:   # containers often forbid it: not an error
         return f"unchanged ({type(e).__name__})"
+
+
+def adversarial_leg(torch, nuslam, dev, local, stream, B, mode, seed, steps=12):
+    """The same kernel on the ADVERSARIAL ring (landmarks on a 0.60 m ring around the robot's circle: bearings all around the robot, so the
+    innovation's atan2 - theta leaves (-pi, pi] for half of the measurements and the conditional wraps of the update are taken). A separate
+    engine, first-touch step + 3 warm-up steps untimed, `steps` steps between two CUDA events. Returns ms per step."""
+    robot0, twists, ids, z_of = make_inputs_device(torch, dev, B, steps + 6, seed=seed, radius=0.60)
+    eng = nuslam.BatchedExtendedKalman(robot0, None, n_landmarks=N_LANDMARKS, mode=mode, device=local, stream=stream.cuda_stream)
+    zs = [z_of(t) for t in range(steps + 4)]
+    for t in range(4):
+        eng.step(twists[t], zs[t], ids)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(4, 4 + steps):
+        eng.step(twists[t], zs[t], ids)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    x, _, _, status = eng.get_state()
+    bad = int((status != 0).sum()) + int((~np.isfinite(x)).any(axis=1).sum())
+    eng.close()
+    return e0.elapsed_time(e1) / steps, bad
 
 
 def config_dict(world):
@@ -298,6 +320,11 @@ def run_ours(args):
     stats = eng.error_stats(truth_pose=truth_pose, truth_map=truth_map)
     bad_nonfinite = (~torch.isfinite(xs)).any(dim=1).sum().to(torch.float64)
 
+    # ---- the adversarial ring, timed once beside the benign number (rank 0's shard) ----
+    adv_ms, adv_bad = (None, 0)
+    if not args.no_extras:
+        adv_ms, adv_bad = adversarial_leg(torch, nuslam, dev, local, stream, B, args.mode, seed=99 + rank)
+
     # ---- end to end through the public API with HOST buffers, and the copy-only ceiling of the same path ----
     Ke = max(3, min(K, args.e2e_steps))
     leg = lambda dry, packed: e2e_leg(eng, torch, dist, world, dev, B, twists, zs, ids, t, Ke, dry=dry, packed=packed)
@@ -338,7 +365,10 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_dict(world),
-            "details": {"mode": args.mode, "filters_this_run": B, "batched_steps_per_s": value / (world * B) if B else None},
+            "details": {"mode": args.mode, "filters_this_run": B, "batched_steps_per_s": value / (world * B) if B else None,
+                        "adversarial_ring": {"ms_per_step": adv_ms, "bad_filters": adv_bad,
+                                             "note": "same kernel, landmarks on a 0.60 m ring around the robot's path (bearings wrap for half of the "
+                                                     "measurements), rank 0's shard, 12 steps"}},
             "clocks": clocks, "gpu_launches": launches * K, "bad_filters": bad,
             "stats": {"reduced": "k_error_stats per rank" + (" + NCCL all_reduce(sum)" if world > 1 else ""), "filters": st["filters"],
                       "rmse_position_m": (st["sq_position_error"] / nf) ** 0.5, "rmse_heading_rad": (st["sq_heading_error"] / nf) ** 0.5,
