@@ -512,7 +512,8 @@ inline int known_ids_kernel()
     if (e && e[0] == 'p') return 1;
     if (e && e[0] == 's') return 0;
     if (e && e[0] == 'f') return 2;
-    if (e && e[0] == 'r') return (e[1] && e[2] && e[3] == '2') ? 4 : 3;   // "res": ekf_res.cuh, "res2": ekf_res2.cuh
+    // "res": ekf_res.cuh, "res2": ekf_res2.cuh, "res2a": ekf_res2.cuh + the resident pair kernel with on-device association (ekf_res2a.cuh)
+    if (e && e[0] == 'r') return (e[1] && e[2] && e[3] == '2') ? (e[4] == 'a' ? 5 : 4) : 3;
     return NUSLAM_DEFAULT_KERNEL;
 }
 

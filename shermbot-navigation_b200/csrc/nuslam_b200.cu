@@ -19,6 +19,7 @@
 #include "ekf_static.cuh"
 #include "ekf_res.cuh"
 #include "ekf_res2.cuh"
+#include "ekf_res2a.cuh"
 #include "scan_moment.cuh"
 #include "scan_detect.cuh"
 #include "ekf_large.cuh"
@@ -200,8 +201,13 @@ int launch_fast_then_strict(nuslam_ekf * h, const nuslam::EkfParams & p, bool do
     // two-filters-per-warp kernel / the dynamic one for A/B timing); everything else: ekf_fast.cuh
     const int which = nuslam::known_ids_kernel();
     const bool special = which != 2 && nuslam::pair_supported(h->cfg.n_landmarks, p);
-    int rc = !special      ? nuslam::launch_fast(h->cfg.n_landmarks, p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
-             : which == 4 ? nuslam::launch_res2_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
+    // unknown correspondence at the BASELINE map size: ekf_fast.cuh's association instantiation; NUSLAM_KERNEL=res2a selects the resident
+    // pair kernel with on-device association (ekf_res2a.cuh: same results, measured no faster -- 12 warps x 2 filters x 266 instructions
+    // per filter-measurement against 16 warps x 357: profiles/r02_kernel_iterations.md)
+    const bool assoc_pair = which == 5 && nuslam::res2a_supported(h->cfg.n_landmarks, p, do_predict);
+    int rc = assoc_pair    ? nuslam::launch_res2a_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
+             : !special    ? nuslam::launch_fast(h->cfg.n_landmarks, p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
+             : which >= 4 ? nuslam::launch_res2_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
              : which == 3 ? nuslam::launch_res_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
              : which == 1 ? nuslam::launch_pair_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
                           : nuslam::launch_static_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream);
