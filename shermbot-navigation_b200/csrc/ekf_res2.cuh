@@ -55,7 +55,11 @@ struct __align__(16) Res2Smem
 };
 
 template <int N, int CH>
+#ifdef NUSLAM_RES2_MAXREG
+__global__ void __maxnreg__(NUSLAM_RES2_MAXREG)
+#else
 __global__ void __launch_bounds__(32 * kRes2Warps, kRes2CtasPerSm)
+#endif
 k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ worklist, int32_t * __restrict__ wl_count)
 {
     using G = FastGeom<N>;
