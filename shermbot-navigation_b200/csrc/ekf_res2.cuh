@@ -52,6 +52,7 @@ struct __align__(16) Res2Smem
     double2 kt[2][CH][28];        // per filter: -Kt of the chunk's updates (DMMA A operand, pending corrections)
     double2 wt[2][CH][28];        // per filter: Wt of the chunk's updates (DMMA B operand)
     double z[2][2 * kFastMMax];   // per filter: this step's measurements
+    unsigned slots_of[2][16];     // per filter: landmark (1-based) -> bit mask of this step's measurement slots that carry it
 };
 
 template <int N, int CH>
@@ -226,6 +227,16 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             if ((bad_w >> hb) & 0xffffu) status |= kStatusBadId;
         }
         const int code = (idok && !dead) ? my_id : 0;   // 0: no update in this slot (a dead filter has none at all)
+        // this lane's slot as the state index of its landmark (-1: none), and -- once per step -- in which slots the landmarks of this
+        // lane's two state indices are measured (index i >= 3 belongs to landmark (i - 1) / 2): the chunk loop then neither decodes ids nor
+        // compares indices
+        const int cval = code ? 1 + 2 * code : -1;
+        f.slots_of[h][q] = 0u;
+        __syncwarp();
+        if (code) atomicOr(&f.slots_of[h][code], 1u << q);
+        __syncwarp();
+        const unsigned hit0 = (q >= 3) ? f.slots_of[h][(q - 1) >> 1] : 0u;
+        const unsigned hit1 = v1 ? f.slots_of[h][(15 + q) >> 1] : 0u;
         if (q < m) *reinterpret_cast<double2 *>(&f.z[h][2 * q]) = make_double2(my_z0, my_z1);
         // ---- robot rows / columns: image -> registers (vector layout, two slots) ----
         double Ct[2], Cx[2], Cy[2], Rt[2], Rx[2], Ry[2];
@@ -288,15 +299,14 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         for (int i0 = 0; i0 < m; i0 += CH)
         {
             int cc[CH];
-            bool mine0 = false, mine1 = false;
 #pragma unroll
             for (int s = 0; s < CH; ++s)
             {
-                const int id = __shfl_sync(kFull, code, hb + ((i0 + s) & 15));   // this half's id of slot i0 + s
-                cc[s] = (id && i0 + s < m) ? 1 + 2 * id : -1;                   // -1: no measurement in this slot of this filter
-                mine0 = mine0 || (cc[s] >= 0 && (unsigned) (q - cc[s]) < 2u);
-                mine1 = mine1 || (cc[s] >= 0 && (unsigned) (16 + q - cc[s]) < 2u);
+                const int cv = __shfl_sync(kFull, cval, hb + ((i0 + s) & 15));   // this half's landmark column of slot i0 + s
+                cc[s] = (i0 + s < kFastMMax) ? cv : -1;                          // -1: no measurement in this slot of this filter
             }
+            const unsigned chunk_bits = ((1u << CH) - 1u) << i0;
+            const bool mine0 = (hit0 & chunk_bits) != 0u, mine1 = (hit1 & chunk_bits) != 0u;
             // the image's robot rows / columns are stale (they live in registers): refresh the entries this chunk's landmarks read
             if (mine0)
             {
