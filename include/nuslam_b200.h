@@ -120,6 +120,10 @@ void nuslam_ekf_default_config(nuslam_ekf_config * cfg, int32_t n_landmarks);
 
 const char * nuslam_last_error(void);
 int nuslam_version(void);
+/* 1: the library was built with device-side tail launches (-rdc=true): a FAST-mode step launches the oracle-order list kernel itself, and
+ * only when a filter was handed over -- one kernel launch per step of a built map; 0: the host launches it after every FAST kernel.
+ * (No reference counterpart: diagnostics for bench.py's launch count.) */
+int nuslam_tail_launch(void);
 
 /* Create B independent filters on `device`. `cuda_stream` is a cudaStream_t (NULL: the handle creates
  * its own non-blocking stream). State memory is owned by the handle unless nuslam_ekf_bind_state is

@@ -35,6 +35,7 @@
 // appended to a work list that the STRICT kernel (ekf_strict.cuh) processes right after on the same stream.
 // Reference: nuslam/src/slam_library.cpp:65-108 (predict), :263-282 (update), nuslam/src/slam.cpp:262-319.
 #pragma once
+#include "ekf_fast_api.cuh"
 #include "ekf_strict.cuh"
 #include "fastmath.cuh"
 #include <stdlib.h>
@@ -54,7 +55,6 @@ constexpr int kFastThreads = 32;                   // one warp = one filter in f
 #endif
 constexpr bool kFastSingleStage = NUSLAM_FAST_SINGLE_STAGE != 0;
 constexpr int kFastCtasPerSm = NUSLAM_FAST_CTAS;   // 16 single-warp CTAs / SM at 128 registers (20 at 96 registers spill; measured slower)
-constexpr int kFastMMax = 16;                      // measurements per step handled by this kernel
 
 // N > 0: the number of landmarks is a compile-time constant (the BASELINE sizes 12 and 6: every index folds). N < 0: a GENERIC
 // instantiation for any n with ceil(2 n / 8) = -N fragment blocks per side (n read from the parameters at run time; n <= 4, 8, 12
@@ -119,14 +119,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void dmma884(double & c0, double & c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// angle -> [-pi, pi]: what rigid2d::normalize_angle (rigid2d.cpp:9-13) returns, to ~1 ulp, without the
-// sin/cos/atan2 round trip; the identity for |a| <= pi, branch-free
-__device__ __forceinline__ double wrap_angle(double a)
-{
-    const double k = rint(a * kFastK[5]);   // 1 / 2 pi; 2 pi = kFastK[3] + kFastK[4]
-    return fma(-k, kFastK[4], fma(-k, kFastK[3], a));
 }
 
 // per-CTA (= per-warp) shared memory: exchange buffers between the fragment and the vector layout. Every vector has
@@ -385,7 +377,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             // predictEstimate :71-94, then the two Jacobian entries of getA :127-148 (theta read AFTER the motion update,
             // :129). sin/cos(theta + dth) of :84-85 and of :131 have the same argument: evaluated once.
             double s0, c0, b10, b20;
-            sincos(th, &s0, &c0);
+            sincos_fast(th, &s0, &c0);
             if (dth == 0.0)
             {
                 px = add_(px, mul_(dxx, c0));
@@ -396,7 +388,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             }
             else
             {
-                const double q = div_(dxx, dth);
+                const double q = div_fast(dxx, dth);
                 // sin / cos of theta + dth and theta + 2 dth by the addition theorems from ONE library sincos(theta) and the
                 // small-angle series of dth (the oracle calls libm three times; the difference is a few ulp, far inside the tolerance)
                 double sd, cd;
@@ -859,13 +851,13 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         NUSLAM_T(7)
     }
     if (BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the last bulk store
+    strict_tail(p, do_predict, worklist, wl_count, (int) gridDim.x, lane);
 #ifdef NUSLAM_TIMING
     if (blockIdx.x == 0 && lane == 0)
         for (int k = 0; k < 8; ++k) atomicAdd((unsigned long long *) &g_fast_timing[k], (unsigned long long) tacc[k]);
 #endif
 }
 
-inline bool fast_supported(int n) { return n >= 1 && n <= 12; }
 
 template <int N>
 int launch_fast_n(const EkfParams & p, bool do_predict, int sm_count, int32_t * worklist, int32_t * wl_count, cudaStream_t stream)

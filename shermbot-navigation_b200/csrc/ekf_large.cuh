@@ -13,7 +13,8 @@
 // <= 1e-9 after the first touch of a landmark (the first touch itself cancels catastrophically in the reference, SURVEY.md
 // Appendix B).
 #pragma once
-#include "ekf_fast.cuh"
+#include "ekf_strict.cuh"
+#include "fastmath.cuh"
 #include <cooperative_groups.h>
 
 namespace nuslam

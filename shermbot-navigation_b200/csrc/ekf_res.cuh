@@ -174,7 +174,7 @@ k_ekf_res_step(const EkfParams p, const int do_predict, int32_t * __restrict__ w
         {
             const double dth = __shfl_sync(kFull, my_tw, 0), dxx = __shfl_sync(kFull, my_tw, 1);
             double s0, c0, b10, b20;
-            sincos(th, &s0, &c0);
+            sincos_fast(th, &s0, &c0);
             if (dth == 0.0)
             {
                 px = add_(px, mul_(dxx, c0));
@@ -185,7 +185,7 @@ k_ekf_res_step(const EkfParams p, const int do_predict, int32_t * __restrict__ w
             }
             else
             {
-                const double q = div_(dxx, dth);
+                const double q = div_fast(dxx, dth);
                 double sd, cd;
                 sincos_small(dth, &sd, &cd);
                 const double s1 = fma(s0, cd, c0 * sd), c1 = fma(c0, cd, -s0 * sd);

@@ -38,6 +38,12 @@ namespace nuslam
 #ifndef NUSLAM_RES2_BRANCHY
 #define NUSLAM_RES2_BRANCHY 0
 #endif
+#ifndef NUSLAM_RES2_PIPE
+#define NUSLAM_RES2_PIPE 0      // 1: the state-only chain (sqrt d, atan2, innovation) of a chunk's FIRST update is issued before the in-place pass
+#endif                          //    of the previous chunk (before predict's covariance part for the first chunk): independent work for the pass
+#ifndef NUSLAM_RES2_EXP
+#define NUSLAM_RES2_EXP 0       // timing what-ifs (WRONG results): 1 no in-place pass, 2 no atan2, 3 no pending corrections, 5 no updates at all,
+#endif                          // 8 in-place pass without its DMMAs
 #ifndef NUSLAM_RES2_WARPS
 #define NUSLAM_RES2_WARPS 1     // warps (= pairs in flight) per CTA; the warps of a CTA share nothing, a CTA of W warps only saves the
 #endif                          // 1 KB of shared memory the hardware reserves per CTA (W = 13, one CTA per SM: 13 pairs per SM instead of 12)
@@ -156,7 +162,7 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         {
             const double dth = __shfl_sync(kFull, my_tw, hb), dxx = __shfl_sync(kFull, my_tw, hb + 1);
             double s0, c0;
-            sincos(th, &s0, &c0);
+            sincos_fast(th, &s0, &c0);
             if (dth == 0.0)
             {
                 px = add_(px, mul_(dxx, c0));
@@ -167,7 +173,7 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             }
             else
             {
-                const double qq = div_(dxx, dth);
+                const double qq = div_fast(dxx, dth);
                 double sd, cd;
                 sincos_small(dth, &sd, &cd);
                 const double s1 = fma(s0, cd, c0 * sd), c1 = fma(c0, cd, -s0 * sd);
@@ -234,10 +240,49 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         f.slots_of[h][q] = 0u;
         __syncwarp();
         if (code) atomicOr(&f.slots_of[h][code], 1u << q);
+        if (q < m) *reinterpret_cast<double2 *>(&f.z[h][2 * q]) = make_double2(my_z0, my_z1);
         __syncwarp();
         const unsigned hit0 = (q >= 3) ? f.slots_of[h][(q - 1) >> 1] : 0u;
         const unsigned hit1 = v1 ? f.slots_of[h][(15 + q) >> 1] : 0u;
-        if (q < m) *reinterpret_cast<double2 *>(&f.z[h][2 * q]) = make_double2(my_z0, my_z1);
+        // the state-only part of an update: landmark position from the lanes that own it, sqrt d, bearing, innovation (:150-160, :272 no wrap)
+        struct StateChain { double dx, dy, d, dsq, n0, n1; };
+        auto state_chain = [&](const int c, const int slot) {
+            const double xa = (c >= 16) ? x[1] : x[0], xb = (c + 1 >= 16) ? x[1] : x[0];
+            const double mxv = __shfl_sync(kFull, xa, hb + (c & 15)), myv = __shfl_sync(kFull, xb, hb + ((c + 1) & 15));
+            const double2 zz = *reinterpret_cast<const double2 *>(&f.z[h][2 * (slot & 15)]);
+            StateChain o;
+            o.dx = mxv - px, o.dy = myv - py;
+            o.d = fma(o.dx, o.dx, o.dy * o.dy);
+            const double rs = rsqrt_1(o.d);
+            double sq = o.d * rs;
+            sq = fma(fma(-sq, sq, o.d), 0.5 * rs, sq);   // sqrt(d) to ~1 ulp
+            o.dsq = o.d * sq;
+#if NUSLAM_RES2_EXP == 2
+            double zb = o.dy * rs - th;
+#else
+            double zb = atan2_unit(o.dy, o.dx, rs) - th;
+#endif
+#if NUSLAM_RES2_BRANCHY
+            if (__any_sync(kFull, abs_ge_hi(zb, kHiPi)))   // the wrap is the identity inside [-pi, pi]
+                if (abs_ge_hi(zb, kHiPi)) zb = wrap_angle(zb);
+#else
+            zb = wrap_angle(zb);   // the identity inside [-pi, pi]; branch-free: the update stays ONE basic block, so that the
+                                   // state-only chain (rsqrt, atan2) and the covariance chain interleave
+#endif
+            o.n0 = sq * (zz.x - sq), o.n1 = o.d * (zz.y - zb);
+            return o;
+        };
+        // this half's landmark column of a measurement slot (-1: none); a half without a measurement computes on a safe index
+        auto col_of_slot = [&](const int slot) {
+            const int cv = __shfl_sync(kFull, cval, hb + (slot & 15));
+            return (slot < kFastMMax) ? cv : -1;
+        };
+        StateChain sc_next = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (NUSLAM_RES2_PIPE)   // the first update's chain: independent work for the register loads and predict's covariance part
+        {
+            const int cn = col_of_slot(0);
+            sc_next = state_chain(cn >= 0 ? cn : 3, 0);
+        }
         // ---- robot rows / columns: image -> registers (vector layout, two slots) ----
         double Ct[2], Cx[2], Cy[2], Rt[2], Rx[2], Ry[2];
         Ct[0] = img[q], Cx[0] = img[LEN + q], Cy[0] = img[2 * LEN + q];
@@ -296,14 +341,13 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
 
         // ---- m sequential updates in delayed chunks of CH (slam.cpp:279-319, known correspondence) ----
 #pragma unroll 1
-        for (int i0 = 0; i0 < m; i0 += CH)
+        for (int i0 = 0; i0 < (NUSLAM_RES2_EXP == 5 ? 0 : m); i0 += CH)
         {
             int cc[CH];
 #pragma unroll
             for (int s = 0; s < CH; ++s)
             {
-                const int cv = __shfl_sync(kFull, cval, hb + ((i0 + s) & 15));   // this half's landmark column of slot i0 + s
-                cc[s] = (i0 + s < kFastMMax) ? cv : -1;                          // -1: no measurement in this slot of this filter
+                cc[s] = col_of_slot(i0 + s);   // this half's landmark column of slot i0 + s; -1: no measurement in this slot of this filter
             }
             const unsigned chunk_bits = ((1u << CH) - 1u) << i0;
             const bool mine0 = (hit0 & chunk_bits) != 0u, mine1 = (hit1 & chunk_bits) != 0u;
@@ -328,26 +372,10 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 if (__any_sync(kFull, live))
                 {
                     const int c = live ? cc[s] : 3;   // a half without a measurement in this slot computes on a safe index and drops the result
-                    // landmark position from the lanes that own it
-                    const double xa = (c >= 16) ? x[1] : x[0], xb = (c + 1 >= 16) ? x[1] : x[0];
-                    const double mxv = __shfl_sync(kFull, xa, hb + (c & 15)), myv = __shfl_sync(kFull, xb, hb + ((c + 1) & 15));
-                    const double2 zz = *reinterpret_cast<const double2 *>(&f.z[h][2 * ((i0 + s) & 15)]);
                     // ---- state-only part: sqrt d, bearing, innovation (:150-160, :272 no wrap) ----
-                    const double dx = mxv - px, dy = myv - py;
-                    const double d = fma(dx, dx, dy * dy);
-                    const double rs = rsqrt_1(d);
-                    double sq = d * rs;
-                    sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);   // sqrt(d) to ~1 ulp
-                    const double dsq = d * sq;
-                    double zb = atan2_unit(dy, dx, rs) - th;
-#if NUSLAM_RES2_BRANCHY
-                    if (__any_sync(kFull, abs_ge_hi(zb, kHiPi)))   // the wrap is the identity inside [-pi, pi]
-                        if (abs_ge_hi(zb, kHiPi)) zb = wrap_angle(zb);
-#else
-                    zb = wrap_angle(zb);   // the identity inside [-pi, pi]; branch-free: the update stays ONE basic block, so that the
-                                           // state-only chain (rsqrt, atan2) and the covariance chain interleave
-#endif
-                    double n0 = sq * (zz.x - sq), n1 = d * (zz.y - zb);
+                    const StateChain sc = (NUSLAM_RES2_PIPE && s == 0) ? sc_next : state_chain(c, i0 + s);
+                    const double dx = sc.dx, dy = sc.dy, d = sc.d, dsq = sc.dsq;
+                    double n0 = sc.n0, n1 = sc.n1;
                     // ---- landmark rows c, c+1 (lane = column) and columns c, c+1 (lane = row) as of the chunk's start, from the image;
                     //      brought up to date with the chunk's earlier updates (delayed-update algebra); Pt / Wt of this lane's slots ----
                     double rho0[2], rho1[2], kap0[2], kap1[2];
@@ -356,7 +384,7 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     rho0[1] = img[i1 * LEN + c], rho1[1] = img[i1 * LEN + c + 1];
                     kap0[1] = img[c * LEN + i1], kap1[1] = img[(c + 1) * LEN + i1];
 #pragma unroll
-                    for (int u = 0; u < s; ++u)
+                    for (int u = 0; u < (NUSLAM_RES2_EXP == 3 ? 0 : s); ++u)
                     {
                         const double2 ka = ktH[u][c], kb = ktH[u][c + 1], wa2 = wtH[u][c], wb2 = wtH[u][c + 1];
 #pragma unroll
@@ -468,12 +496,17 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                     __syncwarp();   // later slots read this slot's Kt / Wt at their landmark's indices
                 }
             }
+            if (NUSLAM_RES2_PIPE && i0 + CH < m)   // the next chunk's first state-only chain: independent of the pass below
+            {
+                const int cn = col_of_slot(i0 + CH);
+                sc_next = state_chain(cn >= 0 ? cn : 3, i0 + CH);
+            }
             // (D) one pass per filter applies the chunk to the landmark block of its image in place: tile += (-Kt) Wt
             __syncwarp();
 #pragma unroll
             for (int ff = 0; ff < 2; ++ff)
             {
-                if (ff == 0 ? !deadA : !deadB)   // warp-uniform
+                if (NUSLAM_RES2_EXP != 1 && (ff == 0 ? !deadA : !deadB))   // warp-uniform
                 {
                     const double * const ka = reinterpret_cast<const double *>(&f.kt[ff][t >> 1][0]) + (t & 1);
                     const double * const wa = reinterpret_cast<const double *>(&f.wt[ff][t >> 1][3 + g]) + (t & 1);
@@ -503,7 +536,14 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
 #pragma unroll
                         for (int bc = 0; bc < NB; ++bc)
 #pragma unroll
-                            for (int br = 0; br < NB; ++br) dmma884(c0[bc][br], c1[bc][br], a[kk][br], b[kk][bc]);
+                            for (int br = 0; br < NB; ++br)
+                            {
+#if NUSLAM_RES2_EXP == 8
+                                c0[bc][br] += a[kk][br], c1[bc][br] += b[kk][bc];
+#else
+                                dmma884(c0[bc][br], c1[bc][br], a[kk][br], b[kk][bc]);
+#endif
+                            }
 #pragma unroll
                     for (int bc = 0; bc < NB; ++bc)
 #pragma unroll
@@ -555,6 +595,7 @@ k_ekf_res2_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
         __syncwarp();
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the last bulk store
+    strict_tail(p, do_predict, worklist, wl_count, (int) gwn, lane);
 }
 
 template <int N>

@@ -122,7 +122,7 @@ k_ekf_res2a_step(const EkfParams p, const int do_predict, int32_t * __restrict__
         {
             const double dth = __shfl_sync(kFull, my_tw, hb), dxx = __shfl_sync(kFull, my_tw, hb + 1);
             double s0, c0;
-            sincos(th, &s0, &c0);
+            sincos_fast(th, &s0, &c0);
             if (dth == 0.0)
             {
                 px = add_(px, mul_(dxx, c0));
@@ -133,7 +133,7 @@ k_ekf_res2a_step(const EkfParams p, const int do_predict, int32_t * __restrict__
             }
             else
             {
-                const double qq = div_(dxx, dth);
+                const double qq = div_fast(dxx, dth);
                 double sd, cd;
                 sincos_small(dth, &sd, &cd);
                 const double s1 = fma(s0, cd, c0 * sd), c1 = fma(c0, cd, -s0 * sd);

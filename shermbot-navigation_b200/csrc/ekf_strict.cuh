@@ -453,6 +453,8 @@ struct EkfParams
                              // device -> host copy reads while the next step already runs)
     double Q[9], R[4];
     double amin, amax;
+    // launch shape of k_ekf_strict_list for the filters a FAST kernel hands over (strict_tail below); tail_blocks == 0: the host launches it
+    int tail_blocks, tail_threads, tail_smem;
 };
 
 // One warp replays reference call OP on filter b; Sigma staged through the warp's slice of shared memory.
@@ -604,6 +606,46 @@ __global__ void __launch_bounds__(128) k_ekf_strict_list(const EkfParams p, cons
             __threadfence();
         }
     }
+}
+
+#ifndef NUSLAM_TAIL_LAUNCH
+#define NUSLAM_TAIL_LAUNCH 0    // 1: built with -rdc=true + cudadevrt; the FAST kernels launch the list kernel themselves, and only when needed
+#endif
+
+// Every warp of a FAST kernel calls this when it has finished its filters. The LAST warp of the grid looks at the work list and, if a
+// filter was handed over, launches k_ekf_strict_list into the tail-launch stream: it runs after this grid has completed and before the
+// next kernel of the host stream starts. A step without a first touch -- every step of a built map -- is ONE launch.
+// wl_count: [0] entries, [1] finished blocks of the list kernel, [2] finished warps of the FAST kernel, [3] sticky device-launch error
+__device__ __forceinline__ void strict_tail(const EkfParams & p, const int do_predict, int32_t * worklist, int32_t * wl_count, const int total_warps,
+                                            const int lane)
+{
+#if NUSLAM_TAIL_LAUNCH && defined(NUSLAM_TU_FAST)   // (a device-side launch compiles only as relocatable device code)
+    if (p.tail_blocks == 0) return;
+    __syncwarp();
+    if (lane == 0)
+    {
+        __threadfence();
+        if (atomicAdd(wl_count + 2, 1) == total_warps - 1)
+        {
+            wl_count[2] = 0;
+            __threadfence();
+            if (*reinterpret_cast<volatile int32_t *>(wl_count) > 0)
+            {
+                // (inlined on purpose: an out-of-line launcher takes the parameter block through the stack and costs the kernels registers)
+                if (do_predict)
+                    k_ekf_strict_list<kOpStep><<<p.tail_blocks, p.tail_threads, p.tail_smem, cudaStreamTailLaunch>>>(p, worklist, wl_count, wl_count + 1);
+                else
+                    k_ekf_strict_list<kOpUpdate><<<p.tail_blocks, p.tail_threads, p.tail_smem, cudaStreamTailLaunch>>>(p, worklist, wl_count, wl_count + 1);
+                const cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess)
+                {
+                    wl_count[3] = (int32_t) e;   // reported by the next synchronize
+                    wl_count[0] = 0;             // the next step must not replay this step's entries
+                }
+            }
+        }
+    }
+#endif
 }
 
 }   // namespace nuslam

@@ -33,6 +33,14 @@ __device__ __forceinline__ double rcp_fast(double x)
     return y;
 }
 
+// a / b by a reciprocal and one correction: <= 1 ulp for normal operands, no slow path (no call into the device library)
+__device__ __forceinline__ double div_fast(double a, double b)
+{
+    const double y = rcp_fast(b);
+    const double q = a * y;
+    return fma(fma(-b, q, a), y, q);
+}
+
 // 1/sqrt(x): MUFU.RSQ64H seed + 2 Newton steps
 __device__ __forceinline__ double rsqrt_fast(double x)
 {
@@ -66,10 +74,10 @@ struct AtanOctant
 };
 #define NUSLAM_Q(k) ((k) * 7.85398163397448279e-01), ((k) * 3.06161699786838302e-17)
 // index = swap | xneg << 1 | yneg << 2
-__constant__ AtanOctant kAtanOct[8] = {{NUSLAM_Q(0.0), 1.0, 0.0},   {NUSLAM_Q(2.0), -1.0, 0.0},  {NUSLAM_Q(4.0), -1.0, 0.0},  {NUSLAM_Q(2.0), 1.0, 0.0},
+static __constant__ AtanOctant kAtanOct[8] = {{NUSLAM_Q(0.0), 1.0, 0.0},   {NUSLAM_Q(2.0), -1.0, 0.0},  {NUSLAM_Q(4.0), -1.0, 0.0},  {NUSLAM_Q(2.0), 1.0, 0.0},
                                        {NUSLAM_Q(-0.0), -1.0, 0.0}, {NUSLAM_Q(-2.0), 1.0, 0.0},  {NUSLAM_Q(-4.0), 1.0, 0.0},  {NUSLAM_Q(-2.0), -1.0, 0.0}};
 #undef NUSLAM_Q
-__constant__ double2 kAtanTab[65] = {
+static __constant__ double2 kAtanTab[65] = {
     {0.0, 0.0},
     {0.015623728620476831, -4.913600136566304e-19},
     {0.031239833430268277, -1.188442711587748e-18},
@@ -138,10 +146,19 @@ __constant__ double2 kAtanTab[65] = {
 
 // fp64 literals of the per-update scalar chain, kept in the constant bank: an instruction reads them as a c[][] operand, where an
 // immediate would be rebuilt in uniform registers (two UMOVs each) on every pass of the update loop
-__constant__ double kFastK[8] = {-1.0 / 7.0, 0.2, -1.0 / 3.0, 6.28318530717958623200, 2.44929359829470641435e-16, 0.15915494309189533577,
+static __constant__ double kFastK[8] = {-1.0 / 7.0, 0.2, -1.0 / 3.0, 6.28318530717958623200, 2.44929359829470641435e-16, 0.15915494309189533577,
                                  1.0e300, 3.14159265358979311600};
 
-__constant__ double kFastK2[4] = {15.0 / 336.0, 3.0 / 40.0, 1.0 / 6.0, 0.0};   // asin series of atan2_unit
+static __constant__ double kFastK2[4] = {15.0 / 336.0, 3.0 / 40.0, 1.0 / 6.0, 0.0};   // asin series of atan2_unit
+
+// angle -> [-pi, pi]: what rigid2d::normalize_angle (rigid2d.cpp:9-13) returns, to ~1 ulp, without the
+// sin/cos/atan2 round trip; the identity for |a| <= pi, branch-free
+__device__ __forceinline__ double wrap_angle(double a)
+{
+    const double k = rint(a * kFastK[5]);   // 1 / 2 pi; 2 pi = kFastK[3] + kFastK[4]
+    return fma(-k, kFastK[4], fma(-k, kFastK[3], a));
+}
+
 
 __device__ __forceinline__ double atan2_fast(double y, double x)
 {
@@ -174,7 +191,7 @@ struct AtanEntry
 {
     double hi, lo, c, s;   // atan(k / 64) as hi + lo, cos and sin of it
 };
-__constant__ AtanEntry kAtanUnit[65] = {
+static __constant__ AtanEntry kAtanUnit[65] = {
     {0.0, 0.0, 1.0, 0.0},
     {0.015623728620476831, -4.913600136566304e-19, 0.9998779520346953, 0.015623093000542114},
     {0.031239833430268277, -1.188442711587748e-18, 0.9995120760870788, 0.031234752377721213},
@@ -260,15 +277,39 @@ __device__ __forceinline__ double atan2_unit(double y, double x, double rs)
 }
 
 
+// sin and cos without a slow path (no call into the device library: under -rdc such a call is an ABI call that costs the FAST kernels
+// registers). Cody-Waite reduction by pi/2 in three 33-bit pieces (exact products for |a| < ~1e6; beyond that the error grows with |a|,
+// a heading is normalised to [-pi, pi] after every update), then the fdlibm kernels on [-pi/4, pi/4] (|error| < 2^-58): <= 1 ulp of
+// the library's results on the headings an EKF sees, far inside FAST mode's 1e-9.
+__host__ __device__ __forceinline__ void sincos_fast(double a, double * sn, double * cs)
+{
+    const double k = rint(a * 6.36619772367581382433e-01);
+    double r = fma(-k, 1.57079632673412561417e+00, a);
+    r = fma(-k, 6.07710050630396597660e-11, r);
+    r = fma(-k, 2.02226624871116645580e-21, r);
+    r = fma(-k, 8.47842766036889956997e-32, r);
+    const double z = r * r;
+    const double ps = fma(fma(fma(fma(fma(1.58969099521155010221e-10, z, -2.50507602534068634195e-08), z, 2.75573137070700676789e-06), z,
+                                  -1.98412698298579493134e-04), z, 8.33333333332248946124e-03), z, -1.66666666666666324348e-01);
+    const double pc = fma(fma(fma(fma(fma(-1.13596475577881948265e-11, z, 2.08757232129817482790e-09), z, -2.75573143513906633035e-07), z,
+                                  2.48015872894767294178e-05), z, -1.38888888888741095749e-03), z, 4.16666666666666019037e-02);
+    const double s = fma(ps * z, r, r);
+    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int n = (int) (long long) k & 3;
+    const double s1 = (n & 1) ? c : s, c1 = (n & 1) ? s : c;
+    *sn = (n & 2) ? -s1 : s1;
+    *cs = ((n + 1) & 2) ? -c1 : c1;
+}
+
 // sin and cos of a SMALL angle (|a| <= 0.25: a wheel-odometry step) straight from the Taylor series, no argument reduction; the
 // truncation error is below 3e-18. Larger arguments take the library path.
-__constant__ double kSinK[6] = {-1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -1.0 / 39916800.0, 1.0 / 6227020800.0};
-__constant__ double kCosK[7] = {-0.5, 1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, -1.0 / 87178291200.0};
+static __constant__ double kSinK[6] = {-1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -1.0 / 39916800.0, 1.0 / 6227020800.0};
+static __constant__ double kCosK[7] = {-0.5, 1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, -1.0 / 87178291200.0};
 __device__ __forceinline__ void sincos_small(double a, double * sn, double * cs)
 {
     if (fabs(a) > 0.25)   // warp-uniform in the EKF kernel (every lane holds the same twist)
     {
-        sincos(a, sn, cs);
+        sincos_fast(a, sn, cs);
         return;
     }
     const double u = a * a;

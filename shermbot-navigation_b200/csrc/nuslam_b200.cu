@@ -14,12 +14,7 @@
 #include "ekf_common.cuh"
 #include "ekf_strict.cuh"
 #include "ekf_misc.cuh"
-#include "ekf_fast.cuh"
-#include "ekf_pair.cuh"
-#include "ekf_static.cuh"
-#include "ekf_res.cuh"
-#include "ekf_res2.cuh"
-#include "ekf_res2a.cuh"
+#include "ekf_fast_api.cuh"   // the FAST kernels live in ekf_fast_tu.cu (relocatable device code: they launch the list kernel themselves)
 #include "scan_moment.cuh"
 #include "scan_detect.cuh"
 #include "ekf_large.cuh"
@@ -119,7 +114,7 @@ struct nuslam_ekf
     DevBuf lg_ids_slot, lg_assoc_result;   // unknown correspondence in large-map mode
     double * x_snap_next = nullptr;        // pipelined host path: where the next step's kernels also write the state vector
     int32_t * worklist = nullptr;   // batch entries
-    int32_t * wl_count = nullptr;   // [0] = entries, [1] = finished blocks of the list kernel
+    int32_t * wl_count = nullptr;   // [0] = entries, [1] = finished blocks of the list kernel, [2] finished warps of the FAST kernel, [3] device-launch error
     size_t strict_smem = 0;   // per-warp shared memory of the strict kernels, bytes
     int strict_warps = 4;
 };
@@ -193,48 +188,24 @@ int launch_strict(nuslam_ekf * h, const nuslam::EkfParams & p)
     return NUSLAM_OK;
 }
 
-// FAST mode: the register kernel, then the strict kernel over the filters it handed over (usually none)
+// FAST mode: the register / resident kernel, then the strict kernel over the filters it handed over (usually none): ekf_fast_tu.cu
 template <int OP>
 int launch_fast_then_strict(nuslam_ekf * h, const nuslam::EkfParams & p, bool do_predict)
 {
-    // known correspondence at the BASELINE map size: the static-schedule kernel (ekf_static.cuh; NUSLAM_KERNEL=pair / fast select the
-    // two-filters-per-warp kernel / the dynamic one for A/B timing); everything else: ekf_fast.cuh
-    const int which = nuslam::known_ids_kernel();
-    const bool special = which != 2 && nuslam::pair_supported(h->cfg.n_landmarks, p);
-    // unknown correspondence at the BASELINE map size: ekf_fast.cuh's association instantiation; NUSLAM_KERNEL=res2a selects the resident
-    // pair kernel with on-device association (ekf_res2a.cuh: same results, measured no faster -- 12 warps x 2 filters x 266 instructions
-    // per filter-measurement against 16 warps x 357: profiles/r02_kernel_iterations.md)
-    const bool assoc_pair = which == 5 && nuslam::res2a_supported(h->cfg.n_landmarks, p, do_predict);
-    int rc = assoc_pair    ? nuslam::launch_res2a_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
-             : !special    ? nuslam::launch_fast(h->cfg.n_landmarks, p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
-             : which >= 4 ? nuslam::launch_res2_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
-             : which == 3 ? nuslam::launch_res_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
-             : which == 1 ? nuslam::launch_pair_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream)
-                          : nuslam::launch_static_n<12>(p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream);
-    // not covered by the register kernels (more than 16 measurements per step, ragged counts with known ids, a state pointer that
-    // is not 8-byte aligned): the oracle-order kernel runs the whole batch
+    nuslam::FastLaunch fl;
+    fl.n_landmarks = h->cfg.n_landmarks;
+    fl.sm_count = h->sm_count;
+    fl.batch = h->batch;
+    fl.worklist = h->worklist;
+    fl.wl_count = h->wl_count;
+    fl.stream = h->stream;
+    fl.strict_warps = h->strict_warps;
+    fl.strict_smem = h->strict_smem;
+    cudaError_t err = cudaSuccess;
+    const char * where = "";
+    const int rc = nuslam::fast_path_launch(fl, p, do_predict, OP, &err, &where);
     if (rc == -1) return launch_strict<OP>(h, p);
-    if (rc) return cuda_fail((cudaError_t) rc, "fast kernel launch");
-    const int warps = h->strict_warps;
-    const size_t smem = h->strict_smem * warps;
-    static size_t configured_dev[nuslam::kMaxDevices][8] = {{0}};
-    size_t * configured = configured_dev[nuslam::device_slot()];
-    if (configured[OP] < smem)
-    {
-        CU(cudaFuncSetAttribute(nuslam::k_ekf_strict_list<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        configured[OP] = smem;
-    }
-    int64_t blocks = (h->batch + warps - 1) / warps;
-    const int64_t resident = (int64_t) h->sm_count * 4;
-    if (blocks > resident) blocks = resident;
-    nuslam::k_ekf_strict_list<OP><<<(unsigned) blocks, warps * 32, smem, h->stream>>>(p, h->worklist, h->wl_count, h->wl_count + 1);
-    const cudaError_t le = cudaGetLastError();
-    if (le != cudaSuccess)
-    {
-        // the list kernel resets the counters itself when it runs; it did not: the next call must not replay this call's entries
-        cudaMemsetAsync(h->wl_count, 0, sizeof(int32_t) * 2, h->stream);
-        return cuda_fail(le, "strict list kernel launch");
-    }
+    if (rc) return cuda_fail(err, where);
     return NUSLAM_OK;
 }
 
@@ -373,9 +344,9 @@ int nuslam_ekf_create(const nuslam_ekf_config * cfg, int64_t batch, int device, 
     cudaError_t e3 = cudaMalloc(&h->seen, sizeof(int32_t) * batch);
     cudaError_t e4 = cudaMalloc(&h->status, sizeof(int32_t) * batch);
     cudaError_t e5 = cudaMalloc(&h->worklist, sizeof(int32_t) * batch);
-    cudaError_t e6 = cudaMalloc(&h->wl_count, sizeof(int32_t) * 2);
+    cudaError_t e6 = cudaMalloc(&h->wl_count, sizeof(int32_t) * 4);
     if (e5 != cudaSuccess || e6 != cudaSuccess) e1 = cudaErrorMemoryAllocation;
-    else cudaMemsetAsync(h->wl_count, 0, sizeof(int32_t) * 2, h->stream);
+    else cudaMemsetAsync(h->wl_count, 0, sizeof(int32_t) * 4, h->stream);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess)
     {
         nuslam_ekf_destroy(h);
@@ -882,19 +853,8 @@ int nuslam_ekf_wait_async(nuslam_ekf * h)
     return NUSLAM_OK;
 }
 
-#ifdef NUSLAM_TIMING
 // kernel-experiment builds only (-DNUSLAM_TIMING): per-phase clock64 sums of block 0 / warp 0 of the FAST kernel
-int nuslam_debug_fast_timing(long long * out16, int reset)
-{
-    if (out16) cudaMemcpyFromSymbol(out16, nuslam::g_fast_timing, sizeof(long long) * 16);
-    if (reset)
-    {
-        long long z[16] = {0};
-        cudaMemcpyToSymbol(nuslam::g_fast_timing, z, sizeof(z));
-    }
-    return 0;
-}
-#endif
+int nuslam_debug_fast_timing(long long * out16, int reset) { return nuslam::fast_timing_read(out16, reset); }
 
 int nuslam_ekf_error_stats(nuslam_ekf * h, const double * truth_pose, const double * truth_map, const int32_t * ids_got, const int32_t * ids_want,
                            int32_t m, double * stats_out)
@@ -922,8 +882,21 @@ int nuslam_ekf_synchronize(nuslam_ekf * h)
     if (!h) return fail(NUSLAM_ERR_INVALID, "null handle");
     if (select_device(h)) return NUSLAM_ERR_CUDA;
     CU(cudaStreamSynchronize(h->stream));
+    if (nuslam::tail_launch_active() && h->wl_count)
+    {
+        // a device-side launch of the list kernel that failed (strict_tail) left its error code here
+        int32_t dev_err = 0;
+        CU(cudaMemcpy(&dev_err, h->wl_count + 3, sizeof(dev_err), cudaMemcpyDeviceToHost));
+        if (dev_err)
+        {
+            cudaMemset(h->wl_count + 3, 0, sizeof(int32_t));
+            return cuda_fail((cudaError_t) dev_err, "device-side launch of the strict list kernel");
+        }
+    }
     return NUSLAM_OK;
 }
+
+int nuslam_tail_launch(void) { return nuslam::tail_launch_active() ? 1 : 0; }
 
 namespace
 {

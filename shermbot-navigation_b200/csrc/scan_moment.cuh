@@ -20,6 +20,7 @@
 // Tolerance on circles: 1e-9 relative (BASELINE.json north_star); cluster ids, cluster and circle counts: exact.
 #pragma once
 #include "scan_detect.cuh"
+#include "fastmath.cuh"
 
 #ifdef NUSLAM_SCAN_DEBUG
 #include <cstdio>
@@ -43,7 +44,6 @@ struct __align__(16) MomentSmem
     double acc[kMomMaxClusters][kMomSums];    // per cluster: the sums above
     double org[kMomMaxClusters][2];           // per cluster: its first point (local origin of the sums)
     short cend[kMomMaxClusters + 8];          // flat position of the cluster's last point
-    unsigned char bclu[kBeams + 8];           // per beam: its pre-erase cluster, 255 when the beam is in no cluster
     short nidx[kMomMaxClusters];              // pre-erase cluster -> index among the returned clusters (-1: erased)
 };
 
@@ -95,7 +95,10 @@ inline float float_above(double v)
     return f;
 }
 
-__global__ void __launch_bounds__(32 * kMomWarps)
+#ifndef NUSLAM_MOM_MINBLOCKS
+#define NUSLAM_MOM_MINBLOCKS 8   // resident CTAs per SM the register allocation aims at (8 x 4 warps: 64 registers)
+#endif
+__global__ void __launch_bounds__(32 * kMomWarps, NUSLAM_MOM_MINBLOCKS)
 k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const double min_range, const double max_range, const ScanGate gate,
               int16_t * __restrict__ cluster_of_beam, int32_t * __restrict__ n_clusters, int32_t * __restrict__ n_circles,
               double * __restrict__ circles, const int max_circles, const int scan_ub, int32_t * __restrict__ slow, int32_t * __restrict__ slow_count)
@@ -105,7 +108,9 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
     MomentSmem & sm = smem_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     constexpr unsigned kFull = 0xffffffffu;
-    constexpr int kChunks = (kBeams + 31) / 32;   // 12
+    constexpr int kPer = 12;                      // beams per lane in the clustering walk
+    static_assert(kBeams % kPer == 0 && kBeams / kPer <= 32 && kPer % 4 == 0, "lane-major walk: 30 lanes x 12 beams");
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(ranges) & 15) == 0;
     const unsigned lt = (1u << lane) - 1u;
     for (int k = threadIdx.x; k < 65 + 16; k += blockDim.x)
     {
@@ -116,25 +121,41 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
     for (int64_t s = (int64_t) blockIdx.x * kMomWarps + (threadIdx.x >> 5); s < n_scans; s += (int64_t) gridDim.x * kMomWarps)
     {
         const float * rs = ranges + s * kBeams;
-        float r[kChunks + 1];
-#pragma unroll
-        for (int k = 0; k < kChunks; ++k) r[k] = (32 * k + lane < kBeams) ? __ldg(rs + 32 * k + lane) : 0.0f;
-        r[kChunks] = 0.0f;
-        const float r_first = __shfl_sync(kFull, r[0], 0);
-        // ---- per-beam predicates, their ballots (circle_fit_library.cpp:146-190), flat positions and cluster ends, in one sweep ----
+        // ---- per-beam predicates (circle_fit_library.cpp:146-190), LANE-MAJOR: lane L owns the kPer = 12 consecutive beams 12 L .. 12 L + 11
+        // (lanes 30 and 31 own none), so a beam's successor sits in the same lane's registers (one shuffle per scan for the lane
+        // boundary), the in-range / closer predicates become two 12-bit masks per lane, and flat positions and cluster numbers come from
+        // ONE warp prefix sum of the two popcounts instead of two ballots and four popcounts per 32 beams ----
         // closer_i = in range and not similar to beam i + 1; the cluster of an in-range beam = closers before it
-        int nc = 0, npts = 0;
-        bool risky = false, wrap = false;
+        const bool own = lane < kBeams / kPer;
+        float r[kPer + 1];
+        if (own && vec_ok)
+        {
+            const float4 * r4 = reinterpret_cast<const float4 *>(rs + kPer * lane);   // 48 B per lane, 16-byte aligned whenever the array is
+#pragma unroll
+            for (int j = 0; j < kPer / 4; ++j)
+            {
+                const float4 v = __ldg(r4 + j);
+                r[4 * j] = v.x, r[4 * j + 1] = v.y, r[4 * j + 2] = v.z, r[4 * j + 3] = v.w;
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) r[k] = own ? __ldg(rs + kPer * lane + k) : 0.0f;
+        }
+        {
+            const float r_first = __shfl_sync(kFull, r[0], 0);
+            const float r_up = __shfl_down_sync(kFull, r[0], 1);
+            r[kPer] = (lane == kBeams / kPer - 1) ? r_first : r_up;   // the successor of beam 359 is beam 0
+        }
+        unsigned inr_bits = 0u, clo_bits = 0u;
+        bool risky = false;
         const bool big_gate = !(gate.max_f <= 32.0f);   // warp-uniform
 #pragma unroll
-        for (int k = 0; k < kChunks; ++k)
+        for (int k = 0; k < kPer; ++k)
         {
-            const int i = 32 * k + lane;
-            // the next beam's range: lane + 1 of this round, lane 0 of the next round for lane 31, beam 0 for beam 359
-            float nb = __shfl_sync(kFull, lane == 0 ? r[k + 1] : r[k], (lane + 1) & 31);
-            if (i == kBeams - 1) nb = r_first;
-            const float rv = r[k];
-            const bool inr = i < kBeams && !(rv > gate.max_f || rv < gate.min_f);   // :149, NaN counts as in range
+            const float rv = r[k], nb = r[k + 1];
+            const bool inr = own && !(rv > gate.max_f || rv < gate.min_f);   // :149, NaN counts as in range
             // :166 |r_i - r_(i+1)| < 0.04 in double. The float difference is within an ulp of the exact one: decided in float; a scan
             // where it lies within 1e-5 of the threshold (or a range is huge / NaN) goes to the oracle-order kernel, which compares
             // in double like the reference
@@ -143,26 +164,25 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
             // (an in-range beam is below max_f; when that is at most 32 m a neighbour of 64 m or more is nowhere near the threshold, and a
             // NaN fails the first test by itself: the magnitude test is needed only for range gates beyond 32 m)
             risky = risky || (inr && (!(fabsf(df - 0.04f) >= 1e-5f) || (big_gate && !(fmaxf(fabsf(rv), fabsf(nb)) < 64.0f))));
-            unsigned inr_m = __ballot_sync(kFull, inr);
-            const unsigned clo_m = __ballot_sync(kFull, inr && !sim);
-            if (k == kChunks - 1)
-            {
-                constexpr int kLastBit = (kBeams - 1) & 31;
-                wrap = ((inr_m >> kLastBit) & 1u) && !((clo_m >> kLastBit) & 1u);
-                // beam 359 in range and similar to beam 0: it is not stored in the flat list but appended to cluster 0 (:170-174)
-                if (wrap) inr_m &= ~(1u << kLastBit);
-            }
-            const bool inr2 = (inr_m >> lane) & 1u;
-            const int pos = npts + __popc(inr_m & lt), clu = nc + __popc(clo_m & lt);
-            if (inr2)
-            {
-                sm.pb[pos] = (unsigned) i | ((unsigned) clu << 16);
-                if ((clo_m >> lane) & 1u) sm.cend[clu & (kMomMaxClusters - 1)] = (short) pos;
-            }
-            if (i < kBeams) sm.bclu[i] = inr2 ? (unsigned char) min(clu, 254) : (unsigned char) 255;
-            npts += __popc(inr_m);
-            nc += __popc(clo_m);
+            if (inr) inr_bits |= 1u << k;
+            if (inr && !sim) clo_bits |= 1u << k;
         }
+        // beam 359 in range and similar to beam 0: it is not stored in the flat list but appended to cluster 0 (:170-174)
+        constexpr unsigned kLastBit = 1u << (kPer - 1);
+        const bool wrap = __shfl_sync(kFull, (int) ((inr_bits & kLastBit) && !(clo_bits & kLastBit)), kBeams / kPer - 1) != 0;
+        if (wrap && lane == kBeams / kPer - 1) inr_bits &= ~kLastBit;
+        // flat position of this lane's first in-range beam and closers before it: one inclusive prefix sum over (points | closers << 16)
+        const unsigned cnt = (unsigned) __popc(inr_bits) | ((unsigned) __popc(clo_bits) << 16);
+        unsigned incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const unsigned up = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += up;
+        }
+        const unsigned total = __shfl_sync(kFull, incl, 31);
+        const int npts = (int) (total & 0xffffu), nc = (int) (total >> 16);
+        const int pos0 = (int) ((incl - cnt) & 0xffffu), clu0 = (int) ((incl - cnt) >> 16);
         const int64_t sb = s * kBeams;
         if (wrap && nc == 0)
         {
@@ -183,6 +203,22 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
             __syncwarp();
             continue;
         }
+        // the flat list of in-range beams (beam | cluster << 16) and the flat position of every cluster's last point
+        {
+            int pos = pos0, clu = clu0;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k)
+            {
+                const bool in = (inr_bits >> k) & 1u, cl = (clo_bits >> k) & 1u;
+                if (in)
+                {
+                    sm.pb[pos] = (unsigned) (kPer * lane + k) | ((unsigned) clu << 16);
+                    if (cl) sm.cend[clu & (kMomMaxClusters - 1)] = (short) pos;
+                }
+                pos += in ? 1 : 0;
+                clu += cl ? 1 : 0;
+            }
+        }
         __syncwarp();
         // ---- one cluster per lane: extent, erase loop (:198-204) in closed form ----
         const int cend = (lane < nc) ? (int) sm.cend[lane] : -1;
@@ -199,26 +235,33 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
         const int nk = nc - __popc(erased_m);
         if (cluster_of_beam)
         {
-            // two beams per lane and pass: the pre-erase cluster of a beam -> its index among the returned clusters through a 32-entry
-            // table, both ids in one 32-bit store (a scan's ids start at a multiple of 4 bytes whenever the array does)
+            // the pre-erase cluster of a beam (closers before it) -> its index among the returned clusters through a 32-entry table; a
+            // lane's 12 ids leave as three 8-byte stores (a scan's ids start at a multiple of 8 bytes whenever the array does)
             const int new0 = __shfl_sync(kFull, newidx, 0);
             sm.nidx[lane] = (short) newidx;
             __syncwarp();
-            const bool pair_ok = (reinterpret_cast<uintptr_t>(cluster_of_beam) & 3) == 0;
-#pragma unroll 1
-            for (int i = 2 * lane; i < kBeams; i += 64)
+            if (own)
             {
-                const unsigned two = *reinterpret_cast<const unsigned short *>(&sm.bclu[i]);
-                const int bc0 = (int) (two & 0xffu), bc1 = (int) (two >> 8);
-                int o0 = (bc0 < nc) ? (int) sm.nidx[bc0 & (kMomMaxClusters - 1)] : -1;   // beams behind the last closer: the open cluster the reference drops
-                int o1 = (bc1 < nc) ? (int) sm.nidx[bc1 & (kMomMaxClusters - 1)] : -1;
-                if (wrap && i + 1 == kBeams - 1) o1 = new0;
-                if (pair_ok)
-                    *reinterpret_cast<unsigned *>(cluster_of_beam + sb + i) = ((unsigned) o0 & 0xffffu) | ((unsigned) o1 << 16);
+                unsigned o[kPer];
+#pragma unroll
+                for (int k = 0; k < kPer; ++k)
+                {
+                    const int c = clu0 + __popc(clo_bits & ((1u << k) - 1u));
+                    // beams out of range, and beams behind the last closer (the open cluster the reference drops): -1
+                    o[k] = (((inr_bits >> k) & 1u) && c < nc) ? (unsigned) (unsigned short) sm.nidx[c & (kMomMaxClusters - 1)] : 0xffffu;
+                }
+                if (wrap && lane == kBeams / kPer - 1) o[kPer - 1] = (unsigned) (unsigned short) new0;   // beam 359 belongs to cluster 0
+                int16_t * dst = cluster_of_beam + sb + kPer * lane;
+                if ((reinterpret_cast<uintptr_t>(cluster_of_beam) & 7) == 0)
+                {
+#pragma unroll
+                    for (int j = 0; j < kPer / 4; ++j)
+                        reinterpret_cast<uint2 *>(dst)[j] = make_uint2(o[4 * j] | (o[4 * j + 1] << 16), o[4 * j + 2] | (o[4 * j + 3] << 16));
+                }
                 else
                 {
-                    cluster_of_beam[sb + i] = (int16_t) o0;
-                    cluster_of_beam[sb + i + 1] = (int16_t) o1;
+#pragma unroll
+                    for (int k = 0; k < kPer; ++k) dst[k] = (int16_t) o[k];
                 }
             }
         }

@@ -37,6 +37,7 @@ EXPORTS = [
     "nuslam_cartesian2polar", "nuslam_normalize_angle", "nuslam_scan_detect", "nuslam_classify_and_fit",
     "nuslam_diffdrive_step", "nuslam_diffdrive_convert_twist", "nuslam_world_step", "nuslam_integrate_twist",
     "nuslam_ekf_get_stream", "nuslam_scan_set_fit", "nuslam_scan_last_fallbacks", "nuslam_ekf_error_stats", "nuslam_ekf_async_dry_run", "nuslam_ekf_set_ids", "nuslam_ekf_step_async_packed",
+    "nuslam_tail_launch",
 ]
 
 

@@ -18,6 +18,7 @@ static const entry_fn k_entry_points[] = {
     (entry_fn) nuslam_normalize_angle, (entry_fn) nuslam_diffdrive_step, (entry_fn) nuslam_diffdrive_convert_twist,
     (entry_fn) nuslam_world_step, (entry_fn) nuslam_integrate_twist, (entry_fn) nuslam_scan_detect, (entry_fn) nuslam_classify_and_fit,
     (entry_fn) nuslam_ekf_get_stream, (entry_fn) nuslam_ekf_set_ids, (entry_fn) nuslam_ekf_step_async_packed, (entry_fn) nuslam_ekf_async_dry_run, (entry_fn) nuslam_ekf_error_stats, (entry_fn) nuslam_scan_set_fit, (entry_fn) nuslam_scan_last_fallbacks,
+    (entry_fn) nuslam_tail_launch,
 };
 
 int main(int argc, char ** argv)
