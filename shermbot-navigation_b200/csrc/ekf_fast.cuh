@@ -138,7 +138,7 @@ struct __align__(16) FastSmem
 
 #ifdef NUSLAM_TIMING
 #define NUSLAM_T(k) { const long long now_ = clock64(); tacc[k] += now_ - tlast; tlast = now_; }
-__device__ long long g_fast_timing[16];
+static __device__ long long g_fast_timing[16];
 #else
 #define NUSLAM_T(k)
 #endif
@@ -151,6 +151,18 @@ __device__ long long g_fast_timing[16];
 // candidate's 5 x 5 block of Sigma, the reference's in-order early exit = lowest deciding lane) and applied at once (rank-2 pass
 // per measurement instead of the lazy chunks). A measurement that opens a NEW landmark (or a singular innovation) hands the whole
 // filter-step to the strict kernel: nothing has been written back yet, so it restarts from the state in HBM.
+// The kernel and its launchers are instantiated in BOTH translation units (ekf_fast_api.cuh): relocatable in ekf_fast_tu.cu (known
+// correspondence: the kernel launches the list kernel itself) and whole-program in nuslam_b200.cu (on-device association, where the
+// relocatable build costs 3 registers and hand-overs to the list kernel are frequent). Internal linkage there keeps the two apart.
+#ifdef NUSLAM_TU_FAST
+#define NUSLAM_TU_LOCAL_BEGIN
+#define NUSLAM_TU_LOCAL_END
+#else
+#define NUSLAM_TU_LOCAL_BEGIN namespace {
+#define NUSLAM_TU_LOCAL_END }
+#endif
+NUSLAM_TU_LOCAL_BEGIN
+
 template <int N, bool BULK, bool ASSOC>
 __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm)
 k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ worklist, int32_t * __restrict__ wl_count)
@@ -908,5 +920,7 @@ inline int launch_fast(int n, const EkfParams & p, bool do_predict, int sm_count
     if (n <= 12) return launch_fast_n<-3>(p, do_predict, sm_count, worklist, wl_count, stream);
     return -1;
 }
+
+NUSLAM_TU_LOCAL_END
 
 }   // namespace nuslam

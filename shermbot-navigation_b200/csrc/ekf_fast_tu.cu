@@ -44,7 +44,7 @@ int fast_path(const FastLaunch & fl, const EkfParams & p_in, bool do_predict, cu
     size_t * configured = configured_dev[device_slot()];
     if (configured[OP] < smem)
     {
-        *err = cudaFuncSetAttribute(k_ekf_strict_list<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        *err = cudaFuncSetAttribute(k_ekf_strict_list<OP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (*err != cudaSuccess)
         {
             *where = "cudaFuncSetAttribute(k_ekf_strict_list)";
@@ -81,7 +81,7 @@ int fast_path(const FastLaunch & fl, const EkfParams & p_in, bool do_predict, cu
         return 1;
     }
     if (tail) return 0;
-    k_ekf_strict_list<OP><<<(unsigned) blocks, warps * 32, smem, fl.stream>>>(p, fl.worklist, fl.wl_count, fl.wl_count + 1);
+    k_ekf_strict_list<OP, 1><<<(unsigned) blocks, warps * 32, smem, fl.stream>>>(p, fl.worklist, fl.wl_count, fl.wl_count + 1);
     const cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess)
     {

@@ -22,9 +22,6 @@
 namespace nuslam
 {
 
-#ifndef NUSLAM_DEFAULT_KERNEL
-#define NUSLAM_DEFAULT_KERNEL 4   // 0 static, 1 pair, 2 fast, 3 resident (ekf_res.cuh), 4 resident pair (ekf_res2.cuh)
-#endif
 #ifndef NUSLAM_STATIC_CTAS
 #define NUSLAM_STATIC_CTAS 16
 #endif
@@ -500,21 +497,6 @@ int launch_static_n(const EkfParams & p, bool do_predict, int sm_count, int32_t 
     }
     k_ekf_static_step<N><<<(unsigned) blocks, 32, 0, stream>>>(p, do_predict ? 1 : 0, worklist, wl_count);
     return (int) cudaGetLastError();
-}
-
-// which register kernel serves known correspondence at the BASELINE map size (NUSLAM_KERNEL, read at every call; A/B timing and
-// the equality tests): "fast" (ekf_fast.cuh, which also serves everything else), "static" (this file), "pair" (ekf_pair.cuh).
-// Measured on B200 (profiles/r02_kernel_iterations.md): the fully unrolled static schedules outgrow the instruction cache
-// (92 KB / 60 KB of code against 32 KB) and lose more to instruction fetch than they save in address arithmetic.
-inline int known_ids_kernel()
-{
-    const char * e = getenv("NUSLAM_KERNEL");
-    if (e && e[0] == 'p') return 1;
-    if (e && e[0] == 's') return 0;
-    if (e && e[0] == 'f') return 2;
-    // "res": ekf_res.cuh, "res2": ekf_res2.cuh, "res2a": ekf_res2.cuh + the resident pair kernel with on-device association (ekf_res2a.cuh)
-    if (e && e[0] == 'r') return (e[1] && e[2] && e[3] == '2') ? (e[4] == 'a' ? 5 : 4) : 3;
-    return NUSLAM_DEFAULT_KERNEL;
 }
 
 }   // namespace nuslam

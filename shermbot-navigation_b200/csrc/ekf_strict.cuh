@@ -583,7 +583,9 @@ __global__ void __launch_bounds__(128) k_ekf_strict(const EkfParams p)
 
 // One warp per filter over a device-side work list (the filters the FAST kernel handed over because their step
 // contains a landmark's first touch). The last block to finish resets the list for the next launch.
-template <int OP>
+// TU: the translation unit that instantiates it (0 nuslam_b200.cu, whole-program; 1 ekf_fast_tu.cu, relocatable): the two builds of the same
+// kernel must not share a name, or the linker would merge their host stubs.
+template <int OP, int TU>
 __global__ void __launch_bounds__(128) k_ekf_strict_list(const EkfParams p, const int32_t * __restrict__ list, int32_t * count, int32_t * done)
 {
     extern __shared__ double smem[];
@@ -633,9 +635,9 @@ __device__ __forceinline__ void strict_tail(const EkfParams & p, const int do_pr
             {
                 // (inlined on purpose: an out-of-line launcher takes the parameter block through the stack and costs the kernels registers)
                 if (do_predict)
-                    k_ekf_strict_list<kOpStep><<<p.tail_blocks, p.tail_threads, p.tail_smem, cudaStreamTailLaunch>>>(p, worklist, wl_count, wl_count + 1);
+                    k_ekf_strict_list<kOpStep, 1><<<p.tail_blocks, p.tail_threads, p.tail_smem, cudaStreamTailLaunch>>>(p, worklist, wl_count, wl_count + 1);
                 else
-                    k_ekf_strict_list<kOpUpdate><<<p.tail_blocks, p.tail_threads, p.tail_smem, cudaStreamTailLaunch>>>(p, worklist, wl_count, wl_count + 1);
+                    k_ekf_strict_list<kOpUpdate, 1><<<p.tail_blocks, p.tail_threads, p.tail_smem, cudaStreamTailLaunch>>>(p, worklist, wl_count, wl_count + 1);
                 const cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess)
                 {

@@ -14,7 +14,8 @@
 #include "ekf_common.cuh"
 #include "ekf_strict.cuh"
 #include "ekf_misc.cuh"
-#include "ekf_fast_api.cuh"   // the FAST kernels live in ekf_fast_tu.cu (relocatable device code: they launch the list kernel themselves)
+#include "ekf_fast_api.cuh"   // the known-correspondence FAST kernels live in ekf_fast_tu.cu (relocatable device code: they launch the list kernel themselves)
+#include "ekf_fast.cuh"       // on-device association: the register-fragment kernel of this unit (whole-program build, internal linkage)
 #include "scan_moment.cuh"
 #include "scan_detect.cuh"
 #include "ekf_large.cuh"
@@ -188,10 +189,41 @@ int launch_strict(nuslam_ekf * h, const nuslam::EkfParams & p)
     return NUSLAM_OK;
 }
 
-// FAST mode: the register / resident kernel, then the strict kernel over the filters it handed over (usually none): ekf_fast_tu.cu
+// FAST mode: the register / resident kernel, then the strict kernel over the filters it handed over (usually none).
+// Known correspondence: ekf_fast_tu.cu -- the kernel launches the list kernel itself, one launch per step of a built map.
+// On-device association: this unit's whole-program build of ekf_fast.cuh + a host launch of the list kernel (the relocatable build costs
+// the association kernel 1.5 %, and with unknown correspondence hand-overs -- new landmarks -- are frequent: closed loop 0.62 against
+// 0.56 ms per step, measured).
 template <int OP>
 int launch_fast_then_strict(nuslam_ekf * h, const nuslam::EkfParams & p, bool do_predict)
 {
+    if (p.ids == nullptr && nuslam::known_ids_kernel() != 5)
+    {
+        const int rc = nuslam::launch_fast(h->cfg.n_landmarks, p, do_predict, h->sm_count, h->worklist, h->wl_count, h->stream);
+        if (rc == -1) return launch_strict<OP>(h, p);
+        if (rc) return cuda_fail((cudaError_t) rc, "fast kernel launch");
+        const int warps = h->strict_warps;
+        const size_t smem = h->strict_smem * warps;
+        static size_t configured_dev[nuslam::kMaxDevices][8] = {{0}};
+        size_t * configured = configured_dev[nuslam::device_slot()];
+        if (configured[OP] < smem)
+        {
+            CU(cudaFuncSetAttribute(nuslam::k_ekf_strict_list<OP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            configured[OP] = smem;
+        }
+        int64_t blocks = (h->batch + warps - 1) / warps;
+        const int64_t resident = (int64_t) h->sm_count * 4;
+        if (blocks > resident) blocks = resident;
+        nuslam::k_ekf_strict_list<OP, 0><<<(unsigned) blocks, warps * 32, smem, h->stream>>>(p, h->worklist, h->wl_count, h->wl_count + 1);
+        const cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess)
+        {
+            // the list kernel resets the counters itself when it runs; it did not: the next call must not replay this call's entries
+            cudaMemsetAsync(h->wl_count, 0, sizeof(int32_t) * 2, h->stream);
+            return cuda_fail(le, "strict list kernel launch");
+        }
+        return NUSLAM_OK;
+    }
     nuslam::FastLaunch fl;
     fl.n_landmarks = h->cfg.n_landmarks;
     fl.sm_count = h->sm_count;

@@ -128,9 +128,9 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
         // closer_i = in range and not similar to beam i + 1; the cluster of an in-range beam = closers before it
         const bool own = lane < kBeams / kPer;
         float r[kPer + 1];
-        if (own && vec_ok)
+        if (vec_ok)   // warp-uniform
         {
-            const float4 * r4 = reinterpret_cast<const float4 *>(rs + kPer * lane);   // 48 B per lane, 16-byte aligned whenever the array is
+            const float4 * r4 = reinterpret_cast<const float4 *>(rs + kPer * (own ? lane : 0));   // 48 B per lane, 16-byte aligned whenever the array is
 #pragma unroll
             for (int j = 0; j < kPer / 4; ++j)
             {
@@ -141,32 +141,42 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
         else
         {
 #pragma unroll
-            for (int k = 0; k < kPer; ++k) r[k] = own ? __ldg(rs + kPer * lane + k) : 0.0f;
+            for (int k = 0; k < kPer; ++k) r[k] = __ldg(rs + kPer * (own ? lane : 0) + k);
         }
         {
             const float r_first = __shfl_sync(kFull, r[0], 0);
             const float r_up = __shfl_down_sync(kFull, r[0], 1);
             r[kPer] = (lane == kBeams / kPer - 1) ? r_first : r_up;   // the successor of beam 359 is beam 0
         }
-        unsigned inr_bits = 0u, clo_bits = 0u;
-        bool risky = false;
+        // (lanes 30 and 31 carry a copy of lane 0's beams: `own` masks their predicates)
+        unsigned inr_bits = 0u, clo_bits = 0u, risky_bits = 0u;
         const bool big_gate = !(gate.max_f <= 32.0f);   // warp-uniform
 #pragma unroll
         for (int k = 0; k < kPer; ++k)
         {
             const float rv = r[k], nb = r[k + 1];
-            const bool inr = own && !(rv > gate.max_f || rv < gate.min_f);   // :149, NaN counts as in range
+            const bool inr = !(rv > gate.max_f) & !(rv < gate.min_f);   // :149, NaN counts as in range
             // :166 |r_i - r_(i+1)| < 0.04 in double. The float difference is within an ulp of the exact one: decided in float; a scan
             // where it lies within 1e-5 of the threshold (or a range is huge / NaN) goes to the oracle-order kernel, which compares
             // in double like the reference
             const float df = fabsf(rv - nb);
             const bool sim = df < 0.04f;
+            const bool near = !(fabsf(df - 0.04f) >= 1e-5f);
+            // branch-free on purpose (no short-circuit operators): three predicate instructions per beam instead of a branch ladder
+            inr_bits |= inr ? (1u << k) : 0u;
+            clo_bits |= (inr & !sim) ? (1u << k) : 0u;
+            risky_bits |= (inr & near) ? 1u : 0u;
+        }
+        if (big_gate)
+        {
             // (an in-range beam is below max_f; when that is at most 32 m a neighbour of 64 m or more is nowhere near the threshold, and a
             // NaN fails the first test by itself: the magnitude test is needed only for range gates beyond 32 m)
-            risky = risky || (inr && (!(fabsf(df - 0.04f) >= 1e-5f) || (big_gate && !(fmaxf(fabsf(rv), fabsf(nb)) < 64.0f))));
-            if (inr) inr_bits |= 1u << k;
-            if (inr && !sim) clo_bits |= 1u << k;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k)
+                risky_bits |= (((inr_bits >> k) & 1u) && !(fmaxf(fabsf(r[k]), fabsf(r[k + 1])) < 64.0f)) ? 1u : 0u;
         }
+        if (!own) inr_bits = clo_bits = risky_bits = 0u;
+        const bool risky = risky_bits != 0u;
         // beam 359 in range and similar to beam 0: it is not stored in the flat list but appended to cluster 0 (:170-174)
         constexpr unsigned kLastBit = 1u << (kPer - 1);
         const bool wrap = __shfl_sync(kFull, (int) ((inr_bits & kLastBit) && !(clo_bits & kLastBit)), kBeams / kPer - 1) != 0;
@@ -210,11 +220,9 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
             for (int k = 0; k < kPer; ++k)
             {
                 const bool in = (inr_bits >> k) & 1u, cl = (clo_bits >> k) & 1u;
-                if (in)
-                {
-                    sm.pb[pos] = (unsigned) (kPer * lane + k) | ((unsigned) clu << 16);
-                    if (cl) sm.cend[clu & (kMomMaxClusters - 1)] = (short) pos;
-                }
+                // two independent predicated stores (a closer is in range): no nested branch
+                if (in) sm.pb[pos] = (unsigned) (kPer * lane + k) | ((unsigned) clu << 16);
+                if (cl) sm.cend[clu & (kMomMaxClusters - 1)] = (short) pos;
                 pos += in ? 1 : 0;
                 clu += cl ? 1 : 0;
             }
@@ -243,12 +251,14 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
             if (own)
             {
                 unsigned o[kPer];
+                int c = clu0;
 #pragma unroll
                 for (int k = 0; k < kPer; ++k)
                 {
-                    const int c = clu0 + __popc(clo_bits & ((1u << k) - 1u));
                     // beams out of range, and beams behind the last closer (the open cluster the reference drops): -1
-                    o[k] = (((inr_bits >> k) & 1u) && c < nc) ? (unsigned) (unsigned short) sm.nidx[c & (kMomMaxClusters - 1)] : 0xffffu;
+                    const unsigned v = (unsigned) (unsigned short) sm.nidx[c & (kMomMaxClusters - 1)];
+                    o[k] = (((inr_bits >> k) & 1u) & (c < nc)) ? v : 0xffffu;
+                    c += (clo_bits >> k) & 1u;
                 }
                 if (wrap && lane == kBeams / kPer - 1) o[kPer - 1] = (unsigned) (unsigned short) new0;   // beam 359 belongs to cluster 0
                 int16_t * dst = cluster_of_beam + sb + kPer * lane;
@@ -389,8 +399,17 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
                 const double A22 = A2 + A2;
                 double eta = 0.0, yv = A0;
                 bool converged = false;
+                // Newton from 0 approaches the smallest non-negative root monotonically and needs 4 - 6 steps on a scan's clusters: the first
+                // three are taken without looking (a breakdown turns into NaN / inf, which the tested steps below reject)
+#pragma unroll
+                for (int it = 0; it < 3; ++it)
+                {
+                    const double Dy = fma(eta, fma(16.0 * eta, eta, A22), A1);
+                    eta = fma(-yv, rcp_fast(Dy), eta);
+                    yv = fma(eta, fma(eta, fma(4.0 * eta, eta, A2), A1), A0);
+                }
 #pragma unroll 1
-                for (int it = 0; it < 16; ++it)
+                for (int it = 3; it < 16; ++it)
                 {
                     const double Dy = fma(eta, fma(16.0 * eta, eta, A22), A1);
                     const double en = fma(-yv, rcp_fast(Dy), eta);

@@ -17,5 +17,5 @@ import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('  scan', d.get('ms_per_pass'), d.get('value'), d.get('scans_rerun_in_oracle_order'), d.get('mean_clusters_per_scan'), d.get('mean_circles_per_scan'))"
   NUSLAM_B200_LIB=$lib timeout -s KILL 300 python tools/bench_closed_loop.py 2>/dev/null | tail -1 | cut -c1-200
 done 2>&1 | tee gpurun_out/ab_bench.log
-timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:k_scan_moment -s 2 -c 1 -f -o gpurun_out/prof_scan_moment_v3 python tools/bench_scan.py > gpurun_out/ab_ncu_scan.log 2>&1
+timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:k_scan_moment -s 2 -c 1 -f -o gpurun_out/prof_scan_moment_v4 python tools/bench_scan.py > gpurun_out/ab_ncu_scan.log 2>&1
 tail -1 gpurun_out/ab_ncu_scan.log | cut -c1-150
