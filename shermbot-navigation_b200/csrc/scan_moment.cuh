@@ -215,16 +215,20 @@ k_scan_moment(const float * __restrict__ ranges, const int64_t n_scans, const do
         }
         // the flat list of in-range beams (beam | cluster << 16) and the flat position of every cluster's last point
         {
-            int pos = pos0, clu = clu0;
+            // running store address, list entry (beam | cluster << 16) and position: one predicated add each per beam
+            unsigned * ap = sm.pb + pos0;
+            unsigned ent = (unsigned) (kPer * lane) | ((unsigned) clu0 << 16);
+            int pos = pos0;
 #pragma unroll
             for (int k = 0; k < kPer; ++k)
             {
                 const bool in = (inr_bits >> k) & 1u, cl = (clo_bits >> k) & 1u;
                 // two independent predicated stores (a closer is in range): no nested branch
-                if (in) sm.pb[pos] = (unsigned) (kPer * lane + k) | ((unsigned) clu << 16);
-                if (cl) sm.cend[clu & (kMomMaxClusters - 1)] = (short) pos;
+                if (in) *ap = ent + (unsigned) k;
+                if (cl) sm.cend[(ent >> 16) & (kMomMaxClusters - 1)] = (short) pos;
+                ap += in ? 1 : 0;
                 pos += in ? 1 : 0;
-                clu += cl ? 1 : 0;
+                ent += cl ? 0x10000u : 0u;
             }
         }
         __syncwarp();
