@@ -388,7 +388,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_filter_step": BYTES_PER_FILTER_STEP,
                          "kernel": (KERNEL_NAMES.get((os.environ.get("NUSLAM_KERNEL") or "res2")[:4].rstrip("t"), KERNEL_NAMES["res2"]) +
-                                    " (+ k_ekf_strict_list over the first-touch work list, empty in steady state)") if args.mode == "fast" else "k_ekf_strict<kOpStep>",
+                                    (" (+ k_ekf_strict_list over the first-touch work list: launched by the step kernel itself, device-side, only when a filter was handed over -- never in the timed steady state)"
+                                     if nuslam.lib().nuslam_tail_launch() else " (+ k_ekf_strict_list over the first-touch work list, empty in steady state)")) if args.mode == "fast" else "k_ekf_strict<kOpStep>",
                          "launch_us": per_launch_s * 1e6, "launches_per_step": launches},
         }
     eng.close()
