@@ -50,6 +50,9 @@ constexpr int kFastThreads = 32;                   // one warp = one filter in f
 #ifndef NUSLAM_EXP
 #define NUSLAM_EXP 0   // timing experiments only (wrong results): 1 no atan2, 2 no publish stores, 3 no DMMA, 4 no robot-vector updates, 5 no predict
 #endif
+#ifndef NUSLAM_ASSOC_DFMA
+#define NUSLAM_ASSOC_DFMA 0   // 1: the association instantiation applies its rank-2 update per measurement by plain FMAs instead of half-empty DMMAs
+#endif
 #ifndef NUSLAM_FAST_SINGLE_STAGE
 #define NUSLAM_FAST_SINGLE_STAGE 0   // 1: one staging buffer per CTA (input image -> exchange area -> output image): half the shared memory
 #endif
@@ -508,30 +511,20 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 const double2 zz = *reinterpret_cast<const double2 *>(&f.z[2 * i0]);
                 const double dx = mxy.x - px, dy = mxy.y - py;
                 const double d = fma(dx, dx, dy * dy);
-                const double h0[5] = {0.0, -dx, -dy, dx, dy}, h1[5] = {-d, dy, -dx, -dy, dx};
+                // psi = Ht B Ht^T + R~ with the division-free rows h0 = (0, -dx, -dy, dx, dy), h1 = (-d, dy, -dx, -dy, dx): written out on the
+                // rows' structure (differences of the landmark and robot entries first), 49 operations instead of the 70 FMAs of the dense
+                // 5 x 5 products -- the same expressions the update uses for M
                 double w0[5], w1[5];
 #pragma unroll
                 for (int q = 0; q < 5; ++q)
                 {
-                    double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                    for (int r = 0; r < 5; ++r)
-                    {
-                        a0 = fma(h0[r], Bm[r][q], a0);
-                        a1 = fma(h1[r], Bm[r][q], a1);
-                    }
-                    w0[q] = a0;
-                    w1[q] = a1;
+                    const double e = Bm[3][q] - Bm[1][q], g2 = Bm[4][q] - Bm[2][q];
+                    w0[q] = fma(dx, e, dy * g2);
+                    w1[q] = fma(dx, g2, fma(-dy, e, -d * Bm[0][q]));
                 }
-                double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-#pragma unroll
-                for (int q = 0; q < 5; ++q)
-                {
-                    s00 = fma(w0[q], h0[q], s00);
-                    s01 = fma(w0[q], h1[q], s01);
-                    s10 = fma(w1[q], h0[q], s10);
-                    s11 = fma(w1[q], h1[q], s11);
-                }
+                const double e0 = w0[3] - w0[1], f0 = w0[4] - w0[2], e1 = w1[3] - w1[1], f1 = w1[4] - w1[2];
+                const double s00 = fma(dx, e0, dy * f0), s01 = fma(dx, f0, fma(-dy, e0, -d * w0[0]));
+                const double s10 = fma(dx, e1, dy * f1), s11 = fma(dx, f1, fma(-dy, e1, -d * w1[0]));
                 const double rs = rsqrt_1(d);
                 double sq = d * rs;
                 sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);
@@ -747,6 +740,28 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
                 }
             }
             // (D) one DMMA pass applies the chunk to the fragments: C += (-Kt) Wt, k = (u0, u1, v0, v1)
+            if (ASSOC && NUSLAM_ASSOC_DFMA)
+            {
+                // one measurement per pass: half of a DMMA's k would be empty, and the fp64 pipe takes as long for an m8n8k4 DMMA as for
+                // eight DFMAs -- the rank-2 update of the 18 fragment entries by 36 plain FMAs holds it half as long as the 9 DMMAs
+                double2 ka2[NB], w0[NB], w1[NB];
+#pragma unroll
+                for (int bb = 0; bb < NB; ++bb)
+                {
+                    ka2[bb] = f.kt[0][3 + 8 * bb + g];
+                    w0[bb] = f.wt[0][3 + 8 * bb + 2 * t];
+                    w1[bb] = f.wt[0][3 + 8 * bb + 2 * t + 1];
+                }
+#pragma unroll
+                for (int br = 0; br < NB; ++br)
+#pragma unroll
+                    for (int bc = 0; bc < NB; ++bc)
+                    {
+                        C[br][bc][0] = fma(ka2[br].x, w0[bc].x, fma(ka2[br].y, w0[bc].y, C[br][bc][0]));
+                        C[br][bc][1] = fma(ka2[br].x, w1[bc].x, fma(ka2[br].y, w1[bc].y, C[br][bc][1]));
+                    }
+            }
+            else
             {
                 const double * ka = reinterpret_cast<const double *>(&f.kt[t >> 1][3 + g]) + (t & 1);
                 const double * wa = reinterpret_cast<const double *>(&f.wt[t >> 1][3 + g]) + (t & 1);

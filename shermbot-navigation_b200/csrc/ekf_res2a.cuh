@@ -289,30 +289,18 @@ k_ekf_res2a_step(const EkfParams p, const int do_predict, int32_t * __restrict__
                     const double2 zz = *reinterpret_cast<const double2 *>(&f.z[h][2 * (im & 15)]);
                     const double dx = mxc - px, dy = myc - py;
                     const double d = fma(dx, dx, dy * dy);
-                    const double h0[5] = {0.0, -dx, -dy, dx, dy}, h1[5] = {-d, dy, -dx, -dy, dx};
+                    // psi = Ht B Ht^T + R~ written out on the structure of the division-free rows (ekf_fast.cuh: 49 operations instead of 70 FMAs)
                     double w0[5], w1[5];
 #pragma unroll
                     for (int qq = 0; qq < 5; ++qq)
                     {
-                        double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                        for (int r = 0; r < 5; ++r)
-                        {
-                            a0 = fma(h0[r], Bm[r][qq], a0);
-                            a1 = fma(h1[r], Bm[r][qq], a1);
-                        }
-                        w0[qq] = a0;
-                        w1[qq] = a1;
+                        const double e = Bm[3][qq] - Bm[1][qq], g2 = Bm[4][qq] - Bm[2][qq];
+                        w0[qq] = fma(dx, e, dy * g2);
+                        w1[qq] = fma(dx, g2, fma(-dy, e, -d * Bm[0][qq]));
                     }
-                    double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-#pragma unroll
-                    for (int qq = 0; qq < 5; ++qq)
-                    {
-                        s00 = fma(w0[qq], h0[qq], s00);
-                        s01 = fma(w0[qq], h1[qq], s01);
-                        s10 = fma(w1[qq], h0[qq], s10);
-                        s11 = fma(w1[qq], h1[qq], s11);
-                    }
+                    const double e0 = w0[3] - w0[1], f0 = w0[4] - w0[2], e1 = w1[3] - w1[1], f1 = w1[4] - w1[2];
+                    const double s00 = fma(dx, e0, dy * f0), s01 = fma(dx, f0, fma(-dy, e0, -d * w0[0]));
+                    const double s10 = fma(dx, e1, dy * f1), s11 = fma(dx, f1, fma(-dy, e1, -d * w1[0]));
                     const double rs = rsqrt_1(d);
                     double sq = d * rs;
                     sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);
