@@ -33,13 +33,12 @@ k_ekf_res2a_step(const EkfParams p, const int do_predict, int32_t * __restrict__
     static_assert(G::FIXED && 2 * N == 8 * G::NB && G::LEN > 16 && G::LEN <= 32, "pair layout: two slots of 16 state indices, unpadded 8 x 8 tiles");
     static_assert(CH >= 2 && CH <= 4, "chunks of 2, 3 or 4 updates");
     constexpr int KS = (CH + 1) / 2;   // DMMA k-steps of a chunk's pass (an odd chunk leaves half of the last one empty)
-    constexpr int NB = G::NB, NL = N, LEN = G::LEN, SIG = G::SIG;
+    constexpr int NB = G::NB, LEN = G::LEN, SIG = G::SIG;
     static_assert(NB == 3, "row permutation written for three row blocks");
     constexpr unsigned kFull = 0xffffffffu;
     constexpr int kImg = SIG * 8, kPairBytes = 2 * kImg;   // a pair is 16-byte aligned in HBM whenever the array is
     // per warp: [the pair's two images][exchange area][mbarrier]
     extern __shared__ __align__(128) unsigned char res2_dyn[];
-    constexpr int kWarpBytes = kPairBytes + (int) sizeof(Res2Smem<CH>) + 16;
     static_assert(kPairBytes % 16 == 0 && sizeof(Res2Smem<CH>) % 16 == 0, "16-byte aligned pieces");
     unsigned char * const stage = res2_dyn;
     Res2Smem<CH> & f = *reinterpret_cast<Res2Smem<CH> *>(stage + kPairBytes);

@@ -1159,7 +1159,6 @@ inline cudaError_t launch_scan_detect(const float * ranges, int64_t n_scans, dou
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int64_t resident = (int64_t) sm_count * 5;
     const int64_t resident_cluster = (int64_t) sm_count * 11;   // clustering only: 90 registers x 64 threads, 8.8 KB of shared memory per CTA
     ScanPipe none;
     memset(&none, 0, sizeof(none));
