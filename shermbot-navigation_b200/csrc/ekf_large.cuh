@@ -196,9 +196,21 @@ __device__ __forceinline__ LargeModel large_model(const double * xl)
 // only). The 2 x 2 part needs W_i at those five columns, i.e. the 5 x 5 sub-block of Sigma_i: every block forms it for itself
 // (25 entries, same operation order as the owner threads use, so the values are bit-identical), which removes the grid-wide
 // hand-over between "W, P" and "K, x" -- one grid barrier (or kernel boundary) per measurement instead of two.
+// shared-memory copies the cooperative single-launch pass makes BEFORE its chain of dependent updates starts (known correspondence: the ids
+// of the whole pass, hence every row / column of Sigma_0 it will read, are known up front): with them an update waits for one round trip
+// to L2 (the earlier updates' K_u / W_u at its five indices, and the state) instead of three dependent ones
+struct LargePre
+{
+    const double * rc;    // [(6 + 4 cnt)][blockDim.x]: this thread's Sigma_0 entries -- rows 0, 1, 2, columns 0, 1, 2, then per update rows c, c + 1, columns c, c + 1
+    const double * blk;   // [cnt][25]: the 5 x 5 sub-block of Sigma_0 of every update
+    const int * id;       // [cnt]
+    const double * z;     // [cnt][2]
+};
+
 __device__ __forceinline__ void large_update(const LargeParams & p, const double * __restrict__ z, const int32_t * __restrict__ ids, int m, int i,
                                              const double * __restrict__ x_old, double * __restrict__ x_new,
-                                             const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen, double * own = nullptr)
+                                             const int32_t * __restrict__ seen_snapshot, int32_t * __restrict__ seen, double * own = nullptr,
+                                             const LargePre * pre = nullptr)
 {
     // own (cooperative single-launch pass only): this block's shared-memory copy of ITS threads' entries of the pass's K_u / W_u,
     // own[(2 r + {0: W, 1: K}) * blockDim.x + threadIdx.x] -- the correction loop then reads no global memory at all; the global U / V
@@ -206,7 +218,8 @@ __device__ __forceinline__ void large_update(const LargeParams & p, const double
     const int b = blockIdx.y;
     const int len = p.len;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int id = ids[b * m + i];
+    const int id = pre ? pre->id[i] : ids[b * m + i];
+    const double z2[2] = {pre ? pre->z[2 * i] : z[(int64_t) (b * m + i) * 2], pre ? pre->z[2 * i + 1] : z[(int64_t) (b * m + i) * 2 + 1]};
     const double * x = x_old + (int64_t) b * len;
     double * xo = x_new + (int64_t) b * len;
     const double * S = p.sigma + (int64_t) b * len * len;
@@ -228,7 +241,23 @@ __device__ __forceinline__ void large_update(const LargeParams & p, const double
     // this thread's entries of the five rows / columns of Sigma_0 and its local state: issued first, so that their latency overlaps
     // the staging of the shared operands below (the strided row gather is the longest load of the update)
     double row[5], col[5];   // Sigma_i(idx[q], j) and Sigma_i(j, idx[q])
-    if (j < len)
+    if (pre)
+    {
+        const double * rc = pre->rc + threadIdx.x;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+        {
+            row[q] = rc[q * blockDim.x];
+            col[q] = rc[(3 + q) * blockDim.x];
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+        {
+            row[3 + q] = rc[(6 + 4 * i + q) * blockDim.x];
+            col[3 + q] = rc[(8 + 4 * i + q) * blockDim.x];
+        }
+    }
+    else if (j < len)
     {
 #pragma unroll
         for (int q = 0; q < 5; ++q)
@@ -238,7 +267,7 @@ __device__ __forceinline__ void large_update(const LargeParams & p, const double
         }
     }
     double xl[5];
-    const bool init = large_local_state(x, c, id, z + (int64_t) (b * m + i) * 2, seen_snapshot, b, xl);
+    const bool init = large_local_state(x, c, id, z2, seen_snapshot, b, xl);
     const double x_own = (j < len) ? x[j] : 0.0;
     // K_u at the five rows and W_u at the five columns of every earlier update of the pass, and the 5 x 5 sub-block of Sigma_0
     __shared__ double ku[2 * kLargeMMax][5], wu[2 * kLargeMMax][5], blk[5][5];
@@ -251,7 +280,7 @@ __device__ __forceinline__ void large_update(const LargeParams & p, const double
     if (threadIdx.x < 25)
     {
         const int r = threadIdx.x / 5, q = threadIdx.x % 5;
-        blk[r][q] = S[idx[r] + (int64_t) idx[q] * len];
+        blk[r][q] = pre ? pre->blk[25 * i + threadIdx.x] : S[idx[r] + (int64_t) idx[q] * len];
     }
     __syncthreads();
     if (threadIdx.x < 25)
@@ -338,7 +367,7 @@ __device__ __forceinline__ void large_update(const LargeParams & p, const double
         own[(2 * (2 * i) + 1) * blockDim.x + threadIdx.x] = k0;
         own[(2 * (2 * i + 1) + 1) * blockDim.x + threadIdx.x] = k1;
     }
-    const double dz0 = z[(int64_t) (b * m + i) * 2] - mdl.zr, dz1 = z[(int64_t) (b * m + i) * 2 + 1] - mdl.zb;   // :272, no wrap
+    const double dz0 = z2[0] - mdl.zr, dz1 = z2[1] - mdl.zb;   // :272, no wrap
     double xn = xj + (k0 * dz0 + k1 * dz1);
     if (j == 0) xn = wrap_angle(xn);   // normalize_angle, slam_library.cpp:276
     xo[j] = xn;
@@ -512,17 +541,24 @@ __global__ void k_large_first_touch(const LargeParams p, const int32_t * __restr
     if (ids && !(p.status[b] & (kStatusMapFull | kStatusSingular)))
     {
         const double * S = p.sigma + (int64_t) b * p.len * p.len;
-        for (int i = 0; i < cnt; ++i)
+        // the variances of every measured landmark are read first (independent loads: one DRAM latency for the pass instead of one
+        // per measurement -- 17 us of the 400 us of an m = 12 scan at 4 096 landmarks), then the first hit decides
+        double d0[kLargeMMax], d1[kLargeMMax];
+#pragma unroll
+        for (int i = 0; i < kLargeMMax; ++i)
         {
-            const int id = ids[(int64_t) b * m + i0 + i];
+            const int id = (i < cnt) ? ids[(int64_t) b * m + i0 + i] : 0;
+            const bool ok = id >= 1 && id <= p.n;
+            const int c = ok ? 3 + 2 * (id - 1) : 0;
+            d0[i] = ok ? S[c + (int64_t) c * p.len] : 0.0;
+            d1[i] = ok ? S[c + 1 + (int64_t) (c + 1) * p.len] : 0.0;
+        }
+#pragma unroll
+        for (int i = kLargeMMax - 1; i >= 0; --i)
+        {
+            const int id = (i < cnt) ? ids[(int64_t) b * m + i0 + i] : 0;
             if (id < 1 || id > p.n) continue;
-            const int c = 3 + 2 * (id - 1);
-            if ((seen_snapshot && id > seen_snapshot[b]) || S[c + (int64_t) c * p.len] > kFirstTouchVariance ||
-                S[c + 1 + (int64_t) (c + 1) * p.len] > kFirstTouchVariance)
-            {
-                sf = i;
-                break;
-            }
+            if ((seen_snapshot && id > seen_snapshot[b]) || d0[i] > kFirstTouchVariance || d1[i] > kFirstTouchVariance) sf = i;
         }
     }
     p.strict_from[b] = sf;
@@ -602,37 +638,55 @@ __global__ void __launch_bounds__(64) k_large_updates_coop(const LargeParams p, 
 {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     __shared__ double own[4 * kLargeMMax * 64];   // 32 KB: this block's entries of the pass's W_u / K_u (large_update)
+    __shared__ int pre_id[kLargeMMax];
+    __shared__ double pre_z[2 * kLargeMMax];
+    extern __shared__ double large_dyn[];           // [(6 + 4 cnt) x 64] rows / columns of Sigma_0, then [cnt x 25] sub-blocks (LargePre)
+    double * pre_rc = large_dyn;
+    double * pre_blk = large_dyn + (6 + 4 * cnt) * 64;
     const double * xc = p.x;
     double * xn = p.x2;
-    // known correspondence: every update of the pass reads five rows and five columns of Sigma_0 whose indices are known now -- pull
-    // them towards L2 before the chain of dependent updates starts (the strided row gather from DRAM was its longest step)
+    // known correspondence: every update of the pass reads five rows and five columns of Sigma_0 whose indices are known now -- they are
+    // loaded into shared memory before the chain of dependent updates starts (the strided row gather from DRAM was its longest step;
+    // round 2, session 3: loads instead of the L2 prefetches of session 2, which still left an L2 round trip per update in the chain)
     {
         const int b = blockIdx.y, len = p.len;
         const int j = blockIdx.x * blockDim.x + threadIdx.x;
+        const int jj = j < len ? j : len - 1;   // the last block's spare threads load a valid entry they never use
         const double * S = p.sigma + (int64_t) b * len * len;
-        if (j < len)
-            for (int k = 0; k < cnt; ++k)
-            {
-                const int id = ids[b * m + k];
-                if (id < 1 || id > p.n) continue;
-                const int c = 3 + 2 * (id - 1);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(S + c + (int64_t) j * len));       // rows c, c + 1 at column j (one sector)
-                if ((j & 3) == 0)
-                {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(S + j + (int64_t) c * len));         // columns c, c + 1: 32-byte sectors
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(S + j + (int64_t) (c + 1) * len));
-                }
-            }
-        if (j < len)
+        if (threadIdx.x < cnt)
         {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(S + (int64_t) j * len));   // rows 0, 1, 2 at column j
-            if ((j & 3) == 0)
-                for (int q = 0; q < 3; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(S + j + (int64_t) q * len));
+            pre_id[threadIdx.x] = ids[b * m + threadIdx.x];
+            pre_z[2 * threadIdx.x] = z[(int64_t) (b * m + threadIdx.x) * 2];
+            pre_z[2 * threadIdx.x + 1] = z[(int64_t) (b * m + threadIdx.x) * 2 + 1];
         }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+        {
+            pre_rc[q * 64 + threadIdx.x] = S[q + (int64_t) jj * len];
+            pre_rc[(3 + q) * 64 + threadIdx.x] = S[jj + (int64_t) q * len];
+        }
+        for (int k = 0; k < cnt; ++k)
+        {
+            const int id = ids[b * m + k];
+            if (id < 1 || id > p.n) continue;   // block-uniform; large_update returns before it reads the slot
+            const int c = 3 + 2 * (id - 1);
+            pre_rc[(6 + 4 * k) * 64 + threadIdx.x] = S[c + (int64_t) jj * len];
+            pre_rc[(7 + 4 * k) * 64 + threadIdx.x] = S[c + 1 + (int64_t) jj * len];
+            pre_rc[(8 + 4 * k) * 64 + threadIdx.x] = S[jj + (int64_t) c * len];
+            pre_rc[(9 + 4 * k) * 64 + threadIdx.x] = S[jj + (int64_t) (c + 1) * len];
+            if (threadIdx.x < 25)
+            {
+                const int idx[5] = {0, 1, 2, c, c + 1};
+                const int r = threadIdx.x / 5, q = threadIdx.x % 5;
+                pre_blk[25 * k + threadIdx.x] = S[idx[r] + (int64_t) idx[q] * len];
+            }
+        }
+        __syncthreads();
     }
+    const LargePre pre = {pre_rc, pre_blk, pre_id, pre_z};
     for (int k = 0; k < cnt; ++k)
     {
-        large_update(p, z, ids, m, k, xc, xn, seen_snapshot, seen, own);
+        large_update(p, z, ids, m, k, xc, xn, seen_snapshot, seen, own, &pre);
         grid.sync();
         const double * t = xc;
         xc = xn;
@@ -658,7 +712,10 @@ __device__ __forceinline__ void dmma884_large(double & c0, double & c1, double a
 // Sigma <- Sigma - K W with K = U^T (len x 2m), W = V (2m x len): CTA tile 64 x 64 (4 warps of 32 x 32), operands staged in
 // shared memory, accumulators initialised from Sigma. kk = padded 2m (multiple of 4).
 constexpr int kLargeTile = 64;
-__global__ void __launch_bounds__(128) k_large_rank_update(const LargeParams p, int kk)
+#ifndef NUSLAM_LARGE_RANK_CTAS
+#define NUSLAM_LARGE_RANK_CTAS 4   // resident CTAs per SM the register allocation aims at (3 at 148 registers: measured slower at rank >= 24)
+#endif
+__global__ void __launch_bounds__(128, NUSLAM_LARGE_RANK_CTAS) k_large_rank_update(const LargeParams p, int kk)
 {
     __shared__ double su[2 * kLargeMMax][kLargeTile + 1];   // -K: su[k][r]
     __shared__ double sv[2 * kLargeMMax][kLargeTile + 1];   //  W: sv[k][c]
@@ -668,16 +725,11 @@ __global__ void __launch_bounds__(128) k_large_rank_update(const LargeParams p, 
     double * S = p.sigma + (int64_t) b * len * len;
     const double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
     const double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
-    for (int e = threadIdx.x; e < kk * kLargeTile; e += blockDim.x)
-    {
-        const int k = e / kLargeTile, o = e % kLargeTile;
-        su[k][o] = (r0 + o < len) ? -U[(int64_t) k * len + r0 + o] : 0.0;
-        sv[k][o] = (c0 + o < len) ? V[(int64_t) k * len + c0 + o] : 0.0;
-    }
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int wr = r0 + 32 * (warp >> 1), wc = c0 + 32 * (warp & 1);
+    // the accumulators (this warp's 32 x 32 piece of Sigma: the DRAM stream of the pass) are requested FIRST, the operand staging below
+    // (kk x 64 entries of K and W each, from L2) runs under their latency
     double C[4][4][2];
 #pragma unroll
     for (int br = 0; br < 4; ++br)
@@ -689,6 +741,14 @@ __global__ void __launch_bounds__(128) k_large_rank_update(const LargeParams p, 
                 const int row = wr + 8 * br + g, col = wc + 8 * bc + 2 * t + e;
                 C[br][bc][e] = (row < len && col < len) ? __ldcs(S + (int64_t) col * len + row) : 0.0;
             }
+#pragma unroll 4
+    for (int e = threadIdx.x; e < kk * kLargeTile; e += blockDim.x)
+    {
+        const int k = e / kLargeTile, o = e % kLargeTile;
+        su[k][o] = (r0 + o < len) ? -U[(int64_t) k * len + r0 + o] : 0.0;
+        sv[k][o] = (c0 + o < len) ? V[(int64_t) k * len + c0 + o] : 0.0;
+    }
+    __syncthreads();
     for (int k0 = 0; k0 < kk; k0 += 4)
     {
         double a[4], bb[4];
@@ -713,6 +773,138 @@ __global__ void __launch_bounds__(128) k_large_rank_update(const LargeParams p, 
                 const int row = wr + 8 * br + g, col = wc + 8 * bc + 2 * t + e;
                 if (row < len && col < len) __stcs(S + (int64_t) col * len + row, C[br][bc][e]);
             }
+}
+
+// The same pass as a persistent, software-pipelined kernel (round 2, session 3). k_large_rank_update above is a load -> compute -> store
+// sequence per CTA whose accumulator registers are the only landing zone of the DRAM stream: at rank 24 its DMMA phase (0.8 us per tile)
+// keeps a third of the resident warps from having loads in flight and the pass drops from 0.82 to 0.55 of the copy roof (290 us against
+// 199 us at rank 4, measured). Here every CTA walks its tiles with the NEXT tile of Sigma on its way into shared memory while the
+// current one is in the DMMAs (8-byte cp.async: Sigma's columns are only 8-byte aligned, len is odd; one 64 x 66 stage per CTA, the
+// padding makes the fragment reads conflict-free per half-warp), so four resident CTAs keep 128 KB per SM in flight all the time; the
+// operands come straight from L2 / L1 in fragment layout (K and W of the pass are 3 MB: no staging phase, no barrier in front of the
+// DMMAs). Same DMMA order per accumulator: bit-identical results.
+// (Two stages per CTA at three CTAs per SM -- 96 KB in flight -- were measured slower than the plain kernel: 0.28 ms at rank 4.)
+constexpr int kRankStageLd = kLargeTile + 2;   // column stride of a stage in doubles (66: 2 x 66 = 4 mod 16, the four t of a half-warp hit disjoint banks)
+constexpr int kRankStageDoubles = kLargeTile * kRankStageLd;
+#ifndef NUSLAM_LARGE_RANK_PIPE
+#define NUSLAM_LARGE_RANK_PIPE 1
+#endif
+constexpr int kRankPipeCtas = 4;
+__global__ void __launch_bounds__(128, kRankPipeCtas) k_large_rank_update_pipe(const LargeParams p, int kk, int tiles)
+{
+    extern __shared__ __align__(16) double rank_stage[];   // [64 columns][66]
+    const int len = p.len;
+    const int64_t ntiles = (int64_t) tiles * tiles * p.batch;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int lr = 32 * (warp >> 1), lc = 32 * (warp & 1);
+    // tile id -> (filter, column block, row block): consecutive ids walk down a column strip
+    auto issue = [&](int64_t tile) {
+        const int b = (int) (tile / ((int64_t) tiles * tiles));
+        const int rem = (int) (tile % ((int64_t) tiles * tiles));
+        const int c0 = (rem / tiles) * kLargeTile, r0 = (rem % tiles) * kLargeTile;
+        const double * S = p.sigma + (int64_t) b * len * len;
+        // thread -> one row of the tile (threadIdx.x & 63) and every second column: one pointer walking 2 len doubles per copy
+        const int row = threadIdx.x & 63, col0 = threadIdx.x >> 6;
+        const bool row_ok = r0 + row < len;
+        const double * src = S + (int64_t) (c0 + col0) * len + r0 + row;
+        const unsigned sa = (unsigned) __cvta_generic_to_shared(rank_stage + col0 * kRankStageLd + row);
+        const int ncol = len - c0 - col0;   // columns c0 + col0 + 2 i with 2 i < ncol exist
+#pragma unroll
+        for (int i = 0; i < kLargeTile / 2; ++i)
+        {
+            const bool ok = row_ok && 2 * i < ncol;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa + (unsigned) (2 * i * kRankStageLd * 8)), "l"(ok ? src : S), "r"(ok ? 8 : 0)
+                         : "memory");   // out of range: zero fill
+            src += 2 * (int64_t) len;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int64_t tile = blockIdx.x;
+    if (tile < ntiles) issue(tile);
+    for (; tile < ntiles; tile += gridDim.x)
+    {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        double C[4][4][2];
+#pragma unroll
+        for (int br = 0; br < 4; ++br)
+#pragma unroll
+            for (int bc = 0; bc < 4; ++bc)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) C[br][bc][e] = rank_stage[(lc + 8 * bc + 2 * t + e) * kRankStageLd + lr + 8 * br + g];
+        __syncthreads();   // the stage is free: the next tile starts its way in while this one is in the DMMAs
+        if (tile + gridDim.x < ntiles) issue(tile + gridDim.x);
+        const int b = (int) (tile / ((int64_t) tiles * tiles));
+        const int rem = (int) (tile % ((int64_t) tiles * tiles));
+        const int c0 = (rem / tiles) * kLargeTile, r0 = (rem % tiles) * kLargeTile;
+        double * S = p.sigma + (int64_t) b * len * len;
+        const double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
+        const double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
+        // operands in fragment layout straight from L2 / L1: a = -K(row, k0 + t), b = W(k0 + t, column); rows / columns beyond len: 0
+        for (int k0 = 0; k0 < kk; k0 += 4)
+        {
+            const double * Uk = U + (int64_t) (k0 + t) * len + r0 + lr + g;
+            const double * Vk = V + (int64_t) (k0 + t) * len + c0 + lc + g;
+            double a[4], bb[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+            {
+                a[q] = (r0 + lr + 8 * q + g < len) ? -__ldg(Uk + 8 * q) : 0.0;
+                bb[q] = (c0 + lc + 8 * q + g < len) ? __ldg(Vk + 8 * q) : 0.0;
+            }
+#pragma unroll
+            for (int br = 0; br < 4; ++br)
+#pragma unroll
+                for (int bc = 0; bc < 4; ++bc) dmma884_large(C[br][bc][0], C[br][bc][1], a[br], bb[bc]);
+        }
+#pragma unroll
+        for (int br = 0; br < 4; ++br)
+#pragma unroll
+            for (int bc = 0; bc < 4; ++bc)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                {
+                    const int row = r0 + lr + 8 * br + g, col = c0 + lc + 8 * bc + 2 * t + e;
+                    if (row < len && col < len) __stcs(S + (int64_t) col * len + row, C[br][bc][e]);
+                }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+inline cudaError_t launch_large_rank_update(const LargeParams & p, int kk, cudaStream_t st)
+{
+    const unsigned tiles = (p.len + kLargeTile - 1) / kLargeTile;
+#if NUSLAM_LARGE_RANK_PIPE
+    // measured at 4 096 landmarks (tools/gpu_round2_ag.sh): rank 4: plain 0.20 ms, pipelined 0.23 ms; rank 24: 0.30 / 0.27 ms; rank 32: 0.37 / 0.33 ms
+    static const int pipe_min_rank = [] {
+        const char * e = getenv("NUSLAM_LARGE_PIPE_MIN_RANK");   // A/B timing
+        return e ? atoi(e) : 16;
+    }();
+    if (kk < pipe_min_rank)
+    {
+        k_large_rank_update<<<dim3(tiles, tiles, (unsigned) p.batch), 128, 0, st>>>(p, kk);
+        return cudaGetLastError();
+    }
+    static int sms_dev[kMaxDevices] = {0};
+    int & sms = sms_dev[device_slot()];
+    constexpr int kSmem = kRankStageDoubles * (int) sizeof(double);
+    if (sms == 0)
+    {
+        int dev = 0, n = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        const cudaError_t e = cudaFuncSetAttribute(k_large_rank_update_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return e;
+        sms = n > 0 ? n : 1;
+    }
+    int64_t blocks = (int64_t) tiles * tiles * p.batch;
+    if (blocks > kRankPipeCtas * (int64_t) sms) blocks = kRankPipeCtas * (int64_t) sms;
+    k_large_rank_update_pipe<<<(unsigned) blocks, 128, kSmem, st>>>(p, kk, (int) tiles);
+#else
+    k_large_rank_update<<<dim3(tiles, tiles, (unsigned) p.batch), 128, 0, st>>>(p, kk);
+#endif
+    return cudaGetLastError();
 }
 
 // initializeLandmark (slam_library.cpp:255-261) for measurement i of the step when its id exceeds the scan's seen snapshot
@@ -780,8 +972,8 @@ inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const
             p.x = p.x2;
             p.x2 = tmp;
         }
-        const unsigned tiles = (p.len + kLargeTile - 1) / kLargeTile;
-        k_large_rank_update<<<dim3(tiles, tiles, (unsigned) p.batch), 128, 0, st>>>(p, kk);
+        const cudaError_t re = launch_large_rank_update(p, kk, st);
+        if (re != cudaSuccess) return re;
         tail();
         return cudaGetLastError();
     }
@@ -798,7 +990,9 @@ inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_large_updates_coop, threads, 0);
+        const size_t dyn_max = ((size_t) (6 + 4 * kLargeMMax) * 64 + 25 * kLargeMMax) * sizeof(double);
+        if (cudaFuncSetAttribute(k_large_updates_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dyn_max) != cudaSuccess) can = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_large_updates_coop, threads, dyn_max);
         coop_blocks_per_sm = can ? nb * sms : 0;
     }
     if ((int64_t) grid.x * grid.y <= coop_blocks_per_sm)
@@ -806,7 +1000,8 @@ inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const
         const double * zz = z + 2 * (int64_t) i0;
         const int32_t * ii = ids + i0;
         void * args[] = {(void *) &p, (void *) &zz, (void *) &ii, (void *) &m, (void *) &cnt, (void *) &seen_snapshot, (void *) &seen};
-        cudaError_t ce = cudaLaunchCooperativeKernel((const void *) k_large_updates_coop, grid, dim3(threads), args, 0, st);
+        const size_t dyn = ((size_t) (6 + 4 * cnt) * 64 + 25 * cnt) * sizeof(double);   // LargePre
+        cudaError_t ce = cudaLaunchCooperativeKernel((const void *) k_large_updates_coop, grid, dim3(threads), args, dyn, st);
         if (ce != cudaSuccess) return ce;
         if (cnt & 1)
         {
@@ -824,8 +1019,8 @@ inline cudaError_t launch_large_updates(LargeParams & p, const double * z, const
         p.x = p.x2;
         p.x2 = tmp;
     }
-    const unsigned tiles = (p.len + kLargeTile - 1) / kLargeTile;
-    k_large_rank_update<<<dim3(tiles, tiles, (unsigned) p.batch), 128, 0, st>>>(p, kk);
+    const cudaError_t re = launch_large_rank_update(p, kk, st);
+    if (re != cudaSuccess) return re;
     tail();
     return cudaGetLastError();
 }

@@ -98,7 +98,6 @@ k_ekf_res2a_step(const EkfParams p, const int do_predict, int32_t * __restrict__
     {
         const int64_t bf = 2 * pr + h;
         const bool has = bf < p.batch;
-        const int64_t bfc = has ? bf : 2 * pr;   // safe addressing for the missing twin of an odd batch
         const bool next = pr + gwn < npairs;
         if (NUSLAM_RES2_L2PREFETCH && lane == 0 && pr + 2 * gwn < npairs)   // the pair after next: towards L2 while this one is computed
         {
