@@ -62,6 +62,17 @@ inline cudaError_t world_tables_init(int device)
     return cudaSuccess;
 }
 
+// world_ray's first decision on its own: true when the ray misses the tube for certain (world_ray then returns max_range + 1, the value
+// the beams are initialised with: such a ray changes nothing). Same expressions, same values as in world_ray.
+__device__ __forceinline__ bool world_ray_far(double x1, double y1, double c, double s, double tube_rad, double max_range)
+{
+    const double x2 = add_(x1, mul_(max_range, c));
+    const double y2 = add_(y1, mul_(max_range, s));
+    const double det = sub_(mul_(x1, y2), mul_(x2, y1));
+    const double rr = mul_(tube_rad, tube_rad);
+    return det * det > fma(rr * (max_range * max_range), 1.0 + 1e-9, 2e-5);
+}
+
 // one ray of simulate_lidar_scanner (tube_world.cpp:429-457): robot at (x1, y1) relative to the tube centre, direction (c, s)
 __device__ __forceinline__ double world_ray(double x1, double y1, double c, double s, double tube_rad, double max_range)
 {
@@ -188,19 +199,56 @@ __global__ void __launch_bounds__(32 * kWorldWarps) k_world_scan(const WorldPara
     }
     __syncwarp();
     const int th_deg = (int) mul_(180.0 / kWorldPi, th);   // int(rad2deg(th)), :459
-    for (int item = lane; item < p.n_tubes * kWorldRays; item += 32)
-    {
+    // Two phases. Most of the 54 rays of a tube's window miss it for certain (world_ray_far: a dozen operations); the few that do not
+    // take the reference's full expressions (five IEEE divisions, four square roots: ~200 instructions). Evaluated in place, almost every
+    // group of 32 consecutive rays contains a near one and the whole warp walks the long path for a handful of lanes; so the near rays
+    // are first compacted into a queue (ballot + popcount) and the long path runs on full warps of them.
+    __shared__ unsigned short s_q[kWorldWarps][64];
+    constexpr unsigned kFull = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    auto ray = [&](const int item) {
         const int t = item / kWorldRays, k = item - t * kWorldRays;
-        const int ta = s_ta[warp][t];
-        if (ta == 1000) continue;
-        const int i = ta - 27 + k;
+        const int i = s_ta[warp][t] - 27 + k;
         const double x1 = sub_(x, p.tubes[2 * t]), y1 = sub_(y, p.tubes[2 * t + 1]);
         const double dist = world_ray(x1, y1, __ldg(&g_world_cos[i - kWorldDegMin]), __ldg(&g_world_sin[i - kWorldDegMin]), p.tube_rad, p.max_range);
         int ind = (i - th_deg) % 360;
         if (ind < 0) ind += 360;
         // `if (distance < ranges[ind]) ranges[ind] = distance` (:462-464): a NaN distance never stores; otherwise the minimum
         if (dist == dist) atomicMin(&s_r[warp][ind], __float_as_int((float) dist));
+    };
+    const int n_items = p.n_tubes * kWorldRays;
+    int nq = 0;
+    for (int base = 0; base < n_items; base += 32)
+    {
+        const int item = base + lane;
+        bool near = false;
+        if (item < n_items)
+        {
+            const int t = item / kWorldRays, k = item - t * kWorldRays;
+            const int ta = s_ta[warp][t];
+            if (ta != 1000)
+            {
+                const int i = ta - 27 + k;
+                const double x1 = sub_(x, p.tubes[2 * t]), y1 = sub_(y, p.tubes[2 * t + 1]);
+                near = !world_ray_far(x1, y1, __ldg(&g_world_cos[i - kWorldDegMin]), __ldg(&g_world_sin[i - kWorldDegMin]), p.tube_rad, p.max_range);
+            }
+        }
+        const unsigned mask = __ballot_sync(kFull, near);
+        if (near) s_q[warp][nq + __popc(mask & lt)] = (unsigned short) item;
+        nq += __popc(mask);
+        __syncwarp();
+        if (nq >= 32)
+        {
+            ray((int) s_q[warp][lane]);
+            const int rest = nq - 32;
+            const unsigned short moved = (lane < rest) ? s_q[warp][32 + lane] : (unsigned short) 0;
+            __syncwarp();
+            if (lane < rest) s_q[warp][lane] = moved;
+            nq = rest;
+            __syncwarp();
+        }
     }
+    if (lane < nq) ray((int) s_q[warp][lane]);
     __syncwarp();
     float * out = p.ranges + 360 * b;
     for (int k = lane; k < 360; k += 32) out[k] = __int_as_float(s_r[warp][k]);
