@@ -842,21 +842,35 @@ __global__ void __launch_bounds__(128, kRankPipeCtas) k_large_rank_update_pipe(c
         const double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
         const double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
         // operands in fragment layout straight from L2 / L1: a = -K(row, k0 + t), b = W(k0 + t, column); rows / columns beyond len: 0
-        for (int k0 = 0; k0 < kk; k0 += 4)
+#ifndef NUSLAM_LARGE_PIPE_KSTEPS
+#define NUSLAM_LARGE_PIPE_KSTEPS 1   // k-steps whose operands are requested together; 2 and 3 measured slower (m = 12 scan 0.408 / 0.419 ms against 0.348)
+#endif
+        constexpr int KS = NUSLAM_LARGE_PIPE_KSTEPS;
+        for (int k0 = 0; k0 < kk; k0 += 4 * KS)
         {
-            const double * Uk = U + (int64_t) (k0 + t) * len + r0 + lr + g;
-            const double * Vk = V + (int64_t) (k0 + t) * len + c0 + lc + g;
-            double a[4], bb[4];
+            double a[KS][4], bb[KS][4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int ks = 0; ks < KS; ++ks)
             {
-                a[q] = (r0 + lr + 8 * q + g < len) ? -__ldg(Uk + 8 * q) : 0.0;
-                bb[q] = (c0 + lc + 8 * q + g < len) ? __ldg(Vk + 8 * q) : 0.0;
+                const bool on = k0 + 4 * ks < kk;   // kk is a multiple of 4, not of 4 KS
+                const double * Uk = U + (int64_t) (k0 + 4 * ks + t) * len + r0 + lr + g;
+                const double * Vk = V + (int64_t) (k0 + 4 * ks + t) * len + c0 + lc + g;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                {
+                    a[ks][q] = (on && r0 + lr + 8 * q + g < len) ? -__ldg(Uk + 8 * q) : 0.0;
+                    bb[ks][q] = (on && c0 + lc + 8 * q + g < len) ? __ldg(Vk + 8 * q) : 0.0;
+                }
             }
 #pragma unroll
-            for (int br = 0; br < 4; ++br)
+            for (int ks = 0; ks < KS; ++ks)
+                if (k0 + 4 * ks < kk)
+                {
 #pragma unroll
-                for (int bc = 0; bc < 4; ++bc) dmma884_large(C[br][bc][0], C[br][bc][1], a[br], bb[bc]);
+                    for (int br = 0; br < 4; ++br)
+#pragma unroll
+                        for (int bc = 0; bc < 4; ++bc) dmma884_large(C[br][bc][0], C[br][bc][1], a[ks][br], bb[ks][bc]);
+                }
         }
 #pragma unroll
         for (int br = 0; br < 4; ++br)

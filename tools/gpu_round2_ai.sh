@@ -1,9 +1,10 @@
 #!/bin/bash
+# large-map pipelined rank update: operands of 1 / 2 / 3 k-steps requested together
 mkdir -p gpurun_out
 timeout -s KILL 900 python -m pytest tests/test_large_gpu.py -m gpu -x -q > gpurun_out/ai_tests.log 2>&1
 echo "large tests rc=$?"; tail -2 gpurun_out/ai_tests.log
-for r in 16 0 1000; do
-NUSLAM_LARGE_PIPE_MIN_RANK=$r timeout -s KILL 600 python tools/bench_large.py > gpurun_out/ai_bench_large.json 2> gpurun_out/ai_bench_large.err; echo "min rank $r bench rc=$?"
+for lib in shermbot-navigation_b200/libnuslam_b200.so build/variants/lib_ks1.so build/variants/lib_ks3.so; do
+NUSLAM_B200_LIB=$lib timeout -s KILL 600 python tools/bench_large.py > gpurun_out/ai_bench_large.json 2> gpurun_out/ai_bench_large.err; echo "$lib bench rc=$?"
 python - <<'P'
 import json
 d=json.loads(open('gpurun_out/ai_bench_large.json').read().strip().splitlines()[-1])
