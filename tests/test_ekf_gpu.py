@@ -664,3 +664,44 @@ def test_against_committed_golden_vectors(cuda_lib, mode, tag):
     print(f"[golden {tag}/{mode}] ids mismatching {mism}, x rel {ex:.2e}, Sigma rel {es:.2e}")
     assert n == 12 and mism == 0 and np.array_equal(seen, g[f"{tag}_seen"]) and not status.any()
     assert ex < TOL and es < TOL
+
+
+def test_device_side_launch_of_the_list_kernel_matches_host_launch(cuda_lib, tmp_path):
+    """FAST mode with known correspondence launches the oracle-order list kernel from the device (tail launch, ekf_strict.cuh
+    strict_tail) -- only when a filter was handed over. A from-scratch run (every landmark's first touch goes through the list kernel,
+    later steps launch nothing) must give bit-identical state to the same run with the host launching the list kernel after every
+    step (NUSLAM_NO_TAIL_LAUNCH=1, read once per process: the second run is a subprocess)."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    if not cuda_lib.lib().nuslam_tail_launch():
+        pytest.skip("library built without device-side launches")
+    B, T, n = 33, 12, 12   # odd batch: the last pair of the resident pair kernel has one filter
+    sc = synth.ekf_scenario(B, T, n=n, geometry="benign", seed=29)
+    eng = make_engine(cuda_lib, sc, "fast")
+    for t in range(T):
+        eng.step(sc["twists"][t], sc["z"][t], sc["ids"][t])
+    x, s, seen, status = eng.get_state()
+    eng.close()
+    out = tmp_path / "host_launch.npz"
+    root = Path(__file__).resolve().parent.parent
+    code = f"""
+import sys
+sys.path.insert(0, {str(root)!r})
+import numpy as np
+from shermbot_navigation_b200 import nuslam, synth
+assert nuslam.lib().nuslam_tail_launch() == 0
+sc = synth.ekf_scenario({B}, {T}, n={n}, geometry="benign", seed=29)
+eng = nuslam.BatchedExtendedKalman(sc["robot0"], sc["map0"], sc["Q"], sc["R"], mode="fast")
+for t in range({T}):
+    eng.step(sc["twists"][t], sc["z"][t], sc["ids"][t])
+x, s, seen, status = eng.get_state()
+np.savez({str(out)!r}, x=x, s=s, seen=seen, status=status)
+"""
+    env = dict(os.environ, NUSLAM_NO_TAIL_LAUNCH="1")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+    ref = np.load(out)
+    assert np.array_equal(x, ref["x"]) and np.array_equal(s, ref["s"])
+    assert np.array_equal(seen, ref["seen"]) and np.array_equal(status, ref["status"]) and not status.any()
