@@ -518,7 +518,7 @@ inline cudaError_t launch_scan_moment(const float * ranges, int64_t n_scans, dou
     gate.max_f = float_below(max_range);
     gate.min_f = float_above(min_range);
     int64_t blocks = (n_scans + kMomWarps - 1) / kMomWarps;
-    const int64_t resident = (int64_t) sm_count * 8;
+    const int64_t resident = (int64_t) sm_count * NUSLAM_MOM_MINBLOCKS;
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
     k_scan_moment<<<(unsigned) blocks, 32 * kMomWarps, 0, stream>>>(ranges, n_scans, min_range, max_range, gate, cluster_of_beam, n_clusters, n_circles,
