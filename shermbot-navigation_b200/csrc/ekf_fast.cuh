@@ -28,11 +28,12 @@
 //
 // Both triangles of Sigma are kept: the reference's Sigma is NOT symmetric (its INT_MAX first touches leave |Sigma - Sigma^T| at
 // ~1e-6 relative and (I - KH) Sigma never restores it), and rows and columns enter the update separately.
-// Arithmetic: predict uses the oracle's operation order on the covariance (it is O(len)), one library sincos plus the
+// Arithmetic: predict uses the oracle's operation order on the covariance (it is O(len)), one call-free sincos (fastmath.cuh sincos_fast) plus the
 // addition theorems for the three angles. A filter-step that contains a landmark's
 // FIRST TOUCH (INT_MAX prior, slam_library.cpp:28-31, where only the reference's own operation order reproduces its
 // catastrophic cancellation) or an initializeLandmark is not evaluated here: the filter is
-// appended to a work list that the STRICT kernel (ekf_strict.cuh) processes right after on the same stream.
+// appended to a work list that the STRICT kernel (ekf_strict.cuh) processes right after on the same stream (launched by this
+// kernel itself in the relocatable unit -- strict_tail -- or by the host in the whole-program unit).
 // Reference: nuslam/src/slam_library.cpp:65-108 (predict), :263-282 (update), nuslam/src/slam.cpp:262-319.
 #pragma once
 #include "ekf_fast_api.cuh"
@@ -404,7 +405,7 @@ k_ekf_fast_step(const EkfParams p, const int do_predict, int32_t * __restrict__ 
             else
             {
                 const double q = div_fast(dxx, dth);
-                // sin / cos of theta + dth and theta + 2 dth by the addition theorems from ONE library sincos(theta) and the
+                // sin / cos of theta + dth and theta + 2 dth by the addition theorems from ONE sincos_fast(theta) and the
                 // small-angle series of dth (the oracle calls libm three times; the difference is a few ulp, far inside the tolerance)
                 double sd, cd;
                 sincos_small(dth, &sd, &cd);

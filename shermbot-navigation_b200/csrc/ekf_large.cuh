@@ -820,10 +820,29 @@ __global__ void __launch_bounds__(128, kRankPipeCtas) k_large_rank_update_pipe(c
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+#ifndef NUSLAM_LARGE_PIPE_L1PF
+#define NUSLAM_LARGE_PIPE_L1PF 2   // (measured: m = 32 scan 0.788 -> 0.775 -> 0.768 ms for 0 / 1 / 2, m = 12 within 1 %) pull a tile's K / W operands (kk x 64 doubles each) towards L1 ahead of the DMMAs: 1 at the top of its own round, 2 one round ahead
+#endif
+    auto prefetch_ops = [&](int64_t tl) {
+        const int b = (int) (tl / ((int64_t) tiles * tiles));
+        const int rem = (int) (tl % ((int64_t) tiles * tiles));
+        const int c0 = (rem / tiles) * kLargeTile, r0 = (rem % tiles) * kLargeTile;
+        const double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
+        const double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
+        // row k of K / W at the tile's 64 rows / columns: 512 bytes = up to five 128-byte lines each
+        for (int e = threadIdx.x; e < kk * 10; e += 128)
+        {
+            const int k = e / 10, w = e % 10;
+            const double * base = (w < 5 ? U + r0 : V + c0) + (int64_t) k * len;
+            const int o = 16 * (w % 5);
+            if ((w < 5 ? r0 : c0) + o < len) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + o));
+        }
+    };
     int64_t tile = blockIdx.x;
     if (tile < ntiles) issue(tile);
     for (; tile < ntiles; tile += gridDim.x)
     {
+        if (NUSLAM_LARGE_PIPE_L1PF == 1) prefetch_ops(tile);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         double C[4][4][2];
@@ -834,7 +853,11 @@ __global__ void __launch_bounds__(128, kRankPipeCtas) k_large_rank_update_pipe(c
 #pragma unroll
                 for (int e = 0; e < 2; ++e) C[br][bc][e] = rank_stage[(lc + 8 * bc + 2 * t + e) * kRankStageLd + lr + 8 * br + g];
         __syncthreads();   // the stage is free: the next tile starts its way in while this one is in the DMMAs
-        if (tile + gridDim.x < ntiles) issue(tile + gridDim.x);
+        if (tile + gridDim.x < ntiles)
+        {
+            issue(tile + gridDim.x);
+            if (NUSLAM_LARGE_PIPE_L1PF == 2) prefetch_ops(tile + gridDim.x);
+        }
         const int b = (int) (tile / ((int64_t) tiles * tiles));
         const int rem = (int) (tile % ((int64_t) tiles * tiles));
         const int c0 = (rem / tiles) * kLargeTile, r0 = (rem % tiles) * kLargeTile;
