@@ -789,7 +789,13 @@ constexpr int kRankStageDoubles = kLargeTile * kRankStageLd;
 #ifndef NUSLAM_LARGE_RANK_PIPE
 #define NUSLAM_LARGE_RANK_PIPE 1
 #endif
-constexpr int kRankPipeCtas = 4;
+#ifndef NUSLAM_LARGE_PIPE_SMEM_OPS
+#define NUSLAM_LARGE_PIPE_SMEM_OPS 0   // (measured slower: m = 12 scan 0.454 ms against 0.345) 1: the tile's K / W operands staged in shared memory (requested before the wait for the tile, read by LDS in the k-loop); 3 CTAs per SM
+#endif
+#ifndef NUSLAM_LARGE_PIPE_CTAS
+#define NUSLAM_LARGE_PIPE_CTAS (NUSLAM_LARGE_PIPE_SMEM_OPS ? 3 : 4)
+#endif
+constexpr int kRankPipeCtas = NUSLAM_LARGE_PIPE_CTAS;
 __global__ void __launch_bounds__(128, kRankPipeCtas) k_large_rank_update_pipe(const LargeParams p, int kk, int tiles)
 {
     extern __shared__ __align__(16) double rank_stage[];   // [64 columns][66]
@@ -843,8 +849,41 @@ __global__ void __launch_bounds__(128, kRankPipeCtas) k_large_rank_update_pipe(c
     for (; tile < ntiles; tile += gridDim.x)
     {
         if (NUSLAM_LARGE_PIPE_L1PF == 1) prefetch_ops(tile);
+#if NUSLAM_LARGE_PIPE_SMEM_OPS
+        // this tile's operands: requested now (their L2 latency runs under the wait for the tile), stored to shared memory behind the barrier
+        double (*su)[kLargeTile + 1] = reinterpret_cast<double (*)[kLargeTile + 1]>(rank_stage + kRankStageDoubles);
+        double (*sv)[kLargeTile + 1] = su + 2 * kLargeMMax;
+        double ur[kLargeMMax], vr[kLargeMMax];
+        {
+            const int b = (int) (tile / ((int64_t) tiles * tiles));
+            const int rem = (int) (tile % ((int64_t) tiles * tiles));
+            const int c0 = (rem / tiles) * kLargeTile, r0 = (rem % tiles) * kLargeTile;
+            const double * U = p.U + (int64_t) b * 2 * kLargeMMax * len;
+            const double * V = p.V + (int64_t) b * 2 * kLargeMMax * len;
+            const int o = threadIdx.x & 63, kh = threadIdx.x >> 6;   // element o of rows kh, kh + 2, ...
+#pragma unroll
+            for (int i = 0; i < kLargeMMax; ++i)
+            {
+                const int k = kh + 2 * i;
+                ur[i] = (k < kk && r0 + o < len) ? -__ldg(U + (int64_t) k * len + r0 + o) : 0.0;
+                vr[i] = (k < kk && c0 + o < len) ? __ldg(V + (int64_t) k * len + c0 + o) : 0.0;
+            }
+        }
+#endif
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+#if NUSLAM_LARGE_PIPE_SMEM_OPS
+        {
+            const int o = threadIdx.x & 63, kh = threadIdx.x >> 6;
+#pragma unroll
+            for (int i = 0; i < kLargeMMax; ++i)
+                if (kh + 2 * i < kk)
+                {
+                    su[kh + 2 * i][o] = ur[i];
+                    sv[kh + 2 * i][o] = vr[i];
+                }
+        }
+#endif
         double C[4][4][2];
 #pragma unroll
         for (int br = 0; br < 4; ++br)
@@ -881,8 +920,15 @@ __global__ void __launch_bounds__(128, kRankPipeCtas) k_large_rank_update_pipe(c
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                 {
+#if NUSLAM_LARGE_PIPE_SMEM_OPS
+                    (void) Uk;
+                    (void) Vk;
+                    a[ks][q] = on ? su[k0 + 4 * ks + t][lr + 8 * q + g] : 0.0;
+                    bb[ks][q] = on ? sv[k0 + 4 * ks + t][lc + 8 * q + g] : 0.0;
+#else
                     a[ks][q] = (on && r0 + lr + 8 * q + g < len) ? -__ldg(Uk + 8 * q) : 0.0;
                     bb[ks][q] = (on && c0 + lc + 8 * q + g < len) ? __ldg(Vk + 8 * q) : 0.0;
+#endif
                 }
             }
 #pragma unroll
@@ -925,7 +971,7 @@ inline cudaError_t launch_large_rank_update(const LargeParams & p, int kk, cudaS
     }
     static int sms_dev[kMaxDevices] = {0};
     int & sms = sms_dev[device_slot()];
-    constexpr int kSmem = kRankStageDoubles * (int) sizeof(double);
+    constexpr int kSmem = (kRankStageDoubles + (NUSLAM_LARGE_PIPE_SMEM_OPS ? 2 * 2 * kLargeMMax * (kLargeTile + 1) : 0)) * (int) sizeof(double);
     if (sms == 0)
     {
         int dev = 0, n = 0;
