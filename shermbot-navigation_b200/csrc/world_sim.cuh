@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(128) k_world_motion(const WorldParams p)
 }
 
 // stage 2: simulate_lidar_scanner :405-471, one WARP per robot: 54 rays x T tubes spread over the lanes
-__global__ void __launch_bounds__(32 * kWorldWarps) k_world_scan(const WorldParams p)
+__global__ void __launch_bounds__(32 * kWorldWarps, 8) k_world_scan(const WorldParams p)
 {
     __shared__ int s_r[kWorldWarps][360];
     __shared__ int s_ta[kWorldWarps][kWorldMaxTubes];
@@ -216,36 +216,38 @@ __global__ void __launch_bounds__(32 * kWorldWarps) k_world_scan(const WorldPara
         // `if (distance < ranges[ind]) ranges[ind] = distance` (:462-464): a NaN distance never stores; otherwise the minimum
         if (dist == dist) atomicMin(&s_r[warp][ind], __float_as_int((float) dist));
     };
-    const int n_items = p.n_tubes * kWorldRays;
     int nq = 0;
-    for (int base = 0; base < n_items; base += 32)
+    // phase 1 tube by tube (warp-uniform tube: its centre and window are read once, no integer division per ray): rays k = lane and
+    // lane + 32 of the tube's 54
+    for (int t = 0; t < p.n_tubes; ++t)
     {
-        const int item = base + lane;
-        bool near = false;
-        if (item < n_items)
+        const int ta = s_ta[warp][t];
+        if (ta == 1000) continue;   // warp-uniform
+        const double x1 = sub_(x, p.tubes[2 * t]), y1 = sub_(y, p.tubes[2 * t + 1]);
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
         {
-            const int t = item / kWorldRays, k = item - t * kWorldRays;
-            const int ta = s_ta[warp][t];
-            if (ta != 1000)
+            const int k = lane + 32 * half;
+            bool near = false;
+            if (k < kWorldRays)
             {
                 const int i = ta - 27 + k;
-                const double x1 = sub_(x, p.tubes[2 * t]), y1 = sub_(y, p.tubes[2 * t + 1]);
                 near = !world_ray_far(x1, y1, __ldg(&g_world_cos[i - kWorldDegMin]), __ldg(&g_world_sin[i - kWorldDegMin]), p.tube_rad, p.max_range);
             }
-        }
-        const unsigned mask = __ballot_sync(kFull, near);
-        if (near) s_q[warp][nq + __popc(mask & lt)] = (unsigned short) item;
-        nq += __popc(mask);
-        __syncwarp();
-        if (nq >= 32)
-        {
-            ray((int) s_q[warp][lane]);
-            const int rest = nq - 32;
-            const unsigned short moved = (lane < rest) ? s_q[warp][32 + lane] : (unsigned short) 0;
+            const unsigned mask = __ballot_sync(kFull, near);
+            if (near) s_q[warp][nq + __popc(mask & lt)] = (unsigned short) (t * kWorldRays + k);
+            nq += __popc(mask);
             __syncwarp();
-            if (lane < rest) s_q[warp][lane] = moved;
-            nq = rest;
-            __syncwarp();
+            if (nq >= 32)
+            {
+                ray((int) s_q[warp][lane]);
+                const int rest = nq - 32;
+                const unsigned short moved = (lane < rest) ? s_q[warp][32 + lane] : (unsigned short) 0;
+                __syncwarp();
+                if (lane < rest) s_q[warp][lane] = moved;
+                nq = rest;
+                __syncwarp();
+            }
         }
     }
     if (lane < nq) ray((int) s_q[warp][lane]);
