@@ -64,6 +64,9 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: Path 
         list(ex.map(lambda c: _run(c, verbose), cmds))
     # nvcc device-links the relocatable object (against cudadevrt) and links the shared library
     _run([nvcc(), *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", str(lib), *map(str, objs), "-lcudadevrt"], verbose)
+    if tag:   # experiment builds leave no objects behind (build/ travels to the GPU box with every gpurun call)
+        for o in objs:
+            o.unlink(missing_ok=True)
     return lib
 
 
