@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128) k_world_motion(const WorldParams p)
 // stage 2: simulate_lidar_scanner :405-471, one WARP per robot: 54 rays x T tubes spread over the lanes
 __global__ void __launch_bounds__(32 * kWorldWarps, 8) k_world_scan(const WorldParams p)
 {
-    __shared__ int s_r[kWorldWarps][360];
+    __shared__ __align__(16) int s_r[kWorldWarps][360];
     __shared__ int s_ta[kWorldWarps][kWorldMaxTubes];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t b = (int64_t) blockIdx.x * kWorldWarps + warp;
@@ -189,7 +189,10 @@ __global__ void __launch_bounds__(32 * kWorldWarps, 8) k_world_scan(const WorldP
     const double x = w[2], y = w[3], th = w[4];   // the configuration after the motion update
     // simulate_lidar_scanner :405-471
     const float fill = (float) add_(p.max_range, 1.0);   // :416
-    for (int k = lane; k < 360; k += 32) s_r[warp][k] = __float_as_int(fill);
+    {
+        const int fi = __float_as_int(fill);
+        for (int k = lane; k < 90; k += 32) reinterpret_cast<int4 *>(s_r[warp])[k] = make_int4(fi, fi, fi, fi);   // 360 beams, four per store
+    }
     for (int t = lane; t < p.n_tubes; t += 32)
     {
         const double xt = p.tubes[2 * t], yt = p.tubes[2 * t + 1];
@@ -253,7 +256,10 @@ __global__ void __launch_bounds__(32 * kWorldWarps, 8) k_world_scan(const WorldP
     if (lane < nq) ray((int) s_q[warp][lane]);
     __syncwarp();
     float * out = p.ranges + 360 * b;
-    for (int k = lane; k < 360; k += 32) out[k] = __int_as_float(s_r[warp][k]);
+    if ((reinterpret_cast<uintptr_t>(p.ranges) & 15) == 0)   // a scan is 1 440 bytes: 16-byte aligned whenever the array is
+        for (int k = lane; k < 90; k += 32) reinterpret_cast<int4 *>(out)[k] = reinterpret_cast<const int4 *>(s_r[warp])[k];
+    else
+        for (int k = lane; k < 360; k += 32) out[k] = __int_as_float(s_r[warp][k]);
 }
 
 inline cudaError_t launch_world_step(const WorldParams & p, int device, cudaStream_t stream)
